@@ -1,0 +1,208 @@
+/*
+ * rehrseg_b200 -- C-ABI of the B200 (sm_100a) hot-path library `librehrseg_b200.so`.
+ *
+ * The reference (zhiyuns/REHRSeg) has no FFI of its own: every heavy op is a torch.nn / ATen / numpy
+ * library call.  Each entry point below therefore names the reference *call site* it replaces
+ * (file:line relative to the reference root).  The Python host layer (rehrseg_b200/*.py) binds these
+ * with ctypes and re-exposes them as nn.Module / autograd.Function drop-ins.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch caching allocator); the library never
+ *    allocates, frees or synchronises.  Every call is enqueued on `stream` and returns immediately.
+ *  - Activations are channels-last ("NDHWC") tensors described by rehr_tensor: logical dims n,d,h,w,c and a
+ *    voxel pitch `ld` (elements between consecutive voxels, >= c) so channel slices of a concat buffer can be
+ *    passed without a copy.  bf16 unless the name says f32.
+ *  - Return value: 0 = OK, negative = rehr_status.  rehr_strerror() translates.  No exceptions cross the ABI.
+ *  - Thread-safe for concurrent calls on distinct streams (no hidden mutable state except a cached driver
+ *    entry point and SM count).
+ */
+#ifndef REHRSEG_B200_H_
+#define REHRSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rehr_stream; /* cudaStream_t */
+
+typedef enum {
+  REHR_OK = 0,
+  REHR_BAD_SHAPE = -1,      /* inconsistent dims between operands */
+  REHR_UNSUPPORTED = -2,    /* configuration outside what the kernels implement */
+  REHR_WORKSPACE = -3,      /* workspace too small */
+  REHR_CUDA_ERROR = -4,     /* a CUDA runtime / driver call failed (see rehr_last_cuda_error) */
+  REHR_BAD_ALIGNMENT = -5   /* pointer / pitch not aligned as required (16 B) */
+} rehr_status;
+
+typedef struct {
+  void* ptr;
+  int n, d, h, w, c;
+  long long ld; /* voxel pitch in elements */
+} rehr_tensor;
+
+/* A 3-D convolution "A <- B": weight Wc[A][B][kd][kh][kw], out[o] = sum_k Wc[k] . in[o*s + k - p].
+ * ConvTranspose3d (weight [Cin][Cout][k]) is the same object read backwards: its forward is
+ * rehr_conv3d_dgrad, its input-gradient is rehr_conv3d_fwd, its weight-gradient is rehr_conv3d_wgrad
+ * with the operands swapped (see rehr_convtranspose3d_* below). */
+typedef struct {
+  int kd, kh, kw; /* kernel  */
+  int sd, sh, sw; /* stride  (1 or 2 per dim) */
+  int pd, ph, pw; /* padding */
+} rehr_conv_desc;
+
+typedef enum { REHR_ACT_NONE = 0, REHR_ACT_RELU = 1, REHR_ACT_LRELU = 2 } rehr_act;
+
+const char* rehr_strerror(int status);
+int rehr_last_cuda_error(void);     /* cudaError_t of the last failing CUDA call on this thread */
+int rehr_version(void);             /* ABI version, currently 1 */
+int rehr_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense convolution engine (tcgen05 / TMEM implicit GEMM, TMA-staged NDHWC bf16 tiles).
+ * Replaces: torch.nn.Conv3d / ConvTranspose3d / Conv2d forward+backward as called by
+ *   dynamic_network_architectures ConvDropoutNormReLU.conv (built at models/seg_model.py:174-191),
+ *   UNetDecoder.transpconvs (models/seg_model.py:36), sr_head (models/seg_model.py:197-199),
+ *   FLAVR Conv3DSimple / Conv_3d / upConv3D / Conv_2d (models/FLAVR/resnet_3D.py:19-33,
+ *   models/FLAVR/FLAVR_arch.py:24-88).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Repack fp32 weights src[(r*sr + c*sc + t*st)] into bf16 dst[r][t][c] (the K-major GEMM operand).
+ *   fwd   of Wc[A][B][T]: R=A, C=B, sr=B*T, sc=T, st=1
+ *   dgrad of Wc[A][B][T]: R=B, C=A, sr=T,   sc=B*T, st=1 */
+int rehr_pack_weight(const float* src, void* dst_bf16, int R, int C, int T, long long sr, long long sc,
+                     long long st, rehr_stream stream);
+
+/* y[A] = act(conv(x[B]) + bias).  w_packed = bf16 [A][T][B].  bias may be NULL.  y may be bf16 or f32.
+ * stats (optional, f32 [rehr_conv3d_stats_tiles()][A][2]) receives per-output-tile (sum, sum of squares)
+ * of the *pre-activation* outputs for the fused InstanceNorm statistics; only legal when
+ * rehr_conv3d_stats_tiles() > 0 (every tile lies inside one sample). */
+int rehr_conv3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                    const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats,
+                    rehr_stream stream);
+/* Number of per-sample stat tiles rehr_conv3d_fwd will write for an output of this shape (0 = not fusable). */
+int rehr_conv3d_stats_tiles(const rehr_tensor* y);
+
+/* dx[B] = act(conv_transpose(dy[A]) + bias).  w_packed = bf16 [B][T][A].  (bias/act are used when this
+ * runs as the *forward* of a ConvTranspose3d; pass NULL / REHR_ACT_NONE for a plain input-gradient.) */
+int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed,
+                      const float* bias, const rehr_tensor* dx, int dx_is_f32, int act, float slope,
+                      rehr_stream stream);
+
+/* dW[A][B][T] (f32, PyTorch layout) = sum_o dy[o,A] (x) x[o*s+k-p, B].  Split-K partials go to `ws`. */
+size_t rehr_conv3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
+int rehr_conv3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy, float* dw,
+                      int accumulate, void* ws, size_t ws_bytes, rehr_stream stream);
+
+/* ConvTranspose3d views of the same engine (weight [Cin][Cout][T]). */
+int rehr_convtranspose3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed /*[Cout][T][Cin]*/,
+                             const float* bias, const rehr_tensor* y, int act, float slope, rehr_stream stream);
+int rehr_convtranspose3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed /*[Cin][T][Cout]*/,
+                               const rehr_tensor* dx, rehr_stream stream);
+size_t rehr_convtranspose3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
+int rehr_convtranspose3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy, float* dw,
+                               int accumulate, void* ws, size_t ws_bytes, rehr_stream stream);
+
+/* Direct convolution for tiny input-channel counts (Cin <= 4: the 1-channel nnU-Net stem, the 2-channel
+ * FLAVR stem k(3,7,7)); x is NCDHW f32 exactly as the caller hands it (train_all.py:524), y NDHWC bf16.
+ * w is the PyTorch f32 weight [Cout][Cin][kd][kh][kw]. */
+int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, int n, int cin, int d, int h, int w,
+                             const float* weight, const float* bias, const rehr_tensor* y, int act, float slope,
+                             float* stats, rehr_stream stream);
+int rehr_conv3d_smallcin_wgrad(const rehr_conv_desc* desc, const float* x_ncdhw, int n, int cin, int d, int h, int w,
+                               const rehr_tensor* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
+                               rehr_stream stream);
+size_t rehr_conv3d_smallcin_wgrad_workspace(const rehr_conv_desc* desc, int cin, const rehr_tensor* dy);
+/* dx (NCDHW f32) for the small-Cin stem -- needed by FLAVR-as-student only; nnU-Net's first layer needs none. */
+int rehr_conv3d_smallcin_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const float* weight,
+                               float* dx_ncdhw, int n, int cin, int d, int h, int w, rehr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * InstanceNorm3d(eps, affine) + LeakyReLU, HBM-bound vectorised kernels.
+ * Replaces ConvDropoutNormReLU.norm / .nonlin (train_all.py:486-491).
+ * ---------------------------------------------------------------------------------------------- */
+/* Per-(n,c) sum / sum-of-squares of a bf16 tensor -> partial[(n*tiles + t)*C*2 ...]; use when the conv
+ * epilogue could not fuse them.  tiles = rehr_instnorm_stats_tiles(x). */
+int rehr_instnorm_stats_tiles(const rehr_tensor* x);
+int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream);
+/* partial [n][tiles][c][2] -> mean[n][c], rstd[n][c] (biased variance, double accumulation). */
+int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long long count, float eps,
+                           float* mean, float* rstd, rehr_stream stream);
+/* a = lrelu(gamma * (y - mean) * rstd + beta)   (slope = 1 -> no activation) */
+int rehr_instnorm_lrelu_apply(const rehr_tensor* y, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float slope, const rehr_tensor* a, rehr_stream stream);
+/* Backward, two passes.  (1) reduce: partial[n][tiles][c][2] = (sum g, sum g*xhat), g = (da1 + da2) * lrelu'.
+ * (2) apply: dy = gamma*rstd*(g - S1/V - xhat*S2/V).  da2 may be NULL (second gradient source of a skip). */
+int rehr_instnorm_lrelu_bwd_reduce(const rehr_tensor* y, const rehr_tensor* da1, const rehr_tensor* da2,
+                                   const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                   float slope, float* partial, rehr_stream stream);
+int rehr_instnorm_lrelu_bwd_finalize(const float* partial, int n, int tiles, int c, const float* rstd,
+                                     float* sums /*[n][c][2]*/, float* dgamma, float* dbeta, int accumulate,
+                                     rehr_stream stream);
+int rehr_instnorm_lrelu_bwd_apply(const rehr_tensor* y, const rehr_tensor* da1, const rehr_tensor* da2,
+                                  const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                  float slope, const float* sums, const rehr_tensor* dy, rehr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small HBM-bound pieces of the two networks.
+ * ---------------------------------------------------------------------------------------------- */
+/* 1x1x1 conv to very few channels (seg_layers[-1], models/seg_model.py:44): y NCDHW f32 [n][cout][vox]. */
+int rehr_pointwise_fwd(const rehr_tensor* x, const float* w /*[cout][cin]*/, const float* bias, float* y_ncdhw,
+                       int cout, rehr_stream stream);
+int rehr_pointwise_bwd(const rehr_tensor* x, const float* dy_ncdhw, const float* w, int cout,
+                       const rehr_tensor* dx, float* dw, float* dbias, int accumulate, void* ws, size_t ws_bytes,
+                       rehr_stream stream);
+size_t rehr_pointwise_bwd_workspace(const rehr_tensor* x, int cout);
+/* per-channel sum over all voxels of a bf16 tensor (bias gradients) */
+int rehr_channel_sum(const rehr_tensor* x, float* out, int accumulate, void* ws, size_t ws_bytes, rehr_stream stream);
+size_t rehr_channel_sum_workspace(const rehr_tensor* x);
+/* F.interpolate(scale_factor=(s,1,1), mode='trilinear', align_corners=True) (models/seg_model.py:204) */
+int rehr_upsample_linear_d(const rehr_tensor* x, const rehr_tensor* y, rehr_stream stream);
+int rehr_upsample_linear_d_bwd(const rehr_tensor* dy, const rehr_tensor* dx, rehr_stream stream);
+/* layout / dtype adapters at the model boundary (train_all.py:524 hands NCDHW f32) */
+int rehr_ncdhw_f32_to_ndhwc_bf16(const float* src, const rehr_tensor* dst, rehr_stream stream);
+int rehr_ndhwc_bf16_to_ncdhw_f32(const rehr_tensor* src, float* dst, rehr_stream stream);
+/* elementwise helpers for FLAVR blocks (models/FLAVR/resnet_3D.py:100-151, FLAVR_arch.py:169-248) */
+int rehr_segate_scale_add_act(const rehr_tensor* x, const float* gate /*[n][c]*/, const rehr_tensor* residual,
+                              int act, float slope, const rehr_tensor* y, rehr_stream stream);
+
+/* dy = da * act'(.) evaluated from the activation OUTPUT a (ReLU, or LeakyReLU with slope > 0): the backward of the
+ * bias+activation epilogues of rehr_conv3d_fwd / rehr_convtranspose3d_fwd (FLAVR_arch.py:86, resnet_3D.py:144-149). */
+int rehr_act_bwd(const rehr_tensor* a, const rehr_tensor* da, int act, float slope, const rehr_tensor* dy,
+                 rehr_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sliding-window Gaussian blend (utils/seg_utils.py:240-287): fp16 accumulators exactly as the reference.
+ *   logits[c, sl] += pred[c] * gauss ;  n_pred[sl] += gauss     (rehr_sw_accumulate)
+ *   logits /= n_pred ; *inf_flag |= any(isinf(logits))          (rehr_sw_finalize)
+ * logits [C][VD][VH][VW] f16, n_pred [VD][VH][VW] f16, pred [C][TD][TH][TW] f16 (or f32), gauss [TD][TH][TW] f16
+ * (NULL = the reference's `gaussian = 1`).
+ * ---------------------------------------------------------------------------------------------- */
+int rehr_sw_accumulate(void* logits_f16, void* npred_f16, const void* pred, int pred_is_f32, const void* gauss_f16,
+                       int C, int VD, int VH, int VW, int TD, int TH, int TW, int od, int oh, int ow,
+                       rehr_stream stream);
+int rehr_sw_finalize(void* logits_f16, const void* npred_f16, int C, long long voxels, int* inf_flag,
+                     rehr_stream stream);
+
+/* Blur degradation F.conv2d(x[Z,1,X,Y], k[1,1,L,1], padding="same") (utils/train_set.py:325,332;
+ * utils/sr_utils.py:272,276,302): L-tap cross-correlation along X, zero padded, f32. */
+int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z, int X, int Y, rehr_stream stream);
+
+/* rotate_vol_2d (utils/rotate.py:5-31): rot90 by k quarter turns over dims (0,1) of vol[X][Y][inner]. */
+int rehr_rot90(const void* src, void* dst, int X, int Y, long long inner_bytes, int k, rehr_stream stream);
+
+/* FBA spectral combine (utils/fba.py:8-16) on K interleaved-complex64 spectra of `n` bins each.
+ * p < 0 : the reference's np.max on complex = lexicographic (real, then imag) maximum.
+ * p >= 0: sum_i w_i v_i with w_i = |v_i|^p / sum_j |v_j|^p. */
+int rehr_fba_combine(const void* const* spectra_dev_ptrs, int K, float p, void* out, long long n,
+                     rehr_stream stream);
+
+/* mean over K volumes (utils/sr_utils.py:65,173,217) */
+int rehr_mean_stack(const float* const* vols_dev_ptrs, int K, float* out, long long n, rehr_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REHRSEG_B200_H_ */

@@ -1,0 +1,169 @@
+// extern "C" surface of the conv engine (see include/rehrseg_b200.h).  Pure shape checking + dispatch; the
+// kernels live in conv_engine.cu / smallcin.cu / elementwise.cu.
+#include "engine.h"
+
+#include <cuda_bf16.h>
+
+using namespace rehr;
+
+namespace {
+
+inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+bool conv_shapes_ok(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* y) {
+  if (!d || !x || !y || !x->ptr || !y->ptr) return false;
+  if (d->kd <= 0 || d->kh <= 0 || d->kw <= 0 || d->sd <= 0 || d->sh <= 0 || d->sw <= 0) return false;
+  if (x->n != y->n) return false;
+  return y->d == conv_out(x->d, d->kd, d->sd, d->pd) && y->h == conv_out(x->h, d->kh, d->sh, d->ph) &&
+         y->w == conv_out(x->w, d->kw, d->sw, d->pw);
+}
+
+// out(class) = act(bias): used for output parity classes no tap reaches.
+__global__ void fill_class_kernel(void* out, int out_f32, long long ld, int cout, const float* bias, int act, float slope,
+                                  int O0, int O1, int O2, int N, int s0, int s1, int s2, int o0, int o1, int o2, int A0, int A1,
+                                  int A2) {
+  const long long total = (long long)N * O2 * O1 * O0 * cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cout);
+    long long r = i / cout;
+    const int w = (int)(r % O0);
+    r /= O0;
+    const int h = (int)(r % O1);
+    r /= O1;
+    const int d = (int)(r % O2);
+    const long long n = r / O2;
+    float v = bias ? bias[c] : 0.f;
+    if (act == REHR_ACT_RELU) v = v > 0.f ? v : 0.f;
+    if (act == REHR_ACT_LRELU) v = v > 0.f ? v : v * slope;
+    const long long vox = ((n * A2 + (d * s2 + o2)) * A1 + (h * s1 + o1)) * A0 + (w * s0 + o0);
+    if (out_f32)
+      reinterpret_cast<float*>(out)[vox * ld + c] = v;
+    else
+      reinterpret_cast<__nv_bfloat16*>(out)[vox * ld + c] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rehr_strerror(int status) {
+  switch (status) {
+    case REHR_OK: return "ok";
+    case REHR_BAD_SHAPE: return "inconsistent or null operand shapes";
+    case REHR_UNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+    case REHR_WORKSPACE: return "workspace missing or too small";
+    case REHR_CUDA_ERROR: return "CUDA call failed (see rehr_last_cuda_error)";
+    case REHR_BAD_ALIGNMENT: return "pointer or pitch not 16-byte aligned";
+    default: return "unknown rehr_status";
+  }
+}
+int rehr_last_cuda_error(void) { return g_last_cuda_error; }
+int rehr_version(void) { return 1; }
+int rehr_device_sm_count(void) { return sm_count(); }
+
+int rehr_pack_weight(const float* src, void* dst_bf16, int R, int C, int T, long long sr, long long sc, long long st,
+                     rehr_stream stream) {
+  if (!src || !dst_bf16 || R <= 0 || C <= 0 || T <= 0) return REHR_BAD_SHAPE;
+  return launch_pack_weight(src, dst_bf16, R, C, T, sr, sc, st, (cudaStream_t)stream);
+}
+
+int rehr_conv3d_stats_tiles(const rehr_tensor* y) {
+  if (!y) return 0;
+  int box[4];
+  choose_box(y->w, y->h, y->d, y->n, 128, box);
+  if (box[3] != 1) return 0;
+  return ((y->w + box[0] - 1) / box[0]) * ((y->h + box[1] - 1) / box[1]) * ((y->d + box[2] - 1) / box[2]);
+}
+
+int rehr_conv3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                    const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats, rehr_stream stream) {
+  if (!conv_shapes_ok(desc, x, y) || !w_packed) return REHR_BAD_SHAPE;
+  TapPlan plan;
+  int rc = build_fwd_taps(*desc, *x, &plan);
+  if (rc != REHR_OK) return rc;
+  const int O[4] = {y->w, y->h, y->d, y->n};
+  const int os[3] = {1, 1, 1}, oo[3] = {0, 0, 0};
+  return launch_tapped_gemm(plan, *x, w_packed, y->c, bias, *y, y_is_f32, O, os, oo, act, slope, stats, (cudaStream_t)stream);
+}
+
+int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
+                      const rehr_tensor* dx, int dx_is_f32, int act, float slope, rehr_stream stream) {
+  // shapes: dy is the conv output grid, dx the conv input grid
+  if (!conv_shapes_ok(desc, dx, dy) || !w_packed) return REHR_BAD_SHAPE;
+  const int s[3] = {desc->sw, desc->sh, desc->sd};
+  const int isz[3] = {dx->w, dx->h, dx->d};
+  for (int cd = 0; cd < s[2]; ++cd)
+    for (int ch = 0; ch < s[1]; ++ch)
+      for (int cw = 0; cw < s[0]; ++cw) {
+        const int cls[3] = {cw, ch, cd};
+        int O[4];
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+          O[a] = (isz[a] - cls[a] + s[a] - 1) / s[a];
+          if (O[a] <= 0) empty = true;
+        }
+        O[3] = dx->n;
+        if (empty) continue;
+        TapPlan plan;
+        int rc = build_dgrad_taps(*desc, cls, &plan);
+        if (rc != REHR_OK) return rc;
+        if (plan.num_taps == 0) {
+          const long long total = (long long)O[0] * O[1] * O[2] * O[3] * dx->c;
+          const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+          fill_class_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dx->ptr, dx_is_f32, dx->ld, dx->c, bias, act, slope, O[0], O[1],
+                                                                     O[2], O[3], s[0], s[1], s[2], cw, ch, cd, dx->w, dx->h, dx->d);
+          REHR_CHECK_LAUNCH();
+          continue;
+        }
+        rc = launch_tapped_gemm(plan, *dy, w_packed, dx->c, bias, *dx, dx_is_f32, O, s, cls, act, slope, nullptr,
+                                (cudaStream_t)stream);
+        if (rc != REHR_OK) return rc;
+      }
+  return REHR_OK;
+}
+
+size_t rehr_conv3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy) {
+  if (!conv_shapes_ok(desc, x, dy)) return 0;
+  TapPlan plan;
+  if (build_fwd_taps(*desc, *x, &plan) != REHR_OK) return 0;
+  return tapped_wgrad_workspace(plan, *x, *dy);
+}
+
+int rehr_conv3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate,
+                      void* ws, size_t ws_bytes, rehr_stream stream) {
+  if (!conv_shapes_ok(desc, x, dy) || !dw) return REHR_BAD_SHAPE;
+  TapPlan plan;
+  int rc = build_fwd_taps(*desc, *x, &plan);
+  if (rc != REHR_OK) return rc;
+  const int T = desc->kd * desc->kh * desc->kw;
+  if (plan.num_taps < T && !accumulate) {
+    // taps that never touch the volume have an exactly-zero gradient
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dy->c * x->c * T, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+  }
+  // dW[a][b][t]: a = dy channel (N side), b = x channel (M side)
+  return launch_tapped_wgrad(plan, *x, *dy, dw, (long long)x->c * T, T, 1, accumulate, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- ConvTranspose3d = the same conv read backwards (weight [Cin][Cout][T], underlying conv Cin <- Cout) ----
+int rehr_convtranspose3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                             const rehr_tensor* y, int act, float slope, rehr_stream stream) {
+  return rehr_conv3d_dgrad(desc, x, w_packed, bias, y, 0, act, slope, stream);
+}
+int rehr_convtranspose3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const rehr_tensor* dx,
+                               rehr_stream stream) {
+  return rehr_conv3d_fwd(desc, dy, w_packed, nullptr, dx, 0, REHR_ACT_NONE, 0.f, nullptr, stream);
+}
+size_t rehr_convtranspose3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy) {
+  return rehr_conv3d_wgrad_workspace(desc, dy, x);
+}
+int rehr_convtranspose3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate,
+                               void* ws, size_t ws_bytes, rehr_stream stream) {
+  return rehr_conv3d_wgrad(desc, dy, x, dw, accumulate, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

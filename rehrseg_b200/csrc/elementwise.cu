@@ -1,0 +1,1035 @@
+// HBM-bound kernels of the hot path: InstanceNorm(+LeakyReLU) forward/backward, the 1x1x1 segmentation head,
+// layout adapters, depth-linear upsampling, SE-gate tail, sliding-window Gaussian blend, blur stencil, rot90,
+// FBA spectral combine.  All are vectorised (16 B per thread access where the layout allows), coalesced and
+// sized as a multiple of the SM count; reductions are shuffle / shared-memory trees with deterministic
+// per-block partials (no float atomics on global memory).
+#include "engine.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+namespace rehr {
+
+static inline int grid_for(long long work_items, int threads, int waves = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)sm_count() * waves;
+  return (int)std::max<long long>(1, std::min<long long>(b, cap));
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+static bool bf16_tensor_ok(const rehr_tensor* t) {
+  return t && t->ptr && t->c % 8 == 0 && t->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(t->ptr) & 15) == 0;
+}
+static inline long long voxels_per_sample(const rehr_tensor* t) { return (long long)t->d * t->h * t->w; }
+
+// =================================================================================================
+// InstanceNorm statistics (stand-alone; the conv epilogue normally produces these)
+// =================================================================================================
+static constexpr int kStatThreads = 256;
+static constexpr int kStatVoxPerBlock = 4096;
+
+// Block = (tile, n).  Thread = (voxel lane, channel group of 8).  Per-thread accumulation, then a
+// shared-memory tree over voxel lanes.  `mode` 0: (sum x, sum x^2); 1: InstanceNorm backward sums.
+struct StatArgs {
+  const __nv_bfloat16* y;
+  const __nv_bfloat16* da1;
+  const __nv_bfloat16* da2;
+  long long ld_y, ld_a1, ld_a2;
+  const float *mean, *rstd, *gamma, *beta;
+  float slope;
+  float* partial;
+  long long V;
+  int C, tiles;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kStatThreads) in_reduce_kernel(const StatArgs a) {
+  extern __shared__ float sh[];  // [lanes][C][2]
+  const int n = blockIdx.y, tile = blockIdx.x;
+  const int groups = a.C / 8;
+  const int lanes = kStatThreads / groups;  // voxel lanes per pass (>=1)
+  const int g = threadIdx.x % groups, vl = threadIdx.x / groups;
+  const long long v0 = (long long)tile * kStatVoxPerBlock;
+  const long long v1 = min(a.V, v0 + kStatVoxPerBlock);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  float sc[8], sf[8], mu[8], rs[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = g * 8 + i;
+      mu[i] = a.mean[n * a.C + c];
+      rs[i] = a.rstd[n * a.C + c];
+      sc[i] = a.gamma ? a.gamma[c] : 1.f;
+      sf[i] = a.beta ? a.beta[c] : 0.f;
+    }
+  }
+  if (vl < lanes) {
+    for (long long v = v0 + vl; v < v1; v += lanes) {
+      const long long vox = (long long)n * a.V + v;
+      float y[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8), y);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += y[i];
+          s2[i] += y[i] * y[i];
+        }
+      } else {
+        float d[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da1 + vox * a.ld_a1 + g * 8), d);
+        if (a.da2) {
+          float d2[8];
+          bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da2 + vox * a.ld_a2 + g * 8), d2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] += d2[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (y[i] - mu[i]) * rs[i];
+          const float z = sc[i] * xh + sf[i];
+          const float gi = z > 0.f ? d[i] : d[i] * a.slope;
+          s1[i] += gi;
+          s2[i] += gi * xh;
+        }
+      }
+    }
+  }
+  if (vl < lanes) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh[(vl * a.C + g * 8 + i) * 2] = s1[i];
+      sh[(vl * a.C + g * 8 + i) * 2 + 1] = s2[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.C; c += kStatThreads) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t1 += sh[(l * a.C + c) * 2];
+      t2 += sh[(l * a.C + c) * 2 + 1];
+    }
+    float* dst = a.partial + (((long long)n * a.tiles + tile) * a.C + c) * 2;
+    dst[0] = t1;
+    dst[1] = t2;
+  }
+}
+
+static int stat_tiles(const rehr_tensor* x) {
+  const long long V = voxels_per_sample(x);
+  return (int)((V + kStatVoxPerBlock - 1) / kStatVoxPerBlock);
+}
+
+template <int MODE>
+static int launch_in_reduce(const StatArgs& a, int N, cudaStream_t st) {
+  const int groups = a.C / 8;
+  if (groups > kStatThreads) return REHR_UNSUPPORTED;
+  const int lanes = kStatThreads / groups;
+  const size_t smem = (size_t)lanes * a.C * 2 * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(in_reduce_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+  }
+  dim3 grid(a.tiles, N);
+  in_reduce_kernel<MODE><<<grid, kStatThreads, smem, st>>>(a);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+// partial [n][tiles][c][2] -> mean, rstd
+__global__ void in_finalize_kernel(const float* partial, int N, int tiles, int C, double inv_count, float eps, float* mean,
+                                   float* rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    const float* p = partial + (((long long)n * tiles + t) * C + c) * 2;
+    s1 += (double)p[0];
+    s2 += (double)p[1];
+  }
+  const double m = s1 * inv_count;
+  double var = s2 * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// partial [n][tiles][c][2] -> sums [n][c][2]; dgamma[c] = sum_n S2, dbeta[c] = sum_n S1
+__global__ void in_bwd_finalize_kernel(const float* partial, int N, int tiles, int C, float* sums, float* dgamma,
+                                       float* dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double g = 0.0, b = 0.0;
+  for (int n = 0; n < N; ++n) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int t = 0; t < tiles; ++t) {
+      const float* p = partial + (((long long)n * tiles + t) * C + c) * 2;
+      s1 += (double)p[0];
+      s2 += (double)p[1];
+    }
+    sums[((long long)n * C + c) * 2] = (float)s1;
+    sums[((long long)n * C + c) * 2 + 1] = (float)s2;
+    b += s1;
+    g += s2;
+  }
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)g : (float)g;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
+}
+
+struct ApplyArgs {
+  const __nv_bfloat16* y;
+  const __nv_bfloat16* da1;
+  const __nv_bfloat16* da2;
+  __nv_bfloat16* out;
+  long long ld_y, ld_a1, ld_a2, ld_o;
+  const float *mean, *rstd, *gamma, *beta, *sums;
+  float slope;
+  long long V;
+  int C;
+};
+
+// MODE 0: a = lrelu(gamma*xhat + beta).  MODE 1: dy = gamma*rstd*(g - S1/V - xhat*S2/V).
+template <int MODE>
+__global__ void __launch_bounds__(256) in_apply_kernel(const ApplyArgs a) {
+  extern __shared__ float sh[];  // MODE0: scale, shift ; MODE1: mean, rstd, gamma, beta, m1, m2
+  const int n = blockIdx.y;
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mu = a.mean[n * C + c], rs = a.rstd[n * C + c];
+    const float ga = a.gamma ? a.gamma[c] : 1.f, be = a.beta ? a.beta[c] : 0.f;
+    if (MODE == 0) {
+      sh[c] = ga * rs;
+      sh[C + c] = be - mu * ga * rs;
+    } else {
+      sh[c] = mu;
+      sh[C + c] = rs;
+      sh[2 * C + c] = ga;
+      sh[3 * C + c] = be;
+      sh[4 * C + c] = a.sums[((long long)n * C + c) * 2] / (float)a.V;
+      sh[5 * C + c] = a.sums[((long long)n * C + c) * 2 + 1] / (float)a.V;
+    }
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  const long long items = a.V * groups;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    const long long vox = (long long)n * a.V + it / groups;
+    float y[8], o[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8), y);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = y[i] * sh[g * 8 + i] + sh[C + g * 8 + i];
+        o[i] = z > 0.f ? z : z * a.slope;
+      }
+    } else {
+      float d[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da1 + vox * a.ld_a1 + g * 8), d);
+      if (a.da2) {
+        float d2[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da2 + vox * a.ld_a2 + g * 8), d2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += d2[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        const float xh = (y[i] - sh[c]) * sh[C + c];
+        const float z = sh[2 * C + c] * xh + sh[3 * C + c];
+        const float gi = z > 0.f ? d[i] : d[i] * a.slope;
+        o[i] = sh[2 * C + c] * sh[C + c] * (gi - sh[4 * C + c] - xh * sh[5 * C + c]);
+      }
+    }
+    *reinterpret_cast<uint4*>(a.out + vox * a.ld_o + g * 8) = float_to_bf16x8(o);
+  }
+}
+
+template <int MODE>
+static int launch_in_apply(const ApplyArgs& a, int N, cudaStream_t st) {
+  const size_t smem = (size_t)(MODE == 0 ? 2 : 6) * a.C * sizeof(float);
+  const long long items = a.V * (a.C / 8);
+  int gx = grid_for(items, 256, 8);
+  gx = std::max(1, gx / std::max(1, N));
+  dim3 grid(gx, N);
+  in_apply_kernel<MODE><<<grid, 256, smem, st>>>(a);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+// =================================================================================================
+// 1x1x1 conv to a few channels (segmentation head), NDHWC bf16 -> NCDHW f32
+// =================================================================================================
+static constexpr int kPwMaxCout = 8;
+static constexpr int kPwMaxCin = 128;
+
+__global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16* x, long long ld, const float* w,
+                                                            const float* bias, float* y, int N, long long V, int cin,
+                                                            int cout) {
+  __shared__ float sw[kPwMaxCout * kPwMaxCin + kPwMaxCout];
+  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[kPwMaxCout * kPwMaxCin + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long total = (long long)N * V;
+  for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < total; vox += (long long)gridDim.x * blockDim.x) {
+    float acc[kPwMaxCout];
+#pragma unroll
+    for (int o = 0; o < kPwMaxCout; ++o) acc[o] = sw[kPwMaxCout * kPwMaxCin + o];
+    const __nv_bfloat16* xp = x + vox * ld;
+    for (int c0 = 0; c0 < cin; c0 += 8) {
+      float f[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(xp + c0), f);
+#pragma unroll
+      for (int o = 0; o < kPwMaxCout; ++o)
+        if (o < cout) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[o] += f[i] * sw[o * cin + c0 + i];
+        }
+    }
+    const long long n = vox / V, v = vox % V;
+#pragma unroll
+    for (int o = 0; o < kPwMaxCout; ++o)
+      if (o < cout) y[(n * cout + o) * V + v] = acc[o];
+  }
+}
+
+// dx[v, ci] = sum_co dy[co, v] w[co][ci]; per-block partials of dw[co][ci] and dbias[co] into ws.
+__global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16* x, long long ldx, const float* dy,
+                                                            const float* w, __nv_bfloat16* dx, long long lddx, float* ws,
+                                                            int N, long long V, int cin, int cout) {
+  __shared__ float sw[kPwMaxCout * kPwMaxCin];
+  __shared__ float sacc[kPwMaxCout * (kPwMaxCin + 1)];
+  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout * (cin + 1); i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int groups = cin / 8;
+  const long long items = (long long)N * V * groups;
+  // thread = (voxel, channel group): keeps dw partials for its 8 channels x cout in registers
+  float pw[kPwMaxCout][8];
+  float pb[kPwMaxCout];
+#pragma unroll
+  for (int o = 0; o < kPwMaxCout; ++o) {
+    pb[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pw[o][i] = 0.f;
+  }
+  // thread = (voxel lane, channel group): a thread always sees the same channel group
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long vlanes = nthreads / groups;
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(gtid % groups);
+  const long long vlane = gtid / groups;
+  (void)items;
+  for (long long vox = vlane; vlane < vlanes && vox < (long long)N * V; vox += vlanes) {
+    const long long n = vox / V, v = vox % V;
+    float f[8], d[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + vox * ldx + g * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < kPwMaxCout; ++o)
+      if (o < cout) {
+        const float gy = dy[(n * cout + o) * V + v];
+        if (g == 0) pb[o] += gy;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          d[i] += gy * sw[o * cin + g * 8 + i];
+          pw[o][i] += gy * f[i];
+        }
+      }
+    if (dx) *reinterpret_cast<uint4*>(dx + vox * lddx + g * 8) = float_to_bf16x8(d);
+  }
+  if (vlane < vlanes)
+#pragma unroll
+  for (int o = 0; o < kPwMaxCout; ++o)
+    if (o < cout) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sacc[o * (cin + 1) + g * 8 + i], pw[o][i]);
+      if (g == 0) atomicAdd(&sacc[o * (cin + 1) + cin], pb[o]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cout * (cin + 1); i += blockDim.x) ws[(long long)blockIdx.x * cout * (cin + 1) + i] = sacc[i];
+}
+
+__global__ void pointwise_bwd_reduce_kernel(const float* ws, int blocks, int cin, int cout, float* dw, float* dbias,
+                                            int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * (cin + 1)) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += (double)ws[(long long)b * cout * (cin + 1) + i];
+  const int o = i / (cin + 1), c = i % (cin + 1);
+  if (c < cin) {
+    if (dw) dw[o * cin + c] = accumulate ? dw[o * cin + c] + (float)s : (float)s;
+  } else {
+    if (dbias) dbias[o] = accumulate ? dbias[o] + (float)s : (float)s;
+  }
+}
+
+static int pointwise_bwd_blocks(const rehr_tensor* x) {
+  const long long items = (long long)x->n * voxels_per_sample(x) * (x->c / 8);
+  return grid_for(items, 256, 4);
+}
+
+// per-channel sum over all voxels (bias gradient): per-block partials + reduce
+__global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* x, long long ld, long long total_vox, int C,
+                                                          float* ws) {
+  extern __shared__ float sh[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int groups = C / 8;
+  const long long items = total_vox * groups;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long vlanes = nthreads / groups;
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(gtid % groups);
+  const long long vlane = gtid / groups;
+  (void)items;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (long long vox = vlane; vlane < vlanes && vox < total_vox; vox += vlanes) {
+    float f[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + vox * ld + g * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += f[i];
+  }
+  if (vlane < vlanes) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sh[g * 8 + i], s[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) ws[(long long)blockIdx.x * C + i] = sh[i];
+}
+__global__ void channel_sum_reduce_kernel(const float* ws, int blocks, int C, float* out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += (double)ws[(long long)b * C + c];
+  out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+static int channel_sum_blocks(const rehr_tensor* x) {
+  const long long items = (long long)x->n * voxels_per_sample(x) * (x->c / 8);
+  return grid_for(items, 256, 4);
+}
+
+// =================================================================================================
+// Depth-only linear upsampling, align_corners=True (ATen area_pixel_compute_source_index semantics)
+// =================================================================================================
+__global__ void __launch_bounds__(256) upsample_d_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* y,
+                                                         long long ldy, int N, int D, int OD, long long HW, int C) {
+  const int groups = C / 8;
+  const long long items = (long long)N * OD * HW * groups;
+  const float scale = OD > 1 ? (float)(D - 1) / (float)(OD - 1) : 0.f;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    long long r = it / groups;
+    const long long hw = r % HW;
+    r /= HW;
+    const int od = (int)(r % OD);
+    const long long n = r / OD;
+    const float src = scale * (float)od;
+    const int i0 = (int)src;
+    const int i1 = i0 + (i0 < D - 1 ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.f - l1;
+    float a[8], b[8], o[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + i0) * HW + hw) * ldx + g * 8), a);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + i1) * HW + hw) * ldx + g * 8), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = l0 * a[i] + l1 * b[i];
+    *reinterpret_cast<uint4*>(y + ((n * OD + od) * HW + hw) * ldy + g * 8) = float_to_bf16x8(o);
+  }
+}
+__global__ void __launch_bounds__(256) upsample_d_bwd_kernel(const __nv_bfloat16* dy, long long lddy, __nv_bfloat16* dx,
+                                                             long long lddx, int N, int D, int OD, long long HW, int C) {
+  const int groups = C / 8;
+  const long long items = (long long)N * D * HW * groups;
+  const float scale = OD > 1 ? (float)(D - 1) / (float)(OD - 1) : 0.f;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    long long r = it / groups;
+    const long long hw = r % HW;
+    r /= HW;
+    const int d = (int)(r % D);
+    const long long n = r / D;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // output planes whose i0 or i1 equals d
+    int j_lo = 0, j_hi = OD - 1;
+    if (scale > 0.f) {
+      j_lo = max(0, (int)floorf((float)(d - 1) / scale) - 1);
+      j_hi = min(OD - 1, (int)ceilf((float)(d + 1) / scale) + 1);
+    }
+    for (int j = j_lo; j <= j_hi; ++j) {
+      const float src = scale * (float)j;
+      const int i0 = (int)src;
+      const int i1 = i0 + (i0 < D - 1 ? 1 : 0);
+      const float l1 = src - (float)i0, l0 = 1.f - l1;
+      float wgt = 0.f;
+      if (i0 == d) wgt += l0;
+      if (i1 == d) wgt += l1;
+      if (wgt != 0.f) {
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(dy + ((n * OD + j) * HW + hw) * lddy + g * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += wgt * f[i];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + ((n * D + d) * HW + hw) * lddx + g * 8) = float_to_bf16x8(acc);
+  }
+}
+
+// =================================================================================================
+// Layout adapters: NCDHW f32 <-> NDHWC bf16 (32x32 shared-memory transpose per sample)
+// =================================================================================================
+__global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* src, __nv_bfloat16* dst, long long ld, long long V,
+                                                             int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k;
+    const long long v = v0 + tx;
+    tile[k][tx] = (c < C && v < V) ? src[((long long)n * C + c) * V + v] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const long long v = v0 + k;
+    const int c = c0 + tx;
+    if (c < C && v < V) dst[((long long)n * V + v) * ld + c] = __float2bfloat16(tile[tx][k]);
+  }
+}
+__global__ void __launch_bounds__(256) ndhwc_to_ncdhw_kernel(const __nv_bfloat16* src, long long ld, float* dst, long long V,
+                                                             int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const long long v = v0 + k;
+    const int c = c0 + tx;
+    tile[k][tx] = (c < C && v < V) ? __bfloat162float(src[((long long)n * V + v) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k;
+    const long long v = v0 + tx;
+    if (c < C && v < V) dst[((long long)n * C + c) * V + v] = tile[tx][k];
+  }
+}
+
+// =================================================================================================
+// SE-gate tail: y = act(x * gate[n,c] (+ residual))
+// =================================================================================================
+__global__ void __launch_bounds__(256) segate_kernel(const __nv_bfloat16* x, long long ldx, const float* gate,
+                                                     const __nv_bfloat16* res, long long ldr, __nv_bfloat16* y,
+                                                     long long ldy, int N, long long V, int C, int act, float slope) {
+  const int groups = C / 8;
+  const long long items = (long long)N * V * groups;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    const long long vox = it / groups;
+    const long long n = vox / V;
+    float f[8], o[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + vox * ldx + g * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = f[i] * (gate ? gate[n * C + g * 8 + i] : 1.f);
+    if (res) {
+      float r[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(res + vox * ldr + g * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (act == REHR_ACT_RELU) o[i] = o[i] > 0.f ? o[i] : 0.f;
+      if (act == REHR_ACT_LRELU) o[i] = o[i] > 0.f ? o[i] : o[i] * slope;
+    }
+    *reinterpret_cast<uint4*>(y + vox * ldy + g * 8) = float_to_bf16x8(o);
+  }
+}
+
+// =================================================================================================
+// Sliding-window Gaussian blend with fp16 accumulators (bit-faithful to ATen half arithmetic:
+// every half op computes in float and rounds once).
+// =================================================================================================
+__global__ void __launch_bounds__(256) sw_accumulate_kernel(__half* logits, __half* npred, const void* pred, int pred_f32,
+                                                            const __half* gauss, int C, int VD, int VH, int VW, int TD,
+                                                            int TH, int TW, int od, int oh, int ow) {
+  const long long tv = (long long)TD * TH * TW;
+  const long long vv = (long long)VD * VH * VW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tv; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % TW);
+    const int y = (int)((i / TW) % TH);
+    const int z = (int)(i / ((long long)TW * TH));
+    const long long vi = ((long long)(od + z) * VH + (oh + y)) * VW + (ow + x);
+    const float g = gauss ? __half2float(gauss[i]) : 1.f;
+    for (int c = 0; c < C; ++c) {
+      const float pf = pred_f32 ? __half2float(__float2half(reinterpret_cast<const float*>(pred)[c * tv + i]))
+                                : __half2float(reinterpret_cast<const __half*>(pred)[c * tv + i]);
+      const __half prod = __float2half(pf * g);
+      logits[c * vv + vi] = __float2half(__half2float(logits[c * vv + vi]) + __half2float(prod));
+    }
+    npred[vi] = __float2half(__half2float(npred[vi]) + g);
+  }
+}
+__global__ void __launch_bounds__(256) sw_finalize_kernel(__half* logits, const __half* npred, int C, long long vv,
+                                                          int* inf_flag) {
+  int bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vv; i += (long long)gridDim.x * blockDim.x) {
+    const float n = __half2float(npred[i]);
+    for (int c = 0; c < C; ++c) {
+      const __half q = __float2half(__half2float(logits[c * vv + i]) / n);
+      logits[c * vv + i] = q;
+      if (__hisinf(q)) bad = 1;
+    }
+  }
+  if (bad && inf_flag) atomicOr(inf_flag, 1);
+}
+
+// =================================================================================================
+// Blur degradation: L-tap cross-correlation along X of x[Z][X][Y] (F.conv2d padding="same")
+// =================================================================================================
+static constexpr int kBlurMaxTaps = 65;
+struct BlurTaps {
+  float t[kBlurMaxTaps];
+};
+__global__ void __launch_bounds__(256) blur1d_kernel(const float* x, float* y, const float* taps, int L, long long Z, int X,
+                                                     int Y) {
+  __shared__ float st[kBlurMaxTaps];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) st[i] = taps[i];
+  __syncthreads();
+  const int left = (L - 1) / 2;
+  const long long total = Z * (long long)X * Y;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int yy = (int)(i % Y);
+    const int xx = (int)((i / Y) % X);
+    const long long z = i / ((long long)Y * X);
+    const float* base = x + z * (long long)X * Y + yy;
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const int xs = xx + l - left;
+      if (xs >= 0 && xs < X) acc += st[l] * base[(long long)xs * Y];
+    }
+    y[i] = acc;
+  }
+}
+
+// =================================================================================================
+// rot90 over dims (0,1) of vol[X][Y][inner], torch.rot90 semantics
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) rot90_kernel(const T* src, T* dst, int X, int Y, long long inner, int k) {
+  const int OX = (k & 1) ? Y : X, OY = (k & 1) ? X : Y;
+  const long long total = (long long)OX * OY * inner;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % inner;
+    const long long ij = i / inner;
+    const int j = (int)(ij % OY), ii = (int)(ij / OY);
+    int sx, sy;
+    if (k == 1) {
+      sx = j;
+      sy = Y - 1 - ii;
+    } else if (k == 2) {
+      sx = X - 1 - ii;
+      sy = Y - 1 - j;
+    } else {  // k == 3
+      sx = X - 1 - j;
+      sy = ii;
+    }
+    dst[i] = src[((long long)sx * Y + sy) * inner + e];
+  }
+}
+
+// =================================================================================================
+// FBA spectral combine and orientation mean
+// =================================================================================================
+static constexpr int kMaxFuse = 16;
+struct PtrPack {
+  const void* p[kMaxFuse];
+};
+__global__ void __launch_bounds__(256) fba_combine_kernel(PtrPack sp, int K, float p, float2* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (p < 0.f) {
+      // numpy max on complex: lexicographic (real, then imag); NaN propagates like np.maximum
+      float2 best = reinterpret_cast<const float2*>(sp.p[0])[i];
+      for (int k = 1; k < K; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(sp.p[k])[i];
+        const bool best_nan = (best.x != best.x) || (best.y != best.y);
+        const bool v_nan = (v.x != v.x) || (v.y != v.y);
+        if (best_nan) continue;
+        if (v_nan || v.x > best.x || (v.x == best.x && v.y > best.y)) best = v;
+      }
+      out[i] = best;
+    } else {
+      float mag[kMaxFuse];
+      float den = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(sp.p[k])[i];
+        mag[k] = powf(hypotf(v.x, v.y), p);
+        den += mag[k];
+      }
+      float2 acc = make_float2(0.f, 0.f);
+      for (int k = 0; k < K; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(sp.p[k])[i];
+        const float w = mag[k] / den;
+        acc.x += w * v.x;
+        acc.y += w * v.y;
+      }
+      out[i] = acc;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) mean_stack_kernel(PtrPack vp, int K, float* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = reinterpret_cast<const float*>(vp.p[0])[i];
+    for (int k = 1; k < K; ++k) s += reinterpret_cast<const float*>(vp.p[k])[i];
+    out[i] = s / (float)K;
+  }
+}
+
+// =================================================================================================
+// Activation backward from the activation OUTPUT: dy = da * (a > 0 ? 1 : slope)   (slope = 0 for ReLU)
+// =================================================================================================
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* da,
+                                                      long long ldda, __nv_bfloat16* dy, long long lddy, long long vox,
+                                                      int C, float slope) {
+  const int groups = C / 8;
+  const long long items = vox * groups;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    const long long v = it / groups;
+    float fa[8], fd[8], o[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(a + v * lda + g * 8), fa);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(da + v * ldda + g * 8), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fa[i] > 0.f ? fd[i] : fd[i] * slope;
+    *reinterpret_cast<uint4*>(dy + v * lddy + g * 8) = float_to_bf16x8(o);
+  }
+}
+
+}  // namespace rehr
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+using namespace rehr;
+
+extern "C" {
+
+int rehr_instnorm_stats_tiles(const rehr_tensor* x) { return x ? stat_tiles(x) : 0; }
+
+int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !partial) return REHR_BAD_SHAPE;
+  StatArgs a{};
+  a.y = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
+  a.ld_y = x->ld;
+  a.partial = partial;
+  a.V = voxels_per_sample(x);
+  a.C = x->c;
+  a.tiles = stat_tiles(x);
+  return launch_in_reduce<0>(a, x->n, (cudaStream_t)stream);
+}
+
+int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long long count, float eps, float* mean,
+                           float* rstd, rehr_stream stream) {
+  if (!partial || !mean || !rstd || count <= 0) return REHR_BAD_SHAPE;
+  in_finalize_kernel<<<(n * c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+                                                                       rstd);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_instnorm_lrelu_apply(const rehr_tensor* y, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float slope, const rehr_tensor* a, rehr_stream stream) {
+  if (!bf16_tensor_ok(y) || !bf16_tensor_ok(a) || y->c != a->c || y->n != a->n || voxels_per_sample(y) != voxels_per_sample(a))
+    return REHR_BAD_SHAPE;
+  ApplyArgs p{};
+  p.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->ptr);
+  p.ld_y = y->ld;
+  p.ld_o = a->ld;
+  p.mean = mean;
+  p.rstd = rstd;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.slope = slope;
+  p.V = voxels_per_sample(y);
+  p.C = y->c;
+  return launch_in_apply<0>(p, y->n, (cudaStream_t)stream);
+}
+
+int rehr_instnorm_lrelu_bwd_reduce(const rehr_tensor* y, const rehr_tensor* da1, const rehr_tensor* da2, const float* mean,
+                                   const float* rstd, const float* gamma, const float* beta, float slope, float* partial,
+                                   rehr_stream stream) {
+  if (!bf16_tensor_ok(y) || !bf16_tensor_ok(da1) || (da2 && !bf16_tensor_ok(da2)) || !partial) return REHR_BAD_SHAPE;
+  StatArgs a{};
+  a.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
+  a.da1 = reinterpret_cast<const __nv_bfloat16*>(da1->ptr);
+  a.da2 = da2 ? reinterpret_cast<const __nv_bfloat16*>(da2->ptr) : nullptr;
+  a.ld_y = y->ld;
+  a.ld_a1 = da1->ld;
+  a.ld_a2 = da2 ? da2->ld : 0;
+  a.mean = mean;
+  a.rstd = rstd;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.slope = slope;
+  a.partial = partial;
+  a.V = voxels_per_sample(y);
+  a.C = y->c;
+  a.tiles = stat_tiles(y);
+  return launch_in_reduce<1>(a, y->n, (cudaStream_t)stream);
+}
+
+int rehr_instnorm_lrelu_bwd_finalize(const float* partial, int n, int tiles, int c, const float* rstd, float* sums,
+                                     float* dgamma, float* dbeta, int accumulate, rehr_stream stream) {
+  (void)rstd;
+  if (!partial || !sums) return REHR_BAD_SHAPE;
+  in_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, sums, dgamma, dbeta, accumulate);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_instnorm_lrelu_bwd_apply(const rehr_tensor* y, const rehr_tensor* da1, const rehr_tensor* da2, const float* mean,
+                                  const float* rstd, const float* gamma, const float* beta, float slope, const float* sums,
+                                  const rehr_tensor* dy, rehr_stream stream) {
+  if (!bf16_tensor_ok(y) || !bf16_tensor_ok(da1) || (da2 && !bf16_tensor_ok(da2)) || !bf16_tensor_ok(dy) || !sums)
+    return REHR_BAD_SHAPE;
+  ApplyArgs p{};
+  p.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
+  p.da1 = reinterpret_cast<const __nv_bfloat16*>(da1->ptr);
+  p.da2 = da2 ? reinterpret_cast<const __nv_bfloat16*>(da2->ptr) : nullptr;
+  p.out = reinterpret_cast<__nv_bfloat16*>(dy->ptr);
+  p.ld_y = y->ld;
+  p.ld_a1 = da1->ld;
+  p.ld_a2 = da2 ? da2->ld : 0;
+  p.ld_o = dy->ld;
+  p.mean = mean;
+  p.rstd = rstd;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.sums = sums;
+  p.slope = slope;
+  p.V = voxels_per_sample(y);
+  p.C = y->c;
+  return launch_in_apply<1>(p, y->n, (cudaStream_t)stream);
+}
+
+int rehr_pointwise_fwd(const rehr_tensor* x, const float* w, const float* bias, float* y_ncdhw, int cout, rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !w || !y_ncdhw) return REHR_BAD_SHAPE;
+  if (cout > kPwMaxCout || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
+  const long long V = voxels_per_sample(x);
+  pointwise_fwd_kernel<<<grid_for((long long)x->n * V, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+size_t rehr_pointwise_bwd_workspace(const rehr_tensor* x, int cout) {
+  if (!x) return 0;
+  return (size_t)pointwise_bwd_blocks(x) * cout * (x->c + 1) * sizeof(float);
+}
+
+int rehr_pointwise_bwd(const rehr_tensor* x, const float* dy_ncdhw, const float* w, int cout, const rehr_tensor* dx, float* dw,
+                       float* dbias, int accumulate, void* ws, size_t ws_bytes, rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !dy_ncdhw || !w || (dx && !bf16_tensor_ok(dx))) return REHR_BAD_SHAPE;
+  if (cout > kPwMaxCout || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
+  if (ws_bytes < rehr_pointwise_bwd_workspace(x, cout) || !ws) return REHR_WORKSPACE;
+  const long long V = voxels_per_sample(x);
+  const int blocks = pointwise_bwd_blocks(x);
+  pointwise_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, dy_ncdhw, w, dx ? reinterpret_cast<__nv_bfloat16*>(dx->ptr) : nullptr,
+      dx ? dx->ld : 0, reinterpret_cast<float*>(ws), x->n, V, x->c, cout);
+  REHR_CHECK_LAUNCH();
+  const int outs = cout * (x->c + 1);
+  pointwise_bwd_reduce_kernel<<<(outs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c,
+                                                                                cout, dw, dbias, accumulate);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+size_t rehr_channel_sum_workspace(const rehr_tensor* x) {
+  if (!x) return 0;
+  return (size_t)channel_sum_blocks(x) * x->c * sizeof(float);
+}
+int rehr_channel_sum(const rehr_tensor* x, float* out, int accumulate, void* ws, size_t ws_bytes, rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !out) return REHR_BAD_SHAPE;
+  if (ws_bytes < rehr_channel_sum_workspace(x) || !ws) return REHR_WORKSPACE;
+  const int blocks = channel_sum_blocks(x);
+  channel_sum_kernel<<<blocks, 256, x->c * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, (long long)x->n * voxels_per_sample(x), x->c, reinterpret_cast<float*>(ws));
+  REHR_CHECK_LAUNCH();
+  channel_sum_reduce_kernel<<<(x->c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c, out,
+                                                                             accumulate);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_upsample_linear_d(const rehr_tensor* x, const rehr_tensor* y, rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !bf16_tensor_ok(y) || x->c != y->c || x->n != y->n || x->h != y->h || x->w != y->w) return REHR_BAD_SHAPE;
+  const long long HW = (long long)x->h * x->w;
+  const long long items = (long long)y->n * y->d * HW * (y->c / 8);
+  upsample_d_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld,
+                                                                           reinterpret_cast<__nv_bfloat16*>(y->ptr), y->ld, x->n, x->d,
+                                                                           y->d, HW, x->c);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+int rehr_upsample_linear_d_bwd(const rehr_tensor* dy, const rehr_tensor* dx, rehr_stream stream) {
+  if (!bf16_tensor_ok(dx) || !bf16_tensor_ok(dy) || dx->c != dy->c || dx->n != dy->n || dx->h != dy->h || dx->w != dy->w)
+    return REHR_BAD_SHAPE;
+  const long long HW = (long long)dx->h * dx->w;
+  const long long items = (long long)dx->n * dx->d * HW * (dx->c / 8);
+  upsample_d_bwd_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy->ptr),
+                                                                               dy->ld, reinterpret_cast<__nv_bfloat16*>(dx->ptr),
+                                                                               dx->ld, dx->n, dx->d, dy->d, HW, dx->c);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_ncdhw_f32_to_ndhwc_bf16(const float* src, const rehr_tensor* dst, rehr_stream stream) {
+  if (!src || !dst || !dst->ptr) return REHR_BAD_SHAPE;
+  const long long V = voxels_per_sample(dst);
+  dim3 grid((unsigned)((V + 31) / 32), (unsigned)((dst->c + 31) / 32), (unsigned)dst->n);
+  ncdhw_to_ndhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst->ptr), dst->ld, V, dst->c);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+int rehr_ndhwc_bf16_to_ncdhw_f32(const rehr_tensor* src, float* dst, rehr_stream stream) {
+  if (!src || !dst || !src->ptr) return REHR_BAD_SHAPE;
+  const long long V = voxels_per_sample(src);
+  dim3 grid((unsigned)((V + 31) / 32), (unsigned)((src->c + 31) / 32), (unsigned)src->n);
+  ndhwc_to_ncdhw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src->ptr), src->ld, dst, V, src->c);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_segate_scale_add_act(const rehr_tensor* x, const float* gate, const rehr_tensor* residual, int act, float slope,
+                              const rehr_tensor* y, rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !bf16_tensor_ok(y) || (residual && !bf16_tensor_ok(residual)) || x->c != y->c) return REHR_BAD_SHAPE;
+  const long long V = voxels_per_sample(x);
+  const long long items = (long long)x->n * V * (x->c / 8);
+  segate_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, gate, residual ? reinterpret_cast<const __nv_bfloat16*>(residual->ptr) : nullptr,
+      residual ? residual->ld : 0, reinterpret_cast<__nv_bfloat16*>(y->ptr), y->ld, x->n, V, x->c, act, slope);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_sw_accumulate(void* logits_f16, void* npred_f16, const void* pred, int pred_is_f32, const void* gauss_f16, int C, int VD,
+                       int VH, int VW, int TD, int TH, int TW, int od, int oh, int ow, rehr_stream stream) {
+  if (!logits_f16 || !npred_f16 || !pred) return REHR_BAD_SHAPE;
+  if (od < 0 || oh < 0 || ow < 0 || od + TD > VD || oh + TH > VH || ow + TW > VW) return REHR_BAD_SHAPE;
+  const long long tv = (long long)TD * TH * TW;
+  sw_accumulate_kernel<<<grid_for(tv, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__half*>(logits_f16), reinterpret_cast<__half*>(npred_f16), pred, pred_is_f32,
+      reinterpret_cast<const __half*>(gauss_f16), C, VD, VH, VW, TD, TH, TW, od, oh, ow);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+int rehr_sw_finalize(void* logits_f16, const void* npred_f16, int C, long long voxels, int* inf_flag, rehr_stream stream) {
+  if (!logits_f16 || !npred_f16) return REHR_BAD_SHAPE;
+  sw_finalize_kernel<<<grid_for(voxels, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__half*>(logits_f16),
+                                                                             reinterpret_cast<const __half*>(npred_f16), C, voxels,
+                                                                             inf_flag);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z, int X, int Y, rehr_stream stream) {
+  if (!x || !taps || !y || L <= 0) return REHR_BAD_SHAPE;
+  if (L > kBlurMaxTaps) return REHR_UNSUPPORTED;
+  blur1d_kernel<<<grid_for(Z * (long long)X * Y, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_rot90(const void* src, void* dst, int X, int Y, long long inner_bytes, int k, rehr_stream stream) {
+  if (!src || !dst || X <= 0 || Y <= 0 || inner_bytes <= 0) return REHR_BAD_SHAPE;
+  k = ((k % 4) + 4) % 4;
+  const long long total_bytes = (long long)X * Y * inner_bytes;
+  if (k == 0) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)total_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+    return REHR_OK;
+  }
+  const bool a16 = inner_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const bool a4 = inner_bytes % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
+  if (a16) {
+    const long long inner = inner_bytes / 16;
+    rot90_kernel<uint4><<<grid_for((long long)X * Y * inner, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), X, Y, inner, k);
+  } else if (a4) {
+    const long long inner = inner_bytes / 4;
+    rot90_kernel<uint32_t><<<grid_for((long long)X * Y * inner, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), X, Y, inner, k);
+  } else {
+    rot90_kernel<uint8_t><<<grid_for(total_bytes, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(src), reinterpret_cast<uint8_t*>(dst), X, Y, inner_bytes, k);
+  }
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_fba_combine(const void* const* spectra, int K, float p, void* out, long long n, rehr_stream stream) {
+  if (!spectra || !out || K <= 0) return REHR_BAD_SHAPE;
+  if (K > kMaxFuse) return REHR_UNSUPPORTED;
+  PtrPack pk{};
+  for (int i = 0; i < K; ++i) pk.p[i] = spectra[i];
+  fba_combine_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(pk, K, p, reinterpret_cast<float2*>(out), n);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+int rehr_mean_stack(const float* const* vols, int K, float* out, long long n, rehr_stream stream) {
+  if (!vols || !out || K <= 0) return REHR_BAD_SHAPE;
+  if (K > kMaxFuse) return REHR_UNSUPPORTED;
+  PtrPack pk{};
+  for (int i = 0; i < K; ++i) pk.p[i] = vols[i];
+  mean_stack_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(pk, K, out, n);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_act_bwd(const rehr_tensor* a, const rehr_tensor* da, int act, float slope, const rehr_tensor* dy, rehr_stream stream) {
+  if (!bf16_tensor_ok(a) || !bf16_tensor_ok(da) || !bf16_tensor_ok(dy)) return REHR_BAD_ALIGNMENT;
+  if (a->c != da->c || a->c != dy->c) return REHR_BAD_SHAPE;
+  if (act != REHR_ACT_RELU && act != REHR_ACT_LRELU) return REHR_UNSUPPORTED;
+  const long long vox = (long long)a->n * voxels_per_sample(a);
+  act_bwd_kernel<<<grid_for(vox * (a->c / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a->ptr), a->ld, reinterpret_cast<const __nv_bfloat16*>(da->ptr), da->ld,
+      reinterpret_cast<__nv_bfloat16*>(dy->ptr), dy->ld, vox, a->c, act == REHR_ACT_RELU ? 0.f : slope);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// Direct convolution for layers whose input has very few channels (Cin <= 4): the 1-channel nnU-Net stem
+// (encoder.stages.0.0.convs.0, built at models/seg_model.py:174-191) and the 2-channel FLAVR stem
+// k(3,7,7) s(1,2,2) (models/FLAVR/resnet_3D.py:42-50).  K = taps*Cin is 27..294, far too thin to feed the
+// tensor cores from an NDHWC tile (Cin would have to be padded 8-16x), and the layer is HBM-bound anyway
+// (26 FLOP/B): the input is read as the caller hands it (NCDHW f32,
+// train_all.py:524), weights live in shared memory, each thread produces one output voxel x 16 channels and
+// writes NDHWC bf16 so the next layer's TMA tiles are ready-made.
+#include "engine.h"
+
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+namespace rehr {
+
+static constexpr int kScMaxCin = 4;
+static constexpr int kScCoutPerThread = 16;
+
+struct SmallCinArgs {
+  const float* x;      // [n][cin][d][h][w]
+  const float* w;      // [cout][cin][T]
+  const float* bias;   // [cout] or null
+  __nv_bfloat16* y;    // NDHWC
+  long long ldy;
+  int n, cin, d, h, wd;     // input dims
+  int od, oh, ow, cout;     // output dims
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int act;
+  float slope;
+};
+
+// weights in smem as [cin*T][cout] (cout fastest) so that a thread's 16 channels are 4 float4 broadcasts.
+__global__ void __launch_bounds__(256) smallcin_fwd_kernel(const SmallCinArgs a) {
+  extern __shared__ float sw[];
+  const int T = a.kd * a.kh * a.kw;
+  const int KT = a.cin * T;
+  for (int i = threadIdx.x; i < KT * a.cout; i += blockDim.x) {
+    const int co = i % a.cout, k = i / a.cout;  // k = ci*T + t
+    sw[i] = a.w[(long long)co * KT + k];
+  }
+  __syncthreads();
+  const int cgroups = (a.cout + kScCoutPerThread - 1) / kScCoutPerThread;
+  const long long ovox = (long long)a.n * a.od * a.oh * a.ow;
+  const long long items = ovox * cgroups;
+  const long long in_plane = (long long)a.h * a.wd, in_vol = in_plane * a.d;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    // consecutive threads -> consecutive output voxels along w (coalesced input reads); channel group outermost
+    const int cg = (int)(it / ovox);
+    long long v = it % ovox;
+    const int ox = (int)(v % a.ow);
+    long long r = v / a.ow;
+    const int oy = (int)(r % a.oh);
+    r /= a.oh;
+    const int oz = (int)(r % a.od);
+    const int nn = (int)(r / a.od);
+    const int c0 = cg * kScCoutPerThread;
+    float acc[kScCoutPerThread];
+#pragma unroll
+    for (int i = 0; i < kScCoutPerThread; ++i) acc[i] = (a.bias && c0 + i < a.cout) ? a.bias[c0 + i] : 0.f;
+    for (int ci = 0; ci < a.cin; ++ci) {
+      const float* xp = a.x + ((long long)nn * a.cin + ci) * in_vol;
+      for (int kz = 0; kz < a.kd; ++kz) {
+        const int iz = oz * a.sd + kz - a.pd;
+        if (iz < 0 || iz >= a.d) continue;
+        for (int ky = 0; ky < a.kh; ++ky) {
+          const int iy = oy * a.sh + ky - a.ph;
+          if (iy < 0 || iy >= a.h) continue;
+          for (int kx = 0; kx < a.kw; ++kx) {
+            const int ix = ox * a.sw + kx - a.pw;
+            if (ix < 0 || ix >= a.wd) continue;
+            const float xv = __ldg(xp + iz * in_plane + (long long)iy * a.wd + ix);
+            const float* wp = sw + (size_t)(ci * T + (kz * a.kh + ky) * a.kw + kx) * a.cout + c0;
+            if (c0 + kScCoutPerThread <= a.cout) {
+#pragma unroll
+              for (int i = 0; i < kScCoutPerThread; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wp + i);
+                acc[i] = fmaf(xv, w4.x, acc[i]);
+                acc[i + 1] = fmaf(xv, w4.y, acc[i + 1]);
+                acc[i + 2] = fmaf(xv, w4.z, acc[i + 2]);
+                acc[i + 3] = fmaf(xv, w4.w, acc[i + 3]);
+              }
+            } else {
+              for (int i = 0; i < kScCoutPerThread; ++i)
+                if (c0 + i < a.cout) acc[i] = fmaf(xv, wp[i], acc[i]);
+            }
+          }
+        }
+      }
+    }
+    __nv_bfloat16* o = a.y + v * a.ldy + c0;
+    if (c0 + kScCoutPerThread <= a.cout) {
+      uint4 lo, hi;
+      float f[kScCoutPerThread];
+#pragma unroll
+      for (int i = 0; i < kScCoutPerThread; ++i) {
+        float z = acc[i];
+        if (a.act == REHR_ACT_RELU) z = z > 0.f ? z : 0.f;
+        if (a.act == REHR_ACT_LRELU) z = z > 0.f ? z : z * a.slope;
+        f[i] = z;
+      }
+      __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        l2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        h2[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+      }
+      reinterpret_cast<uint4*>(o)[0] = lo;
+      reinterpret_cast<uint4*>(o)[1] = hi;
+    } else {
+      for (int i = 0; i < kScCoutPerThread; ++i)
+        if (c0 + i < a.cout) {
+          float z = acc[i];
+          if (a.act == REHR_ACT_RELU) z = z > 0.f ? z : 0.f;
+          if (a.act == REHR_ACT_LRELU) z = z > 0.f ? z : z * a.slope;
+          o[i] = __float2bfloat16(z);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dw[co][ci][t] = sum_o dy[o, co] * x[ci, o*s + t - p].
+// Warp = a run of output voxels, lane = output channel (coalesced 64 B dy rows); each lane keeps kWgAcc
+// (ci, tap) accumulators in registers; layers with more than kWgAcc (ci, tap) pairs make several passes
+// (blockIdx.y).  Per-block partials go to the workspace [pass][block][kWgAcc][cout] and a second kernel
+// reduces them in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+static constexpr int kWgAcc = 27;
+static constexpr int kWgBlocks = 592;  // 4 x 148
+
+struct SmallCinWgradArgs {
+  const float* x;
+  const __nv_bfloat16* dy;
+  long long lddy;
+  float* ws;
+  int n, cin, d, h, wd, od, oh, ow, cout;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+};
+
+__global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const SmallCinWgradArgs a) {
+  __shared__ float red[8][kWgAcc][32];
+  const int T = a.kd * a.kh * a.kw, KT = a.cin * T;
+  const int pass = blockIdx.y;
+  const int k0 = pass * kWgAcc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ovox = (long long)a.n * a.od * a.oh * a.ow;
+  const long long in_plane = (long long)a.h * a.wd, in_vol = in_plane * a.d;
+  const int cblocks = (a.cout + 31) / 32;
+  for (int cb = 0; cb < cblocks; ++cb) {
+    const int co = cb * 32 + lane;
+    float acc[kWgAcc];
+#pragma unroll
+    for (int i = 0; i < kWgAcc; ++i) acc[i] = 0.f;
+    for (long long v = (long long)blockIdx.x * 8 + warp; v < ovox; v += (long long)gridDim.x * 8) {
+      const float g = co < a.cout ? __bfloat162float(a.dy[v * a.lddy + co]) : 0.f;
+      const int ox = (int)(v % a.ow);
+      long long r = v / a.ow;
+      const int oy = (int)(r % a.oh);
+      r /= a.oh;
+      const int oz = (int)(r % a.od);
+      const int nn = (int)(r / a.od);
+#pragma unroll
+      for (int i = 0; i < kWgAcc; ++i) {
+        const int k = k0 + i;
+        if (k < KT) {
+          const int ci = k / T, t = k % T;
+          const int kx = t % a.kw, ky = (t / a.kw) % a.kh, kz = t / (a.kw * a.kh);
+          const int iz = oz * a.sd + kz - a.pd, iy = oy * a.sh + ky - a.ph, ix = ox * a.sw + kx - a.pw;
+          if (iz >= 0 && iz < a.d && iy >= 0 && iy < a.h && ix >= 0 && ix < a.wd)
+            acc[i] = fmaf(g, __ldg(a.x + ((long long)nn * a.cin + ci) * in_vol + iz * in_plane + (long long)iy * a.wd + ix), acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kWgAcc; ++i) red[warp][i][lane] = acc[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWgAcc * 32; i += blockDim.x) {
+      const int k = i / 32, l = i % 32;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][k][l];
+      if (cb * 32 + l < a.cout)
+        a.ws[(((long long)pass * gridDim.x + blockIdx.x) * kWgAcc + k) * a.cout + cb * 32 + l] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void smallcin_wgrad_reduce_kernel(const float* ws, int blocks, int passes, int KT, int cout, float* dw,
+                                             int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KT * cout) return;
+  const int co = i % cout, k = i / cout;
+  const int pass = k / kWgAcc, kk = k % kWgAcc;
+  (void)passes;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += ws[(((long long)pass * blocks + b) * kWgAcc + kk) * cout + co];
+  float* d = dw + (long long)co * KT + k;
+  *d = accumulate ? *d + s : s;
+}
+
+// Input gradient (gather form): dx[n][ci][i] = sum_{co,t : (i+p-t) % s == 0} dy[(i+p-t)/s, co] * w[co][ci][t]
+struct SmallCinDgradArgs {
+  const __nv_bfloat16* dy;
+  long long lddy;
+  const float* w;
+  float* dx;
+  int n, cin, d, h, wd, od, oh, ow, cout;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+};
+
+__global__ void __launch_bounds__(256) smallcin_dgrad_kernel(const SmallCinDgradArgs a) {
+  const int T = a.kd * a.kh * a.kw;
+  const long long ivox = (long long)a.n * a.d * a.h * a.wd;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < ivox * a.cin; it += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(it / ivox);
+    long long v = it % ivox;
+    const int ix = (int)(v % a.wd);
+    long long r = v / a.wd;
+    const int iy = (int)(r % a.h);
+    r /= a.h;
+    const int iz = (int)(r % a.d);
+    const int nn = (int)(r / a.d);
+    float acc = 0.f;
+    for (int kz = 0; kz < a.kd; ++kz) {
+      const int ez = iz + a.pd - kz;
+      if (ez < 0 || ez % a.sd != 0 || ez / a.sd >= a.od) continue;
+      for (int ky = 0; ky < a.kh; ++ky) {
+        const int ey = iy + a.ph - ky;
+        if (ey < 0 || ey % a.sh != 0 || ey / a.sh >= a.oh) continue;
+        for (int kx = 0; kx < a.kw; ++kx) {
+          const int ex = ix + a.pw - kx;
+          if (ex < 0 || ex % a.sw != 0 || ex / a.sw >= a.ow) continue;
+          const long long o = (((long long)nn * a.od + ez / a.sd) * a.oh + ey / a.sh) * a.ow + ex / a.sw;
+          const int t = (kz * a.kh + ky) * a.kw + kx;
+          const __nv_bfloat16* g = a.dy + o * a.lddy;
+          for (int co = 0; co < a.cout; ++co) acc = fmaf(__bfloat162float(g[co]), __ldg(a.w + ((long long)co * a.cin + ci) * T + t), acc);
+        }
+      }
+    }
+    a.dx[((long long)nn * a.cin + ci) * ((long long)a.d * a.h * a.wd) + ((long long)iz * a.h + iy) * a.wd + ix] = acc;
+  }
+}
+
+}  // namespace rehr
+
+using namespace rehr;
+
+namespace {
+inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+bool shapes_ok(const rehr_conv_desc* d, int n, int cin, int D, int H, int W, const rehr_tensor* y) {
+  if (!d || !y || !y->ptr || n <= 0 || cin <= 0 || cin > kScMaxCin) return false;
+  if (y->n != n) return false;
+  return y->d == conv_out(D, d->kd, d->sd, d->pd) && y->h == conv_out(H, d->kh, d->sh, d->ph) &&
+         y->w == conv_out(W, d->kw, d->sw, d->pw);
+}
+}  // namespace
+
+extern "C" {
+
+int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream);
+
+int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, int n, int cin, int d, int h, int w,
+                             const float* weight, const float* bias, const rehr_tensor* y, int act, float slope,
+                             float* stats, rehr_stream stream) {
+  if (!shapes_ok(desc, n, cin, d, h, w, y) || !x_ncdhw || !weight) return REHR_BAD_SHAPE;
+  if (y->ld % 8 != 0 || (reinterpret_cast<uintptr_t>(y->ptr) & 15) != 0) return REHR_BAD_ALIGNMENT;
+  if (y->c % 4 != 0) return REHR_UNSUPPORTED;
+  const int T = desc->kd * desc->kh * desc->kw;
+  const size_t smem = (size_t)cin * T * y->c * sizeof(float);
+  if (smem > 200 * 1024) return REHR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(smallcin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+  }
+  SmallCinArgs a;
+  a.x = x_ncdhw;
+  a.w = weight;
+  a.bias = bias;
+  a.y = reinterpret_cast<__nv_bfloat16*>(y->ptr);
+  a.ldy = y->ld;
+  a.n = n; a.cin = cin; a.d = d; a.h = h; a.wd = w;
+  a.od = y->d; a.oh = y->h; a.ow = y->w; a.cout = y->c;
+  a.kd = desc->kd; a.kh = desc->kh; a.kw = desc->kw;
+  a.sd = desc->sd; a.sh = desc->sh; a.sw = desc->sw;
+  a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
+  a.act = act;
+  a.slope = slope;
+  const long long items = (long long)n * y->d * y->h * y->w * ((y->c + kScCoutPerThread - 1) / kScCoutPerThread);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)sm_count() * 8));
+  smallcin_fwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(a);
+  REHR_CHECK_LAUNCH();
+  if (stats) {
+    if (act != REHR_ACT_NONE) return REHR_UNSUPPORTED;  // statistics are defined on the pre-activation output
+    return rehr_instnorm_stats(y, stats, stream);
+  }
+  return REHR_OK;
+}
+
+size_t rehr_conv3d_smallcin_wgrad_workspace(const rehr_conv_desc* desc, int cin, const rehr_tensor* dy) {
+  if (!desc || !dy || cin <= 0 || cin > kScMaxCin) return 0;
+  const int KT = cin * desc->kd * desc->kh * desc->kw;
+  const int passes = (KT + kWgAcc - 1) / kWgAcc;
+  return (size_t)passes * kWgBlocks * kWgAcc * dy->c * sizeof(float);
+}
+
+int rehr_conv3d_smallcin_wgrad(const rehr_conv_desc* desc, const float* x_ncdhw, int n, int cin, int d, int h, int w,
+                               const rehr_tensor* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
+                               rehr_stream stream) {
+  if (!shapes_ok(desc, n, cin, d, h, w, dy) || !x_ncdhw || !dw) return REHR_BAD_SHAPE;
+  const size_t need = rehr_conv3d_smallcin_wgrad_workspace(desc, cin, dy);
+  if (!ws || ws_bytes < need) return REHR_WORKSPACE;
+  const int KT = cin * desc->kd * desc->kh * desc->kw;
+  const int passes = (KT + kWgAcc - 1) / kWgAcc;
+  SmallCinWgradArgs a;
+  a.x = x_ncdhw;
+  a.dy = reinterpret_cast<const __nv_bfloat16*>(dy->ptr);
+  a.lddy = dy->ld;
+  a.ws = reinterpret_cast<float*>(ws);
+  a.n = n; a.cin = cin; a.d = d; a.h = h; a.wd = w;
+  a.od = dy->d; a.oh = dy->h; a.ow = dy->w; a.cout = dy->c;
+  a.kd = desc->kd; a.kh = desc->kh; a.kw = desc->kw;
+  a.sd = desc->sd; a.sh = desc->sh; a.sw = desc->sw;
+  a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
+  dim3 grid(kWgBlocks, passes);
+  smallcin_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  REHR_CHECK_LAUNCH();
+  const int total = KT * dy->c;
+  smallcin_wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.ws, kWgBlocks, passes, KT, dy->c, dw,
+                                                                                     accumulate);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_conv3d_smallcin_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const float* weight, float* dx_ncdhw,
+                               int n, int cin, int d, int h, int w, rehr_stream stream) {
+  if (!shapes_ok(desc, n, cin, d, h, w, dy) || !weight || !dx_ncdhw) return REHR_BAD_SHAPE;
+  SmallCinDgradArgs a;
+  a.dy = reinterpret_cast<const __nv_bfloat16*>(dy->ptr);
+  a.lddy = dy->ld;
+  a.w = weight;
+  a.dx = dx_ncdhw;
+  a.n = n; a.cin = cin; a.d = d; a.h = h; a.wd = w;
+  a.od = dy->d; a.oh = dy->h; a.ow = dy->w; a.cout = dy->c;
+  a.kd = desc->kd; a.kh = desc->kh; a.kw = desc->kw;
+  a.sd = desc->sd; a.sh = desc->sh; a.sw = desc->sw;
+  a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
+  const long long items = (long long)n * cin * d * h * w;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)sm_count() * 8));
+  smallcin_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,493 @@
+"""autograd.Function wrappers over the C-ABI (include/rehrseg_b200.h).
+
+Activations travel between these functions as channels-last bf16 tensors of logical shape [N, D, H, W, C]
+(`_lib.as_cl`); parameters stay the caller's fp32 `nn.Parameter`s in PyTorch layout, so `state_dict()`,
+optimisers and checkpoints of the reference (train_all.py:496-499,513,566-573) are untouched.  bf16 GEMM-operand
+copies of the weights are derived caches keyed on the parameter's version counter.
+
+Reference call sites replaced are listed per function.  There is no PyTorch fallback: every op calls the
+library and raises `RehrError` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, as_cl, check, conv_desc, lib, ptr, rt, stream_ptr
+
+Triple = Tuple[int, int, int]
+
+# --------------------------------------------------------------------------------------------------
+# launch accounting (bench.py reports `gpu_launches`)
+# --------------------------------------------------------------------------------------------------
+_launches = 0
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+# --------------------------------------------------------------------------------------------------
+# packed-weight cache
+# --------------------------------------------------------------------------------------------------
+_wcache: dict = {}
+
+
+def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor:
+    """bf16 K-major operand of `weight` ([A][B][T...] fp32) -- kind 'fwd': [A][T][B], 'dgrad': [B][T][A].
+    Cached per parameter object and version counter (an optimiser step bumps the version -> repack)."""
+    key = (id(weight), kind)
+    ver = weight._version
+    if cache:
+        hit = _wcache.get(key)
+        if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
+            return hit[2]
+    A, B = weight.shape[0], weight.shape[1]
+    T = weight[0, 0].numel()
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    if w.dtype != torch.float32:
+        w = w.float()
+    if kind == "fwd":
+        out = torch.empty((A, T, B), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight(ptr(w), ptr(out), A, B, T, B * T, T, 1, stream_ptr()), "pack_weight")
+    else:
+        out = torch.empty((B, T, A), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight(ptr(w), ptr(out), B, A, T, T, B * T, 1, stream_ptr()), "pack_weight")
+    _count()
+    if cache:
+        _wcache[key] = (weakref.ref(weight), ver, out)
+    return out
+
+
+def clear_weight_cache() -> None:
+    _wcache.clear()
+
+
+def _out_size(i: int, k: int, s: int, p: int) -> int:
+    return (i + 2 * p - k) // s + 1
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# raw (non-autograd) helpers
+# --------------------------------------------------------------------------------------------------
+def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], kernel: Triple, stride: Triple,
+               padding: Triple, act: int = ACT_NONE, slope: float = 0.0, want_stats: bool = False,
+               out_f32: bool = False, out: Optional[torch.Tensor] = None):
+    """y = act(conv3d(x) + bias) on NDHWC bf16 `x`; optionally per-tile InstanceNorm partial sums.
+    Returns (y, stats_partial or None, tiles)."""
+    x = as_cl(x)
+    n, d, h, w, cin = x.shape
+    cout = weight.shape[0]
+    od, oh, ow = (_out_size(i, k, s, p) for i, k, s, p in zip((d, h, w), kernel, stride, padding))
+    if out is None:
+        out = torch.empty((n, od, oh, ow, cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    yt = rt(out)
+    desc = conv_desc(kernel, stride, padding)
+    stats = None
+    tiles = 0
+    if want_stats:
+        tiles = lib().rehr_conv3d_stats_tiles(C.byref(yt))
+        if tiles > 0:
+            stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
+    wp = _packed(weight, "fwd")
+    xt = rt(x)
+    check(lib().rehr_conv3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
+                                float(slope), ptr(stats), stream_ptr()), "conv3d_fwd")
+    _count()
+    if want_stats and stats is None:
+        stats, tiles = instnorm_stats_raw(out)
+    return out, stats, tiles
+
+
+def instnorm_stats_raw(y: torch.Tensor):
+    yt = rt(y)
+    tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
+    stats = torch.empty((y.shape[0], tiles, y.shape[4], 2), dtype=torch.float32, device=y.device)
+    check(lib().rehr_instnorm_stats(C.byref(yt), ptr(stats), stream_ptr()), "instnorm_stats")
+    _count()
+    return stats, tiles
+
+
+def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[int], kernel: Triple, stride: Triple,
+                     padding: Triple, cache: bool = True) -> torch.Tensor:
+    dy = as_cl(dy)
+    n, d, h, w, cin = in_shape
+    dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=dy.device)
+    desc = conv_desc(kernel, stride, padding)
+    wp = _packed(weight, "dgrad", cache)
+    dyt, dxt = rt(dy), rt(dx)
+    check(lib().rehr_conv3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0,
+                                  stream_ptr()), "conv3d_dgrad")
+    _count(stride[0] * stride[1] * stride[2])
+    return dx
+
+
+def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], kernel: Triple, stride: Triple,
+                     padding: Triple) -> torch.Tensor:
+    x, dy = as_cl(x), as_cl(dy)
+    dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)
+    desc = conv_desc(kernel, stride, padding)
+    xt, dyt = rt(x), rt(dy)
+    need = lib().rehr_conv3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
+    if need == 0:
+        raise L.RehrError(f"conv3d_wgrad: unsupported configuration x={tuple(x.shape)} dy={tuple(dy.shape)}")
+    ws = _ws(need, x.device)
+    check(lib().rehr_conv3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
+          "conv3d_wgrad")
+    _count(2)
+    return dw
+
+
+def channel_sum_raw(x: torch.Tensor) -> torch.Tensor:
+    x = as_cl(x)
+    xt = rt(x)
+    out = torch.empty((x.shape[4],), dtype=torch.float32, device=x.device)
+    need = lib().rehr_channel_sum_workspace(C.byref(xt))
+    ws = _ws(need, x.device)
+    check(lib().rehr_channel_sum(C.byref(xt), ptr(out), 0, ptr(ws), need, stream_ptr()), "channel_sum")
+    _count(2)
+    return out
+
+
+def act_bwd_raw(a: torch.Tensor, da: torch.Tensor, act: int, slope: float) -> torch.Tensor:
+    """dy = da * act'(.) evaluated from the activation OUTPUT `a` (valid for ReLU and LeakyReLU with slope > 0)."""
+    a, da = as_cl(a), as_cl(da)
+    if act == ACT_NONE:
+        return da
+    dy = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    at, dat, dyt = rt(a), rt(da), rt(dy)
+    check(lib().rehr_act_bwd(C.byref(at), C.byref(dat), act, float(slope), C.byref(dyt), stream_ptr()), "act_bwd")
+    _count()
+    return dy
+
+
+# --------------------------------------------------------------------------------------------------
+# Conv3d -> InstanceNorm3d(affine) -> LeakyReLU   (dynamic_network_architectures ConvDropoutNormReLU,
+# constructed at models/seg_model.py:174-191 with the ops chosen at train_all.py:474-493)
+# --------------------------------------------------------------------------------------------------
+class ConvNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, kernel, stride, padding, eps, slope, small_cin):
+        dev = x.device
+        cout = weight.shape[0]
+        desc = conv_desc(kernel, stride, padding)
+        if small_cin:
+            # x is the caller's NCDHW fp32 tensor (train_all.py:524)
+            xs = _f32(x)
+            n, cin, d, h, w = xs.shape
+            od, oh, ow = (_out_size(i, k, s, p) for i, k, s, p in zip((d, h, w), kernel, stride, padding))
+            y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=dev)
+            yt = rt(y)
+            tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
+            stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
+            check(lib().rehr_conv3d_smallcin_fwd(C.byref(desc), ptr(xs), n, cin, d, h, w, ptr(_f32(weight)), ptr(_f32(bias)),
+                                                 C.byref(yt), ACT_NONE, 0.0, ptr(stats), stream_ptr()), "smallcin_fwd")
+            _count(2)
+            x_saved = xs
+        else:
+            x_saved = as_cl(x)
+            y, stats, tiles = conv3d_raw(x_saved, weight, bias, kernel, stride, padding, want_stats=True)
+        n = y.shape[0]
+        vox = y.shape[1] * y.shape[2] * y.shape[3]
+        mean = torch.empty((n, cout), dtype=torch.float32, device=dev)
+        rstd = torch.empty((n, cout), dtype=torch.float32, device=dev)
+        check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, cout, vox, float(eps), ptr(mean), ptr(rstd), stream_ptr()),
+              "instnorm_finalize")
+        a = torch.empty_like(y)
+        yt, at = rt(y), rt(a)
+        g32, b32 = _f32(gamma), _f32(beta)
+        check(lib().rehr_instnorm_lrelu_apply(C.byref(yt), ptr(mean), ptr(rstd), ptr(g32), ptr(b32), float(slope), C.byref(at),
+                                              stream_ptr()), "instnorm_lrelu_apply")
+        _count(2)
+        ctx.save_for_backward(x_saved, weight, gamma, beta, y, mean, rstd)
+        ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, weight, gamma, beta, y, mean, rstd = ctx.saved_tensors
+        kernel, stride, padding, slope, small_cin, has_bias = ctx.cfg
+        dev = y.device
+        da = as_cl(da)
+        n, cout = y.shape[0], y.shape[4]
+        vox = y.shape[1] * y.shape[2] * y.shape[3]
+        yt, dat = rt(y), rt(da)
+        g32 = _f32(gamma) if gamma is not None else None
+        b32 = _f32(beta) if beta is not None else None
+        tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
+        partial = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
+        check(lib().rehr_instnorm_lrelu_bwd_reduce(C.byref(yt), C.byref(dat), None, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
+                                                   float(slope), ptr(partial), stream_ptr()), "instnorm_bwd_reduce")
+        sums = torch.empty((n, cout, 2), dtype=torch.float32, device=dev)
+        dgamma = torch.empty((cout,), dtype=torch.float32, device=dev)
+        dbeta = torch.empty((cout,), dtype=torch.float32, device=dev)
+        check(lib().rehr_instnorm_lrelu_bwd_finalize(ptr(partial), n, tiles, cout, ptr(rstd), ptr(sums), ptr(dgamma), ptr(dbeta),
+                                                     0, stream_ptr()), "instnorm_bwd_finalize")
+        dy = torch.empty_like(y)
+        dyt = rt(dy)
+        check(lib().rehr_instnorm_lrelu_bwd_apply(C.byref(yt), C.byref(dat), None, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
+                                                  float(slope), ptr(sums), C.byref(dyt), stream_ptr()), "instnorm_bwd_apply")
+        _count(3)
+        desc = conv_desc(kernel, stride, padding)
+        dx = None
+        if small_cin:
+            nb, cin, d, h, w = x.shape
+            need = lib().rehr_conv3d_smallcin_wgrad_workspace(C.byref(desc), cin, C.byref(dyt))
+            ws = _ws(need, dev)
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+            check(lib().rehr_conv3d_smallcin_wgrad(C.byref(desc), ptr(x), nb, cin, d, h, w, C.byref(dyt), ptr(dw), 0, ptr(ws),
+                                                   need, stream_ptr()), "smallcin_wgrad")
+            _count(2)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(x.shape, dtype=torch.float32, device=dev)
+                check(lib().rehr_conv3d_smallcin_dgrad(C.byref(desc), C.byref(dyt), ptr(_f32(weight)), ptr(dx), nb, cin, d, h, w,
+                                                       stream_ptr()), "smallcin_dgrad")
+                _count()
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding)
+            dw = conv3d_wgrad_raw(x, dy, weight.shape, kernel, stride, padding)
+        # A per-channel constant added before InstanceNorm is removed by the mean subtraction: d(loss)/d(bias) == 0
+        # exactly (PyTorch's value is rounding noise of the same sum).
+        dbias = torch.zeros((cout,), dtype=torch.float32, device=dev) if has_bias else None
+        return dx, dw.to(weight.dtype), dbias, dgamma if gamma is not None else None, dbeta if beta is not None else None, \
+            None, None, None, None, None, None
+
+
+def conv_norm_act(x, weight, bias, gamma, beta, kernel, stride, padding, eps=1e-5, slope=0.01, small_cin=False):
+    return ConvNormAct.apply(x, weight, bias, gamma, beta, tuple(kernel), tuple(stride), tuple(padding), float(eps),
+                             float(slope), bool(small_cin))
+
+
+# --------------------------------------------------------------------------------------------------
+# Conv3d (+bias) (+ReLU / LeakyReLU), no norm: sr_head (models/seg_model.py:197-199), FLAVR Conv3DSimple /
+# Conv_3d / Conv_2d (models/FLAVR/resnet_3D.py:19-33, models/FLAVR/FLAVR_arch.py:24-88)
+# --------------------------------------------------------------------------------------------------
+class ConvAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope, out_f32):
+        x = as_cl(x)
+        y, _, _ = conv3d_raw(x, weight, bias, kernel, stride, padding, act=act, slope=slope, out_f32=out_f32)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, da):
+        x, weight, y = ctx.saved_tensors
+        kernel, stride, padding, act, slope, has_bias = ctx.cfg
+        dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
+        cout = weight.shape[0]
+        if cout % 16 != 0:
+            # thin heads (sr_head.2: 16 -> 2, models/seg_model.py:199): the GEMM operands need >= 16 channels, so the
+            # gradient is zero-padded to 16 channels (exact: the padded filters are zero)
+            cp = (cout + 15) // 16 * 16
+            dyp = torch.zeros((*dy.shape[:4], cp), dtype=torch.bfloat16, device=dy.device)
+            dyp[..., :cout] = dy
+            wpad = torch.zeros((cp, *weight.shape[1:]), dtype=torch.float32, device=dy.device)
+            wpad[:cout] = weight.detach()
+            dx = conv3d_dgrad_raw(dyp, wpad, x.shape, kernel, stride, padding, cache=False) if ctx.needs_input_grad[0] else None
+            dw = conv3d_wgrad_raw(x, dyp, wpad.shape, kernel, stride, padding)[:cout]
+            dy = dyp
+        else:
+            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding) if ctx.needs_input_grad[0] else None
+            dw = conv3d_wgrad_raw(x, dy, weight.shape, kernel, stride, padding)
+        db = channel_sum_raw(dy)[:cout] if has_bias else None
+        return dx, dw.to(weight.dtype), db, None, None, None, None, None, None
+
+
+def conv_act(x, weight, bias, kernel, stride, padding, act=ACT_NONE, slope=0.0, out_f32=False):
+    return ConvAct.apply(x, weight, bias, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope), bool(out_f32))
+
+
+# --------------------------------------------------------------------------------------------------
+# ConvTranspose3d: nnU-Net decoder up-sampling, kernel == stride (models/seg_model.py:36 via UNetDecoder.transpconvs),
+# and FLAVR upConv3D k(3,4,4) s(1,2,2) p(1,1,1) (models/FLAVR/FLAVR_arch.py:49-51)
+# --------------------------------------------------------------------------------------------------
+class ConvTranspose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope):
+        x = as_cl(x)
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        od, oh, ow = ((i - 1) * s - 2 * p + k for i, k, s, p in zip((d, h, w), kernel, stride, padding))
+        y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
+        desc = conv_desc(kernel, stride, padding)
+        wp = _packed(weight, "dgrad")  # [Cout][T][Cin]
+        xt, yt = rt(x), rt(y)
+        check(lib().rehr_convtranspose3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act, float(slope),
+                                             stream_ptr()), "convtranspose3d_fwd")
+        _count(stride[0] * stride[1] * stride[2])
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, da):
+        x, weight, y = ctx.saved_tensors
+        kernel, stride, padding, act, slope, has_bias = ctx.cfg
+        dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
+        desc = conv_desc(kernel, stride, padding)
+        dyt, xt = rt(dy), rt(x)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            dxt = rt(dx)
+            wp = _packed(weight, "fwd")  # [Cin][T][Cout]
+            check(lib().rehr_convtranspose3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), stream_ptr()),
+                  "convtranspose3d_dgrad")
+            _count()
+        need = lib().rehr_convtranspose3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
+        if need == 0:
+            raise L.RehrError("convtranspose3d_wgrad: unsupported configuration")
+        ws = _ws(need, x.device)
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+        check(lib().rehr_convtranspose3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
+              "convtranspose3d_wgrad")
+        _count(2)
+        db = channel_sum_raw(dy) if has_bias else None
+        return dx, dw.to(weight.dtype), db, None, None, None, None, None
+
+
+def conv_transpose(x, weight, bias, kernel, stride, padding=(0, 0, 0), act=ACT_NONE, slope=0.0):
+    return ConvTranspose.apply(x, weight, bias, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
+
+
+# --------------------------------------------------------------------------------------------------
+# 1x1x1 segmentation head (decoder.seg_layers[-1], models/seg_model.py:44): NDHWC bf16 -> NCDHW fp32 logits
+# --------------------------------------------------------------------------------------------------
+class SegHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = as_cl(x)
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[0]
+        y = torch.empty((n, cout, d, h, w), dtype=torch.float32, device=x.device)
+        w2 = _f32(weight).reshape(cout, cin)
+        xt = rt(x)
+        check(lib().rehr_pointwise_fwd(C.byref(xt), ptr(w2), ptr(_f32(bias)), ptr(y), cout, stream_ptr()), "pointwise_fwd")
+        _count()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        cout, cin = weight.shape[0], weight.shape[1]
+        dy = _f32(dy)
+        xt = rt(x)
+        dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        dxt = rt(dx)
+        dw = torch.empty((cout, cin), dtype=torch.float32, device=x.device)
+        db = torch.empty((cout,), dtype=torch.float32, device=x.device)
+        need = lib().rehr_pointwise_bwd_workspace(C.byref(xt), cout)
+        ws = _ws(need, x.device)
+        check(lib().rehr_pointwise_bwd(C.byref(xt), ptr(dy), ptr(_f32(weight).reshape(cout, cin)), cout, C.byref(dxt), ptr(dw), ptr(db),
+                                       0, ptr(ws), need, stream_ptr()), "pointwise_bwd")
+        _count(2)
+        return dx, dw.reshape(weight.shape).to(weight.dtype), db if ctx.has_bias else None
+
+
+def seg_head(x, weight, bias):
+    return SegHead.apply(x, weight, bias)
+
+
+# --------------------------------------------------------------------------------------------------
+# F.interpolate(scale_factor=(s,1,1), mode='trilinear', align_corners=True)  (models/seg_model.py:204)
+# --------------------------------------------------------------------------------------------------
+class UpsampleD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_d):
+        x = as_cl(x)
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, out_d, h, w, c), dtype=torch.bfloat16, device=x.device)
+        xt, yt = rt(x), rt(y)
+        check(lib().rehr_upsample_linear_d(C.byref(xt), C.byref(yt), stream_ptr()), "upsample_linear_d")
+        _count()
+        ctx.in_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_cl(dy)
+        dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dy.device)
+        dyt, dxt = rt(dy), rt(dx)
+        check(lib().rehr_upsample_linear_d_bwd(C.byref(dyt), C.byref(dxt), stream_ptr()), "upsample_linear_d_bwd")
+        _count()
+        return dx, None
+
+
+def upsample_linear_d(x, out_d: int):
+    return UpsampleD.apply(x, int(out_d))
+
+
+# --------------------------------------------------------------------------------------------------
+# layout adapters at the model boundary
+# --------------------------------------------------------------------------------------------------
+class ToChannelsLast(torch.autograd.Function):
+    """NCDHW fp32 -> NDHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xs = _f32(x)
+        n, c, d, h, w = xs.shape
+        y = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=xs.device)
+        yt = rt(y)
+        check(lib().rehr_ncdhw_f32_to_ndhwc_bf16(ptr(xs), C.byref(yt), stream_ptr()), "ncdhw_to_ndhwc")
+        _count()
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return FromChannelsLast.apply(dy)
+
+
+class FromChannelsLast(torch.autograd.Function):
+    """NDHWC bf16 -> NCDHW fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_cl(x)
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
+        xt = rt(x)
+        check(lib().rehr_ndhwc_bf16_to_ncdhw_f32(C.byref(xt), ptr(y), stream_ptr()), "ndhwc_to_ncdhw")
+        _count()
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ToChannelsLast.apply(dy)
+
+
+def to_channels_last(x):
+    return ToChannelsLast.apply(x)
+
+
+def from_channels_last(x):
+    return FromChannelsLast.apply(x)

@@ -1,0 +1,240 @@
+"""GPU parity of the conv engine (through the C-ABI) against torch fp32 convolutions on the same bf16-rounded
+operands.  Tolerance: relative L2 <= 1e-2 (north_star's bf16 bound); in practice ~2e-3 (one bf16 rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+FWD_CASES = [
+    # n, cin, cout, (d,h,w), k, s, p
+    (1, 32, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 64, 64, (8, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 16, 16, (8, 8, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 32, 64, (16, 16, 16), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (2, 320, 320, (4, 4, 4), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 256, 320, (8, 8, 8), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (1, 32, 32, (4, 16, 16), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 64, 128, (4, 16, 16), (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+    (1, 32, 48, (7, 9, 11), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 16, 2, (8, 8, 8), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
+    (1, 64, 64, (1, 16, 16), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    (1, 128, 64, (4, 16, 16), (1, 1, 1), (1, 2, 2), (0, 0, 0)),
+    (1, 256, 64, (1, 16, 16), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+]
+
+
+def _mk(n, cin, cout, dhw, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n, cin, *dhw), generator=g)
+    w = torch.randn((cout, cin, *k), generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5
+    b = torch.randn((cout,), generator=g)
+    return x.cuda(), w.cuda(), b.cuda()
+
+
+@pytest.mark.parametrize("case", FWD_CASES)
+def test_conv3d_fwd(case):
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, k, s, p = case
+    x, w, b = _mk(n, cin, cout, dhw, k)
+    ref = F.conv3d(bf16r(x), bf16r(w), b, stride=s, padding=p)
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    y, _, _ = Fn.conv3d_raw(xcl, w, b, k, s, p)
+    torch.cuda.synchronize()
+    got = y.float().permute(0, 4, 1, 2, 3)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < TOL, (case, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("case", FWD_CASES[:4] + FWD_CASES[6:9])
+def test_conv3d_fwd_act_f32(case):
+    from rehrseg_b200 import functional as Fn
+    from rehrseg_b200._lib import ACT_LRELU
+    n, cin, cout, dhw, k, s, p = case
+    x, w, b = _mk(n, cin, cout, dhw, k, seed=1)
+    ref = F.leaky_relu(F.conv3d(bf16r(x), bf16r(w), b, stride=s, padding=p), 0.2)
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    y, _, _ = Fn.conv3d_raw(xcl, w, b, k, s, p, act=ACT_LRELU, slope=0.2, out_f32=True)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float32
+    assert rel_l2(y.permute(0, 4, 1, 2, 3), ref) < 1e-4, case  # fp32 output: only accumulation-order noise
+
+
+@pytest.mark.parametrize("case", [c for c in FWD_CASES if c[2] % 16 == 0])
+def test_conv3d_dgrad(case):
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, k, s, p = case
+    x, w, _ = _mk(n, cin, cout, dhw, k, seed=2)
+    x.requires_grad_(True)
+    y = F.conv3d(x, bf16r(w), None, stride=s, padding=p)
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    (ref,) = torch.autograd.grad(y, x, bf16r(g))
+    gcl = g.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    dx = Fn.conv3d_dgrad_raw(gcl, w, (n, *dhw, cin), k, s, p, cache=False)
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float().permute(0, 4, 1, 2, 3), ref) < TOL, case
+
+
+@pytest.mark.parametrize("case", [c for c in FWD_CASES if c[2] % 16 == 0])
+def test_conv3d_wgrad(case):
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, k, s, p = case
+    x, w, _ = _mk(n, cin, cout, dhw, k, seed=4)
+    w.requires_grad_(True)
+    y = F.conv3d(bf16r(x), w, None, stride=s, padding=p)
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    (ref,) = torch.autograd.grad(y, w, bf16r(g))
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    gcl = g.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    dw = Fn.conv3d_wgrad_raw(xcl, gcl, w.shape, k, s, p)
+    torch.cuda.synchronize()
+    assert dw.shape == ref.shape
+    assert rel_l2(dw, ref) < 1e-3, (case, rel_l2(dw, ref))  # fp32 accumulate of exact bf16 products
+
+
+TCONV_CASES = [
+    (2, 64, 32, (8, 8, 8), (2, 2, 2), (2, 2, 2), (0, 0, 0)),
+    (2, 320, 320, (4, 4, 4), (2, 2, 2), (2, 2, 2), (0, 0, 0)),
+    (1, 64, 32, (4, 8, 8), (1, 2, 2), (1, 2, 2), (0, 0, 0)),
+    (1, 128, 64, (4, 8, 8), (3, 4, 4), (1, 2, 2), (1, 1, 1)),   # FLAVR upConv3D (FLAVR_arch.py:49-51)
+]
+
+
+@pytest.mark.parametrize("case", TCONV_CASES)
+def test_conv_transpose_fwd_bwd(case):
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, k, s, p = case
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((n, cin, *dhw), generator=g).cuda()
+    w = (torch.randn((cin, cout, *k), generator=g) / cin ** 0.5).cuda()
+    b = torch.randn((cout,), generator=g).cuda()
+    xr = bf16r(x).requires_grad_(True)
+    wr = bf16r(w).requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv_transpose3d(xr, wr, br, stride=s, padding=p)
+    go = torch.randn(ref.shape, generator=g).cuda()
+    rdx, rdw, rdb = torch.autograd.grad(ref, (xr, wr, br), bf16r(go))
+
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).requires_grad_(True)
+    wp = w.clone().requires_grad_(True)
+    bp = b.clone().requires_grad_(True)
+    y = Fn.conv_transpose(xcl, wp, bp, k, s, p)
+    assert rel_l2(y.float().permute(0, 4, 1, 2, 3), ref) < TOL, case
+    gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    dx, dw, db = torch.autograd.grad(y, (xcl, wp, bp), gcl)
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float().permute(0, 4, 1, 2, 3), rdx) < TOL, case
+    assert rel_l2(dw, rdw) < 2e-3, case
+    assert rel_l2(db, rdb) < 2e-3, case
+
+
+@pytest.mark.parametrize("shape", [(2, 32, (16, 16, 16)), (1, 64, (8, 8, 8)), (2, 320, (4, 4, 4)), (1, 48, (7, 9, 11))])
+@pytest.mark.parametrize("stride", [(1, 1, 1), (2, 2, 2)])
+def test_conv_norm_act_block(shape, stride):
+    """Conv3d -> InstanceNorm3d(affine) -> LeakyReLU forward + full backward vs torch autograd (fp32)."""
+    from rehrseg_b200 import functional as Fn
+    n, c, dhw = shape
+    cin = 32
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((n, cin, *dhw), generator=g).cuda()
+    w = (torch.randn((c, cin, 3, 3, 3), generator=g) / (27 * cin) ** 0.5).cuda()
+    b = torch.randn((c,), generator=g).cuda()
+    ga = (1 + 0.1 * torch.randn((c,), generator=g)).cuda()
+    be = (0.1 * torch.randn((c,), generator=g)).cuda()
+    xr = bf16r(x).requires_grad_(True)
+    wr = bf16r(w).requires_grad_(True)
+    gar, ber = ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    ref = F.leaky_relu(F.instance_norm(F.conv3d(xr, wr, b, stride=stride, padding=1), weight=gar, bias=ber, eps=1e-5), 0.01)
+    go = torch.randn(ref.shape, generator=g).cuda()
+    rdx, rdw, rdg, rdb = torch.autograd.grad(ref, (xr, wr, gar, ber), bf16r(go))
+
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).requires_grad_(True)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    gap, bep = ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    a = Fn.conv_norm_act(xcl, wp, bp, gap, bep, (3, 3, 3), stride, (1, 1, 1), eps=1e-5, slope=0.01)
+    assert rel_l2(a.float().permute(0, 4, 1, 2, 3), ref) < TOL
+    gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    dx, dw, dbias, dg, dbeta = torch.autograd.grad(a, (xcl, wp, bp, gap, bep), gcl)
+    torch.cuda.synchronize()
+    # the backward consumes the bf16-rounded conv output, so compare at the bf16 bound
+    assert rel_l2(dx.float().permute(0, 4, 1, 2, 3), rdx) < 2e-2
+    assert rel_l2(dw, rdw) < 2e-2
+    assert rel_l2(dg, rdg) < 2e-2
+    assert rel_l2(dbeta, rdb) < 2e-2
+    assert float(dbias.abs().max()) == 0.0
+
+
+def test_smallcin_stem_block():
+    """1-channel nnU-Net stem: NCDHW fp32 in, Conv3d(1->32,k3) -> IN -> LeakyReLU, weight gradient."""
+    from rehrseg_b200 import functional as Fn
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((2, 1, 16, 24, 24), generator=g).cuda()
+    w = (torch.randn((32, 1, 3, 3, 3), generator=g) / 27 ** 0.5).cuda()
+    b = torch.randn((32,), generator=g).cuda()
+    ga = (1 + 0.1 * torch.randn((32,), generator=g)).cuda()
+    be = (0.1 * torch.randn((32,), generator=g)).cuda()
+    wr, gar, ber = (t.clone().requires_grad_(True) for t in (w, ga, be))
+    ref = F.leaky_relu(F.instance_norm(F.conv3d(x, wr, b, padding=1), weight=gar, bias=ber, eps=1e-5), 0.01)
+    go = torch.randn(ref.shape, generator=g).cuda()
+    rdw, rdg, rdb = torch.autograd.grad(ref, (wr, gar, ber), bf16r(go))
+    wp, bp, gap, bep = (t.clone().requires_grad_(True) for t in (w, b, ga, be))
+    a = Fn.conv_norm_act(x, wp, bp, gap, bep, (3, 3, 3), (1, 1, 1), (1, 1, 1), small_cin=True)
+    assert rel_l2(a.float().permute(0, 4, 1, 2, 3), ref) < TOL
+    gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    dw, dg, dbeta = torch.autograd.grad(a, (wp, gap, bep), gcl)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, rdw) < 2e-2
+    assert rel_l2(dg, rdg) < 2e-2
+    assert rel_l2(dbeta, rdb) < 2e-2
+
+
+def test_flavr_stem_smallcin_raw():
+    """2-channel FLAVR stem k(3,7,7) s(1,2,2) p(1,3,3) + ReLU (resnet_3D.py:42-50) forward / wgrad / dgrad."""
+    import ctypes as C
+    from rehrseg_b200 import _lib as L
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((1, 2, 4, 32, 32), generator=g).cuda()
+    w = (torch.randn((64, 2, 3, 7, 7), generator=g) / 294 ** 0.5).cuda()
+    b = torch.randn((64,), generator=g).cuda()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.relu(F.conv3d(xr, wr, b, stride=(1, 2, 2), padding=(1, 3, 3)))
+    y = torch.empty((1, 4, 16, 16, 64), dtype=torch.bfloat16, device="cuda")
+    desc = L.conv_desc((3, 7, 7), (1, 2, 2), (1, 3, 3))
+    yt = L.rt(y)
+    L.check(L.lib().rehr_conv3d_smallcin_fwd(C.byref(desc), L.ptr(x), 1, 2, 4, 32, 32, L.ptr(w), L.ptr(b), C.byref(yt),
+                                             L.ACT_RELU, 0.0, None, L.stream_ptr()))
+    assert rel_l2(y.float().permute(0, 4, 1, 2, 3), ref) < TOL
+    go = torch.randn(ref.shape, generator=g).cuda()
+    pre = F.conv3d(xr, wr, b, stride=(1, 2, 2), padding=(1, 3, 3))
+    rdx, rdw = torch.autograd.grad(pre, (xr, wr), bf16r(go))
+    gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    gt = L.rt(gcl)
+    need = L.lib().rehr_conv3d_smallcin_wgrad_workspace(C.byref(desc), 2, C.byref(gt))
+    ws = torch.empty((need,), dtype=torch.uint8, device="cuda")
+    dw = torch.empty_like(w)
+    L.check(L.lib().rehr_conv3d_smallcin_wgrad(C.byref(desc), L.ptr(x), 1, 2, 4, 32, 32, C.byref(gt), L.ptr(dw), 0, L.ptr(ws), need,
+                                               L.stream_ptr()))
+    dx = torch.empty_like(x)
+    L.check(L.lib().rehr_conv3d_smallcin_dgrad(C.byref(desc), C.byref(gt), L.ptr(w), L.ptr(dx), 1, 2, 4, 32, 32, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(dw, rdw) < 1e-3
+    assert rel_l2(dx, rdx) < 1e-3

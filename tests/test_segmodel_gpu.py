@@ -1,0 +1,52 @@
+"""Whole-network parity: B200 engine (bf16, through the C-ABI) vs the oracle SegModel on CPU (fp32), same weights
+and inputs.  Bounds from north_star: relative L2 <= 1e-2 on logits, argmax agreement >= 99.9 % of voxels."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_segmodel_tiny_fwd_bwd():
+    from oracle import parity
+    res = parity.segmodel_parity(patch=(16, 32, 32), batch=2, plan="tiny", backward=True)
+    print(res)
+    assert res["rel_l2_logits"] <= 1e-2
+    assert res["rel_l2_hr_logits"] <= 1e-2
+    assert res["argmax_agreement"] >= 0.999
+    assert res["rel_l2_grads_global"] <= 3e-2
+
+
+def test_segmodel_3d_fullres_fwd_bwd_64():
+    from oracle import parity
+    res = parity.segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", backward=True)
+    print(res)
+    assert res["rel_l2_logits"] <= 1e-2
+    assert res["rel_l2_hr_logits"] <= 1e-2
+    assert res["argmax_agreement"] >= 0.999
+    assert res["rel_l2_grads_global"] <= 5e-2
+
+
+def test_segmodel_anisotropic_fwd():
+    from oracle import parity
+    res = parity.segmodel_parity(patch=(8, 64, 64), batch=1, plan="anisotropic", backward=False)
+    print(res)
+    assert res["rel_l2_logits"] <= 1e-2
+    assert res["argmax_agreement"] >= 0.999
+
+
+def test_convert_reference_shaped_model_shares_parameters():
+    """convert() on an oracle-built (reference-shaped) module: same Parameter objects, engine forward."""
+    from oracle import seg_model as ref_seg
+    from rehrseg_b200 import seg_model as sm
+    ref = ref_seg.build("tiny")
+    x = torch.randn((1, 1, 16, 32, 32), generator=torch.Generator().manual_seed(0))
+    want, want_up = ref(x)
+    before = {k: id(p) for k, p in ref.named_parameters()}
+    keys = list(ref.state_dict().keys())
+    m = sm.convert(ref).cuda()
+    assert {k: id(p) for k, p in m.named_parameters()} == before
+    assert list(m.state_dict().keys()) == keys
+    out, up, skips = m(x.cuda(), return_inetermediate_feature=True)
+    assert (out.float().cpu() - want).norm() / want.norm() <= 1e-2
+    assert (up.float().cpu() - want_up).norm() / want_up.norm() <= 1e-2
+    assert skips[1].shape == (1, 64, 8, 16, 16) and skips[1].dtype == torch.float32
