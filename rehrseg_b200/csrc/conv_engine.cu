@@ -104,6 +104,34 @@ static int encode_weight_map(CUtensorMap* m, const void* base, long long K, int 
   return REHR_OK;
 }
 
+// Generic bf16 tiled tensor map (used by the marching kernel): dims / strides innermost first, strides in bytes.
+int encode_tiled_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* gdim,
+                      const unsigned long long* gstride_bytes, const unsigned* box, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return REHR_CUDA_ERROR;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bd[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = gdim[i];
+    bd[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gs[i] = gstride_bytes[i];
+    if ((gs[i] & 15) != 0) return REHR_BAD_ALIGNMENT;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return REHR_BAD_ALIGNMENT;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bd, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = (int)r;
+    return REHR_CUDA_ERROR;
+  }
+  return REHR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host: tap tables.
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ def _count(n: int = 1) -> None:
 # packed-weight cache
 # --------------------------------------------------------------------------------------------------
 _wcache: dict = {}
+USE_MARCH = True  # route eligible k3/s1/p1 layers through the halo-resident marching kernel (csrc/conv_march.cu)
 
 
 def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor:
@@ -58,7 +59,13 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor
         w = w.contiguous()
     if w.dtype != torch.float32:
         w = w.float()
-    if kind == "fwd":
+    if kind == "march_fwd":      # conv A<-B, marching-kernel layout
+        out = torch.empty((A * B * T,), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), A, B, B * T, T, 0, stream_ptr()), "pack_weight_march")
+    elif kind == "march_dgrad":  # its input-gradient B<-A (transposed, taps flipped)
+        out = torch.empty((A * B * T,), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, T, B * T, 1, stream_ptr()), "pack_weight_march")
+    elif kind == "fwd":
         out = torch.empty((A, T, B), dtype=torch.bfloat16, device=w.device)
         check(lib().rehr_pack_weight(ptr(w), ptr(out), A, B, T, B * T, T, 1, stream_ptr()), "pack_weight")
     else:
@@ -109,6 +116,16 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     desc = conv_desc(kernel, stride, padding)
     stats = None
     tiles = 0
+    if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), cin, cout):
+        xt = rt(x)
+        if want_stats:
+            tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt))
+            stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
+        wp = _packed(weight, "march_fwd")
+        check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act, float(slope),
+                                          ptr(stats), stream_ptr()), "conv3d_march_fwd")
+        _count()
+        return out, stats, tiles
     if want_stats:
         tiles = lib().rehr_conv3d_stats_tiles(C.byref(yt))
         if tiles > 0:
@@ -138,6 +155,13 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
     n, d, h, w, cin = in_shape
     dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     desc = conv_desc(kernel, stride, padding)
+    if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), dy.shape[4], cin):
+        wp = _packed(weight, "march_dgrad", cache)
+        dyt, dxt = rt(dy), rt(dx)
+        check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0, None, stream_ptr()),
+              "conv3d_march_dgrad")
+        _count()
+        return dx
     wp = _packed(weight, "dgrad", cache)
     dyt, dxt = rt(dy), rt(dx)
     check(lib().rehr_conv3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0,
