@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- the measured line for the REHRSeg hot path on B200.
+
+Workload (BASELINE.json `metric`: "patch fwd+bwd/sec & conv TFLOP/s vs bf16 peak"; north_star target "PlainConvUNet
+3d_fullres 128^3 patch fwd+bwd"): one STEP = forward + backward of the nnU-Net PlainConvUNet (3d_fullres plan, 6 stages,
+features 32..320, InstanceNorm + LeakyReLU) on a synthetic batch of 2 patches [2,1,128,128,128] per GPU, bf16 tensor-core
+arithmetic with fp32 accumulation, fp32 master weights re-packed to bf16 every step (as after an optimiser update),
+and -- for N > 1 -- the data-parallel gradient all-reduce over NCCL.  `value` = patches / s over all ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a engine
+    python bench.py --impl reference ...                            # the reference's CPU PyTorch path (oracle port)
+    python bench.py --impl eager_gpu ...                            # informational: torch eager + cuDNN on the same GPU
+
+Keys follow the driver contract: value (inputs resident in HBM), e2e (inputs copied from pinned host memory inside the
+timed region through the public nn.Module API, loss read back), roofline (dominant kernel, measured live with CUDA
+events), cpu_baseline (oracle on the host cores), clocks (nvidia-smi sampled during the timed region), gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PATCH = (128, 128, 128)
+BATCH = 2
+METRIC = "patch_fwd_bwd_per_s"
+UNIT = "patches/s"
+WORKLOAD = "nnUNet PlainConvUNet 3d_fullres fwd+bwd, synthetic 2x1x128x128x128 patch per GPU"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+def conv_flops(model: torch.nn.Module, in_shape) -> dict:
+    """Algorithmic FLOPs (2*M*N*K) of every conv / transposed conv of `model` for one forward on `in_shape`
+    ([B,C,D,H,W]) by shape propagation on the module tree (encoder stages -> decoder), and the fwd+bwd total:
+    dgrad + wgrad = 2x fwd, except that the very first conv needs no input gradient."""
+    b, c, d, h, w = in_shape
+    fwd = 0.0
+    first = None
+    sp = [(d, h, w)]
+    cur = (d, h, w)
+    for stage in model.encoder.stages:
+        for blk in stage[0].convs:
+            cv = blk.conv
+            cur = tuple((i + 2 * p - k) // s + 1 for i, k, s, p in zip(cur, cv.kernel_size, cv.stride, cv.padding))
+            f = 2.0 * b * cur[0] * cur[1] * cur[2] * cv.out_channels * cv.in_channels * cv.kernel_size[0] * cv.kernel_size[1] * cv.kernel_size[2]
+            if first is None:
+                first = f
+            fwd += f
+        sp.append(cur)
+    skips = sp[1:]
+    cur = skips[-1]
+    dec = model.decoder
+    for s in range(len(dec.stages)):
+        tc = dec.transpconvs[s]
+        # kernel == stride transposed conv: every input voxel meets every weight once
+        fwd += 2.0 * b * cur[0] * cur[1] * cur[2] * tc.in_channels * tc.out_channels * tc.kernel_size[0] * tc.kernel_size[1] * tc.kernel_size[2]
+        cur = skips[-(s + 2)]
+        for blk in dec.stages[s].convs:
+            cv = blk.conv
+            fwd += 2.0 * b * cur[0] * cur[1] * cur[2] * cv.out_channels * cv.in_channels * cv.kernel_size[0] * cv.kernel_size[1] * cv.kernel_size[2]
+    seg = dec.seg_layers[-1]
+    fwd += 2.0 * b * cur[0] * cur[1] * cur[2] * seg.in_channels * seg.out_channels
+    return {"fwd": fwd, "fwd_bwd": 3.0 * fwd - first}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._pump, daemon=True)
+        self.thr.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's PlainConvUNet on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def _oracle_unet():
+    from oracle import seg_model as ref_seg, third_party as tp
+    kw = ref_seg.plan_kwargs("3d_fullres")
+    kw.pop("upscale")
+    torch.manual_seed(1234)
+    return tp.PlainConvUNet(**kw)
+
+
+def _cpu_step(model, x, g):
+    for p in model.parameters():
+        p.grad = None
+    out = model(x)
+    loss = (out * g).sum() / out.numel()
+    loss.backward()
+    return float(loss.detach())
+
+
+def cpu_sample_inputs(ds: int, batch: int = 1):
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn((batch, 1, ds, PATCH[1], PATCH[2]), generator=gen)
+    g = torch.randn((batch, 2, ds, PATCH[1], PATCH[2]), generator=torch.Generator().manual_seed(1))
+    return x, g
+
+
+def cpu_baseline(budget_s: float = 25.0) -> dict:
+    """One bounded fwd+bwd of the oracle PlainConvUNet on the host cores: a depth slab [1,1,Ds,128,128] of one patch,
+    Ds in {32,64,128} picked from a 32-slab calibration so that the timed sample is <= ~budget_s."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = _oracle_unet()
+    x, g = cpu_sample_inputs(32)
+    _cpu_step(model, x, g)  # oneDNN primitive warm-up + calibration
+    t0 = time.perf_counter(); _cpu_step(model, x, g); t32 = time.perf_counter() - t0
+    ds = 128 if t32 * 4 <= budget_s else (64 if t32 * 2 <= budget_s else 32)
+    if ds != 32:
+        x, g = cpu_sample_inputs(ds)
+        t0 = time.perf_counter(); _cpu_step(model, x, g); t = time.perf_counter() - t0
+    else:
+        t = t32
+    return {"value": (ds / PATCH[0]) / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 fwd+bwd of [1,1,{ds},128,128] ({ds}/128 of one patch), fp32 oracle PlainConvUNet, torch "
+                      f"{torch.__version__} CPU, {t:.2f} s", "seconds": t}
+
+
+def reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = _oracle_unet()
+    x, g = cpu_sample_inputs(32)
+    _cpu_step(model, x, g)
+    t0 = time.perf_counter(); _cpu_step(model, x, g); t32 = time.perf_counter() - t0
+    total = max(1, args.steps + args.warmup)
+    budget = 150.0 / total
+    ds = 128 if t32 * 4 <= budget else (64 if t32 * 2 <= budget else 32)
+    x, g = cpu_sample_inputs(ds)
+    for _ in range(args.warmup):
+        _cpu_step(model, x, g)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _cpu_step(model, x, g)
+    el = time.perf_counter() - t0
+    val = args.steps * (ds / PATCH[0]) / el
+    sample = f"each step = 1 fwd+bwd of [1,1,{ds},128,128] ({ds}/128 of one 128^3 patch), fp32, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "device": "host CPU", "what": "oracle port of the reference PlainConvUNet "
+                       "(dynamic_network_architectures 0.3.1 restated; /root/reference is absent on the GPU box)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager_gpu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the B200 arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rehrseg_b200 import functional as Fn
+
+    if args.impl == "b200":
+        from rehrseg_b200 import seg_model as sm
+        torch.manual_seed(1234)
+        model = sm.plainconv_unet_3d_fullres().to(dev)
+        dtype = "bf16"
+    else:
+        model = _oracle_unet().to(dev).to(memory_format=torch.channels_last_3d)
+        dtype = "bf16 autocast (cuDNN)"
+    params = [p for p in model.parameters()]
+    flops = conv_flops(model, (BATCH, 1, *PATCH))
+
+    gen = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.randn((BATCH, 1, *PATCH), generator=gen).pin_memory()
+    g_host = torch.randn((BATCH, 2, *PATCH), generator=gen).pin_memory()
+    x_dev, g_dev = x_host.to(dev), g_host.to(dev)
+    flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def fwd_bwd(x, g):
+        for p in params:
+            p.grad = None
+        if args.impl == "b200":
+            Fn.clear_weight_cache()  # bf16 operand copies are re-derived every step, as after an optimiser update
+            out = model(x)
+        else:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = model(x)
+        loss = (out.float() * g).sum() / out.numel()
+        loss.backward()
+        if world > 1:  # data-parallel gradient mean over NVLink (one flat bucket)
+            off = 0
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.grad.reshape(-1))
+                off += n
+            dist.all_reduce(flat)
+            flat.div_(world)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+        return loss
+
+    def step_resident():
+        return fwd_bwd(x_dev, g_dev)
+
+    def step_e2e():
+        x = x_host.to(dev, non_blocking=True)
+        g = g_host.to(dev, non_blocking=True)
+        return float(fwd_bwd(x, g))  # .item(): device -> host read of the loss
+
+    def timed(step_fn, steps, sampler=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = Fn.launches()
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = Fn.launches() - l0
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), launches, clocks
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    phys = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local
+    ms, launches, clocks = timed(step_resident, args.steps, ClockSampler(phys) if rank == 0 else None)
+    step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # roofline of the dominant kernel: one instrumented step, CUDA events around every conv-engine launch
+    roof = None
+    kernels = {}
+    if args.impl == "b200":
+        torch.cuda.synchronize()
+        with Fn.kernel_timer() as kt:
+            torch.cuda._sleep(200_000_000)  # let the host run ahead so launch latency stays out of the event pairs
+            step_resident()
+        summ = kt.summary()
+        peaks = measured_peaks()
+        for name, (n, tms, fl) in summ.items():
+            kernels[name] = {"launches": n, "ms": round(tms, 4), "tflops": round(fl / tms / 1e9, 1) if tms > 0 else None}
+        if summ:
+            top = max(summ.items(), key=lambda kv: kv[1][1])
+            name, (n, tms, fl) = top
+            achieved = fl / tms / 1e9
+            peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+            roof = {"kernel": name, "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "launches_per_step": n,
+                    "avg_launch_ms": round(tms / n, 4), "flops_per_launch": fl / n,
+                    "share_of_step": round(tms / (ms / args.steps), 4),
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']}); kernel timed inside a step",
+                    "frac_of_burst": round(achieved / float(peaks["bf16_tflops"]), 4)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    per_step = ms / args.steps
+    value = world * BATCH * args.steps / (ms / 1e3)
+    e2e_val = world * BATCH * args.steps / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+    tfl = flops["fwd_bwd"] / (per_step * 1e-3) / 1e12
+    line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "patch": list(PATCH),
+                       "parallelism": f"dp{world}" if world > 1 else "single", "cache": "per-step working set ~8 GB >> 126 MB L2",
+                       "weights_repacked_each_step": True, "algorithmic_tflop_per_step": round(flops["fwd_bwd"] / 1e12, 4)},
+            "conv_tflops_per_gpu": round(tfl, 1), "frac_bf16_peak_burst": round(tfl / float(peaks["bf16_tflops"]), 4),
+            "frac_bf16_peak_sustained": round(tfl / float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), 4),
+            "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": world * (x_host.numel() + g_host.numel()) * 4,
+                    "d2h_bytes_per_step": world * 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
+    if args.impl != "b200":
+        line["impl"] = args.impl
+        line["gpu_launches"] = None
+    if world == 1 and args.impl == "b200" and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,8 @@
 #include "reduce.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -55,6 +57,8 @@ struct alignas(64) MarchParams {
   float slope;
   float* stats;  // [N][tiles_per_sample][Cout][2] or null
   int* err;
+  long long* prof;  // development only: per-role cycle counters of CTA 0 (env REHR_MARCH_PROF)
+  int debug;  // development only (env REHR_MARCH_DEBUG): bit0 skip input TMA, bit1 skip epilogue body, bit2 skip MMAs
 };
 
 __device__ __forceinline__ float march_act(float v, int act, float slope) {
@@ -85,11 +89,12 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
-// BKT = channels per K chunk (16 / 32 / 64 -> 32 / 64 / 128 B swizzled rows), CHUNKS = Cin / BKT.  Compile-time so that
+// BKT = channels per K chunk (16 / 32 / 64 -> 32 / 64 / 128 B swizzled rows), CHUNKS = Cin / BKT, CT = output-channel
+// tile (epilogue keeps CT running column sums per thread in registers).  Compile-time so that
 // the MMA issue sequence of one input plane (9 * CHUNKS * BKT/16 instructions) is fully unrolled with constant
 // descriptor increments: a single thread must issue one tcgen05.mma every ~50 clk (tools/umma_rate2.cu measures
 // 40 clk/MMA for this code shape vs 120-280 clk/MMA with run-time descriptor arithmetic).
-template <int BKT, int CHUNKS>
+template <int BKT, int CHUNKS, int CT>
 __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __grid_constant__ MarchParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,6 +111,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
   float* part = reinterpret_cast<float*>(tmem_slot + 4);   // [4 warps][2][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kSlots = (512 / CT) < kMaxSlots ? (512 / CT) : kMaxSlots;  // power of two
+  constexpr int kSlotMask = kSlots - 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.x_map);
@@ -155,11 +162,17 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
         const int h0 = c.th * kTileH - 1, w0 = c.tw * kTileW - 1;
         for (int pl = pa; pl <= pb; ++pl) {
+          const long long tp0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 22);
-          mbar_arrive_expect_tx(&full_bar[stage], p.plane_bytes);
-          uint8_t* dst = s_ring + (size_t)stage * p.slot_stride;
-          for (int ch = 0; ch < p.chunks; ++ch)
-            tma_load_5d(&p.x_map, &full_bar[stage], dst + (size_t)ch * p.chunk_stride, ch * p.BK, w0, h0, pl, c.n);
+          if (p.prof && blockIdx.x == 0) { p.prof[0] += clock64() - tp0; p.prof[1] += 1; }
+          if (p.debug & 1) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], p.plane_bytes);
+            uint8_t* dst = s_ring + (size_t)stage * p.slot_stride;
+            for (int ch = 0; ch < p.chunks; ++ch)
+              tma_load_5d(&p.x_map, &full_bar[stage], dst + (size_t)ch * p.chunk_stride, ch * p.BK, w0, h0, pl, c.n);
+          }
           if (++stage == p.ring) {
             stage = 0;
             phase ^= 1u;
@@ -196,24 +209,27 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
       int next_open = d0;
       for (int pl = pa; pl <= pb; ++pl) {
         const int qa = max(pl - 1, d0), qb = min(pl + 1, d1 - 1);
+        const long long tm0 = clock64();
         while (next_open <= qb) {  // first touch of an output plane's TMEM slot: wait until it was drained + zeroed
-          const int s = (next_open - d0) % p.slots;
+          const int s = (next_open - d0) & kSlotMask;
           mbar_wait(&tempty_bar[s], (tempty_par >> s) & 1u, p.err, 32);
           tempty_par ^= 1u << s;
           ++next_open;
         }
+        const long long tm1 = clock64();
         mbar_wait(&full_bar[stage], phase, p.err, 33);
         tc_fence_after();
+        const long long tm2 = clock64();
         const uint32_t a_lo = sring_lo + (uint32_t)stage * slot_lo;
         // contiguous TMEM slot runs covering output planes qa..qb (one run unless the slot ring wraps)
         int ra = qa;
         while (ra <= qb) {
           int rb = ra;
-          while (rb < qb && ((rb + 1 - d0) % p.slots) != 0) ++rb;
-          const uint32_t idesc = make_idesc_bf16(128, (rb - ra + 1) * p.Ct, 0, 0);
-          const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + 1) * p.Ct) * kRowB) >> 4);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(((ra - d0) % p.slots) * p.Ct);
-          if (elect_one_sync()) {
+          while (rb < qb && ((rb + 1 - d0) & kSlotMask) != 0) ++rb;
+          const uint32_t idesc = make_idesc_bf16(128, (rb - ra + 1) * CT, 0, 0);
+          const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + 1) * CT) * kRowB) >> 4);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(((ra - d0) & kSlotMask) * CT);
+          if (!(p.debug & 4) && elect_one_sync()) {
 #pragma unroll
             for (int khw = 0; khw < 9; ++khw) {
 #pragma unroll
@@ -235,12 +251,16 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         if (elect_one_sync()) {
           umma_commit(&empty_bar[stage]);
           // finished output planes
-          if (pl - 1 >= d0) umma_commit(&tfull_bar[(pl - 1 - d0) % p.slots]);
+          if (pl - 1 >= d0) umma_commit(&tfull_bar[(pl - 1 - d0) & kSlotMask]);
           if (pl == pb) {
-            for (int q = max(pl, d0); q <= d1 - 1; ++q) umma_commit(&tfull_bar[(q - d0) % p.slots]);
+            for (int q = max(pl, d0); q <= d1 - 1; ++q) umma_commit(&tfull_bar[(q - d0) & kSlotMask]);
           }
         }
         __syncwarp();
+        if (p.prof && blockIdx.x == 0 && lane == 0) {
+          const long long tm3 = clock64();
+          p.prof[4] += tm1 - tm0; p.prof[5] += tm2 - tm1; p.prof[6] += tm3 - tm2; p.prof[7] += 1;
+        }
         if (++stage == p.ring) {
           stage = 0;
           phase ^= 1u;
@@ -273,110 +293,114 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
     }
     uint32_t tfull_par = 0;
     const int et = threadIdx.x - 64;
-    const int nchunk = p.Ct / 16;
+    constexpr int kW = CT >= 32 ? 32 : 16;  // columns per TMEM round trip
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
       const int oh = c.th * kTileH + hl, ow = c.tw * kTileW + wl;
       const bool valid = oh < p.H && ow < p.W;
-      const int cbase = c.ct * p.Ct;
-      float ts1[4], ts2[4];  // running column sums owned by this lane pair (Ct <= 64 -> 4 chunks of 16)
+      const int cbase = c.ct * CT;
+      // per-thread running column sums of this item (this thread's output row, all planes of the segment)
+      float s1[CT], s2[CT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ts1[i] = ts2[i] = 0.f;
+      for (int i = 0; i < CT; ++i) s1[i] = s2[i] = 0.f;
       for (int q = d0; q < d1; ++q) {
-        const int s = (q - d0) % p.slots;
+        const int s = (q - d0) & kSlotMask;
+        const long long te0 = clock64();
         mbar_wait(&tfull_bar[s], (tfull_par >> s) & 1u, p.err, 41);
         tfull_par ^= 1u << s;
         tc_fence_after();
-        const uint32_t taddr = lane_addr + (uint32_t)(s * p.Ct);
+        const long long te1 = clock64();
+        const uint32_t taddr = lane_addr + (uint32_t)(s * CT);
         const long long vox = (((long long)c.n * p.D + q) * p.H + oh) * p.W + ow;
-#pragma unroll 1
-        for (int ci = 0; ci < nchunk; ++ci) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(ci * 16), v);
+#pragma unroll
+        for (int c0 = 0; c0 < CT; c0 += kW) {
+          if (p.debug & 2) break;
+          uint32_t v[kW];
+          if constexpr (kW == 32) tmem_ld32(taddr + (uint32_t)c0, v); else tmem_ld16(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
-          float f[16];
+          float f[kW];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(v[i]);
-            if (p.bias != nullptr) x += __ldg(p.bias + cbase + ci * 16 + i);
-            f[i] = x;
-          }
-          if (p.stats != nullptr) {
-            float s1[16], s2[16];
+          for (int i = 0; i < kW; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = valid ? f[i] : 0.f;
-              s1[i] = x;
-              s2[i] = x * x;
+            for (int i = 0; i < kW; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + c0 + i));
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
             }
-            warp_colsum16(s1, lane);
-            warp_colsum16(s2, lane);
-            // accumulate in a fixed register (compile-time index) per chunk
+          }
+          if (p.stats != nullptr && valid) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k == ci) {
-                ts1[k] += s1[0];
-                ts2[k] += s2[0];
-              }
+            for (int i = 0; i < kW; ++i) {
+              s1[c0 + i] += f[i];
+              s2[c0 + i] = fmaf(f[i], f[i], s2[c0 + i]);
+            }
           }
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = march_act(f[i], p.act, p.slope);
-            const int cc = cbase + ci * 16;
+            for (int i = 0; i < kW; ++i) f[i] = march_act(f[i], p.act, p.slope);
+            const int cc = cbase + c0;
             if (p.out_f32) {
               float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cc;
-              if (cc + 16 <= p.Cout && (p.out_ld & 3) == 0) {
+              if ((p.out_ld & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                for (int i = 0; i < kW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
               } else {
-                for (int i = 0; i < 16; ++i)
-                  if (cc + i < p.Cout) o[i] = f[i];
+#pragma unroll
+                for (int i = 0; i < kW; ++i) o[i] = f[i];
               }
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cc;
-              if (cc + 16 <= p.Cout && (p.out_ld & 7) == 0) {
-                uint4 lo, hi;
-                lo.x = pack_bf16x2(f[0], f[1]);
-                lo.y = pack_bf16x2(f[2], f[3]);
-                lo.z = pack_bf16x2(f[4], f[5]);
-                lo.w = pack_bf16x2(f[6], f[7]);
-                hi.x = pack_bf16x2(f[8], f[9]);
-                hi.y = pack_bf16x2(f[10], f[11]);
-                hi.z = pack_bf16x2(f[12], f[13]);
-                hi.w = pack_bf16x2(f[14], f[15]);
-                reinterpret_cast<uint4*>(o)[0] = lo;
-                reinterpret_cast<uint4*>(o)[1] = hi;
+              if ((p.out_ld & 7) == 0) {
+#pragma unroll
+                for (int i = 0; i < kW; i += 8) {
+                  uint4 u;
+                  u.x = pack_bf16x2(f[i], f[i + 1]);
+                  u.y = pack_bf16x2(f[i + 2], f[i + 3]);
+                  u.z = pack_bf16x2(f[i + 4], f[i + 5]);
+                  u.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(o + i) = u;
+                }
               } else {
-                for (int i = 0; i < 16; ++i)
-                  if (cc + i < p.Cout) o[i] = __float2bfloat16(f[i]);
+#pragma unroll
+                for (int i = 0; i < kW; ++i) o[i] = __float2bfloat16(f[i]);
               }
             }
           }
-          // re-zero the chunk just read
-          uint32_t z[16];
+          // re-zero the columns just read
+          uint32_t z[kW];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) z[i] = 0u;
-          tmem_st16(taddr + (uint32_t)(ci * 16), z);
+          for (int i = 0; i < kW; ++i) z[i] = 0u;
+          if constexpr (kW == 32) tmem_st32(taddr + (uint32_t)c0, z); else tmem_st16(taddr + (uint32_t)c0, z);
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[s]);
+        if (p.prof && blockIdx.x == 0 && threadIdx.x == 64) {
+          p.prof[8] += te1 - te0; p.prof[9] += clock64() - te1; p.prof[10] += 1;
+        }
       }
       if (p.stats != nullptr) {
-        // per-warp column totals -> shared -> one partial per (item, channel)
-        if ((lane & 1) == 0) {
-          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        // cross-lane column totals (once per item) -> shared -> one partial per (item, channel)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < nchunk) {
-              part[(q4 * 2 + 0) * 64 + k * 16 + col] = ts1[k];
-              part[(q4 * 2 + 1) * 64 + k * 16 + col] = ts2[k];
-            }
+        for (int c0 = 0; c0 < CT; c0 += 16) {
+          float a1[16], a2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            a1[i] = s1[c0 + i];
+            a2[i] = s2[c0 + i];
+          }
+          warp_colsum16(a1, lane);
+          warp_colsum16(a2, lane);
+          if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            part[(q4 * 2 + 0) * 64 + c0 + col] = a1[0];
+            part[(q4 * 2 + 1) * 64 + c0 + col] = a2[0];
+          }
         }
         named_bar_sync(1, 128);
-        if (et < p.Ct) {
+        if (et < CT) {
           float a = 0.f, b = 0.f;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -385,11 +409,9 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           }
           const int tiles_per_sample = p.n_seg * p.tiles_h * p.tiles_w;
           const int tile = (c.seg * p.tiles_h + c.th) * p.tiles_w + c.tw;
-          if (cbase + et < p.Cout) {
-            float* dst = p.stats + (((long long)c.n * tiles_per_sample + tile) * p.Cout + cbase + et) * 2;
-            dst[0] = a;
-            dst[1] = b;
-          }
+          float* dst = p.stats + (((long long)c.n * tiles_per_sample + tile) * p.Cout + cbase + et) * 2;
+          dst[0] = a;
+          dst[1] = b;
         }
         named_bar_sync(1, 128);
       }
@@ -412,7 +434,7 @@ static const size_t kMarchWeightBudget = 112 * 1024;
 int march_ct(int cin, int cout) {
   if (cin % 16 != 0 || cout % 16 != 0) return 0;
   if (cin != 16 && cin != 32 && cin != 64 && cin != 128) return 0;  // instantiated (BK, chunks) variants
-  for (int ct : {64, 48, 32, 16}) {
+  for (int ct : {64, 32, 16}) {
     if (cout % ct != 0) continue;
     if ((size_t)27 * cin * ct * 2 <= kMarchWeightBudget) return ct;
   }
@@ -472,6 +494,8 @@ int march_stats_tiles(const rehr_tensor& x, const rehr_tensor& y) {
   return pl.p.n_seg * pl.p.tiles_h * pl.p.tiles_w;
 }
 
+static int dispatch_march(const MarchPlan& pl, cudaStream_t stream);
+
 int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int y_is_f32, int act,
                  float slope, float* stats, cudaStream_t stream) {
   MarchPlan pl;
@@ -487,6 +511,20 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
   p.slope = slope;
   p.stats = stats;
   p.err = nullptr;
+  {
+    const char* dbg = getenv("REHR_MARCH_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    static long long* prof_buf = nullptr;
+    if (getenv("REHR_MARCH_PROF")) {
+      if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(long long));
+      long long h[16];
+      if (cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[7] > 0 && h[7] < (1LL << 40))
+        fprintf(stderr, "[march prof, previous launch, CTA0] producer wait_empty %.0f/plane (%lld) | mma wait_tempty %.0f wait_full %.0f issue+commit %.0f /plane (%lld) | epi wait_tfull %.0f body %.0f /plane (%lld)\n",
+                (double)h[0] / h[1], h[1], (double)h[4] / h[7], (double)h[5] / h[7], (double)h[6] / h[7], h[7], (double)h[8] / h[10], (double)h[9] / h[10], h[10]);
+      cudaMemset(prof_buf, 0, 16 * sizeof(long long));
+      p.prof = prof_buf;
+    }
+  }
   {
     const unsigned long long gdim[5] = {(unsigned long long)x.c, (unsigned long long)x.w, (unsigned long long)x.h,
                                         (unsigned long long)x.d, (unsigned long long)x.n};
@@ -504,35 +542,37 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
     rc = encode_tiled_bf16(&p.w_map, w_march, 2, gdim, gstr, box, p.BK * 2);
     if (rc != REHR_OK) return rc;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(conv_march_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(conv_march_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(conv_march_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(conv_march_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-  });
+  return dispatch_march(pl, stream);
+}
+
+template <int BKT, int CHUNKS, int CT>
+static int launch_variant(const MarchPlan& pl, cudaStream_t stream) {
+  static cudaError_t attr_err = cudaFuncSetAttribute(conv_march_kernel<BKT, CHUNKS, CT>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_err != cudaSuccess) {
     g_last_cuda_error = (int)attr_err;
     return REHR_CUDA_ERROR;
   }
-  if (p.BK == 16 && p.chunks == 1)
-    conv_march_kernel<16, 1><<<pl.grid, kMarchThreads, pl.smem, stream>>>(p);
-  else if (p.BK == 32 && p.chunks == 1)
-    conv_march_kernel<32, 1><<<pl.grid, kMarchThreads, pl.smem, stream>>>(p);
-  else if (p.BK == 64 && p.chunks == 1)
-    conv_march_kernel<64, 1><<<pl.grid, kMarchThreads, pl.smem, stream>>>(p);
-  else if (p.BK == 64 && p.chunks == 2)
-    conv_march_kernel<64, 2><<<pl.grid, kMarchThreads, pl.smem, stream>>>(p);
-  else
-    return REHR_UNSUPPORTED;
+  conv_march_kernel<BKT, CHUNKS, CT><<<pl.grid, kMarchThreads, pl.smem, stream>>>(pl.p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
+}
+
+static int dispatch_march(const MarchPlan& pl, cudaStream_t stream) {
+  const int bk = pl.p.BK, ch = pl.p.chunks, ct = pl.p.Ct;
+#define REHR_MARCH_CASE(B, C, T) \
+  if (bk == B && ch == C && ct == T) return launch_variant<B, C, T>(pl, stream);
+  REHR_MARCH_CASE(16, 1, 16)
+  REHR_MARCH_CASE(16, 1, 32)
+  REHR_MARCH_CASE(16, 1, 64)
+  REHR_MARCH_CASE(32, 1, 16)
+  REHR_MARCH_CASE(32, 1, 32)
+  REHR_MARCH_CASE(32, 1, 64)
+  REHR_MARCH_CASE(64, 1, 16)
+  REHR_MARCH_CASE(64, 1, 32)
+  REHR_MARCH_CASE(64, 2, 16)
+#undef REHR_MARCH_CASE
+  return REHR_UNSUPPORTED;
 }
 
 // ------------------------------------------------------------------------------------------------

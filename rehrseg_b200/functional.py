@@ -37,6 +37,54 @@ def _count(n: int = 1) -> None:
 
 
 # --------------------------------------------------------------------------------------------------
+# optional per-kernel device timing (bench.py's roofline leg): CUDA events on the launching stream around each
+# conv-engine launch, tagged with the kernel family and its ALGORITHMIC flops (2*M*N*K of the layer).
+# --------------------------------------------------------------------------------------------------
+_ktimer: Optional[list] = None
+
+
+class kernel_timer:
+    """with kernel_timer() as rec: ...; rec.summary() -> {family: (launches, total_ms, total_flops)}"""
+
+    def __enter__(self):
+        global _ktimer
+        self.records: list = []
+        _ktimer = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _ktimer
+        _ktimer = None
+        return False
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out: dict = {}
+        for name, flops, e0, e1 in self.records:
+            n, ms, fl = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), fl + flops)
+        return out
+
+
+class _timed:
+    def __init__(self, name: str, flops: float):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _ktimer is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _ktimer is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _ktimer.append((self.name, self.flops, self.e0, e1))
+        return False
+
+
+# --------------------------------------------------------------------------------------------------
 # packed-weight cache
 # --------------------------------------------------------------------------------------------------
 _wcache: dict = {}
@@ -116,14 +164,16 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     desc = conv_desc(kernel, stride, padding)
     stats = None
     tiles = 0
+    flops = 2.0 * n * od * oh * ow * cout * cin * kernel[0] * kernel[1] * kernel[2]
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), cin, cout):
         xt = rt(x)
         if want_stats:
             tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt))
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
         wp = _packed(weight, "march_fwd")
-        check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act, float(slope),
-                                          ptr(stats), stream_ptr()), "conv3d_march_fwd")
+        with _timed("conv_march_kernel", flops):
+            check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
+                                              float(slope), ptr(stats), stream_ptr()), "conv3d_march_fwd")
         _count()
         return out, stats, tiles
     if want_stats:
@@ -132,8 +182,9 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
     wp = _packed(weight, "fwd")
     xt = rt(x)
-    check(lib().rehr_conv3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
-                                float(slope), ptr(stats), stream_ptr()), "conv3d_fwd")
+    with _timed("conv_tapped_gemm_kernel", flops):
+        check(lib().rehr_conv3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
+                                    float(slope), ptr(stats), stream_ptr()), "conv3d_fwd")
     _count()
     if want_stats and stats is None:
         stats, tiles = instnorm_stats_raw(out)
@@ -155,17 +206,20 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
     n, d, h, w, cin = in_shape
     dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     desc = conv_desc(kernel, stride, padding)
+    flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * cin * kernel[0] * kernel[1] * kernel[2]
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), dy.shape[4], cin):
         wp = _packed(weight, "march_dgrad", cache)
         dyt, dxt = rt(dy), rt(dx)
-        check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0, None, stream_ptr()),
-              "conv3d_march_dgrad")
+        with _timed("conv_march_kernel", flops):
+            check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0, None,
+                                              stream_ptr()), "conv3d_march_dgrad")
         _count()
         return dx
     wp = _packed(weight, "dgrad", cache)
     dyt, dxt = rt(dy), rt(dx)
-    check(lib().rehr_conv3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0,
-                                  stream_ptr()), "conv3d_dgrad")
+    with _timed("conv_tapped_gemm_kernel", flops):
+        check(lib().rehr_conv3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0,
+                                      stream_ptr()), "conv3d_dgrad")
     _count(stride[0] * stride[1] * stride[2])
     return dx
 
@@ -180,8 +234,10 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
     if need == 0:
         raise L.RehrError(f"conv3d_wgrad: unsupported configuration x={tuple(x.shape)} dy={tuple(dy.shape)}")
     ws = _ws(need, x.device)
-    check(lib().rehr_conv3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
-          "conv3d_wgrad")
+    flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * x.shape[4] * kernel[0] * kernel[1] * kernel[2]
+    with _timed("conv_wgrad_kernel", flops):
+        check(lib().rehr_conv3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
+              "conv3d_wgrad")
     _count(2)
     return dw
 
@@ -228,13 +284,15 @@ class ConvNormAct(torch.autograd.Function):
             yt = rt(y)
             tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
-            check(lib().rehr_conv3d_smallcin_fwd(C.byref(desc), ptr(xs), n, cin, d, h, w, ptr(_f32(weight)), ptr(_f32(bias)),
+            # NB the conv bias is NOT added: a per-channel constant is removed exactly by the InstanceNorm that follows
+            # (mean shifts by the same constant, variance is unchanged), so lrelu(IN(conv+b)) == lrelu(IN(conv)).
+            check(lib().rehr_conv3d_smallcin_fwd(C.byref(desc), ptr(xs), n, cin, d, h, w, ptr(_f32(weight)), None,
                                                  C.byref(yt), ACT_NONE, 0.0, ptr(stats), stream_ptr()), "smallcin_fwd")
             _count(2)
             x_saved = xs
         else:
             x_saved = as_cl(x)
-            y, stats, tiles = conv3d_raw(x_saved, weight, bias, kernel, stride, padding, want_stats=True)
+            y, stats, tiles = conv3d_raw(x_saved, weight, None, kernel, stride, padding, want_stats=True)
         n = y.shape[0]
         vox = y.shape[1] * y.shape[2] * y.shape[3]
         mean = torch.empty((n, cout), dtype=torch.float32, device=dev)

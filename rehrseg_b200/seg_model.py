@@ -319,6 +319,31 @@ class UNetDecoder(nn.Module):
         return decoder_forward(self, skips)
 
 
+class PlainConvUNet(nn.Module):
+    """dynamic_network_architectures.architectures.unet.PlainConvUNet (the class the reference subclasses at
+    models/seg_model.py:153): encoder -> decoder, forward returns the segmentation logits only."""
+
+    def __init__(self, input_channels, n_stages, features_per_stage, conv_op, kernel_sizes, strides, n_conv_per_stage,
+                 num_classes, n_conv_per_stage_decoder, conv_bias=False, norm_op=None, norm_op_kwargs=None,
+                 dropout_op=None, dropout_op_kwargs=None, nonlin=None, nonlin_kwargs=None, deep_supervision=False,
+                 nonlin_first=False):
+        super().__init__()
+        if conv_op is not nn.Conv3d:
+            raise RehrError("the REHRSeg segmentation network is 3-D (train_all.py:479)")
+        if nonlin_first:
+            raise RehrError("nonlin_first=True is not used by the reference and is not implemented")
+        self.encoder = PlainConvEncoder(input_channels, n_stages, features_per_stage, conv_op, kernel_sizes, strides,
+                                        n_conv_per_stage, conv_bias, norm_op, norm_op_kwargs, dropout_op, dropout_op_kwargs,
+                                        nonlin, nonlin_kwargs)
+        self.decoder = UNetDecoder(self.encoder, num_classes, n_conv_per_stage_decoder, deep_supervision,
+                                   nonlin_first=nonlin_first, deep_features=False)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RehrError("rehrseg_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        return decoder_forward(self.decoder, encoder_forward(self.encoder, x))
+
+
 class SegModel(nn.Module):
     """Same signature as the reference SegModel (models/seg_model.py:154-173)."""
 
@@ -344,11 +369,20 @@ class SegModel(nn.Module):
         return segmodel_forward(self, x, return_inetermediate_feature)
 
 
+def fullres_kwargs(num_classes: int = 2, input_channels: int = 1) -> dict:
+    """nnU-Net 3d_fullres defaults used by BASELINE configs 1 and 3."""
+    return dict(input_channels=input_channels, n_stages=6, features_per_stage=[32, 64, 128, 256, 320, 320],
+                conv_op=nn.Conv3d, kernel_sizes=[[3, 3, 3]] * 6, strides=[[1, 1, 1]] + [[2, 2, 2]] * 5,
+                n_conv_per_stage=[2] * 6, num_classes=num_classes, n_conv_per_stage_decoder=[2] * 5, conv_bias=True,
+                norm_op=nn.InstanceNorm3d, norm_op_kwargs={"eps": 1e-5, "affine": True}, dropout_op=None,
+                dropout_op_kwargs=None, nonlin=nn.LeakyReLU, nonlin_kwargs={"inplace": True}, deep_supervision=False)
+
+
 def plainconv_3d_fullres(num_classes: int = 2, upscale: int = 4, input_channels: int = 1) -> SegModel:
-    """nnU-Net 3d_fullres defaults used by BASELINE config 1."""
-    return SegModel(input_channels=input_channels, n_stages=6, features_per_stage=[32, 64, 128, 256, 320, 320],
-                    conv_op=nn.Conv3d, kernel_sizes=[[3, 3, 3]] * 6,
-                    strides=[[1, 1, 1]] + [[2, 2, 2]] * 5, n_conv_per_stage=[2] * 6, num_classes=num_classes,
-                    upscale=upscale, n_conv_per_stage_decoder=[2] * 5, conv_bias=True, norm_op=nn.InstanceNorm3d,
-                    norm_op_kwargs={"eps": 1e-5, "affine": True}, dropout_op=None, dropout_op_kwargs=None,
-                    nonlin=nn.LeakyReLU, nonlin_kwargs={"inplace": True}, deep_supervision=False)
+    """The full REHRSeg SegModel (U-Net + x`upscale` SR head) on the 3d_fullres plan."""
+    return SegModel(upscale=upscale, **fullres_kwargs(num_classes, input_channels))
+
+
+def plainconv_unet_3d_fullres(num_classes: int = 2, input_channels: int = 1) -> PlainConvUNet:
+    """The pure PlainConvUNet of BASELINE config 1 (no SR head)."""
+    return PlainConvUNet(**fullres_kwargs(num_classes, input_channels))

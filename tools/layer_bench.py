@@ -20,6 +20,7 @@ def timeit(fn, iters=3):
     ts = []
     for _ in range(iters):
         flush.zero_()
+        torch.cuda._sleep(1_500_000)  # let the CPU run ahead so launch latency is not inside the timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
