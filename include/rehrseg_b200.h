@@ -120,6 +120,14 @@ int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y);
 int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int y_is_f32,
                           int act, float slope, float* stats, rehr_stream stream);
 
+/* Marching weight-gradient kernel for k=(3,3,3), stride 1, pad 1 (csrc/wgrad_march.cu): both activations are TMA-loaded once
+ * per plane, the 27 taps are UMMA descriptor offsets / a kd-fused N = 96 MMA, accumulators live in TMEM for the whole CTA.
+ * Same call site as rehr_conv3d_wgrad (dW f32 [Cout][Cin][3][3][3]); needs cin, cout multiples of 32. */
+int rehr_conv3d_wgrad_march_supported(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
+size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy);
+int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate, void* ws,
+                            size_t ws_bytes, rehr_stream stream);
+
 /* Direct convolution for tiny input-channel counts (Cin <= 4: the 1-channel nnU-Net stem, the 2-channel
  * FLAVR stem k(3,7,7)); x is NCDHW f32 exactly as the caller hands it (train_all.py:524), y NDHWC bf16.
  * w is the PyTorch f32 weight [Cout][Cin][kd][kh][kw]. */

@@ -84,32 +84,50 @@ __global__ void __launch_bounds__(kStatThreads) in_reduce_kernel(const StatArgs 
     }
   }
   if (vl < lanes) {
-    for (long long v = v0 + vl; v < v1; v += lanes) {
-      const long long vox = (long long)n * a.V + v;
-      float y[8];
-      bf16x8_to_float(*reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8), y);
-      if (MODE == 0) {
+    constexpr int U = 4;  // voxels in flight per thread: all loads of a batch are issued before any arithmetic
+    for (long long vb = v0 + vl; vb < v1; vb += (long long)lanes * U) {
+      uint4 yv[U], dv[U], ev[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s1[i] += y[i];
-          s2[i] += y[i] * y[i];
+      for (int u = 0; u < U; ++u) {
+        const long long v = vb + (long long)u * lanes;
+        if (v < v1) {
+          const long long vox = (long long)n * a.V + v;
+          yv[u] = *reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8);
+          if (MODE == 1) {
+            dv[u] = *reinterpret_cast<const uint4*>(a.da1 + vox * a.ld_a1 + g * 8);
+            if (a.da2) ev[u] = *reinterpret_cast<const uint4*>(a.da2 + vox * a.ld_a2 + g * 8);
+          }
         }
-      } else {
-        float d[8];
-        bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da1 + vox * a.ld_a1 + g * 8), d);
-        if (a.da2) {
-          float d2[8];
-          bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da2 + vox * a.ld_a2 + g * 8), d2);
+      }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] += d2[i];
-        }
+      for (int u = 0; u < U; ++u) {
+        const long long v = vb + (long long)u * lanes;
+        if (v >= v1) break;
+        float y[8];
+        bf16x8_to_float(yv[u], y);
+        if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (y[i] - mu[i]) * rs[i];
-          const float z = sc[i] * xh + sf[i];
-          const float gi = z > 0.f ? d[i] : d[i] * a.slope;
-          s1[i] += gi;
-          s2[i] += gi * xh;
+          for (int i = 0; i < 8; ++i) {
+            s1[i] += y[i];
+            s2[i] += y[i] * y[i];
+          }
+        } else {
+          float d[8];
+          bf16x8_to_float(dv[u], d);
+          if (a.da2) {
+            float d2[8];
+            bf16x8_to_float(ev[u], d2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] += d2[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (y[i] - mu[i]) * rs[i];
+            const float z = sc[i] * xh + sf[i];
+            const float gi = z > 0.f ? d[i] : d[i] * a.slope;
+            s1[i] += gi;
+            s2[i] += gi * xh;
+          }
         }
       }
     }
@@ -158,45 +176,84 @@ static int launch_in_reduce(const StatArgs& a, int N, cudaStream_t st) {
   return REHR_OK;
 }
 
-// partial [n][tiles][c][2] -> mean, rstd
-__global__ void in_finalize_kernel(const float* partial, int N, int tiles, int C, double inv_count, float eps, float* mean,
-                                   float* rstd) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i % C;
+// partial [n][tiles][c][2] -> mean, rstd.  Block = (32 channels) x (32 tile lanes); grid = (C/32 ceil, N).  The tile
+// lanes stride through the partial list (coalesced 256 B rows), accumulate in double and meet in a shared-memory tree,
+// so a 1024-tile list costs ~32 dependent-free loads per thread instead of 1024 serial ones.
+static constexpr int kFinLanes = 32;
+
+__global__ void __launch_bounds__(32 * kFinLanes) in_finalize_kernel(const float* partial, int N, int tiles, int C,
+                                                                      double inv_count, float eps, float* mean, float* rstd) {
+  __shared__ double sh1[kFinLanes][33], sh2[kFinLanes][33];
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int n = blockIdx.y, c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    const float* p = partial + (((long long)n * tiles + t) * C + c) * 2;
-    s1 += (double)p[0];
-    s2 += (double)p[1];
+  if (c < C) {
+    const float2* p = reinterpret_cast<const float2*>(partial) + (long long)n * tiles * C + c;
+#pragma unroll 4
+    for (int t = tl; t < tiles; t += kFinLanes) {
+      const float2 v = p[(long long)t * C];
+      s1 += (double)v.x;
+      s2 += (double)v.y;
+    }
   }
-  const double m = s1 * inv_count;
-  double var = s2 * inv_count - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  sh1[tl][cl] = s1;
+  sh2[tl][cl] = s2;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int l = 0; l < kFinLanes; ++l) {
+      a += sh1[l][cl];
+      b += sh2[l][cl];
+    }
+    const double m = a * inv_count;
+    double var = b * inv_count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[n * C + c] = (float)m;
+    rstd[n * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
-// partial [n][tiles][c][2] -> sums [n][c][2]; dgamma[c] = sum_n S2, dbeta[c] = sum_n S1
-__global__ void in_bwd_finalize_kernel(const float* partial, int N, int tiles, int C, float* sums, float* dgamma,
-                                       float* dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// partial [n][tiles][c][2] -> sums [n][c][2]; dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.  Same thread layout; grid = C/32.
+__global__ void __launch_bounds__(32 * kFinLanes) in_bwd_finalize_kernel(const float* partial, int N, int tiles, int C,
+                                                                          float* sums, float* dgamma, float* dbeta,
+                                                                          int accumulate) {
+  __shared__ double sh1[kFinLanes][33], sh2[kFinLanes][33];
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double g = 0.0, b = 0.0;
   for (int n = 0; n < N; ++n) {
     double s1 = 0.0, s2 = 0.0;
-    for (int t = 0; t < tiles; ++t) {
-      const float* p = partial + (((long long)n * tiles + t) * C + c) * 2;
-      s1 += (double)p[0];
-      s2 += (double)p[1];
+    if (c < C) {
+      const float2* p = reinterpret_cast<const float2*>(partial) + (long long)n * tiles * C + c;
+#pragma unroll 4
+      for (int t = tl; t < tiles; t += kFinLanes) {
+        const float2 v = p[(long long)t * C];
+        s1 += (double)v.x;
+        s2 += (double)v.y;
+      }
     }
-    sums[((long long)n * C + c) * 2] = (float)s1;
-    sums[((long long)n * C + c) * 2 + 1] = (float)s2;
-    b += s1;
-    g += s2;
+    __syncthreads();
+    sh1[tl][cl] = s1;
+    sh2[tl][cl] = s2;
+    __syncthreads();
+    if (tl == 0 && c < C) {
+      double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int l = 0; l < kFinLanes; ++l) {
+        a1 += sh1[l][cl];
+        a2 += sh2[l][cl];
+      }
+      sums[((long long)n * C + c) * 2] = (float)a1;
+      sums[((long long)n * C + c) * 2 + 1] = (float)a2;
+      b += a1;
+      g += a2;
+    }
   }
-  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)g : (float)g;
-  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
+  if (tl == 0 && c < C) {
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)g : (float)g;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
+  }
 }
 
 struct ApplyArgs {
@@ -760,7 +817,7 @@ int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream
 int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long long count, float eps, float* mean,
                            float* rstd, rehr_stream stream) {
   if (!partial || !mean || !rstd || count <= 0) return REHR_BAD_SHAPE;
-  in_finalize_kernel<<<(n * c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+  in_finalize_kernel<<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
                                                                        rstd);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
@@ -812,7 +869,7 @@ int rehr_instnorm_lrelu_bwd_finalize(const float* partial, int n, int tiles, int
                                      float* dgamma, float* dbeta, int accumulate, rehr_stream stream) {
   (void)rstd;
   if (!partial || !sums) return REHR_BAD_SHAPE;
-  in_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, sums, dgamma, dbeta, accumulate);
+  in_bwd_finalize_kernel<<<(c + 31) / 32, 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, sums, dgamma, dbeta, accumulate);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -187,6 +187,108 @@ __global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const SmallCinWgrad
   }
 }
 
+// Fast path for k = 3x3x3, stride 1, pad 1 (the nnU-Net stem, 4.2 M voxels x 32 channels at the C1 size): the layer is
+// bound by streaming dy once (268 MB bf16), so the work is organised around that stream.  A CTA stages the 3 x 10 x (W+2)
+// fp32 input rows that 8 output rows (one per warp) need into shared memory; lane = output channel, so a voxel's dy row
+// is one coalesced 64 B load and every x value is a shared-memory broadcast; a thread walks its row 4 voxels at a time
+// (6 x values feed 12 FMAs) and keeps the CIN*27 per-channel accumulators in registers across all its tiles.  Same
+// workspace layout / second-stage reduction as the generic kernel above.
+template <int CIN>
+__global__ void __launch_bounds__(256) smallcin_wgrad_k3_kernel(const SmallCinWgradArgs a) {
+  extern __shared__ float sx[];  // [CIN][3][10][Wa] then reused as red[8][27][32]
+  const int Wa = a.wd + 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co = blockIdx.y * 32 + lane;
+  const bool cok = co < a.cout;
+  float acc[CIN * 27];
+#pragma unroll
+  for (int i = 0; i < CIN * 27; ++i) acc[i] = 0.f;
+  const int ytiles = (a.oh + 7) / 8;
+  const long long tiles = (long long)a.n * a.od * ytiles;
+  const long long in_plane = (long long)a.h * a.wd, in_vol = in_plane * a.d;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int yt = (int)(tile % ytiles);
+    long long r = tile / ytiles;
+    const int oz = (int)(r % a.od);
+    const int nn = (int)(r / a.od);
+    const int oy0 = yt * 8;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CIN * 30 * Wa; i += 256) {
+      const int xx = i % Wa;
+      int q = i / Wa;
+      const int yy = q % 10;
+      q /= 10;
+      const int kz = q % 3, ci = q / 3;
+      const int iz = oz + kz - 1, iy = oy0 + yy - 1, ix = xx - 1;
+      float v = 0.f;
+      if (iz >= 0 && iz < a.d && iy >= 0 && iy < a.h && ix >= 0 && ix < a.wd)
+        v = __ldg(a.x + ((long long)nn * CIN + ci) * in_vol + iz * in_plane + (long long)iy * a.wd + ix);
+      sx[i] = v;
+    }
+    __syncthreads();
+    const int oy = oy0 + warp;
+    if (oy < a.oh) {
+      const __nv_bfloat16* dyrow = a.dy + ((((long long)nn * a.od + oz) * a.oh + oy) * a.ow) * a.lddy + co;
+      for (int ox0 = 0; ox0 < a.ow; ox0 += 4) {
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = (cok && ox0 + j < a.ow) ? __bfloat162float(dyrow[(long long)(ox0 + j) * a.lddy]) : 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+          for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const float* xr = sx + ((ci * 3 + kz) * 10 + warp + ky) * Wa + ox0;
+              float xv[6];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) xv[j] = xr[j];
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  acc[ci * 27 + (kz * 3 + ky) * 3 + kx] = fmaf(g[j], xv[j + kx], acc[ci * 27 + (kz * 3 + ky) * 3 + kx]);
+            }
+      }
+    }
+  }
+  float* red = sx;  // [8][27][32]
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci) {
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 27; ++t) red[(warp * 27 + t) * 32 + lane] = acc[ci * 27 + t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+      const int t = i / 32, l = i % 32;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[(w * 27 + t) * 32 + l];
+      if (blockIdx.y * 32 + l < a.cout)
+        a.ws[(((long long)ci * gridDim.x + blockIdx.x) * kWgAcc + t) * a.cout + blockIdx.y * 32 + l] = sum;
+    }
+  }
+}
+
+template <int CIN>
+static int launch_smallcin_wgrad_k3(const SmallCinWgradArgs& a, cudaStream_t stream) {
+  const size_t smem = std::max<size_t>((size_t)CIN * 30 * (a.wd + 6) * sizeof(float), (size_t)8 * 27 * 32 * sizeof(float));
+  if (smem > 200 * 1024) return REHR_UNSUPPORTED;
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(smallcin_wgrad_k3_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+    attr_smem = smem;
+  }
+  dim3 grid(kWgBlocks, (a.cout + 31) / 32);
+  smallcin_wgrad_k3_kernel<CIN><<<grid, 256, smem, stream>>>(a);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
 __global__ void smallcin_wgrad_reduce_kernel(const float* ws, int blocks, int passes, int KT, int cout, float* dw,
                                              int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,9 +428,24 @@ int rehr_conv3d_smallcin_wgrad(const rehr_conv_desc* desc, const float* x_ncdhw,
   a.kd = desc->kd; a.kh = desc->kh; a.kw = desc->kw;
   a.sd = desc->sd; a.sh = desc->sh; a.sw = desc->sw;
   a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
-  dim3 grid(kWgBlocks, passes);
-  smallcin_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-  REHR_CHECK_LAUNCH();
+  const bool k3 = desc->kd == 3 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
+                  desc->pd == 1 && desc->ph == 1 && desc->pw == 1;
+  int rc = REHR_UNSUPPORTED;
+  if (k3) {
+    switch (cin) {
+      case 1: rc = launch_smallcin_wgrad_k3<1>(a, (cudaStream_t)stream); break;
+      case 2: rc = launch_smallcin_wgrad_k3<2>(a, (cudaStream_t)stream); break;
+      case 3: rc = launch_smallcin_wgrad_k3<3>(a, (cudaStream_t)stream); break;
+      case 4: rc = launch_smallcin_wgrad_k3<4>(a, (cudaStream_t)stream); break;
+      default: break;
+    }
+    if (rc != REHR_OK && rc != REHR_UNSUPPORTED) return rc;
+  }
+  if (rc == REHR_UNSUPPORTED) {
+    dim3 grid(kWgBlocks, passes);
+    smallcin_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    REHR_CHECK_LAUNCH();
+  }
   const int total = KT * dy->c;
   smallcin_wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.ws, kWgBlocks, passes, KT, dy->c, dw,
                                                                                      accumulate);

@@ -1,0 +1,477 @@
+// "Marching" weight-gradient kernel for sm_100a: k = 3x3x3, stride 1, pad 1 layers (the ones that hold 3/4 of the
+// nnU-Net FLOPs -- SURVEY.md section 7.3).  Companion of conv_march.cu (forward / input-gradient).
+//
+//   dW[co][ci][kd][kh][kw] = sum_{n,d,h,w} dY[n,d,h,w,co] * X[n,d+kd-1,h+kh-1,w+kw-1,ci]
+//
+// is a GEMM whose K dimension is the VOXEL index, so both operands are "MN-major" views of the channels-last
+// activation tiles exactly as TMA writes them (no transposes, no im2col).  Of the two tensors one plays the halo
+// operand Hh (M side) and the other the plain operand Pp (N side); per CTA and per input plane q the kernel computes
+//
+//   G[a][j][ch][cp] += sum_{u in 16x8 tile} Hh[q][u + off(a) - (1,1)][ch] * Pp[q-1+j][u][cp],   a = 3*oh+ow in 0..8, j in 0..2
+//
+//   * Hh plane q is TMA-loaded ONCE as an 18x10 halo'd tile (CH = 32 or 64 channels of it); the 9 in-plane offsets are
+//     NOT re-loaded: they are row shifts folded into the UMMA descriptor start address, and 128/CH of them are stacked
+//     along M through the descriptor's leading-dimension byte offset (LBO = the row distance between two offsets) --
+//     verified on B200 by tools/umma_probe_mn.cu (profiles/r01_umma_mn_major_probe.log);
+//   * the three depth offsets are fused along N: Pp planes q-1, q, q+1 (32 channels each) sit in adjacent slots of a
+//     shared-memory ring (slots 0,1 are mirrored behind the last slot so the triple is always contiguous), one
+//     tcgen05.mma has N = 96;
+//   * the accumulators (groups x 96 columns x 128 lanes fp32) stay in TMEM for the whole life of the CTA: there is
+//     no epilogue inside the loop, the MMA thread issues back to back, and each CTA writes one partial dW at the end;
+//     a second tiny kernel sums the <= 148 partials (deterministic order, no atomics) and scatters into PyTorch layout.
+// Role A: Hh = X, Pp = dY  (kh = oh, kw = ow, kd = 2-j);   role B: Hh = dY, Pp = X  (kh = 2-oh, kw = 2-ow, kd = j).
+// Channel counts beyond one piece (CH of Hh, 32 of Pp) are covered by independent (h-split, p-split) "combos", each
+// owned by its own set of CTAs.
+//
+// Reference call sites replaced: the weight-gradient half of torch.nn.Conv3d.backward for ConvDropoutNormReLU.conv of
+// the full / half resolution stages (built at models/seg_model.py:174-191, driven by loss.backward() at
+// train_all.py:555).
+#include "engine.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace rehr {
+
+int encode_tiled_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* gdim,
+                      const unsigned long long* gstride_bytes, const unsigned* box, int swizzle_bytes);
+
+static constexpr int kWgmThreads = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 TMEM zero / final drain
+static constexpr int kWTileH = 16, kWTileW = 8;
+static constexpr int kWHaloH = 18, kWHaloW = 10, kWHaloRows = kWHaloH * kWHaloW;
+static constexpr int kHStages = 4;        // halo-plane ring
+static constexpr int kPRing = 6;          // plain-plane ring (+2 mirrored positions)
+static constexpr int kPC = 32;            // channels per plain-operand piece
+static constexpr uint32_t kPSlotBytes = kWTileH * kWTileW * kPC * 2;  // 8192
+
+struct alignas(64) WgmParams {
+  CUtensorMap h_map;  // 5-D NDHWC, box (CH, 10, 18, 1, 1)
+  CUtensorMap p_map;  // 5-D NDHWC, box (32, 8, 16, 1, 1)
+  int N, D, H, W;
+  int tiles_h, tiles_w, Ds, n_seg;
+  int n_hs, n_ps, n_combo, ctas_per_combo, items_per_combo;
+  uint32_t h_stride;  // bytes per halo stage (1024-aligned)
+  float* ws;          // [cta][group][128][96]
+  int* err;
+};
+
+template <int CH>
+struct WgmCfg {
+  static constexpr int kGroups = CH == 32 ? 3 : 5;
+  static constexpr uint32_t kRowB = CH * 2;
+  static constexpr uint32_t kLayout = kRowB == 128 ? 2u : 4u;
+  // halo-tile row of atom 0 of group g, and the row distance (LBO) to the next atom
+  __host__ __device__ static constexpr int row0(int g) { return CH == 32 ? g * kWHaloW : ((2 * g) / 3) * kWHaloW + (2 * g) % 3; }
+  __host__ __device__ static constexpr int lbo_rows(int g) {
+    if (CH == 32) return 1;          // (oh, 0), (oh, 1), (oh, 2), (oh, 3 = discarded)
+    if (g == 4) return 1;            // (2, 2) and its right neighbour; the latter is discarded
+    const int a0 = 2 * g, a1 = 2 * g + 1;
+    return ((a1 / 3) * kWHaloW + a1 % 3) - ((a0 / 3) * kWHaloW + a0 % 3);
+  }
+};
+
+__device__ __forceinline__ bool wgm_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+struct WgmItem {
+  int n, seg, th, tw;
+};
+__device__ __forceinline__ WgmItem wgm_decode(const WgmParams& p, int item) {
+  WgmItem c;
+  c.tw = item % p.tiles_w;
+  item /= p.tiles_w;
+  c.th = item % p.tiles_h;
+  item /= p.tiles_h;
+  c.seg = item % p.n_seg;
+  c.n = item / p.n_seg;
+  return c;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __grid_constant__ WgmParams p) {
+  using Cfg = WgmCfg<CH>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_p = smem;                                          // (kPRing + 2) x 8 KB
+  uint8_t* s_h = smem + (size_t)(kPRing + 2) * kPSlotBytes;     // kHStages x h_stride
+  uint8_t* tail = s_h + (size_t)kHStages * p.h_stride;
+  uint64_t* full_h = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_h = full_h + kHStages;
+  uint64_t* full_p = empty_h + kHStages;
+  uint64_t* empty_p = full_p + kPRing;
+  uint64_t* zero_bar = empty_p + kPRing;
+  uint64_t* done_bar = zero_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.h_map);
+    tma_prefetch_desc(&p.p_map);
+    for (int i = 0; i < kHStages; ++i) {
+      mbar_init(&full_h[i], 1);
+      mbar_init(&empty_h[i], 1);
+    }
+    for (int i = 0; i < kPRing; ++i) {
+      mbar_init(&full_p[i], 1);
+      mbar_init(&empty_p[i], 1);
+    }
+    mbar_init(zero_bar, 4);
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int combo = blockIdx.x % p.n_combo;
+  const int rank = blockIdx.x / p.n_combo;
+  const int hs = combo / p.n_ps, ps = combo % p.n_ps;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t kh = 0, kp = 0;  // running plane counters (ring position = counter % ring, parity = (counter / ring) & 1)
+      for (int item = rank; item < p.items_per_combo; item += p.ctas_per_combo) {
+        const WgmItem c = wgm_decode(p, item);
+        const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
+        const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
+        const int h0 = c.th * kWTileH, w0 = c.tw * kWTileW;
+        int next_p = pa;
+        for (int q = d0; q < d1; ++q) {
+          const int need = min(q + 1, pb);
+          while (next_p <= need) {
+            const uint32_t slot = kp % kPRing;
+            mbar_wait(&empty_p[slot], ((kp / kPRing) & 1u) ^ 1u, p.err, 51);
+            mbar_arrive_expect_tx(&full_p[slot], slot < 2 ? 2 * kPSlotBytes : kPSlotBytes);
+            tma_load_5d(&p.p_map, &full_p[slot], s_p + (size_t)slot * kPSlotBytes, ps * kPC, w0, h0, next_p, c.n);
+            if (slot < 2)
+              tma_load_5d(&p.p_map, &full_p[slot], s_p + (size_t)(slot + kPRing) * kPSlotBytes, ps * kPC, w0, h0, next_p, c.n);
+            ++kp;
+            ++next_p;
+          }
+          const uint32_t st = kh % kHStages;
+          mbar_wait(&empty_h[st], ((kh / kHStages) & 1u) ^ 1u, p.err, 52);
+          mbar_arrive_expect_tx(&full_h[st], kWHaloRows * Cfg::kRowB);
+          tma_load_5d(&p.h_map, &full_h[st], s_h + (size_t)st * p.h_stride, hs * CH, w0 - 1, h0 - 1, q, c.n);
+          ++kh;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    // descriptor high words: SBO (bits 32..45) = pitch between 8-voxel groups, version 1 (bit 46), swizzle (61..63)
+    constexpr uint32_t kAHi = ((kWHaloW * Cfg::kRowB) >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+    constexpr uint32_t kBHi = ((8u * kPC * 2u) >> 4) | (1u << 14) | (4u << 29);
+    constexpr uint32_t kBLoLbo = (kPSlotBytes >> 4) << 16;
+    const uint32_t sp_lo = smem_u32(s_p) >> 4, sh_lo = smem_u32(s_h) >> 4;
+    const uint32_t hstride_lo = p.h_stride >> 4;
+    mbar_wait(zero_bar, 0, p.err, 61);  // accumulators zeroed by the drain warps
+    tc_fence_after();
+    uint32_t kh = 0, kp = 0;
+    for (int item = rank; item < p.items_per_combo; item += p.ctas_per_combo) {
+      const WgmItem c = wgm_decode(p, item);
+      const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
+      const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
+      const uint32_t cnt0 = kp;  // counter of plane pa
+      int waited = pa - 1;
+      for (int q = d0; q < d1; ++q) {
+        const int need = min(q + 1, pb);
+        while (waited < need) {
+          ++waited;
+          const uint32_t cc = cnt0 + (uint32_t)(waited - pa);
+          mbar_wait(&full_p[cc % kPRing], (cc / kPRing) & 1u, p.err, 62);
+        }
+        const uint32_t st = kh % kHStages;
+        mbar_wait(&full_h[st], (kh / kHStages) & 1u, p.err, 63);
+        tc_fence_after();
+        const int jlo = q == 0 ? 1 : 0, jhi = q == p.D - 1 ? 1 : 2;
+        const uint32_t cbase = cnt0 + (uint32_t)(q - 1 + jlo - pa);
+        const uint32_t s0 = cbase % kPRing;
+        const uint32_t idesc = make_idesc_bf16(128, (jhi - jlo + 1) * kPC, 1, 1);
+        const uint32_t a_lo = sh_lo + st * hstride_lo;
+        const uint32_t b_lo = (sp_lo + s0 * (kPSlotBytes >> 4)) | kBLoLbo;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(jlo * kPC);
+        if (wgm_elect()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(b_lo + (uint32_t)((ks * 16 * kPC * 2) >> 4));
+#pragma unroll
+            for (int g = 0; g < Cfg::kGroups; ++g) {
+              const uint32_t a_off = (uint32_t)(((2 * ks * kWHaloW + Cfg::row0(g)) * Cfg::kRowB) >> 4) |
+                                     ((uint32_t)((Cfg::lbo_rows(g) * Cfg::kRowB) >> 4) << 16);
+              const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(a_lo + a_off);
+              umma_bf16(d_tmem + (uint32_t)(g * 3 * kPC), ad, bd, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_h[st]);
+          // plain planes whose last reader is this step
+          if (q - 1 >= pa) umma_commit(&empty_p[(cnt0 + (uint32_t)(q - 1 - pa)) % kPRing]);
+          if (q == d1 - 1) {
+            for (int r = max(q, pa); r <= pb; ++r) umma_commit(&empty_p[(cnt0 + (uint32_t)(r - pa)) % kPRing]);
+          }
+        }
+        __syncwarp();
+        ++kh;
+      }
+      kp = cnt0 + (uint32_t)(pb - pa + 1);
+    }
+    if (wgm_elect()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // ============================== TMEM zero, then final drain (warps 2..5) ==============================
+    const int q4 = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    {
+      uint32_t z[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) z[i] = 0u;
+      for (int c0 = 0; c0 < 512; c0 += 32) tmem_st32(lane_addr + (uint32_t)c0, z);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(zero_bar);
+    }
+    mbar_wait(done_bar, 0, p.err, 71);
+    tc_fence_after();
+    const int row = q4 * 32 + lane;
+    float* dst = p.ws + ((size_t)blockIdx.x * Cfg::kGroups * 128 + row) * 96;
+    for (int g = 0; g < Cfg::kGroups; ++g) {
+#pragma unroll
+      for (int c0 = 0; c0 < 96; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)(g * 96 + c0), v);
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(dst + (size_t)g * 128 * 96 + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                             __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// partial sums -> dW (PyTorch layout [co][ci][27], fp32)
+// ------------------------------------------------------------------------------------------------
+struct WgmReduceParams {
+  const float* ws;
+  float* dw;
+  int CH, groups, n_hs, n_ps, n_combo, ctas_per_combo;
+  int role;  // 0: Hh = X (ch = ci, cp = co), 1: Hh = dY (ch = co, cp = ci)
+  int Ci, Co;
+  int accumulate;
+};
+
+// block = 32 (cp within piece) x 8 (slices of the partial list); grid.x enumerates (hs, ps, a, j, ch)
+__global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduceParams p) {
+  __shared__ float red[8][33];
+  const int cpl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  int idx = blockIdx.x;
+  const int ch = idx % p.CH;
+  idx /= p.CH;
+  const int j = idx % 3;
+  idx /= 3;
+  const int a = idx % 9;
+  idx /= 9;
+  const int ps = idx % p.n_ps;
+  const int hs = idx / p.n_ps;
+  const int vpg = p.CH == 32 ? 3 : 2;  // in-plane offsets kept per MMA group (the 4th atom of a 32-channel group is discarded)
+  const int g = a / vpg, m = (a % vpg) * p.CH + ch;
+  const int combo = hs * p.n_ps + ps;
+  const size_t per_cta = (size_t)p.groups * 128 * 96;
+  const size_t off = ((size_t)g * 128 + m) * 96 + j * 32 + cpl;
+  float acc = 0.f;
+  for (int k = slice; k < p.ctas_per_combo; k += 8) acc += p.ws[(size_t)(k * p.n_combo + combo) * per_cta + off];
+  red[slice][cpl] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) t += red[s][cpl];
+    const int chH = hs * p.CH + ch, chP = ps * 32 + cpl;
+    const int oh = a / 3, ow = a % 3;
+    int co, ci, kd, kh, kw;
+    if (p.role == 0) {
+      ci = chH; co = chP; kh = oh; kw = ow; kd = 2 - j;
+    } else {
+      co = chH; ci = chP; kh = 2 - oh; kw = 2 - ow; kd = j;
+    }
+    float* d = p.dw + ((size_t)co * p.Ci + ci) * 27 + (kd * 3 + kh) * 3 + kw;
+    *d = p.accumulate ? (*d + t) : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host planning
+// ------------------------------------------------------------------------------------------------
+struct WgmPlan {
+  WgmParams p;
+  int CH, role, grid;
+  size_t smem, ws_bytes;
+};
+
+static int wgm_groups(int ch) { return ch == 32 ? 3 : 5; }
+
+// pick the role / piece sizes with the fewest MMAs per voxel tile; 0 = unsupported
+static int wgm_choose(int ci, int co, int* role, int* CH) {
+  int best = 0;
+  for (int r = 0; r < 2; ++r) {
+    const int chh = r == 0 ? ci : co, chp = r == 0 ? co : ci;
+    if (chp % 32 != 0) continue;
+    for (int ch : {64, 32}) {
+      if (chh % ch != 0) continue;
+      const int cost = (chh / ch) * (chp / 32) * wgm_groups(ch);
+      if (best == 0 || cost < best) {
+        best = cost;
+        *role = r;
+        *CH = ch;
+      }
+      break;
+    }
+  }
+  return best;
+}
+
+static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, WgmPlan* out) {
+  WgmParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  if (x.n != dy.n || x.d != dy.d || x.h != dy.h || x.w != dy.w) return REHR_BAD_SHAPE;
+  int role = 0, CH = 0;
+  if (wgm_choose(x.c, dy.c, &role, &CH) == 0) return REHR_UNSUPPORTED;
+  const rehr_tensor& hh = role == 0 ? x : dy;
+  const rehr_tensor& pp = role == 0 ? dy : x;
+  if (hh.ld % 8 != 0 || pp.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
+  out->CH = CH;
+  out->role = role;
+  p.N = x.n; p.D = x.d; p.H = x.h; p.W = x.w;
+  p.tiles_h = (p.H + kWTileH - 1) / kWTileH;
+  p.tiles_w = (p.W + kWTileW - 1) / kWTileW;
+  p.n_hs = hh.c / CH;
+  p.n_ps = pp.c / kPC;
+  p.n_combo = p.n_hs * p.n_ps;
+  const int sms = sm_count();
+  if (p.n_combo > sms) return REHR_UNSUPPORTED;
+  p.ctas_per_combo = sms / p.n_combo;
+  const long long cols = (long long)p.N * p.tiles_h * p.tiles_w;
+  // depth segments: long (less plane re-loading) but >= ~6 items per CTA for balance
+  int ds = p.D;
+  while (ds > 4 && cols * ((p.D + ds - 1) / ds) < 6LL * p.ctas_per_combo) ds = (ds + 1) / 2;
+  p.Ds = ds;
+  p.n_seg = (p.D + ds - 1) / ds;
+  p.items_per_combo = (int)(cols * p.n_seg);
+  if (p.items_per_combo < p.ctas_per_combo) p.ctas_per_combo = p.items_per_combo;
+  // too little work to amortise the per-CTA partial dW and its reduction (measured on B200: the generic split-K kernel
+  // wins at 16^3 and below, this one from 32^3 up): leave small volumes to conv_wgrad_kernel
+  if (cols * p.D < 256) return REHR_UNSUPPORTED;
+  p.h_stride = ((uint32_t)(kWHaloRows + 2) * CH * 2 + 1023u) & ~1023u;
+  out->grid = p.n_combo * p.ctas_per_combo;
+  const size_t tailb = (2 * kHStages + 2 * kPRing + 2) * 8 + 16;
+  out->smem = 1024 + (size_t)(kPRing + 2) * kPSlotBytes + (size_t)kHStages * p.h_stride + tailb;
+  out->ws_bytes = (size_t)out->grid * wgm_groups(CH) * 128 * 96 * sizeof(float);
+  return REHR_OK;
+}
+
+template <int CH>
+static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
+  static cudaError_t attr_err =
+      cudaFuncSetAttribute(wgrad_march_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (attr_err != cudaSuccess) {
+    g_last_cuda_error = (int)attr_err;
+    return REHR_CUDA_ERROR;
+  }
+  wgrad_march_kernel<CH><<<pl.grid, kWgmThreads, pl.smem, stream>>>(pl.p);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+}  // namespace rehr
+
+using namespace rehr;
+
+extern "C" {
+
+int rehr_conv3d_wgrad_march_supported(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy) {
+  if (!d || !x || !dy) return 0;
+  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd != 1 || d->ph != 1 || d->pw != 1)
+    return 0;
+  WgmPlan pl;
+  return plan_wgm(*x, *dy, &pl) == REHR_OK ? 1 : 0;
+}
+
+size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy) {
+  if (!x || !dy) return 0;
+  WgmPlan pl;
+  if (plan_wgm(*x, *dy, &pl) != REHR_OK) return 0;
+  return pl.ws_bytes;
+}
+
+int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
+                            rehr_stream stream_) {
+  if (!x || !dy || !x->ptr || !dy->ptr || !dw) return REHR_BAD_SHAPE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  WgmPlan pl;
+  int rc = plan_wgm(*x, *dy, &pl);
+  if (rc != REHR_OK) return rc;
+  if (!ws || ws_bytes < pl.ws_bytes) return REHR_WORKSPACE;
+  WgmParams& p = pl.p;
+  p.ws = reinterpret_cast<float*>(ws);
+  p.err = nullptr;
+  const rehr_tensor& hh = pl.role == 0 ? *x : *dy;
+  const rehr_tensor& pp = pl.role == 0 ? *dy : *x;
+  {
+    const unsigned long long gdim[5] = {(unsigned long long)hh.c, (unsigned long long)hh.w, (unsigned long long)hh.h,
+                                        (unsigned long long)hh.d, (unsigned long long)hh.n};
+    const unsigned long long pitch = (unsigned long long)hh.ld * 2;
+    const unsigned long long gstr[4] = {pitch, pitch * hh.w, pitch * hh.w * hh.h, pitch * hh.w * hh.h * hh.d};
+    const unsigned box[5] = {(unsigned)pl.CH, (unsigned)kWHaloW, (unsigned)kWHaloH, 1u, 1u};
+    rc = encode_tiled_bf16(&p.h_map, hh.ptr, 5, gdim, gstr, box, pl.CH * 2);
+    if (rc != REHR_OK) return rc;
+  }
+  {
+    const unsigned long long gdim[5] = {(unsigned long long)pp.c, (unsigned long long)pp.w, (unsigned long long)pp.h,
+                                        (unsigned long long)pp.d, (unsigned long long)pp.n};
+    const unsigned long long pitch = (unsigned long long)pp.ld * 2;
+    const unsigned long long gstr[4] = {pitch, pitch * pp.w, pitch * pp.w * pp.h, pitch * pp.w * pp.h * pp.d};
+    const unsigned box[5] = {(unsigned)kPC, (unsigned)kWTileW, (unsigned)kWTileH, 1u, 1u};
+    rc = encode_tiled_bf16(&p.p_map, pp.ptr, 5, gdim, gstr, box, kPC * 2);
+    if (rc != REHR_OK) return rc;
+  }
+  rc = pl.CH == 32 ? launch_wgm<32>(pl, stream) : launch_wgm<64>(pl, stream);
+  if (rc != REHR_OK) return rc;
+  WgmReduceParams r;
+  r.ws = p.ws;
+  r.dw = dw;
+  r.CH = pl.CH;
+  r.groups = pl.CH == 32 ? 3 : 5;
+  r.n_hs = p.n_hs;
+  r.n_ps = p.n_ps;
+  r.n_combo = p.n_combo;
+  r.ctas_per_combo = p.ctas_per_combo;
+  r.role = pl.role;
+  r.Ci = x->c;
+  r.Co = dy->c;
+  r.accumulate = accumulate;
+  const int blocks = p.n_hs * p.n_ps * 9 * 3 * pl.CH;
+  wgrad_march_reduce_kernel<<<blocks, 256, 0, stream>>>(r);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+}  // extern "C"

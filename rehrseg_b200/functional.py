@@ -230,11 +230,19 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
     dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)
     desc = conv_desc(kernel, stride, padding)
     xt, dyt = rt(x), rt(dy)
+    flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * x.shape[4] * kernel[0] * kernel[1] * kernel[2]
+    if USE_MARCH and lib().rehr_conv3d_wgrad_march_supported(C.byref(desc), C.byref(xt), C.byref(dyt)):
+        need = lib().rehr_conv3d_wgrad_march_workspace(C.byref(xt), C.byref(dyt))
+        ws = _ws(need, x.device)
+        with _timed("wgrad_march_kernel", flops):
+            check(lib().rehr_conv3d_wgrad_march(C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
+                  "conv3d_wgrad_march")
+        _count(2)
+        return dw
     need = lib().rehr_conv3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
     if need == 0:
         raise L.RehrError(f"conv3d_wgrad: unsupported configuration x={tuple(x.shape)} dy={tuple(dy.shape)}")
     ws = _ws(need, x.device)
-    flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * x.shape[4] * kernel[0] * kernel[1] * kernel[2]
     with _timed("conv_wgrad_kernel", flops):
         check(lib().rehr_conv3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
               "conv3d_wgrad")

@@ -112,8 +112,27 @@ def test_conv3d_dgrad(case, engine):
     assert rel_l2(dx.float().permute(0, 4, 1, 2, 3), ref) < TOL, case
 
 
-@pytest.mark.parametrize("case", [c for c in FWD_CASES if c[2] % 16 == 0])
-def test_conv3d_wgrad(case):
+WGRAD_MARCH_CASES = [
+    # marching weight-gradient shapes: role A / B, 32- and 64-channel halo pieces, channel splits, volume-edge planes,
+    # ragged tiles, depth segments, a channel slice of a wider (concat) buffer is covered in test_wgrad_march_pitched
+    (2, 32, 32, (20, 32, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 32, 32, (16, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 32, 32, (33, 40, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 32, (32, 64, 64), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 128, 64, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 32, (9, 16, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 32, 64, (6, 32, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 64, 64, (5, 20, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 128, 64, (8, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 128, 128, (4, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 96, (4, 16, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 32, 32, (1, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 256, 320, (4, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", [c for c in FWD_CASES if c[2] % 16 == 0] + WGRAD_MARCH_CASES)
+def test_conv3d_wgrad(case, engine):
     from rehrseg_b200 import functional as Fn
     n, cin, cout, dhw, k, s, p = case
     x, w, _ = _mk(n, cin, cout, dhw, k, seed=4)
@@ -127,6 +146,19 @@ def test_conv3d_wgrad(case):
     torch.cuda.synchronize()
     assert dw.shape == ref.shape
     assert rel_l2(dw, ref) < 1e-3, (case, rel_l2(dw, ref))  # fp32 accumulate of exact bf16 products
+
+
+def test_wgrad_march_routing():
+    """The big k3/s1/p1 layers must take the marching weight-gradient kernel (and tiny volumes the split-K one), so the
+    parity cases above really cover both kernels."""
+    import ctypes as C
+    from rehrseg_b200 import _lib as L
+    desc = L.conv_desc((3, 3, 3), (1, 1, 1), (1, 1, 1))
+    for (n, ci, co, dhw), want in [((2, 32, 32, (16, 32, 32)), 1), ((1, 64, 32, (32, 64, 64)), 1), ((1, 128, 64, (32, 32, 32)), 1),
+                                   ((2, 32, 32, (128, 128, 128)), 1), ((2, 320, 320, (4, 4, 4)), 0), ((1, 16, 16, (32, 32, 32)), 0)]:
+        x = L.RehrTensor(16, n, *dhw, ci, ci)
+        dy = L.RehrTensor(16, n, *dhw, co, co)
+        assert L.lib().rehr_conv3d_wgrad_march_supported(C.byref(desc), C.byref(x), C.byref(dy)) == want, (n, ci, co, dhw)
 
 
 TCONV_CASES = [
