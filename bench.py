@@ -266,7 +266,7 @@ def main() -> None:
         else:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 out = model(x)
-        loss = (out.float() * g).sum() / out.numel()
+        loss = torch.dot(out.float().reshape(-1), g.reshape(-1)) / out.numel()  # <logits, g> / numel
         loss.backward()
         if world > 1:  # data-parallel gradient mean over NVLink (one flat bucket)
             off = 0

@@ -99,6 +99,12 @@ int rehr_conv3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const re
 /* ConvTranspose3d views of the same engine (weight [Cin][Cout][T]). */
 int rehr_convtranspose3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed /*[Cout][T][Cin]*/,
                              const float* bias, const rehr_tensor* y, int act, float slope, rehr_stream stream);
+/* kernel == stride, padding 0 (the nnU-Net decoder up-sampling): ONE GEMM with N = classes x Cout and a scatter epilogue.
+ * w_packed = bf16 [T][Cout][Cin] (rehr_pack_weight with R = T, C = Cin, T = Cout, sr = 1, sc = Cout*T, st = T).
+ * y may be a channel slice of a wider concat buffer (ld > c). */
+int rehr_convtranspose3d_fused_supported(const rehr_conv_desc* desc, int cin, int cout);
+int rehr_convtranspose3d_fused_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                                   const rehr_tensor* y, int act, float slope, rehr_stream stream);
 int rehr_convtranspose3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed /*[Cin][T][Cout]*/,
                                const rehr_tensor* dx, rehr_stream stream);
 size_t rehr_convtranspose3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);

@@ -149,6 +149,37 @@ int rehr_conv3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const re
   return launch_tapped_wgrad(plan, *x, *dy, dw, (long long)x->c * T, T, 1, accumulate, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+// kernel == stride, padding 0 transposed conv as ONE GEMM: rows = input voxels, N = classes x Cout, scatter epilogue.
+// w_packed = bf16 [T][Cout][Cin] (rehr_pack_weight with R = T, C = Cin, T = Cout, sr = 1, sc = Cout*T, st = T).
+int rehr_convtranspose3d_fused_supported(const rehr_conv_desc* d, int cin, int cout) {
+  if (!d) return 0;
+  if (d->kd != d->sd || d->kh != d->sh || d->kw != d->sw || d->pd || d->ph || d->pw) return 0;
+  if (cout % 16 != 0 || cin % 16 != 0) return 0;
+  return 1;
+}
+int rehr_convtranspose3d_fused_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                                   const rehr_tensor* y, int act, float slope, rehr_stream stream) {
+  if (!desc || !x || !y || !x->ptr || !y->ptr || !w_packed) return REHR_BAD_SHAPE;
+  if (!rehr_convtranspose3d_fused_supported(desc, x->c, y->c)) return REHR_UNSUPPORTED;
+  if (x->n != y->n || y->d != x->d * desc->sd || y->h != x->h * desc->sh || y->w != x->w * desc->sw) return REHR_BAD_SHAPE;
+  TapPlan plan;
+  plan.num_maps = 1;
+  for (int a = 0; a < 3; ++a) {
+    plan.map_r[0][a] = 0;
+    plan.map_s[0][a] = 1;
+    plan.map_ext[0][a] = 0;
+  }
+  plan.num_taps = 1;
+  plan.weight_taps = 1;
+  plan.taps[0].map_id = 0;
+  plan.taps[0].dw = plan.taps[0].dh = plan.taps[0].dd = 0;
+  plan.taps[0].widx = 0;
+  const int O[4] = {x->w, x->h, x->d, x->n};
+  const int os[3] = {1, 1, 1}, oo[3] = {0, 0, 0};
+  const int sc[3] = {desc->sw, desc->sh, desc->sd};
+  return launch_tapped_gemm(plan, *x, w_packed, 0, bias, *y, 0, O, os, oo, act, slope, nullptr, (cudaStream_t)stream, sc);
+}
+
 // ---- ConvTranspose3d = the same conv read backwards (weight [Cin][Cout][T], underlying conv Cin <- Cout) ----
 int rehr_convtranspose3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
                              const rehr_tensor* y, int act, float slope, rehr_stream stream) {

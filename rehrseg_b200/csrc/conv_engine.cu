@@ -286,6 +286,10 @@ struct alignas(64) FwdParams {
   int act;
   float slope;
   float* stats;    // [m_tile][cout][2] or null
+  // "scatter" epilogue of a kernel == stride transposed conv computed as ONE GEMM with N = classes x cout:
+  // column block (cls, co) of row (input voxel i) is output voxel i*s + r(cls), channel co.  0 = off.
+  int sc_cout;
+  int sc_s[3];     // stride per dim (w h d)
   int* err;
 };
 
@@ -448,6 +452,36 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
         tmem_ld16(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
         float f[16];
+        if (p.sc_cout > 0) {
+          // scatter epilogue: this 16-column chunk belongs to one output parity class
+          const int col = nbase + c0;
+          const int cls = col / p.sc_cout, co0 = col - cls * p.sc_cout;
+          const int ncls = p.sc_s[0] * p.sc_s[1] * p.sc_s[2];
+          if (valid && cls < ncls) {
+            const int rw = cls % p.sc_s[0], rh = (cls / p.sc_s[0]) % p.sc_s[1], rd = cls / (p.sc_s[0] * p.sc_s[1]);
+            const long long ov = (((long long)on * p.AO[2] + (od * p.sc_s[2] + rd)) * p.AO[1] + (oh * p.sc_s[1] + rh)) * p.AO[0] +
+                                 (ow * p.sc_s[0] + rw);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = __uint_as_float(v[i]);
+              if (p.bias != nullptr) x += __ldg(p.bias + co0 + i);
+              f[i] = apply_act(x, p.act, p.slope);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ov * p.out_ld + co0;
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(f[0], f[1]);
+            lo.y = pack_bf16x2(f[2], f[3]);
+            lo.z = pack_bf16x2(f[4], f[5]);
+            lo.w = pack_bf16x2(f[6], f[7]);
+            hi.x = pack_bf16x2(f[8], f[9]);
+            hi.y = pack_bf16x2(f[10], f[11]);
+            hi.z = pack_bf16x2(f[12], f[13]);
+            hi.w = pack_bf16x2(f[14], f[15]);
+            reinterpret_cast<uint4*>(o)[0] = lo;
+            reinterpret_cast<uint4*>(o)[1] = hi;
+          }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int c = nbase + c0 + i;
@@ -543,8 +577,11 @@ static size_t fwd_smem_tail_bytes() { return (2 * kMaxStages + 4) * 8 + 16 + 2 *
 // transform (os, oo); AO = actual output extents.
 int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w_packed, int w_rows,
                        const float* bias, const rehr_tensor& out, int out_f32, const int O[4], const int os[3],
-                       const int oo[3], int act, float slope, float* stats, cudaStream_t stream) {
-  const int cin = in.c, cout = out.c;
+                       const int oo[3], int act, float slope, float* stats, cudaStream_t stream, const int* scatter_s) {
+  const int cin = in.c;
+  const int ncls = scatter_s ? scatter_s[0] * scatter_s[1] * scatter_s[2] : 1;
+  const int cout = out.c * ncls;  // GEMM N: all parity classes side by side in scatter mode
+  if (scatter_s && (out.c % 16 != 0 || out_f32 || stats != nullptr || out.ld % 8 != 0)) return REHR_UNSUPPORTED;
   const int BK = chunk_for_channels(cin);
   if (BK == 0) return REHR_UNSUPPORTED;
   if (in.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
@@ -585,6 +622,10 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
   p.slope = slope;
   p.stats = stats;
   p.err = nullptr;
+  if (scatter_s) {
+    p.sc_cout = out.c;
+    for (int a = 0; a < 3; ++a) p.sc_s[a] = scatter_s[a];
+  }
   int tc = 32;
   while (tc < 2 * BN) tc <<= 1;
   p.tmem_cols = tc;

@@ -44,7 +44,21 @@ static inline long long voxels_per_sample(const rehr_tensor* t) { return (long l
 // InstanceNorm statistics (stand-alone; the conv epilogue normally produces these)
 // =================================================================================================
 static constexpr int kStatThreads = 256;
-static constexpr int kStatVoxPerBlock = 4096;
+static constexpr int kStatMaxVoxPerBlock = 2048;
+
+// Voxels per reduction block: as many as 2048 (full-resolution tensors: ~1000+ blocks), but never so many that a
+// small deep-layer tensor is reduced by a handful of blocks (aim for >= 2 blocks per SM across the batch).
+static int stat_vox_per_block(const rehr_tensor* x) {
+  const long long V = (long long)x->d * x->h * x->w;
+  const int groups = std::max(1, x->c / 8);
+  const int lanes = std::max(1, kStatThreads / groups);
+  const long long want_tiles = std::max<long long>(1, (2LL * sm_count() + x->n - 1) / std::max(1, x->n));
+  long long vpb = (V + want_tiles - 1) / want_tiles;
+  vpb = std::max<long long>(vpb, (long long)lanes * 4);
+  vpb = std::min<long long>(vpb, kStatMaxVoxPerBlock);
+  vpb = (vpb + lanes - 1) / lanes * lanes;
+  return (int)vpb;
+}
 
 // Block = (tile, n).  Thread = (voxel lane, channel group of 8).  Per-thread accumulation, then a
 // shared-memory tree over voxel lanes.  `mode` 0: (sum x, sum x^2); 1: InstanceNorm backward sums.
@@ -57,7 +71,7 @@ struct StatArgs {
   float slope;
   float* partial;
   long long V;
-  int C, tiles;
+  int C, tiles, vpb;
 };
 
 template <int MODE>
@@ -67,8 +81,8 @@ __global__ void __launch_bounds__(kStatThreads) in_reduce_kernel(const StatArgs 
   const int groups = a.C / 8;
   const int lanes = kStatThreads / groups;  // voxel lanes per pass (>=1)
   const int g = threadIdx.x % groups, vl = threadIdx.x / groups;
-  const long long v0 = (long long)tile * kStatVoxPerBlock;
-  const long long v1 = min(a.V, v0 + kStatVoxPerBlock);
+  const long long v0 = (long long)tile * a.vpb;
+  const long long v1 = min(a.V, v0 + a.vpb);
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
@@ -154,7 +168,8 @@ __global__ void __launch_bounds__(kStatThreads) in_reduce_kernel(const StatArgs 
 
 static int stat_tiles(const rehr_tensor* x) {
   const long long V = voxels_per_sample(x);
-  return (int)((V + kStatVoxPerBlock - 1) / kStatVoxPerBlock);
+  const int vpb = stat_vox_per_block(x);
+  return (int)((V + vpb - 1) / vpb);
 }
 
 template <int MODE>
@@ -292,36 +307,57 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const ApplyArgs a) {
   __syncthreads();
   const int groups = C / 8;
   const long long items = a.V * groups;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(it % groups);
-    const long long vox = (long long)n * a.V + it / groups;
-    float y[8], o[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8), y);
-    if (MODE == 0) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 2;  // items in flight per thread: both batches of loads are issued before the arithmetic
+  for (long long it0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; it0 < items; it0 += stride * U) {
+    uint4 yv[U], dv[U], ev[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = y[i] * sh[g * 8 + i] + sh[C + g * 8 + i];
-        o[i] = z > 0.f ? z : z * a.slope;
-      }
-    } else {
-      float d[8];
-      bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da1 + vox * a.ld_a1 + g * 8), d);
-      if (a.da2) {
-        float d2[8];
-        bf16x8_to_float(*reinterpret_cast<const uint4*>(a.da2 + vox * a.ld_a2 + g * 8), d2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] += d2[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = g * 8 + i;
-        const float xh = (y[i] - sh[c]) * sh[C + c];
-        const float z = sh[2 * C + c] * xh + sh[3 * C + c];
-        const float gi = z > 0.f ? d[i] : d[i] * a.slope;
-        o[i] = sh[2 * C + c] * sh[C + c] * (gi - sh[4 * C + c] - xh * sh[5 * C + c]);
+    for (int u = 0; u < U; ++u) {
+      const long long it = it0 + u * stride;
+      if (it < items) {
+        const int g = (int)(it % groups);
+        const long long vox = (long long)n * a.V + it / groups;
+        yv[u] = __ldcs(reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8));
+        if (MODE == 1) {
+          dv[u] = __ldcs(reinterpret_cast<const uint4*>(a.da1 + vox * a.ld_a1 + g * 8));
+          if (a.da2) ev[u] = __ldcs(reinterpret_cast<const uint4*>(a.da2 + vox * a.ld_a2 + g * 8));
+        }
       }
     }
-    *reinterpret_cast<uint4*>(a.out + vox * a.ld_o + g * 8) = float_to_bf16x8(o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long it = it0 + u * stride;
+      if (it >= items) break;
+      const int g = (int)(it % groups);
+      const long long vox = (long long)n * a.V + it / groups;
+      float y[8], o[8];
+      bf16x8_to_float(yv[u], y);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = y[i] * sh[g * 8 + i] + sh[C + g * 8 + i];
+          o[i] = z > 0.f ? z : z * a.slope;
+        }
+      } else {
+        float d[8];
+        bf16x8_to_float(dv[u], d);
+        if (a.da2) {
+          float d2[8];
+          bf16x8_to_float(ev[u], d2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] += d2[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = g * 8 + i;
+          const float xh = (y[i] - sh[c]) * sh[C + c];
+          const float z = sh[2 * C + c] * xh + sh[3 * C + c];
+          const float gi = z > 0.f ? d[i] : d[i] * a.slope;
+          o[i] = sh[2 * C + c] * sh[C + c] * (gi - sh[4 * C + c] - xh * sh[5 * C + c]);
+        }
+      }
+      *reinterpret_cast<uint4*>(a.out + vox * a.ld_o + g * 8) = float_to_bf16x8(o);
+    }
   }
 }
 
@@ -811,6 +847,7 @@ int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream
   a.V = voxels_per_sample(x);
   a.C = x->c;
   a.tiles = stat_tiles(x);
+  a.vpb = stat_vox_per_block(x);
   return launch_in_reduce<0>(a, x->n, (cudaStream_t)stream);
 }
 
@@ -862,6 +899,7 @@ int rehr_instnorm_lrelu_bwd_reduce(const rehr_tensor* y, const rehr_tensor* da1,
   a.V = voxels_per_sample(y);
   a.C = y->c;
   a.tiles = stat_tiles(y);
+  a.vpb = stat_vox_per_block(y);
   return launch_in_reduce<1>(a, y->n, (cudaStream_t)stream);
 }
 

@@ -60,15 +60,20 @@ class kernel_timer:
     def summary(self) -> dict:
         torch.cuda.synchronize()
         out: dict = {}
-        for name, flops, e0, e1 in self.records:
+        for name, flops, e0, e1, _tag in self.records:
             n, ms, fl = out.get(name, (0, 0.0, 0.0))
             out[name] = (n + 1, ms + e0.elapsed_time(e1), fl + flops)
         return out
 
+    def rows(self) -> list:
+        """[(family, tag, ms, flops)] per launch, in launch order."""
+        torch.cuda.synchronize()
+        return [(name, tag, e0.elapsed_time(e1), flops) for name, flops, e0, e1, tag in self.records]
+
 
 class _timed:
-    def __init__(self, name: str, flops: float):
-        self.name, self.flops = name, flops
+    def __init__(self, name: str, flops: float, tag: str = ""):
+        self.name, self.flops, self.tag = name, flops, tag
 
     def __enter__(self):
         if _ktimer is not None:
@@ -80,7 +85,7 @@ class _timed:
         if _ktimer is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _ktimer.append((self.name, self.flops, self.e0, e1))
+            _ktimer.append((self.name, self.flops, self.e0, e1, self.tag))
         return False
 
 
@@ -113,6 +118,9 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor
     elif kind == "march_dgrad":  # its input-gradient B<-A (transposed, taps flipped)
         out = torch.empty((A * B * T,), dtype=torch.bfloat16, device=w.device)
         check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, T, B * T, 1, stream_ptr()), "pack_weight_march")
+    elif kind == "tconv_fused":  # ConvTranspose weight [Cin=A][Cout=B][T] -> [T][Cout][Cin]
+        out = torch.empty((T, B, A), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight(ptr(w), ptr(out), T, A, B, 1, B * T, T, stream_ptr()), "pack_weight")
     elif kind == "fwd":
         out = torch.empty((A, T, B), dtype=torch.bfloat16, device=w.device)
         check(lib().rehr_pack_weight(ptr(w), ptr(out), A, B, T, B * T, T, 1, stream_ptr()), "pack_weight")
@@ -142,6 +150,18 @@ def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _alias(storage_of: torch.Tensor, offset: int, size, stride) -> torch.Tensor:
+    """A fresh tensor over `storage_of`'s storage with NO autograd view relationship (the concat buffers below are
+    written through raw pointers by the kernels, which autograd's view+inplace tracking cannot follow)."""
+    t = torch.empty((0,), dtype=storage_of.dtype, device=storage_of.device)
+    return t.set_(storage_of.untyped_storage(), offset, tuple(size), tuple(stride))
+
+
+def concat_room_of(t: torch.Tensor):
+    """(total_channels, channel_offset) if `t` was produced inside a wider concat buffer (see conv_norm_act), else None."""
+    return getattr(t, "_rehr_cat", None)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
 
@@ -165,13 +185,14 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     stats = None
     tiles = 0
     flops = 2.0 * n * od * oh * ow * cout * cin * kernel[0] * kernel[1] * kernel[2]
+    tag = f"fwd {cin}->{cout} in{d}x{h}x{w} k{kernel} s{stride}" if _ktimer is not None else ""
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), cin, cout):
         xt = rt(x)
         if want_stats:
             tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt))
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
         wp = _packed(weight, "march_fwd")
-        with _timed("conv_march_kernel", flops):
+        with _timed("conv_march_kernel", flops, tag):
             check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
                                               float(slope), ptr(stats), stream_ptr()), "conv3d_march_fwd")
         _count()
@@ -182,7 +203,7 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
     wp = _packed(weight, "fwd")
     xt = rt(x)
-    with _timed("conv_tapped_gemm_kernel", flops):
+    with _timed("conv_tapped_gemm_kernel", flops, tag):
         check(lib().rehr_conv3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
                                     float(slope), ptr(stats), stream_ptr()), "conv3d_fwd")
     _count()
@@ -207,17 +228,18 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
     dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     desc = conv_desc(kernel, stride, padding)
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * cin * kernel[0] * kernel[1] * kernel[2]
+    tag = f"dgrad {cin}<-{dy.shape[4]} in{d}x{h}x{w} k{kernel} s{stride}" if _ktimer is not None else ""
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), dy.shape[4], cin):
         wp = _packed(weight, "march_dgrad", cache)
         dyt, dxt = rt(dy), rt(dx)
-        with _timed("conv_march_kernel", flops):
+        with _timed("conv_march_kernel", flops, tag):
             check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0, None,
                                               stream_ptr()), "conv3d_march_dgrad")
         _count()
         return dx
     wp = _packed(weight, "dgrad", cache)
     dyt, dxt = rt(dy), rt(dx)
-    with _timed("conv_tapped_gemm_kernel", flops):
+    with _timed("conv_tapped_gemm_kernel", flops, tag):
         check(lib().rehr_conv3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0,
                                       stream_ptr()), "conv3d_dgrad")
     _count(stride[0] * stride[1] * stride[2])
@@ -231,10 +253,11 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
     desc = conv_desc(kernel, stride, padding)
     xt, dyt = rt(x), rt(dy)
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * x.shape[4] * kernel[0] * kernel[1] * kernel[2]
+    tag = f"wgrad {x.shape[4]}->{dy.shape[4]} in{x.shape[1]}x{x.shape[2]}x{x.shape[3]} k{kernel} s{stride}" if _ktimer is not None else ""
     if USE_MARCH and lib().rehr_conv3d_wgrad_march_supported(C.byref(desc), C.byref(xt), C.byref(dyt)):
         need = lib().rehr_conv3d_wgrad_march_workspace(C.byref(xt), C.byref(dyt))
         ws = _ws(need, x.device)
-        with _timed("wgrad_march_kernel", flops):
+        with _timed("wgrad_march_kernel", flops, tag):
             check(lib().rehr_conv3d_wgrad_march(C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
                   "conv3d_wgrad_march")
         _count(2)
@@ -243,7 +266,7 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
     if need == 0:
         raise L.RehrError(f"conv3d_wgrad: unsupported configuration x={tuple(x.shape)} dy={tuple(dy.shape)}")
     ws = _ws(need, x.device)
-    with _timed("conv_wgrad_kernel", flops):
+    with _timed("conv_wgrad_kernel", flops, tag):
         check(lib().rehr_conv3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
               "conv3d_wgrad")
     _count(2)
@@ -279,7 +302,7 @@ def act_bwd_raw(a: torch.Tensor, da: torch.Tensor, act: int, slope: float) -> to
 # --------------------------------------------------------------------------------------------------
 class ConvNormAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, kernel, stride, padding, eps, slope, small_cin):
+    def forward(ctx, x, weight, bias, gamma, beta, kernel, stride, padding, eps, slope, small_cin, cat_room):
         dev = x.device
         cout = weight.shape[0]
         desc = conv_desc(kernel, stride, padding)
@@ -307,7 +330,13 @@ class ConvNormAct(torch.autograd.Function):
         rstd = torch.empty((n, cout), dtype=torch.float32, device=dev)
         check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, cout, vox, float(eps), ptr(mean), ptr(rstd), stream_ptr()),
               "instnorm_finalize")
-        a = torch.empty_like(y)
+        if cat_room:
+            # the activation doubles as the skip half of the decoder's concat buffer [up | skip] (models/seg_model.py:37):
+            # allocate 2C channels and write this layer's output into the upper half, so torch.cat never runs
+            buf = torch.empty((*y.shape[:4], 2 * cout), dtype=torch.bfloat16, device=dev)
+            a = _alias(buf, cout, y.shape, buf.stride())
+        else:
+            a = torch.empty_like(y)
         yt, at = rt(y), rt(a)
         g32, b32 = _f32(gamma), _f32(beta)
         check(lib().rehr_instnorm_lrelu_apply(C.byref(yt), ptr(mean), ptr(rstd), ptr(g32), ptr(b32), float(slope), C.byref(at),
@@ -365,12 +394,16 @@ class ConvNormAct(torch.autograd.Function):
         # exactly (PyTorch's value is rounding noise of the same sum).
         dbias = torch.zeros((cout,), dtype=torch.float32, device=dev) if has_bias else None
         return dx, dw.to(weight.dtype), dbias, dgamma if gamma is not None else None, dbeta if beta is not None else None, \
-            None, None, None, None, None, None
+            None, None, None, None, None, None, None
 
 
-def conv_norm_act(x, weight, bias, gamma, beta, kernel, stride, padding, eps=1e-5, slope=0.01, small_cin=False):
-    return ConvNormAct.apply(x, weight, bias, gamma, beta, tuple(kernel), tuple(stride), tuple(padding), float(eps),
-                             float(slope), bool(small_cin))
+def conv_norm_act(x, weight, bias, gamma, beta, kernel, stride, padding, eps=1e-5, slope=0.01, small_cin=False,
+                  cat_room=False):
+    a = ConvNormAct.apply(x, weight, bias, gamma, beta, tuple(kernel), tuple(stride), tuple(padding), float(eps),
+                          float(slope), bool(small_cin), bool(cat_room))
+    if cat_room:
+        a._rehr_cat = (2 * weight.shape[0], weight.shape[0])
+    return a
 
 
 # --------------------------------------------------------------------------------------------------
@@ -419,27 +452,53 @@ def conv_act(x, weight, bias, kernel, stride, padding, act=ACT_NONE, slope=0.0, 
 # and FLAVR upConv3D k(3,4,4) s(1,2,2) p(1,1,1) (models/FLAVR/FLAVR_arch.py:49-51)
 # --------------------------------------------------------------------------------------------------
 class ConvTranspose(torch.autograd.Function):
+    """`skip` (optional): an encoder activation that lives in the upper half of a 2C concat buffer (conv_norm_act with
+    cat_room); the up-sampled tensor is then written straight into the lower half and the whole buffer is returned --
+    `torch.cat((up, skip), 1)` of models/seg_model.py:37 without the copy."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope):
+    def forward(ctx, x, weight, bias, skip, kernel, stride, padding, act, slope):
         x = as_cl(x)
         n, d, h, w, cin = x.shape
         cout = weight.shape[1]
         od, oh, ow = ((i - 1) * s - 2 * p + k for i, k, s, p in zip((d, h, w), kernel, stride, padding))
-        y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
         desc = conv_desc(kernel, stride, padding)
-        wp = _packed(weight, "dgrad")  # [Cout][T][Cin]
+        ctx.cat = skip is not None
+        if skip is not None:
+            tot, off = skip._rehr_cat
+            if tot != 2 * cout or off != cout or tuple(skip.shape) != (n, od, oh, ow, cout):
+                raise L.RehrError("conv_transpose: skip does not sit in a matching [up | skip] concat buffer")
+            full = _alias(skip, skip.storage_offset() - off, (n, od, oh, ow, tot),
+                          (od * oh * ow * tot, oh * ow * tot, ow * tot, tot, 1))
+            y = full[..., :cout]
+        else:
+            full = None
+            y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
         xt, yt = rt(x), rt(y)
-        check(lib().rehr_convtranspose3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act, float(slope),
-                                             stream_ptr()), "convtranspose3d_fwd")
-        _count(stride[0] * stride[1] * stride[2])
+        if lib().rehr_convtranspose3d_fused_supported(C.byref(desc), cin, cout):
+            wp = _packed(weight, "tconv_fused")  # [T][Cout][Cin]
+            check(lib().rehr_convtranspose3d_fused_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
+                                                       float(slope), stream_ptr()), "convtranspose3d_fused_fwd")
+            _count()
+        else:
+            wp = _packed(weight, "dgrad")  # [Cout][T][Cin]
+            check(lib().rehr_convtranspose3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
+                                                 float(slope), stream_ptr()), "convtranspose3d_fwd")
+            _count(stride[0] * stride[1] * stride[2])
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
-        return y
+        return full if skip is not None else y
 
     @staticmethod
     def backward(ctx, da):
         x, weight, y = ctx.saved_tensors
         kernel, stride, padding, act, slope, has_bias = ctx.cfg
+        dskip = None
+        if ctx.cat:  # da is the gradient of the whole [up | skip] buffer
+            cout = weight.shape[1]
+            da = as_cl(da)
+            dskip = da[..., cout:]
+            da = da[..., :cout]
         dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
         desc = conv_desc(kernel, stride, padding)
         dyt, xt = rt(dy), rt(x)
@@ -460,11 +519,14 @@ class ConvTranspose(torch.autograd.Function):
               "convtranspose3d_wgrad")
         _count(2)
         db = channel_sum_raw(dy) if has_bias else None
-        return dx, dw.to(weight.dtype), db, None, None, None, None, None
+        return dx, dw.to(weight.dtype), db, dskip, None, None, None, None, None
 
 
-def conv_transpose(x, weight, bias, kernel, stride, padding=(0, 0, 0), act=ACT_NONE, slope=0.0):
-    return ConvTranspose.apply(x, weight, bias, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
+def conv_transpose(x, weight, bias, kernel, stride, padding=(0, 0, 0), act=ACT_NONE, slope=0.0, skip=None):
+    """ConvTranspose3d; with `skip` (an activation produced with cat_room) returns the [up | skip] concat buffer."""
+    if skip is not None and concat_room_of(skip) is None:
+        raise L.RehrError("conv_transpose(skip=...): the skip tensor was not produced with cat_room=True")
+    return ConvTranspose.apply(x, weight, bias, skip, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
 
 
 # --------------------------------------------------------------------------------------------------

@@ -57,8 +57,9 @@ def _act_of(nonlin) -> tuple:
     raise RehrError(f"activation {type(nonlin).__name__} is not implemented")
 
 
-def run_conv_block(block: nn.Module, x: torch.Tensor, first: bool = False) -> torch.Tensor:
-    """One ConvDropoutNormReLU (conv -> [norm] -> [nonlin]).  `first`: x is the caller's NCDHW fp32 input."""
+def run_conv_block(block: nn.Module, x: torch.Tensor, first: bool = False, cat_room: bool = False) -> torch.Tensor:
+    """One ConvDropoutNormReLU (conv -> [norm] -> [nonlin]).  `first`: x is the caller's NCDHW fp32 input.
+    `cat_room`: produce the activation inside a 2C-channel buffer so the decoder can concatenate without a copy."""
     conv, norm, nonlin = block.conv, getattr(block, "norm", None), getattr(block, "nonlin", None)
     if getattr(block, "dropout", None) is not None:
         raise RehrError("dropout_op is None in the reference configuration (train_all.py:487-488); not implemented")
@@ -74,21 +75,23 @@ def run_conv_block(block: nn.Module, x: torch.Tensor, first: bool = False) -> to
         if act == ACT_RELU:
             slope = 0.0
         return F_.conv_norm_act(x, conv.weight, conv.bias, norm.weight, norm.bias, k, s, p, eps=norm.eps, slope=slope,
-                                small_cin=small)
+                                small_cin=small, cat_room=cat_room)
     if small:
         raise RehrError("small-Cin stem without InstanceNorm: use rehrseg_b200.flavr for the FLAVR stem")
     return F_.conv_act(x, conv.weight, conv.bias, k, s, p, act=act, slope=slope)
 
 
-def run_stacked(blocks: nn.Module, x: torch.Tensor, first: bool = False) -> torch.Tensor:
+def run_stacked(blocks: nn.Module, x: torch.Tensor, first: bool = False, cat_room: bool = False) -> torch.Tensor:
     """StackedConvBlocks (has .convs) or an nn.Sequential wrapping one."""
     if hasattr(blocks, "convs"):
+        last = len(blocks.convs) - 1
         for i, b in enumerate(blocks.convs):
-            x = run_conv_block(b, x, first=first and i == 0)
+            x = run_conv_block(b, x, first=first and i == 0, cat_room=cat_room and i == last)
         return x
     if isinstance(blocks, nn.Sequential):
+        last = len(blocks) - 1
         for i, m in enumerate(blocks):
-            x = run_stacked(m, x, first=first and i == 0)
+            x = run_stacked(m, x, first=first and i == 0, cat_room=cat_room and i == last)
         return x
     raise RehrError(f"unexpected module {type(blocks).__name__} in a PlainConvUNet stage (pooling variants are not "
                     "used by the reference, which builds pool='conv')")
@@ -96,17 +99,26 @@ def run_stacked(blocks: nn.Module, x: torch.Tensor, first: bool = False) -> torc
 
 def encoder_forward(encoder: nn.Module, x: torch.Tensor) -> List[torch.Tensor]:
     skips = []
+    n = len(encoder.stages)
     for s, stage in enumerate(encoder.stages):
-        x = run_stacked(stage, x, first=(s == 0))
+        # every stage output but the bottleneck is later concatenated with an up-sampled tensor of the same width
+        x = run_stacked(stage, x, first=(s == 0), cat_room=(s < n - 1))
         skips.append(x)
     return skips
 
 
-def run_transpconv(tc: nn.ConvTranspose3d, x: torch.Tensor) -> torch.Tensor:
+def run_transpconv(tc: nn.ConvTranspose3d, x: torch.Tensor, skip: torch.Tensor = None) -> torch.Tensor:
+    """ConvTranspose3d; with `skip` returns torch.cat((up, skip), channel) (models/seg_model.py:36-37)."""
     _check_conv(tc)
     if any(o != 0 for o in _triple(tc.output_padding)):
         raise RehrError("output_padding is not implemented")
-    return F_.conv_transpose(x, tc.weight, tc.bias, _triple(tc.kernel_size), _triple(tc.stride), _triple(tc.padding))
+    k, s, p = _triple(tc.kernel_size), _triple(tc.stride), _triple(tc.padding)
+    if skip is None:
+        return F_.conv_transpose(x, tc.weight, tc.bias, k, s, p)
+    room = F_.concat_room_of(skip)
+    if room is not None and room == (2 * tc.out_channels, tc.out_channels):
+        return F_.conv_transpose(x, tc.weight, tc.bias, k, s, p, skip=skip)
+    return torch.cat((F_.conv_transpose(x, tc.weight, tc.bias, k, s, p), skip), dim=4)
 
 
 def decoder_forward(decoder: nn.Module, skips: Sequence[torch.Tensor]):
@@ -116,8 +128,7 @@ def decoder_forward(decoder: nn.Module, skips: Sequence[torch.Tensor]):
     features = []
     n = len(decoder.stages)
     for s in range(n):
-        x = run_transpconv(decoder.transpconvs[s], lres)
-        x = torch.cat((x, skips[-(s + 2)]), dim=4)  # channel concat, upsampled features first (seg_model.py:37)
+        x = run_transpconv(decoder.transpconvs[s], lres, skip=skips[-(s + 2)])  # [up | skip], seg_model.py:36-37
         x = run_stacked(decoder.stages[s], x)
         if getattr(decoder, "deep_features", False) and s == n - 1:
             features = x

@@ -1,0 +1,24 @@
+"""Development tool: per-launch device time of the conv-engine calls of one C1 step (CUDA events), with shapes."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from rehrseg_b200 import seg_model as sm, functional as Fn
+torch.manual_seed(0)
+m = sm.plainconv_unet_3d_fullres().cuda()
+x = torch.randn(2, 1, 128, 128, 128, device='cuda')
+def step():
+    for p in m.parameters():
+        p.grad = None
+    out = m(x)
+    out.float().mean().backward()
+for i in range(3):
+    step()
+torch.cuda.synchronize()
+with Fn.kernel_timer() as kt:
+    torch.cuda._sleep(300_000_000)
+    step()
+rows = kt.rows()
+tot = sum(r[2] for r in rows)
+print(f"conv-engine calls: {len(rows)}, total {tot:.3f} ms")
+for name, tag, ms, fl in sorted(rows, key=lambda r: -r[2]):
+    print(f"{ms:8.3f} ms {fl / ms / 1e9:8.1f} TF/s  {name:26s} {tag}")
