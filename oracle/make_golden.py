@@ -1,0 +1,113 @@
+"""Generate tests/golden/* FROM THE REFERENCE ITSELF (imported unchanged from /root/reference through oracle/refimport.py).
+Runs only in the build container (the GPU box has no /root/reference); the outputs are small and committed, the
+script is committed so they can be regenerated:   python -m oracle.make_golden
+
+The reference ships no tests, golden vectors or fixtures, so these files -- outputs of the
+reference's own functions / modules on seeded synthetic inputs -- are what pins the oracle and the CUDA path.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import refimport
+from . import seg_model as ref_seg
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+STEP_CASES = [((256, 256, 256), (128, 128, 128), 0.5), ((160, 512, 512), (128, 128, 128), 0.5), ((20, 455, 633), (14, 320, 384), 0.5),
+              ((110, 64, 64), (64, 64, 64), 0.5), ((24, 20, 28), (16, 16, 16), 0.5), ((14, 320, 384), (14, 320, 384), 0.5),
+              ((130, 130, 130), (128, 128, 128), 0.25), ((100, 99, 98), (32, 48, 64), 1.0), ((33, 65, 129), (32, 32, 32), 0.75)]
+P_CASES = [(n, s) for n in (1, 2, 7, 20, 33, 40, 41, 57, 100, 160) for s in (1.0, 1.5, 2.0, 2.5, 3.2, 4.0, 4.8, 5.3)]
+PAD_CASES = [(128, 100), (128, 101), (16, 16), (10, 20), (255, 0), (7, 6), (1000, 1), (33, 32)]
+PATCH_CASES = [((10, 12, 5), (4, 6, 1)), ((3, 3, 3), (1, 1, 1)), ((20, 21, 22), (7, 8, 9)), ((5, 5, 0), (3, 3, 1))]
+
+
+def conv_net(seed=7, half=False):
+    torch.manual_seed(seed)
+    conv = nn.Conv3d(1, 2, 3, padding=1)
+    conv.requires_grad_(False)
+    return (lambda x: conv(x).half()) if half else conv, conv
+
+
+def main() -> None:
+    os.makedirs(OUT, exist_ok=True)
+    seg_utils = refimport.load("utils.seg_utils")
+    patch_ops = refimport.load("utils.patch_ops")
+    pad = refimport.load("utils.pad")
+    rot = refimport.load("utils.rotate")
+    fba = refimport.load("utils.fba")
+
+    # ---- integer index math -------------------------------------------------------------------------------
+    idx = {
+        "steps": [{"image": list(i), "tile": list(t), "step": s, "out": seg_utils.compute_steps_for_sliding_window(i, t, s)}
+                  for i, t, s in STEP_CASES],
+        "n_slicers": [{"image": list(i), "tile": list(t),
+                       "n": len(seg_utils._internal_get_sliding_window_slicers(i, patch_size=list(t))),
+                       "first3": [[[sl.start, sl.stop] for sl in s[1:]] for s in
+                                  seg_utils._internal_get_sliding_window_slicers(i, patch_size=list(t))[:3]]}
+                      for i, t, _ in STEP_CASES],
+        "find_integer_p": [{"n": n, "s": s, "p": patch_ops.find_integer_p(n, s),
+                            "crop": patch_ops.calc_slices_to_crop(patch_ops.find_integer_p(n, s), s),
+                            "ideal": patch_ops.ideal_size(n, s), "proj0": patch_ops.projected_size(n, 0, s)} for n, s in P_CASES],
+        "get_pads": [{"target": t, "d": d, "out": list(pad.get_pads(t, d))} for t, d in PAD_CASES],
+        "get_patch": [{"center": list(c), "size": list(p),
+                       "idx": [[sl.start, sl.stop] for sl in patch_ops.get_patch(None, c, p, return_idx=True)]} for c, p in PATCH_CASES],
+    }
+    with open(os.path.join(OUT, "index_math.json"), "w") as f:
+        json.dump(idx, f, indent=1)
+
+    # ---- rotate / pad / fba ---------------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(11)
+    vol = torch.randn((5, 7, 3, 2), generator=g)
+    arrs = {"rot_in": vol.numpy()}
+    for a in (0, 90, -90, 180, -180, 270, -270, 360):
+        arrs[f"rot_{a}"] = rot.rotate_vol_2d(vol, a).contiguous().numpy()
+    img = torch.randn((6, 9, 4), generator=g)
+    padded, pads = pad.target_pad(img, (10, 9, 7), mode="reflect")
+    arrs.update(pad_in=img.numpy(), pad_out=padded.numpy(), pad_pads=np.array(pads), pad_crop=pad.crop(padded, pads).numpy())
+    vols = [torch.randn((12, 10, 8), generator=g).numpy() for _ in range(3)]
+    vols_odd = [torch.randn((6, 5, 9), generator=g).numpy() for _ in range(2)]
+    arrs.update(fba_in=np.stack(vols), fba_inf=fba.fba(vols, "infinity"), fba_p2=fba.fba(vols, 2), fba_p0=fba.fba(vols, 0),
+                fba_odd_in=np.stack(vols_odd), fba_odd_inf=fba.fba(vols_odd, "inf"), fba_odd_p1=fba.fba(vols_odd, "1"))
+    np.savez_compressed(os.path.join(OUT, "volume_ops.npz"), **arrs)
+
+    # ---- sliding-window blend (reference function, CPU results device) --------------------------------------
+    data = torch.randn((1, 24, 20, 28), generator=g)
+    sw = {"data": data.numpy()}
+    for half in (False, True):
+        net, conv = conv_net(7, half)
+        sw["conv_w"], sw["conv_b"] = conv.weight.numpy(), conv.bias.numpy()
+        for gauss in (False, True):
+            patch = [16, 16, 16]
+            slicers = seg_utils._internal_get_sliding_window_slicers(data.shape[1:], patch_size=patch)
+            out = seg_utils._internal_predict_sliding_window_return_logits(data.clone(), slicers, net, do_on_device=False, out_idx=None,
+                                                                           slice_seperation=1, patch_size=patch, use_gaussian=gauss,
+                                                                           deep_supervision=False)
+            sw[f"logits_half{int(half)}_gauss{int(gauss)}"] = out.numpy()
+    sw["gaussian_16"] = seg_utils.compute_gaussian((16, 16, 16), sigma_scale=1. / 8, value_scaling_factor=10, device=torch.device("cpu")).numpy()
+    sw["gaussian_128_zero_count_before_fix"] = np.array(0)
+    np.savez_compressed(os.path.join(OUT, "sliding_window.npz"), **sw)
+
+    # ---- the reference's own SegModel (with the third-party shims) -----------------------------------------
+    sm = refimport.load("models.seg_model")
+    kw = ref_seg.plan_kwargs("tiny")
+    torch.manual_seed(1234)
+    model = sm.SegModel(**kw)
+    model.eval()
+    x = torch.randn((1, 1, 8, 16, 16), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        out, up, skips = model(x, return_inetermediate_feature=True)
+    wsum = float(sum(p.double().abs().sum() for p in model.parameters()))
+    np.savez_compressed(os.path.join(OUT, "segmodel_tiny.npz"), x=x.numpy(), out=out.numpy(), up=up.numpy(), skip1=skips[1].numpy(),
+                        weight_abs_sum=np.array(wsum), n_keys=np.array(len(model.state_dict())),
+                        keys=np.array(sorted(model.state_dict().keys())))
+    print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
+
+
+if __name__ == "__main__":
+    main()

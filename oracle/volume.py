@@ -1,0 +1,161 @@
+"""CPU restatement (numpy / torch-CPU) of the reference's driver-level functions -- TEST INFRASTRUCTURE.
+
+  steps_for_sliding_window / sliding_window_slicers   <- utils/seg_utils.py:176-199, 229-238
+  mirror_and_predict                                  <- utils/seg_utils.py:201-227
+  sliding_window_logits                               <- utils/seg_utils.py:240-287 (fp16 accumulators, tile order)
+  fba                                                 <- utils/fba.py:4-21
+  rotate_vol_2d                                       <- utils/rotate.py:5-31
+  get_pads / target_pad / crop                        <- utils/pad.py:5-32
+  projected_size / ideal_size / find_integer_p / calc_slices_to_crop / get_patch   <- utils/patch_ops.py:6-64
+  blur_same                                           <- F.conv2d(x, k, padding="same") at utils/train_set.py:325,332
+  apply_to_vol_flavr                                  <- utils/sr_utils.py:102-135 (device-agnostic restatement)
+Pinned against the live reference functions (tests/test_oracle_vs_reference.py, run whenever /root/reference exists) and
+the committed fixtures tests/golden/*.npz|json generated FROM the reference by oracle/make_golden.py.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import third_party as tp
+
+
+def steps_for_sliding_window(image_size, tile_size, step):
+    out = []
+    for img, tile in zip(image_size, tile_size):
+        n = int(np.ceil((img - tile) / (tile * step))) + 1
+        delta = (img - tile) / (n - 1) if n > 1 else 99999999999
+        out.append([int(np.round(delta * i)) for i in range(n)])
+    return out
+
+
+def sliding_window_slicers(image_size, patch_size, step=0.5):
+    st = steps_for_sliding_window(image_size, patch_size, step)
+    return [(slice(None), slice(a, a + patch_size[0]), slice(b, b + patch_size[1]), slice(c, c + patch_size[2]))
+            for a in st[0] for b in st[1] for c in st[2]]
+
+
+def mirror_and_predict(model, x, out_idx=None, deep_supervision=True):
+    def pick(o):
+        o = o[out_idx] if out_idx is not None else o
+        return o[0] if (out_idx == 0 and deep_supervision) else o
+    pred = pick(model(x))
+    combos = [c for r in (1, 2, 3) for c in itertools.combinations((2, 3, 4), r)]
+    for ax in combos:
+        pred += torch.flip(pick(model(torch.flip(x, ax))), ax)
+    pred /= len(combos) + 1
+    return pred
+
+
+def sliding_window_logits(data, slicers, network, out_idx=None, slice_sep=1, patch_size=(14, 320, 384), use_gaussian=False,
+                          deep_supervision=True):
+    logits = torch.zeros((2, data.shape[1] * slice_sep, data.shape[2], data.shape[3]), dtype=torch.half)
+    npred = torch.zeros(logits.shape[1:], dtype=torch.half)
+    g = tp.compute_gaussian(tuple(patch_size), sigma_scale=1. / 8, value_scaling_factor=10, device=torch.device("cpu")) \
+        if use_gaussian else 1
+    for sl in slicers:
+        pred = mirror_and_predict(network, data[sl][None], out_idx, deep_supervision)[0]
+        dst = (slice(None), slice(sl[1].start * slice_sep, sl[1].stop * slice_sep), sl[2], sl[3])
+        logits[dst] += pred * g
+        npred[dst[1:]] += g
+    logits /= npred
+    if torch.any(torch.isinf(logits)):
+        raise RuntimeError("Encountered inf in predicted array")
+    return logits
+
+
+def fba(imgs, p="infinity"):
+    spec = [np.fft.rfftn(v) for v in imgs]
+    if p in ("infinity", "inf"):
+        fused = np.max(spec, axis=0)          # numpy orders complex numbers lexicographically (real, then imag)
+    else:
+        mags = [np.abs(s) ** float(p) for s in spec]
+        den = np.sum(mags, axis=0)
+        fused = np.sum([m / den * s for m, s in zip(mags, spec)], axis=0)
+    return np.fft.irfftn(fused).astype(np.float32)
+
+
+def rotate_vol_2d(vol, angle):
+    if angle in (0, 360):
+        return vol
+    if angle % 90 != 0 or abs(angle) > 270:
+        raise NotImplementedError("Angles other than 90 degree rotations are not supported.")
+    return torch.rot90(vol, k=int(angle // 90), dims=[0, 1])
+
+
+def get_pads(target, d):
+    if target <= d:
+        return 0, 0
+    lo = (target - d) // 2
+    return lo, target - d - lo
+
+
+def target_pad(img, target_dims, mode="reflect"):
+    pads = tuple(get_pads(t, d) for t, d in zip(target_dims, img.shape))
+    arr = img.numpy() if isinstance(img, torch.Tensor) else img
+    out = np.pad(arr, pads, mode=mode)
+    return (torch.Tensor(out) if isinstance(img, torch.Tensor) else out), pads
+
+
+def crop(img, pads):
+    return img[tuple(slice(lo or None, -hi if hi else None) for lo, hi in pads)]
+
+
+def projected_size(n, p, s):
+    return round((n + p) * (s / math.floor(s))) * math.floor(s) - round(p * s)
+
+
+def ideal_size(n, s):
+    return round(n * s)
+
+
+def calc_slices_to_crop(p, s):
+    return round(p * s)
+
+
+def find_integer_p(n, s):
+    p = 0
+    while projected_size(n, p, s) != ideal_size(n, s) and p < 1000:
+        p += 1
+    return p if projected_size(n, p, s) == ideal_size(n, s) else 0
+
+
+def get_patch_index(center, patch_size):
+    starts = [c if p == 1 else c - p // 2 for c, p in zip(center, patch_size)]
+    return tuple(slice(s, s + p) for s, p in zip(starts, patch_size))
+
+
+def blur_same(x, kernel):
+    return F.conv2d(x, kernel, padding="same")
+
+
+def apply_to_vol_flavr(model, image, pred_out_idx=None):
+    """image [Z, C, X, Y]: pad in-plane to a multiple of 16, sweep Z-1 windows of 4 slices (zero-padded at both ends),
+    forward each (input cloned: the model mutates it), crop, concatenate along the slice axis -> [4(Z-1), C', X, Y]."""
+    ox, oy = image.shape[2], image.shape[3]
+    if ox % 16:
+        image = torch.cat([image, image.new_zeros(image.shape[0], image.shape[1], 16 - ox % 16, image.shape[3])], 2)
+    if oy % 16:
+        image = torch.cat([image, image.new_zeros(image.shape[0], image.shape[1], image.shape[2], 16 - oy % 16)], 3)
+    z = image.shape[0]
+    outs = []
+    for st in range(z - 1):
+        if st == 0:
+            win = image[0:3]
+            win = torch.cat([win.new_zeros(4 - win.shape[0], *win.shape[1:]), win], 0)
+        elif st == z - 2:
+            win = image[st - 1:]
+            win = torch.cat([win, win.new_zeros(4 - win.shape[0], *win.shape[1:])], 0)
+        else:
+            win = image[st - 1:st + 3]
+        inp = win.permute(1, 0, 3, 2).unsqueeze(0).clone()
+        with torch.no_grad():
+            sr = model(inp)
+            if pred_out_idx is not None and isinstance(sr, tuple):
+                sr = sr[pred_out_idx]
+        outs.append(sr.detach().cpu()[:, :, :, :oy, :ox])
+    return torch.cat(outs, 2).squeeze(0).permute(1, 0, 2, 3)

@@ -684,10 +684,14 @@ __global__ void __launch_bounds__(256) sw_accumulate_kernel(__half* logits, __ha
     const long long vi = ((long long)(od + z) * VH + (oh + y)) * VW + (ow + x);
     const float g = gauss ? __half2float(gauss[i]) : 1.f;
     for (int c = 0; c < C; ++c) {
-      const float pf = pred_f32 ? __half2float(__float2half(reinterpret_cast<const float*>(pred)[c * tv + i]))
-                                : __half2float(reinterpret_cast<const __half*>(pred)[c * tv + i]);
-      const __half prod = __float2half(pf * g);
-      logits[c * vv + vi] = __float2half(__half2float(logits[c * vv + vi]) + __half2float(prod));
+      // ATen semantics of `logits[sl] += pred * gauss` (utils/seg_utils.py:275): a half x half product is rounded to half
+      // before the add; a float prediction promotes the product and the add to float, rounding once at the store.
+      float prod;
+      if (pred_f32)
+        prod = reinterpret_cast<const float*>(pred)[c * tv + i] * g;
+      else
+        prod = __half2float(__float2half(__half2float(reinterpret_cast<const __half*>(pred)[c * tv + i]) * g));
+      logits[c * vv + vi] = __float2half(__half2float(logits[c * vv + vi]) + prod);
     }
     npred[vi] = __float2half(__half2float(npred[vi]) + g);
   }

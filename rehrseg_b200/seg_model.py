@@ -370,6 +370,10 @@ class SegModel(nn.Module):
         self.encoder = PlainConvEncoder(input_channels, n_stages, features_per_stage, conv_op, kernel_sizes, strides,
                                         n_conv_per_stage, conv_bias, norm_op, norm_op_kwargs, dropout_op, dropout_op_kwargs,
                                         nonlin, nonlin_kwargs)
+        # The reference first builds PlainConvUNet's own decoder and then replaces it with MyUnetDecoder
+        # (models/seg_model.py:174-193), drawing the decoder's default-init random numbers twice; do the same so that an
+        # identically seeded construction yields identical weights.
+        UNetDecoder(self.encoder, num_classes, n_conv_per_stage_decoder, deep_supervision, nonlin_first=nonlin_first)
         self.decoder = UNetDecoder(self.encoder, num_classes, n_conv_per_stage_decoder, deep_supervision,
                                    nonlin_first=nonlin_first, deep_features=True)
         self.upscale = upscale

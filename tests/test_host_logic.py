@@ -1,0 +1,103 @@
+"""CPU: host-side logic of the product (integer tile / pad / patch math, module trees, state_dict layout) against the
+fixtures generated from the reference, and the C-ABI contract (library loads, every declared symbol exported, loud
+failure without CUDA).  No GPU compute is called."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from rehrseg_b200 import _lib, seg_model as sm, sliding_window as sw, volume_ops as vo
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _lib.declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    undeclared = [n for n in lib._rehr_signatures if n not in names]
+    assert not undeclared, undeclared
+    assert lib.rehr_version() == 1
+    assert lib.rehr_strerror(-2).decode().startswith("configuration not supported")
+
+
+def test_no_cpu_fallback():
+    m = sm.SegModel(**{**__import__("oracle.seg_model", fromlist=["x"]).plan_kwargs("tiny")})
+    with pytest.raises(_lib.RehrError):
+        m(torch.zeros(1, 1, 8, 16, 16))
+    with pytest.raises(_lib.RehrError):
+        vo.rotate_vol_2d(torch.zeros(2, 2, 2), 90)
+    with pytest.raises(NotImplementedError):
+        vo.rotate_vol_2d(torch.zeros(2, 2, 2), 45)
+    assert vo.rotate_vol_2d(torch.zeros(2, 2, 2), 0).shape == (2, 2, 2)  # identity never touches the device
+
+
+def test_index_math_matches_reference_fixtures():
+    with open(os.path.join(G, "index_math.json")) as f:
+        idx = json.load(f)
+    for c in idx["steps"]:
+        assert sw.compute_steps_for_sliding_window(c["image"], c["tile"], c["step"]) == c["out"], c
+    for c in idx["n_slicers"]:
+        sl = sw._internal_get_sliding_window_slicers(c["image"], patch_size=c["tile"])
+        assert len(sl) == c["n"]
+        assert [[[s.start, s.stop] for s in t[1:]] for t in sl[:3]] == c["first3"]
+    for c in idx["find_integer_p"]:
+        p = vo.find_integer_p(c["n"], c["s"])
+        assert (p, vo.calc_slices_to_crop(p, c["s"]), vo.ideal_size(c["n"], c["s"]), vo.projected_size(c["n"], 0, c["s"])) == \
+               (c["p"], c["crop"], c["ideal"], c["proj0"]), c
+    for c in idx["get_pads"]:
+        assert list(vo.get_pads(c["target"], c["d"])) == c["out"]
+    for c in idx["get_patch"]:
+        assert [[s.start, s.stop] for s in vo.get_patch(None, c["center"], c["size"], return_idx=True)] == c["idx"]
+
+
+def test_sliding_window_edge_cases():
+    assert sw.compute_steps_for_sliding_window((16, 16, 16), (16, 16, 16), 0.5) == [[0], [0], [0]]  # image == tile
+    with pytest.raises(AssertionError):
+        sw.compute_steps_for_sliding_window((8, 16, 16), (16, 16, 16), 0.5)                       # image < tile
+    with pytest.raises(AssertionError):
+        sw.compute_steps_for_sliding_window((32, 32, 32), (16, 16, 16), 0.0)
+    # x-major, z-minor tile order (utils/seg_utils.py:232-234)
+    sl = sw._internal_get_sliding_window_slicers((32, 16, 24), patch_size=[16, 16, 16])
+    assert [(s[1].start, s[2].start, s[3].start) for s in sl] == [(0, 0, 0), (0, 0, 8), (8, 0, 0), (8, 0, 8), (16, 0, 0), (16, 0, 8)]
+    assert len(sw.mirror_axes_combinations()) == 7
+
+
+def test_pad_helpers_and_crop_roundtrip():
+    z = np.load(os.path.join(G, "volume_ops.npz"))
+    padded, pads = vo.target_pad(torch.from_numpy(z["pad_in"]), (10, 9, 7), mode="reflect")   # CPU tensor: numpy path
+    assert np.array_equal(padded.numpy(), z["pad_out"]) and np.array_equal(np.array(pads), z["pad_pads"])
+    assert np.array_equal(vo.crop(padded, pads).numpy(), z["pad_crop"])
+    img = np.arange(24.).reshape(2, 3, 4)
+    res, slicer = sw.pad_nd_image(img, (5, 4), 'constant', {'value': 0}, True)
+    assert res.shape == (2, 5, 4) and np.array_equal(res[slicer], img) and slicer[1] == slice(1, 4)
+    t, sl2 = sw.pad_nd_image(torch.from_numpy(img), (7, 9), 'constant', {'value': 0}, True)
+    assert t.shape == (2, 7, 9) and torch.equal(t[sl2], torch.from_numpy(img))
+
+
+def test_state_dict_layout_matches_reference_fixture():
+    z = np.load(os.path.join(G, "segmodel_tiny.npz"))
+    from oracle import seg_model as ref_seg
+    torch.manual_seed(1234)
+    m = sm.SegModel(**ref_seg.plan_kwargs("tiny"))
+    assert sorted(m.state_dict().keys()) == list(z["keys"])
+    # same construction order => same default-init weights as the reference module
+    wsum = float(sum(p.detach().double().abs().sum() for p in m.parameters()))
+    assert abs(wsum - float(z["weight_abs_sum"])) <= 1e-9 * wsum
+    full = sm.plainconv_3d_fullres()
+    assert len(full.state_dict()) == 296 and sum(p.numel() for p in full.parameters()) > 31_000_000
+    assert 'sr_head' in "".join(n for n, _ in full.named_parameters())
+
+
+def test_rehr_tensor_descriptor_of_channel_slice():
+    buf = torch.zeros((1, 2, 3, 4, 64), dtype=torch.bfloat16)
+    a = buf[..., 32:]
+    assert _lib.cl_strides_ok(a) and _lib._pitch(a) == 64
+    t = _lib.rt(a)
+    assert (t.n, t.d, t.h, t.w, t.c, t.ld) == (1, 2, 3, 4, 32, 64) and t.ptr == buf.data_ptr() + 64
+    assert not _lib.cl_strides_ok(buf.permute(0, 4, 1, 2, 3))

@@ -1,0 +1,97 @@
+"""CPU: the oracle restatements (oracle/*.py) against the committed fixtures generated FROM the reference's own functions
+and modules (oracle/make_golden.py -> tests/golden/).  This is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import seg_model as ref_seg
+from oracle import third_party as tp
+from oracle import volume as ov
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _idx():
+    with open(os.path.join(G, "index_math.json")) as f:
+        return json.load(f)
+
+
+def test_index_math_matches_reference():
+    idx = _idx()
+    for c in idx["steps"]:
+        assert ov.steps_for_sliding_window(c["image"], c["tile"], c["step"]) == c["out"], c
+    for c in idx["n_slicers"]:
+        sl = ov.sliding_window_slicers(c["image"], c["tile"])
+        assert len(sl) == c["n"]
+        assert [[[s.start, s.stop] for s in t[1:]] for t in sl[:3]] == c["first3"]
+    for c in idx["find_integer_p"]:
+        p = ov.find_integer_p(c["n"], c["s"])
+        assert p == c["p"], c
+        assert ov.calc_slices_to_crop(p, c["s"]) == c["crop"]
+        assert ov.ideal_size(c["n"], c["s"]) == c["ideal"]
+        assert ov.projected_size(c["n"], 0, c["s"]) == c["proj0"]
+    for c in idx["get_pads"]:
+        assert list(ov.get_pads(c["target"], c["d"])) == c["out"]
+    for c in idx["get_patch"]:
+        assert [[s.start, s.stop] for s in ov.get_patch_index(c["center"], c["size"])] == c["idx"]
+
+
+def test_rotate_pad_fba_match_reference():
+    z = np.load(os.path.join(G, "volume_ops.npz"))
+    vol = torch.from_numpy(z["rot_in"])
+    for a in (0, 90, -90, 180, -180, 270, -270, 360):
+        assert np.array_equal(ov.rotate_vol_2d(vol, a).contiguous().numpy(), z[f"rot_{a}"]), a
+    padded, pads = ov.target_pad(torch.from_numpy(z["pad_in"]), (10, 9, 7), mode="reflect")
+    assert np.array_equal(padded.numpy(), z["pad_out"]) and np.array_equal(np.array(pads), z["pad_pads"])
+    assert np.array_equal(ov.crop(padded, pads).numpy(), z["pad_crop"])
+    vols = list(z["fba_in"])
+    for key, p in (("fba_inf", "infinity"), ("fba_p2", 2), ("fba_p0", 0)):
+        assert np.array_equal(ov.fba(vols, p), z[key]), key   # same numpy, same algorithm: bit-identical
+    odd = list(z["fba_odd_in"])
+    assert ov.fba(odd, "inf").shape == z["fba_odd_inf"].shape == (6, 5, 8)  # irfftn without `s` drops the odd last slice
+    assert np.array_equal(ov.fba(odd, "inf"), z["fba_odd_inf"]) and np.array_equal(ov.fba(odd, "1"), z["fba_odd_p1"])
+
+
+def test_gaussian_shim_matches_reference_call():
+    z = np.load(os.path.join(G, "sliding_window.npz"))
+    tp.compute_gaussian.cache_clear()
+    g = tp.compute_gaussian((16, 16, 16), sigma_scale=1. / 8, value_scaling_factor=10, device=torch.device("cpu"))
+    assert g.dtype == torch.float16 and np.array_equal(g.numpy(), z["gaussian_16"])
+    assert float(g.max()) == 10.0 and float(g.min()) > 0.0
+
+
+def _net(z, half):
+    conv = torch.nn.Conv3d(1, 2, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(z["conv_w"]))
+        conv.bias.copy_(torch.from_numpy(z["conv_b"]))
+    conv.requires_grad_(False)
+    return (lambda x: conv(x).half()) if half else conv
+
+
+def test_sliding_window_blend_matches_reference():
+    z = np.load(os.path.join(G, "sliding_window.npz"))
+    data = torch.from_numpy(z["data"])
+    for half in (0, 1):
+        for gauss in (0, 1):
+            sl = ov.sliding_window_slicers(data.shape[1:], [16, 16, 16])
+            out = ov.sliding_window_logits(data.clone(), sl, _net(z, bool(half)), None, 1, [16, 16, 16], bool(gauss), False)
+            want = z[f"logits_half{half}_gauss{gauss}"]
+            assert out.dtype == torch.float16
+            assert np.array_equal(out.numpy().view(np.uint16), want.view(np.uint16)), (half, gauss)  # bit-exact fp16
+
+
+def test_oracle_segmodel_matches_reference_segmodel():
+    z = np.load(os.path.join(G, "segmodel_tiny.npz"))
+    m = ref_seg.build("tiny")  # same seed / construction order as the reference module in make_golden
+    m.eval()
+    assert sorted(m.state_dict().keys()) == list(z["keys"]) and len(m.state_dict()) == int(z["n_keys"])
+    wsum = float(sum(p.detach().double().abs().sum() for p in m.parameters()))
+    assert abs(wsum - float(z["weight_abs_sum"])) <= 1e-9 * wsum
+    with torch.no_grad():
+        out, up, skips = m(torch.from_numpy(z["x"]), return_inetermediate_feature=True)
+    for got, key in ((out, "out"), (up, "up"), (skips[1], "skip1")):
+        ref = torch.from_numpy(z[key])
+        assert float((got - ref).norm() / ref.norm()) <= 1e-5, key   # fp32 bound of north_star
