@@ -255,7 +255,7 @@ def main() -> None:
     x_host = torch.randn((BATCH, 1, *PATCH), generator=gen).pin_memory()
     g_host = torch.randn((BATCH, 2, *PATCH), generator=gen).pin_memory()
     x_dev, g_dev = x_host.to(dev), g_host.to(dev)
-    flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev) if world > 1 else None
+    dp = {"flat": None, "active": None}  # gradient bucket, sized after the first backward (unused seg layers get no grad)
 
     def fwd_bwd(x, g):
         for p in params:
@@ -269,18 +269,16 @@ def main() -> None:
         loss = torch.dot(out.float().reshape(-1), g.reshape(-1)) / out.numel()  # <logits, g> / numel
         loss.backward()
         if world > 1:  # data-parallel gradient mean over NVLink (one flat bucket)
-            off = 0
-            for p in params:
-                n = p.numel()
-                flat[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
-            dist.all_reduce(flat)
-            flat.div_(world)
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            if dp["active"] is None:
+                dp["active"] = [p for p in params if p.grad is not None]
+            grads = [p.grad for p in dp["active"]]
+            flat = torch.cat([g.reshape(-1) for g in grads])      # one gather kernel into the bucket
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)            # NCCL ring / NVLS over NVLink
+            off, views = 0, []
+            for g in grads:
+                views.append(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            torch._foreach_copy_(grads, views)                     # one batched scatter back into .grad
         return loss
 
     def step_resident():
