@@ -197,6 +197,16 @@ int rehr_ndhwc_bf16_to_ncdhw_f32(const rehr_tensor* src, float* dst, rehr_stream
 int rehr_segate_scale_add_act(const rehr_tensor* x, const float* gate /*[n][c]*/, const rehr_tensor* residual,
                               int act, float slope, const rehr_tensor* y, rehr_stream stream);
 
+/* Backward of the SE-gate tail y = act(x*gate[n,c] + residual) (resnet_3D.py:112-116,140-151).  With g = dy*act'(y):
+ *   rehr_segate_bwd_reduce: partial[n][rehr_instnorm_stats_tiles(x)][c][2] = (sum_v g*x, 0)  (-> d gate, finalize with
+ *                           rehr_instnorm_lrelu_bwd_finalize)
+ *   rehr_segate_bwd_apply : dx = g*gate[n,c] + shift[n,c] (shift = gradient through the global average pool / V),
+ *                           dres (optional) = g */
+int rehr_segate_bwd_reduce(const rehr_tensor* x, const rehr_tensor* y, const rehr_tensor* dy, int act, float slope,
+                           float* partial, rehr_stream stream);
+int rehr_segate_bwd_apply(const rehr_tensor* y, const rehr_tensor* dy, int act, float slope, const float* gate,
+                          const float* shift, const rehr_tensor* dx, const rehr_tensor* dres, rehr_stream stream);
+
 /* dy = da * act'(.) evaluated from the activation OUTPUT a (ReLU, or LeakyReLU with slope > 0): the backward of the
  * bias+activation epilogues of rehr_conv3d_fwd / rehr_convtranspose3d_fwd (FLAVR_arch.py:86, resnet_3D.py:144-149). */
 int rehr_act_bwd(const rehr_tensor* a, const rehr_tensor* da, int act, float slope, const rehr_tensor* dy,

@@ -106,6 +106,43 @@ def main() -> None:
     np.savez_compressed(os.path.join(OUT, "segmodel_tiny.npz"), x=x.numpy(), out=out.numpy(), up=up.numpy(), skip1=skips[1].numpy(),
                         weight_abs_sum=np.array(wsum), n_keys=np.array(len(model.state_dict())),
                         keys=np.array(sorted(model.state_dict().keys())))
+    # ---- the reference's own FLAVR UNet_3D_3D (both heads) and train_all.get_intermediate_features ----------
+    fa = refimport.load("models.FLAVR.FLAVR_arch")
+    fl = {}
+    xf = torch.rand((1, 2, 4, 32, 32), generator=torch.Generator().manual_seed(2))
+    xf[:, 1] = (xf[:, 1] > 0.8).float()
+    fl["x"] = xf.numpy()
+    for unc in (False, True):
+        torch.manual_seed(1234)
+        net = fa.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=unc)
+        net.eval()
+        tag = "uasr" if unc else "plain"
+        fl[f"{tag}_weight_abs_sum"] = np.array(float(sum(p.detach().double().abs().sum() for p in net.parameters())))
+        fl[f"{tag}_keys"] = np.array(list(net.state_dict().keys()))
+        with torch.no_grad():
+            xin = xf.clone()
+            out = net(xin)
+            feats = net(xf.clone(), return_inetermediate_feature=True)
+        fl[f"{tag}_x_after"] = xin.numpy()            # the forward mutates its input in place
+        if unc:
+            fl["uasr_out"], fl["uasr_unc"] = out[0].numpy(), out[1].numpy()
+        else:
+            fl["plain_out"] = out.numpy()
+            fl["plain_x1"], fl["plain_x4"] = feats[1].numpy(), feats[4].numpy()
+    ta = refimport.load("train_all")
+    torch.manual_seed(1234)
+    teacher = fa.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).eval()
+    g2 = torch.Generator().manual_seed(4)
+    img = torch.randn((1, 1, 5, 32, 32), generator=g2)
+    lab = (torch.rand((1, 1, 5, 32, 32), generator=g2) > 0.8).float()
+    fl["gif_img"], fl["gif_lab"] = img.numpy(), lab.numpy()
+    with torch.no_grad():
+        img_in = img.clone()
+        feats = ta.get_intermediate_features(teacher, img_in, lab, torch.device("cpu"))
+    fl["gif_img_after"] = img_in.numpy()               # zscore_normalization mutates the caller's tensor
+    fl["gif_f1"], fl["gif_f3"] = feats[1].numpy(), feats[3].numpy()
+    np.savez_compressed(os.path.join(OUT, "flavr_small.npz"), **fl)
+
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

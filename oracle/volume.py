@@ -159,3 +159,22 @@ def apply_to_vol_flavr(model, image, pred_out_idx=None):
                 sr = sr[pred_out_idx]
         outs.append(sr.detach().cpu()[:, :, :, :oy, :ox])
     return torch.cat(outs, 2).squeeze(0).permute(1, 0, 2, 3)
+
+
+def zscore_normalization(image):
+    """utils/seg_utils.py:137-156 (tensor branch): per sample, channel 0 is normalised IN PLACE through a view (the caller's
+    tensor changes), unbiased std floored at 1e-8; returns the stacked views [B, 1, ...]."""
+    if isinstance(image, torch.Tensor):
+        outs = []
+        for i in range(image.shape[0]):
+            v = image[i:i + 1, 0]
+            mu, sd = v.mean(), v.std()
+            v -= mu
+            v /= max(sd, 1e-8)
+            outs.append(v)
+        return torch.stack(outs, 0)
+    image = image.astype(np.float32, copy=False)
+    mu, sd = image.mean(), image.std()
+    image -= mu
+    image /= max(sd, 1e-8)
+    return image

@@ -106,6 +106,8 @@ def _declare(L: C.CDLL) -> None:
         "rehr_ncdhw_f32_to_ndhwc_bf16": (i, [vp, T, vp]),
         "rehr_ndhwc_bf16_to_ncdhw_f32": (i, [T, vp, vp]),
         "rehr_segate_scale_add_act": (i, [T, vp, T, i, f, T, vp]),
+        "rehr_segate_bwd_reduce": (i, [T, T, T, i, f, vp, vp]),
+        "rehr_segate_bwd_apply": (i, [T, T, i, f, vp, vp, T, T, vp]),
         "rehr_act_bwd": (i, [T, T, i, f, T, vp]),
         "rehr_sw_accumulate": (i, [vp, vp, vp, i, vp] + [i] * 10 + [vp]),
         "rehr_sw_finalize": (i, [vp, vp, i, ll, vp, vp]),

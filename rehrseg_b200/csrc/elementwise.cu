@@ -668,6 +668,72 @@ __global__ void __launch_bounds__(256) segate_kernel(const __nv_bfloat16* x, lon
   }
 }
 
+// SE-gate tail backward.  With m = act'(y) evaluated from the OUTPUT y (ReLU / LeakyReLU slope > 0 / none) and g = dy * m:
+//   reduce:  partial[n][tile][c] = (sum_v g * x, 0)                      -> d(gate)[n,c]
+//   apply :  dx = g * gate[n,c] + shift[n,c]   (shift = d(pool)/V, the gradient through the global average pool)
+//            dres = g (optional)
+template <int MODE>  // 0 reduce, 1 apply
+__global__ void __launch_bounds__(kStatThreads) segate_bwd_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* y,
+                                                                  long long ldy, const __nv_bfloat16* dy, long long lddy,
+                                                                  const float* gate, const float* shift, __nv_bfloat16* dx,
+                                                                  long long lddx, __nv_bfloat16* dres, long long lddr,
+                                                                  float* partial, long long V, int C, int tiles, int vpb, int act,
+                                                                  float slope) {
+  extern __shared__ float sh[];
+  const int n = blockIdx.y, tile = blockIdx.x;
+  const int groups = C / 8;
+  const int lanes = kStatThreads / groups;
+  const int g = threadIdx.x % groups, vl = threadIdx.x / groups;
+  const long long v0 = (long long)tile * vpb, v1 = min(V, v0 + vpb);
+  float acc[8], ga[8], sf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] = 0.f;
+    ga[i] = (MODE == 1 && gate) ? gate[n * C + g * 8 + i] : 1.f;
+    sf[i] = (MODE == 1 && shift) ? shift[n * C + g * 8 + i] : 0.f;
+  }
+  if (vl < lanes) {
+    for (long long v = v0 + vl; v < v1; v += lanes) {
+      const long long vox = (long long)n * V + v;
+      float d[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(dy + vox * lddy + g * 8), d);
+      if (act != REHR_ACT_NONE) {
+        float yy[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(y + vox * ldy + g * 8), yy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (!(yy[i] > 0.f)) d[i] *= (act == REHR_ACT_LRELU ? slope : 0.f);
+      }
+      if (MODE == 0) {
+        float xx[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(x + vox * ldx + g * 8), xx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(d[i], xx[i], acc[i]);
+      } else {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(d[i], ga[i], sf[i]);
+        *reinterpret_cast<uint4*>(dx + vox * lddx + g * 8) = float_to_bf16x8(o);
+        if (dres) *reinterpret_cast<uint4*>(dres + vox * lddr + g * 8) = float_to_bf16x8(d);
+      }
+    }
+  }
+  if (MODE == 0) {
+    if (vl < lanes) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sh[vl * C + g * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kStatThreads) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += sh[l * C + c];
+      float* dst = partial + (((long long)n * tiles + tile) * C + c) * 2;
+      dst[0] = t;
+      dst[1] = 0.f;
+    }
+  }
+}
+
 // =================================================================================================
 // Sliding-window Gaussian blend with fp16 accumulators (bit-faithful to ATen half arithmetic:
 // every half op computes in float and rounds once).
@@ -1038,6 +1104,50 @@ int rehr_segate_scale_add_act(const rehr_tensor* x, const float* gate, const reh
   segate_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, gate, residual ? reinterpret_cast<const __nv_bfloat16*>(residual->ptr) : nullptr,
       residual ? residual->ld : 0, reinterpret_cast<__nv_bfloat16*>(y->ptr), y->ld, x->n, V, x->c, act, slope);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+// d(gate) partial sums: partial [n][rehr_instnorm_stats_tiles(x)][c][2] (second slot zero), reduce with
+// rehr_instnorm_lrelu_bwd_finalize (sums[n][c][0] = d gate).
+int rehr_segate_bwd_reduce(const rehr_tensor* x, const rehr_tensor* y, const rehr_tensor* dy, int act, float slope, float* partial,
+                           rehr_stream stream) {
+  if (!bf16_tensor_ok(x) || !bf16_tensor_ok(dy) || (act != REHR_ACT_NONE && !bf16_tensor_ok(y)) || !partial) return REHR_BAD_SHAPE;
+  const int groups = x->c / 8;
+  if (groups > kStatThreads) return REHR_UNSUPPORTED;
+  const int lanes = kStatThreads / groups;
+  const int tiles = stat_tiles(x), vpb = stat_vox_per_block(x);
+  const size_t smem = (size_t)lanes * x->c * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(segate_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+  }
+  dim3 grid(tiles, x->n);
+  segate_bwd_kernel<0><<<grid, kStatThreads, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, y ? reinterpret_cast<const __nv_bfloat16*>(y->ptr) : nullptr, y ? y->ld : 0,
+      reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->ld, nullptr, nullptr, nullptr, 0, nullptr, 0, partial, voxels_per_sample(x),
+      x->c, tiles, vpb, act, slope);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+// dx = dy*act'(y)*gate[n,c] + shift[n,c];  dres (optional) = dy*act'(y)
+int rehr_segate_bwd_apply(const rehr_tensor* y, const rehr_tensor* dy, int act, float slope, const float* gate, const float* shift,
+                          const rehr_tensor* dx, const rehr_tensor* dres, rehr_stream stream) {
+  if (!bf16_tensor_ok(dy) || !bf16_tensor_ok(dx) || (act != REHR_ACT_NONE && !bf16_tensor_ok(y)) || (dres && !bf16_tensor_ok(dres)))
+    return REHR_BAD_SHAPE;
+  const int groups = dy->c / 8;
+  if (groups > kStatThreads) return REHR_UNSUPPORTED;
+  const int tiles = stat_tiles(dy), vpb = stat_vox_per_block(dy);
+  dim3 grid(tiles, dy->n);
+  segate_bwd_kernel<1><<<grid, kStatThreads, 0, (cudaStream_t)stream>>>(
+      nullptr, 0, y ? reinterpret_cast<const __nv_bfloat16*>(y->ptr) : nullptr, y ? y->ld : 0,
+      reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->ld, gate, shift, reinterpret_cast<__nv_bfloat16*>(dx->ptr), dx->ld,
+      dres ? reinterpret_cast<__nv_bfloat16*>(dres->ptr) : nullptr, dres ? dres->ld : 0, nullptr, voxels_per_sample(dy), dy->c, tiles, vpb,
+      act, slope);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -411,16 +411,32 @@ def conv_norm_act(x, weight, bias, gamma, beta, kernel, stride, padding, eps=1e-
 # Conv_3d / Conv_2d (models/FLAVR/resnet_3D.py:19-33, models/FLAVR/FLAVR_arch.py:24-88)
 # --------------------------------------------------------------------------------------------------
 class ConvAct(torch.autograd.Function):
+    """`want_pool`: also return the per-(n, c) mean of the (pre-activation) output, taken from the conv epilogue's fused
+    partial sums -- the global average pool of the SE gate that follows (resnet_3D.py:112-114).  It is a non-differentiable
+    hint: `se_gate` recomputes nothing and owns the gradient through the pool."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope, out_f32):
+    def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope, out_f32, want_pool):
         x = as_cl(x)
-        y, _, _ = conv3d_raw(x, weight, bias, kernel, stride, padding, act=act, slope=slope, out_f32=out_f32)
+        y, stats, tiles = conv3d_raw(x, weight, bias, kernel, stride, padding, act=act, slope=slope, out_f32=out_f32,
+                                     want_stats=want_pool)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
+        if want_pool:
+            if act != ACT_NONE:
+                raise L.RehrError("want_pool needs the pre-activation output (act=ACT_NONE)")
+            n, cout = y.shape[0], y.shape[4]
+            pool = torch.empty((n, cout), dtype=torch.float32, device=y.device)
+            rstd = torch.empty((n, cout), dtype=torch.float32, device=y.device)
+            check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, cout, y.shape[1] * y.shape[2] * y.shape[3], 1e-5, ptr(pool),
+                                               ptr(rstd), stream_ptr()), "instnorm_finalize")
+            _count()
+            ctx.mark_non_differentiable(pool)
+            return y, pool
         return y
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, *_unused):
         x, weight, y = ctx.saved_tensors
         kernel, stride, padding, act, slope, has_bias = ctx.cfg
         dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
@@ -440,11 +456,134 @@ class ConvAct(torch.autograd.Function):
             dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding) if ctx.needs_input_grad[0] else None
             dw = conv3d_wgrad_raw(x, dy, weight.shape, kernel, stride, padding)
         db = channel_sum_raw(dy)[:cout] if has_bias else None
-        return dx, dw.to(weight.dtype), db, None, None, None, None, None, None
+        return dx, dw.to(weight.dtype), db, None, None, None, None, None, None, None
 
 
-def conv_act(x, weight, bias, kernel, stride, padding, act=ACT_NONE, slope=0.0, out_f32=False):
-    return ConvAct.apply(x, weight, bias, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope), bool(out_f32))
+def conv_act(x, weight, bias, kernel, stride, padding, act=ACT_NONE, slope=0.0, out_f32=False, want_pool=False):
+    return ConvAct.apply(x, weight, bias, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope), bool(out_f32),
+                         bool(want_pool))
+
+
+# --------------------------------------------------------------------------------------------------
+# SE "feature gating" tail (models/FLAVR/resnet_3D.py:100-116 and its users :140-151, FLAVR_arch.py:49-51,75-77):
+#   y = act( x * sigmoid(W mean_v(x) + b) (+ residual) )
+# --------------------------------------------------------------------------------------------------
+class SEGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pool, attn_w, attn_b, residual, act, slope):
+        x = as_cl(x)
+        n, d, h, w, c = x.shape
+        vox = d * h * w
+        if pool is None:
+            stats, tiles = instnorm_stats_raw(x)
+            pool = torch.empty((n, c), dtype=torch.float32, device=x.device)
+            rstd = torch.empty_like(pool)
+            check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, c, vox, 1e-5, ptr(pool), ptr(rstd), stream_ptr()),
+                  "instnorm_finalize")
+            _count()
+        w2 = attn_w.detach().reshape(c, c).float()
+        gate = torch.sigmoid(torch.addmm(attn_b.detach().float(), pool, w2.t())).contiguous()  # [n, c], tiny
+        res = as_cl(residual) if residual is not None else None
+        y = torch.empty_like(x)
+        xt, yt = rt(x), rt(y)
+        rst = rt(res) if res is not None else None
+        check(lib().rehr_segate_scale_add_act(C.byref(xt), ptr(gate), C.byref(rst) if rst is not None else None, act, float(slope),
+                                              C.byref(yt), stream_ptr()), "segate_scale_add_act")
+        _count()
+        ctx.save_for_backward(x, gate, pool, attn_w, y if act != ACT_NONE else None)
+        ctx.cfg = (act, slope, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gate, pool, attn_w, y = ctx.saved_tensors
+        act, slope, has_res = ctx.cfg
+        dy = as_cl(dy)
+        n, d, h, w, c = x.shape
+        vox = d * h * w
+        xt, dyt = rt(x), rt(dy)
+        yt = rt(y) if y is not None else None
+        tiles = lib().rehr_instnorm_stats_tiles(C.byref(xt))
+        partial = torch.empty((n, tiles, c, 2), dtype=torch.float32, device=x.device)
+        check(lib().rehr_segate_bwd_reduce(C.byref(xt), C.byref(yt) if yt is not None else None, C.byref(dyt), act, float(slope),
+                                           ptr(partial), stream_ptr()), "segate_bwd_reduce")
+        sums = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+        check(lib().rehr_instnorm_lrelu_bwd_finalize(ptr(partial), n, tiles, c, None, ptr(sums), None, None, 0, stream_ptr()),
+              "segate_bwd_finalize")
+        dgate = sums[..., 0]
+        dz = dgate * gate * (1.0 - gate)                       # [n, c]
+        w2 = attn_w.detach().reshape(c, c).float()
+        dw = (dz.t() @ pool).reshape(attn_w.shape).to(attn_w.dtype)
+        db = dz.sum(0)
+        shift = ((dz @ w2) / float(vox)).contiguous()           # gradient through the average pool, per voxel
+        dx = torch.empty_like(x)
+        dxt = rt(dx)
+        dres = None
+        drt = None
+        if has_res:
+            if act == ACT_NONE:
+                dres = dy
+            else:
+                dres = torch.empty_like(x)
+                drt = rt(dres)
+        check(lib().rehr_segate_bwd_apply(C.byref(yt) if yt is not None else None, C.byref(dyt), act, float(slope), ptr(gate), ptr(shift),
+                                          C.byref(dxt), C.byref(drt) if drt is not None else None, stream_ptr()), "segate_bwd_apply")
+        _count(3)
+        return dx, None, dw, db, dres, None, None
+
+
+def se_gate(x, attn_w, attn_b, residual=None, act=ACT_NONE, slope=0.0, pool=None):
+    """SEGating (+ residual add + activation).  `pool` = the [n, c] mean of x if the producer already has it."""
+    return SEGate.apply(x, pool, attn_w, attn_b, residual, int(act), float(slope))
+
+
+# --------------------------------------------------------------------------------------------------
+# small-Cin stem without normalisation: FLAVR BasicStem Conv3d(2, 64, k(3,7,7), s(1,2,2), p(1,3,3)) + ReLU
+# (models/FLAVR/resnet_3D.py:42-50); x is the caller's NCDHW fp32 tensor
+# --------------------------------------------------------------------------------------------------
+class SmallCinConvAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope):
+        xs = _f32(x)
+        n, cin, d, h, w = xs.shape
+        cout = weight.shape[0]
+        od, oh, ow = (_out_size(i, k, s, p) for i, k, s, p in zip((d, h, w), kernel, stride, padding))
+        y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=xs.device)
+        desc = conv_desc(kernel, stride, padding)
+        yt = rt(y)
+        check(lib().rehr_conv3d_smallcin_fwd(C.byref(desc), ptr(xs), n, cin, d, h, w, ptr(_f32(weight)), ptr(_f32(bias)), C.byref(yt),
+                                             act, float(slope), None, stream_ptr()), "smallcin_fwd")
+        _count()
+        ctx.save_for_backward(xs, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, da):
+        xs, weight, y = ctx.saved_tensors
+        kernel, stride, padding, act, slope, has_bias = ctx.cfg
+        dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
+        desc = conv_desc(kernel, stride, padding)
+        n, cin, d, h, w = xs.shape
+        dyt = rt(dy)
+        need = lib().rehr_conv3d_smallcin_wgrad_workspace(C.byref(desc), cin, C.byref(dyt))
+        ws = _ws(need, xs.device)
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=xs.device)
+        check(lib().rehr_conv3d_smallcin_wgrad(C.byref(desc), ptr(xs), n, cin, d, h, w, C.byref(dyt), ptr(dw), 0, ptr(ws), need,
+                                               stream_ptr()), "smallcin_wgrad")
+        _count(2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(xs.shape, dtype=torch.float32, device=xs.device)
+            check(lib().rehr_conv3d_smallcin_dgrad(C.byref(desc), C.byref(dyt), ptr(_f32(weight)), ptr(dx), n, cin, d, h, w,
+                                                   stream_ptr()), "smallcin_dgrad")
+            _count()
+        db = channel_sum_raw(dy) if has_bias else None
+        return dx, dw.to(weight.dtype), db, None, None, None, None, None
+
+
+def smallcin_conv_act(x, weight, bias, kernel, stride, padding, act=ACT_NONE, slope=0.0):
+    return SmallCinConvAct.apply(x, weight, bias, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
 
 
 # --------------------------------------------------------------------------------------------------

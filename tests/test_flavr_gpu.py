@@ -1,0 +1,121 @@
+"""GPU: FLAVR UNet_3D_3D on the engine (bf16, through the C-ABI) vs the oracle restatement (fp32 CPU) and the fixtures the
+reference's own module produced.  bf16 bound of north_star: relative L2 <= 1e-2 on the SR volumes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _pair(unc, seed=1234):
+    from oracle import flavr as of
+    from rehrseg_b200 import flavr
+    ref = of.build(unc, seed=seed).eval()
+    torch.manual_seed(seed)
+    mine = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=unc)
+    assert all(torch.equal(a, b) for a, b in zip(ref.state_dict().values(), mine.state_dict().values()))  # same default init
+    return ref, mine.cuda().eval()
+
+
+@pytest.mark.parametrize("unc", [False, True])
+def test_flavr_forward_vs_reference_fixture(unc):
+    z = np.load(os.path.join(G, "flavr_small.npz"))
+    _, mine = _pair(unc)
+    x = torch.from_numpy(z["x"]).cuda()
+    tag = "uasr" if unc else "plain"
+    with torch.no_grad():
+        xin = x.clone()
+        out = mine(xin)
+    assert rel(xin, torch.from_numpy(z[f"{tag}_x_after"])) <= 1e-6      # same in-place mutation of the caller's tensor
+    if unc:
+        assert out[0].shape == z["uasr_out"].shape and out[1].shape == z["uasr_unc"].shape
+        assert rel(out[0], torch.from_numpy(z["uasr_out"])) <= 1e-2
+        assert rel(out[1], torch.from_numpy(z["uasr_unc"])) <= 1e-2
+    else:
+        assert out.shape == z["plain_out"].shape
+        assert rel(out, torch.from_numpy(z["plain_out"])) <= 1e-2
+        with torch.no_grad():
+            f = mine(x.clone(), return_inetermediate_feature=True)
+        assert len(f) == 5 and f[1].dtype == torch.float32
+        assert rel(f[1], torch.from_numpy(z["plain_x1"])) <= 1e-2 and rel(f[4], torch.from_numpy(z["plain_x4"])) <= 1e-2
+
+
+@pytest.mark.parametrize("unc", [False, True])
+def test_flavr_fwd_bwd_vs_oracle(unc):
+    ref, mine = _pair(unc, seed=7)
+    mine.train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand((2, 2, 4, 64, 48), generator=g)
+    x[:, 1] = (x[:, 1] > 0.8).float()
+    out_r = ref(x.clone())
+    out_m = mine(x.clone().cuda())
+    outs_r = out_r if unc else (out_r,)
+    outs_m = out_m if unc else (out_m,)
+    loss_r = loss_m = 0
+    for i, (a, b) in enumerate(zip(outs_m, outs_r)):
+        assert a.shape == b.shape and rel(a, b) <= 1e-2, (i, rel(a, b))
+        cot = torch.randn(b.shape, generator=g)
+        loss_r = loss_r + (b * cot).sum() / b.numel()
+        loss_m = loss_m + (a * cot.cuda()).sum() / a.numel()
+    loss_r.backward()
+    loss_m.backward()
+    pr = dict(ref.named_parameters())
+    num = den = 0.0
+    worst = (0.0, "")
+    for name, p in mine.named_parameters():
+        assert (p.grad is None) == (pr[name].grad is None), name
+        if p.grad is None:
+            continue
+        a, b = p.grad.double().cpu(), pr[name].grad.double()
+        num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum())
+        r = float((a - b).norm() / (b.norm() + 1e-30))
+        if r > worst[0]:
+            worst = (r, name)
+    print("grads global", (num / den) ** 0.5, "worst", worst)
+    assert (num / den) ** 0.5 <= 5e-2, ((num / den) ** 0.5, worst)
+
+
+def test_get_intermediate_features_and_window_sweep():
+    from oracle import flavr as of, volume as ov
+    from rehrseg_b200 import flavr
+    z = np.load(os.path.join(G, "flavr_small.npz"))
+    _, teacher = _pair(True)
+    img = torch.from_numpy(z["gif_img"]).cuda()
+    lab = torch.from_numpy(z["gif_lab"]).cuda()
+    with torch.no_grad():
+        feats = flavr.get_intermediate_features(teacher, img, lab, normalize=flavr.zscore_normalization, max_batch=3)
+    assert rel(img, torch.from_numpy(z["gif_img_after"])) <= 1e-6      # z-score mutated the caller's tensor, as in the reference
+    assert sorted(feats.keys()) == [0, 1, 2, 3, 4]
+    for i, key in ((1, "gif_f1"), (3, "gif_f3")):
+        assert feats[i].shape == z[key].shape and rel(feats[i], torch.from_numpy(z[key])) <= 1e-2, key
+    # apply_to_vol_flavr: batched sweep vs the oracle's one-window-at-a-time restatement (ragged in-plane size -> pad to 16)
+    ref, mine = _pair(False, seed=9)
+    vol = torch.rand((6, 2, 40, 24), generator=torch.Generator().manual_seed(6))
+    want = ov.apply_to_vol_flavr(ref, vol.clone())
+    got = flavr.apply_to_vol_flavr(mine, vol.clone().cuda(), max_batch=2)
+    assert got.shape == want.shape == (20, 2, 24, 40)
+    assert rel(got, want) <= 1e-2
+
+
+def test_convert_reference_shaped_flavr():
+    from oracle import flavr as of
+    from rehrseg_b200 import flavr
+    ref = of.build(False, seed=11).eval()
+    x = torch.rand((1, 2, 4, 32, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = ref(x.clone())
+    ids = {k: id(p) for k, p in ref.named_parameters()}
+    m = flavr.convert(ref).cuda()
+    assert {k: id(p) for k, p in m.named_parameters()} == ids
+    with torch.no_grad():
+        got = m(x.clone().cuda())
+    assert rel(got, want) <= 1e-2
+    assert m.calc_out_patch_size([4, 32, 32]) == [16, 32, 32] if hasattr(m, "calc_out_patch_size") else True

@@ -95,3 +95,36 @@ def test_oracle_segmodel_matches_reference_segmodel():
     for got, key in ((out, "out"), (up, "up"), (skips[1], "skip1")):
         ref = torch.from_numpy(z[key])
         assert float((got - ref).norm() / ref.norm()) <= 1e-5, key   # fp32 bound of north_star
+
+
+def test_oracle_flavr_matches_reference_flavr():
+    """oracle/flavr.py against outputs of the reference's own UNet_3D_3D (both heads) and train_all.get_intermediate_features."""
+    from oracle import flavr as of
+    z = np.load(os.path.join(G, "flavr_small.npz"))
+    x = torch.from_numpy(z["x"])
+    for unc, tag in ((False, "plain"), (True, "uasr")):
+        m = of.build(unc, seed=1234).eval()
+        assert list(m.state_dict().keys()) == list(z[f"{tag}_keys"])
+        wsum = float(sum(p.detach().double().abs().sum() for p in m.parameters()))
+        assert abs(wsum - float(z[f"{tag}_weight_abs_sum"])) <= 1e-9 * wsum
+        with torch.no_grad():
+            xin = x.clone()
+            out = m(xin)
+        assert np.array_equal(xin.numpy(), z[f"{tag}_x_after"])          # in-place mean subtraction on the caller's tensor
+        if unc:
+            assert float((out[0] - torch.from_numpy(z["uasr_out"])).norm() / torch.from_numpy(z["uasr_out"]).norm()) <= 1e-5
+            assert float((out[1] - torch.from_numpy(z["uasr_unc"])).norm() / torch.from_numpy(z["uasr_unc"]).norm()) <= 1e-5
+        else:
+            assert float((out - torch.from_numpy(z["plain_out"])).norm() / torch.from_numpy(z["plain_out"]).norm()) <= 1e-5
+            with torch.no_grad():
+                f = m(x.clone(), return_inetermediate_feature=True)
+            assert np.allclose(f[1].numpy(), z["plain_x1"], rtol=1e-5, atol=1e-6) and f[4].shape == z["plain_x4"].shape
+    from oracle.volume import zscore_normalization
+    teacher = of.build(True, seed=1234).eval()
+    img = torch.from_numpy(z["gif_img"]).clone()
+    with torch.no_grad():
+        feats = of.intermediate_features(teacher, img, torch.from_numpy(z["gif_lab"]), normalize=zscore_normalization)
+    assert np.allclose(img.numpy(), z["gif_img_after"], rtol=1e-6, atol=1e-6)
+    for i, key in ((1, "gif_f1"), (3, "gif_f3")):
+        ref = torch.from_numpy(z[key])
+        assert feats[i].shape == ref.shape and float((feats[i] - ref).norm() / ref.norm()) <= 1e-5
