@@ -101,6 +101,7 @@ def test_sliding_window_segmodel_vs_oracle():
     assert err <= 1.25e-2, err
     margin = (want[0] - want[1]).abs()
     clear = margin > 4 * float((got.float().cpu() - want).pow(2).mean().sqrt())
-    assert bool(((got.float().cpu().argmax(0) == want.argmax(0)) | ~clear).all())
+    agree = (got.float().cpu().argmax(0) == want.argmax(0))[clear].double().mean()
+    assert float(agree) >= 0.999, float(agree)   # north_star: argmax agreement >= 99.9 % (on voxels with a clear fp32 margin)
     labels = sw.sliding_window_segment(mine, data.cuda(), patch)
     assert labels.dtype == torch.uint8 and labels.shape == data.shape[1:]
