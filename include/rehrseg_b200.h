@@ -57,7 +57,7 @@ typedef enum { REHR_ACT_NONE = 0, REHR_ACT_RELU = 1, REHR_ACT_LRELU = 2 } rehr_a
 
 const char* rehr_strerror(int status);
 int rehr_last_cuda_error(void);     /* cudaError_t of the last failing CUDA call on this thread */
-int rehr_version(void);             /* ABI version, currently 1 */
+int rehr_version(void);             /* ABI version, currently 2 */
 int rehr_device_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -111,19 +111,20 @@ size_t rehr_convtranspose3d_wgrad_workspace(const rehr_conv_desc* desc, const re
 int rehr_convtranspose3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy, float* dw,
                                int accumulate, void* ws, size_t ws_bytes, rehr_stream stream);
 
-/* "Marching" kernel for k=(3,3,3), stride 1, pad 1 layers with few channels (Cin in {16,32,48,64,128,...}, Cout % 16 == 0):
- * the halo'd input plane is TMA-loaded ONCE into a shared-memory ring and the 27 taps become UMMA descriptor offsets /
- * a kd-fused N = 3*Ct MMA (see csrc/conv_march.cu).  Same call sites as rehr_conv3d_fwd; it needs its own packed weights.
- *   rehr_pack_weight_march: dst bf16 (rehr_conv3d_march_weight_bytes) from fp32 src[co*s_co + ci*s_ci + t]:
- *     forward of W[Cout][Cin][27]: cout, cin, s_co = Cin*27, s_ci = 27, flip = 0
- *     input-gradient dx[B] <- dy[A] of W[A][B][27]: cout := B, cin := A, s_co = 27, s_ci = B*27, flip = 1
+/* "Marching" kernel for cubic kernels ks = 3 or 5, stride 1, pad (ks-1)/2, with few input channels (Cin in {16,32,64,128}
+ * for ks = 3, Cin = 16 for ks = 5; any Cout): the halo'd input plane is TMA-loaded ONCE into a shared-memory ring and the
+ * ks^3 taps become UMMA descriptor offsets / a kd-fused N = ks*Ct MMA (see csrc/conv_march.cu).  Same call sites as
+ * rehr_conv3d_fwd (and sr_head.2, the 5x5x5 16->2 conv of models/seg_model.py:199); it needs its own packed weights.
+ *   rehr_pack_weight_march: dst bf16 (rehr_conv3d_march_weight_bytes) from fp32 src[co*s_co + ci*s_ci + t], T = ks^3:
+ *     forward of W[Cout][Cin][T]: cout, cin, s_co = Cin*T, s_ci = T, flip = 0
+ *     input-gradient dx[B] <- dy[A] of W[A][B][T]: cout := B, cin := A, s_co = T, s_ci = B*T, flip = 1
  *   rehr_conv3d_march_fwd: y = act(conv(x) + bias); stats (optional) = f32 [n][rehr_conv3d_march_stats_tiles][cout][2]. */
 int rehr_conv3d_march_supported(const rehr_conv_desc* desc, int cin, int cout);
-size_t rehr_conv3d_march_weight_bytes(int cin, int cout);
-int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, long long s_co, long long s_ci, int flip,
+size_t rehr_conv3d_march_weight_bytes(int cin, int cout, int ks);
+int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
                            rehr_stream stream);
-int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y);
-int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int y_is_f32,
+int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y, int ks);
+int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int ks, int y_is_f32,
                           int act, float slope, float* stats, rehr_stream stream);
 
 /* Marching weight-gradient kernel for k=(3,3,3), stride 1, pad 1 (csrc/wgrad_march.cu): both activations are TMA-loaded once

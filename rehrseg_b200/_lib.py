@@ -78,10 +78,10 @@ def _declare(L: C.CDLL) -> None:
         "rehr_convtranspose3d_wgrad_workspace": (sz, [D, T, T]),
         "rehr_convtranspose3d_wgrad": (i, [D, T, T, vp, i, vp, sz, vp]),
         "rehr_conv3d_march_supported": (i, [D, i, i]),
-        "rehr_conv3d_march_weight_bytes": (sz, [i, i]),
-        "rehr_pack_weight_march": (i, [vp, vp, i, i, ll, ll, i, vp]),
-        "rehr_conv3d_march_stats_tiles": (i, [T, T]),
-        "rehr_conv3d_march_fwd": (i, [T, vp, vp, T, i, i, f, vp, vp]),
+        "rehr_conv3d_march_weight_bytes": (sz, [i, i, i]),
+        "rehr_pack_weight_march": (i, [vp, vp, i, i, i, ll, ll, i, vp]),
+        "rehr_conv3d_march_stats_tiles": (i, [T, T, i]),
+        "rehr_conv3d_march_fwd": (i, [T, vp, vp, T, i, i, i, f, vp, vp]),
         "rehr_conv3d_wgrad_march_supported": (i, [D, T, T]),
         "rehr_conv3d_wgrad_march_workspace": (sz, [T, T]),
         "rehr_conv3d_wgrad_march": (i, [T, T, vp, i, vp, sz, vp]),

@@ -36,7 +36,12 @@ int encode_tiled_bf16(CUtensorMap* m, const void* base, int rank, const unsigned
 
 static constexpr int kMarchThreads = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
 static constexpr int kTileH = 16, kTileW = 8;
-static constexpr int kHaloH = kTileH + 2, kHaloW = kTileW + 2, kHaloRows = kHaloH * kHaloW;  // 18 x 10 = 180
+// kernel size KS (3 or 5, cubic, stride 1, pad (KS-1)/2): halo'd input tile of (16 + KS - 1) x (8 + KS - 1) voxels
+template <int KS>
+struct MarchGeo {
+  static constexpr int R = (KS - 1) / 2;
+  static constexpr int kHaloH = kTileH + KS - 1, kHaloW = kTileW + KS - 1, kHaloRows = kHaloH * kHaloW;  // k3: 18 x 10 = 180
+};
 static constexpr int kMaxRing = 8;
 static constexpr int kMaxSlots = 16;
 
@@ -44,6 +49,7 @@ struct alignas(64) MarchParams {
   CUtensorMap x_map;  // 5-D NDHWC, box (BK, 10, 18, 1, 1)
   CUtensorMap w_map;  // 2-D [n_ct*9*chunks*3Ct rows][BK], box (BK, 3Ct)
   int N, D, H, W, Cin, Cout;
+  int ks;  // 3 or 5
   int Ct, n_ct, BK, chunks;
   int tiles_h, tiles_w, Ds, n_seg;
   int ring, slots;
@@ -94,8 +100,10 @@ __device__ __forceinline__ bool elect_one_sync() {
 // the MMA issue sequence of one input plane (9 * CHUNKS * BKT/16 instructions) is fully unrolled with constant
 // descriptor increments: a single thread must issue one tcgen05.mma every ~50 clk (tools/umma_rate2.cu measures
 // 40 clk/MMA for this code shape vs 120-280 clk/MMA with run-time descriptor arithmetic).
-template <int BKT, int CHUNKS, int CT>
+template <int BKT, int CHUNKS, int CT, int KS>
 __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __grid_constant__ MarchParams p) {
+  constexpr int R = MarchGeo<KS>::R;
+  constexpr int kHaloW = MarchGeo<KS>::kHaloW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;                                   // resident weights
@@ -154,13 +162,13 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           }
           cur_ct = c.ct;
           mbar_arrive_expect_tx(wfull_bar, p.w_bytes);
-          const int tiles = 9 * p.chunks;
+          const int tiles = KS * KS * p.chunks;
           for (int t = 0; t < tiles; ++t)
-            tma_load_2d(&p.w_map, wfull_bar, s_w + (size_t)t * p.wtile_bytes, 0, (c.ct * tiles + t) * 3 * p.Ct);
+            tma_load_2d(&p.w_map, wfull_bar, s_w + (size_t)t * p.wtile_bytes, 0, (c.ct * tiles + t) * KS * p.Ct);
         }
         const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
-        const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
-        const int h0 = c.th * kTileH - 1, w0 = c.tw * kTileW - 1;
+        const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
+        const int h0 = c.th * kTileH - R, w0 = c.tw * kTileW - R;
         for (int pl = pa; pl <= pb; ++pl) {
           const long long tp0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 22);
@@ -205,10 +213,10 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         tc_fence_after();
       }
       const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
-      const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
+      const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
       int next_open = d0;
       for (int pl = pa; pl <= pb; ++pl) {
-        const int qa = max(pl - 1, d0), qb = min(pl + 1, d1 - 1);
+        const int qa = max(pl - R, d0), qb = min(pl + R, d1 - 1);
         const long long tm0 = clock64();
         while (next_open <= qb) {  // first touch of an output plane's TMEM slot: wait until it was drained + zeroed
           const int s = (next_open - d0) & kSlotMask;
@@ -227,14 +235,14 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           int rb = ra;
           while (rb < qb && ((rb + 1 - d0) & kSlotMask) != 0) ++rb;
           const uint32_t idesc = make_idesc_bf16(128, (rb - ra + 1) * CT, 0, 0);
-          const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + 1) * CT) * kRowB) >> 4);
+          const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + R) * CT) * kRowB) >> 4);
           const uint32_t d_tmem = tmem_base + (uint32_t)(((ra - d0) & kSlotMask) * CT);
           if (!(p.debug & 4) && elect_one_sync()) {
 #pragma unroll
-            for (int khw = 0; khw < 9; ++khw) {
+            for (int khw = 0; khw < KS * KS; ++khw) {
 #pragma unroll
               for (int ch = 0; ch < CHUNKS; ++ch) {
-                const uint32_t a_t = a_lo + (uint32_t)((((khw / 3) * kHaloW + (khw % 3)) * kRowB) >> 4) + (uint32_t)ch * chunk_lo;
+                const uint32_t a_t = a_lo + (uint32_t)((((khw / KS) * kHaloW + (khw % KS)) * kRowB) >> 4) + (uint32_t)ch * chunk_lo;
                 const uint32_t b_t = b_lo + (uint32_t)(khw * CHUNKS + ch) * wtile_lo;
 #pragma unroll
                 for (int k = 0; k < kSteps; ++k) {
@@ -251,9 +259,9 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         if (elect_one_sync()) {
           umma_commit(&empty_bar[stage]);
           // finished output planes
-          if (pl - 1 >= d0) umma_commit(&tfull_bar[(pl - 1 - d0) & kSlotMask]);
+          if (pl - R >= d0) umma_commit(&tfull_bar[(pl - R - d0) & kSlotMask]);
           if (pl == pb) {
-            for (int q = max(pl, d0); q <= d1 - 1; ++q) umma_commit(&tfull_bar[(q - d0) & kSlotMask]);
+            for (int q = max(pl - R + 1, d0); q <= d1 - 1; ++q) umma_commit(&tfull_bar[(q - d0) & kSlotMask]);
           }
         }
         __syncwarp();
@@ -322,11 +330,18 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           float f[kW];
 #pragma unroll
           for (int i = 0; i < kW; ++i) f[i] = __uint_as_float(v[i]);
+          const int nvalid = p.Cout - (cbase + c0);  // channels of this group that exist (Cout need not fill the tile)
           if (p.bias != nullptr) {
+            if (nvalid >= kW) {
 #pragma unroll
-            for (int i = 0; i < kW; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + c0 + i));
-              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              for (int i = 0; i < kW; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + c0 + i));
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < kW; ++i)
+                if (i < nvalid) f[i] += __ldg(p.bias + cbase + c0 + i);
             }
           }
           if (p.stats != nullptr && valid) {
@@ -340,7 +355,19 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < kW; ++i) f[i] = march_act(f[i], p.act, p.slope);
             const int cc = cbase + c0;
-            if (p.out_f32) {
+            if (nvalid < kW) {
+              if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cc;
+#pragma unroll
+                for (int i = 0; i < kW; ++i)
+                  if (i < nvalid) o[i] = f[i];
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cc;
+#pragma unroll
+                for (int i = 0; i < kW; ++i)
+                  if (i < nvalid) o[i] = __float2bfloat16(f[i]);
+              }
+            } else if (p.out_f32) {
               float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cc;
               if ((p.out_ld & 3) == 0) {
 #pragma unroll
@@ -400,7 +427,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           }
         }
         named_bar_sync(1, 128);
-        if (et < CT) {
+        if (et < CT && cbase + et < p.Cout) {
           float a = 0.f, b = 0.f;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -431,12 +458,20 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 static const size_t kMarchWeightBudget = 112 * 1024;
 
-int march_ct(int cin, int cout) {
-  if (cin % 16 != 0 || cout % 16 != 0) return 0;
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+// output-channel tile for a (cin, cout, ks) layer; 0 = not supported by the marching kernel
+int march_ct(int cin, int cout, int ks) {
+  if (ks != 3 && ks != 5) return 0;
+  if (cin % 16 != 0 || cout <= 0) return 0;
   if (cin != 16 && cin != 32 && cin != 64 && cin != 128) return 0;  // instantiated (BK, chunks) variants
+  if (ks == 5 && cin != 16) return 0;                               // instantiated k5 variant: sr_head.2 (models/seg_model.py:199)
+  const int cp = pad16(cout);
   for (int ct : {64, 32, 16}) {
-    if (cout % ct != 0) continue;
-    if ((size_t)27 * cin * ct * 2 <= kMarchWeightBudget) return ct;
+    if (cp % ct != 0) continue;
+    if (ks * ct > 256) continue;  // kd-fused N and the weight TMA box are limited to 256 rows
+    if (ks == 5 && ct != 16) continue;
+    if ((size_t)ks * ks * ks * cin * ct * 2 <= kMarchWeightBudget) return ct;
   }
   return 0;
 }
@@ -449,26 +484,28 @@ struct MarchPlan {
 
 static size_t march_tail_bytes() { return (2 * kMaxRing + 2 * kMaxSlots + 2) * 8 + 16 + 4 * 2 * 64 * 4; }
 
-static int plan_march(const rehr_tensor& x, const rehr_tensor& y, MarchPlan* out, int ds_override) {
+static int plan_march(const rehr_tensor& x, const rehr_tensor& y, int ks, MarchPlan* out, int ds_override) {
   MarchParams& p = out->p;
   memset(&p, 0, sizeof(p));
-  const int ct = march_ct(x.c, y.c);
+  const int ct = march_ct(x.c, y.c, ks);
   if (ct == 0) return REHR_UNSUPPORTED;
   if (x.n != y.n || x.d != y.d || x.h != y.h || x.w != y.w) return REHR_BAD_SHAPE;
   p.N = x.n; p.D = x.d; p.H = x.h; p.W = x.w; p.Cin = x.c; p.Cout = y.c;
+  p.ks = ks;
   p.Ct = ct;
-  p.n_ct = y.c / ct;
+  p.n_ct = pad16(y.c) / ct;
   p.BK = std::min(x.c, 64);
   p.chunks = x.c / p.BK;
   p.tiles_h = (p.H + kTileH - 1) / kTileH;
   p.tiles_w = (p.W + kTileW - 1) / kTileW;
   p.slots = std::min(kMaxSlots, 512 / ct);
   const uint32_t rowb = p.BK * 2;
-  p.wtile_bytes = 3 * ct * rowb;
-  p.w_bytes = 9 * p.chunks * p.wtile_bytes;
-  p.chunk_stride = (kHaloRows * rowb + 1023u) & ~1023u;
+  const int halo_rows = (kTileH + ks - 1) * (kTileW + ks - 1);
+  p.wtile_bytes = ks * ct * rowb;
+  p.w_bytes = ks * ks * p.chunks * p.wtile_bytes;
+  p.chunk_stride = (halo_rows * rowb + 1023u) & ~1023u;
   p.slot_stride = p.chunks * p.chunk_stride;
-  p.plane_bytes = p.chunks * kHaloRows * rowb;
+  p.plane_bytes = p.chunks * halo_rows * rowb;
   const size_t fixed = 1024 + ((p.w_bytes + 1023u) & ~1023u) + march_tail_bytes();
   const size_t budget = 227 * 1024;
   if (fixed + 2 * (size_t)p.slot_stride > budget) return REHR_UNSUPPORTED;
@@ -488,18 +525,18 @@ static int plan_march(const rehr_tensor& x, const rehr_tensor& y, MarchPlan* out
   return REHR_OK;
 }
 
-int march_stats_tiles(const rehr_tensor& x, const rehr_tensor& y) {
+int march_stats_tiles(const rehr_tensor& x, const rehr_tensor& y, int ks) {
   MarchPlan pl;
-  if (plan_march(x, y, &pl, 0) != REHR_OK) return 0;
+  if (plan_march(x, y, ks, &pl, 0) != REHR_OK) return 0;
   return pl.p.n_seg * pl.p.tiles_h * pl.p.tiles_w;
 }
 
 static int dispatch_march(const MarchPlan& pl, cudaStream_t stream);
 
-int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int y_is_f32, int act,
+int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int ks, int y_is_f32, int act,
                  float slope, float* stats, cudaStream_t stream) {
   MarchPlan pl;
-  int rc = plan_march(x, y, &pl, 0);
+  int rc = plan_march(x, y, ks, &pl, 0);
   if (rc != REHR_OK) return rc;
   MarchParams& p = pl.p;
   if (x.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
@@ -530,38 +567,42 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
                                         (unsigned long long)x.d, (unsigned long long)x.n};
     const unsigned long long pitch = (unsigned long long)x.ld * 2;
     const unsigned long long gstr[4] = {pitch, pitch * x.w, pitch * x.w * x.h, pitch * x.w * x.h * x.d};
-    const unsigned box[5] = {(unsigned)p.BK, (unsigned)kHaloW, (unsigned)kHaloH, 1u, 1u};
+    const unsigned box[5] = {(unsigned)p.BK, (unsigned)(kTileW + ks - 1), (unsigned)(kTileH + ks - 1), 1u, 1u};
     rc = encode_tiled_bf16(&p.x_map, x.ptr, 5, gdim, gstr, box, p.BK * 2);
     if (rc != REHR_OK) return rc;
   }
   {
-    const unsigned long long rows = (unsigned long long)p.n_ct * 9 * p.chunks * 3 * p.Ct;
+    const unsigned long long rows = (unsigned long long)p.n_ct * ks * ks * p.chunks * ks * p.Ct;
     const unsigned long long gdim[2] = {(unsigned long long)p.BK, rows};
     const unsigned long long gstr[1] = {(unsigned long long)p.BK * 2};
-    const unsigned box[2] = {(unsigned)p.BK, (unsigned)(3 * p.Ct)};
+    const unsigned box[2] = {(unsigned)p.BK, (unsigned)(ks * p.Ct)};
     rc = encode_tiled_bf16(&p.w_map, w_march, 2, gdim, gstr, box, p.BK * 2);
     if (rc != REHR_OK) return rc;
   }
   return dispatch_march(pl, stream);
 }
 
-template <int BKT, int CHUNKS, int CT>
+template <int BKT, int CHUNKS, int CT, int KS>
 static int launch_variant(const MarchPlan& pl, cudaStream_t stream) {
-  static cudaError_t attr_err = cudaFuncSetAttribute(conv_march_kernel<BKT, CHUNKS, CT>,
+  static cudaError_t attr_err = cudaFuncSetAttribute(conv_march_kernel<BKT, CHUNKS, CT, KS>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_err != cudaSuccess) {
     g_last_cuda_error = (int)attr_err;
     return REHR_CUDA_ERROR;
   }
-  conv_march_kernel<BKT, CHUNKS, CT><<<pl.grid, kMarchThreads, pl.smem, stream>>>(pl.p);
+  conv_march_kernel<BKT, CHUNKS, CT, KS><<<pl.grid, kMarchThreads, pl.smem, stream>>>(pl.p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
 
 static int dispatch_march(const MarchPlan& pl, cudaStream_t stream) {
-  const int bk = pl.p.BK, ch = pl.p.chunks, ct = pl.p.Ct;
+  const int bk = pl.p.BK, ch = pl.p.chunks, ct = pl.p.Ct, ks = pl.p.ks;
+  if (ks == 5) {
+    if (bk == 16 && ch == 1 && ct == 16) return launch_variant<16, 1, 16, 5>(pl, stream);
+    return REHR_UNSUPPORTED;
+  }
 #define REHR_MARCH_CASE(B, C, T) \
-  if (bk == B && ch == C && ct == T) return launch_variant<B, C, T>(pl, stream);
+  if (bk == B && ch == C && ct == T) return launch_variant<B, C, T, 3>(pl, stream);
   REHR_MARCH_CASE(16, 1, 16)
   REHR_MARCH_CASE(16, 1, 32)
   REHR_MARCH_CASE(16, 1, 64)
@@ -576,30 +617,31 @@ static int dispatch_march(const MarchPlan& pl, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight packing for the marching kernel:
-//   dst[ct][khw][chunk][j*Ct + col][BK]   with  j = 2 - kd,  co = ct*Ct + col,  ci = chunk*BK + k
-//   src element = w[co*s_co + ci*s_ci + (flip ? 26 - t : t)],  t = (kd*3 + kh)*3 + kw
-// forward of W[Cout][Cin][27]: s_co = Cin*27, s_ci = 27, flip = 0;
-// input-gradient (dx[B] from dy[A]) of W[A][B][27]: cout := B, cin := A, s_co = 27, s_ci = B*27, flip = 1.
+// Weight packing for the marching kernel (T = KS^3 taps):
+//   dst[ct][khw][chunk][j*Ct + col][BK]   with  j = KS-1 - kd,  co = ct*Ct + col (zero rows for co >= cout),  ci = chunk*BK + k
+//   src element = w[co*s_co + ci*s_ci + (flip ? T-1 - t : t)],  t = (kd*KS + kh)*KS + kw
+// forward of W[Cout][Cin][T]: s_co = Cin*T, s_ci = T, flip = 0;
+// input-gradient (dx[B] from dy[A]) of W[A][B][T]: cout := B, cin := A, s_co = T, s_ci = B*T, flip = 1.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int cout, int cin, int Ct, int BK,
-                                  long long s_co, long long s_ci, int flip) {
+__global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int cout, int cout_pad, int cin,
+                                  int Ct, int BK, int ks, long long s_co, long long s_ci, int flip) {
   const int chunks = cin / BK;
-  const long long total = (long long)cout * cin * 27;
+  const int T = ks * ks * ks;
+  const long long total = (long long)cout_pad * cin * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % BK);
     long long r = i / BK;
-    const int rowi = (int)(r % (3 * Ct));
-    r /= 3 * Ct;
+    const int rowi = (int)(r % (ks * Ct));
+    r /= ks * Ct;
     const int chunk = (int)(r % chunks);
     r /= chunks;
-    const int khw = (int)(r % 9);
-    const int ct = (int)(r / 9);
+    const int khw = (int)(r % (ks * ks));
+    const int ct = (int)(r / (ks * ks));
     const int j = rowi / Ct, col = rowi % Ct;
-    const int kd = 2 - j, kh = khw / 3, kw = khw % 3;
-    const int t = (kd * 3 + kh) * 3 + kw;
+    const int kd = ks - 1 - j, kh = khw / ks, kw = khw % ks;
+    const int t = (kd * ks + kh) * ks + kw;
     const int co = ct * Ct + col, ci = chunk * BK + k;
-    dst[i] = __float2bfloat16(src[co * s_co + ci * s_ci + (flip ? 26 - t : t)]);
+    dst[i] = co < cout ? __float2bfloat16(src[co * s_co + ci * s_ci + (flip ? T - 1 - t : t)]) : __float2bfloat16(0.f);
   }
 }
 
@@ -607,41 +649,49 @@ __global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* 
 
 using namespace rehr;
 
+static int march_ks_of(const rehr_conv_desc* d) {
+  if (!d) return 0;
+  if (d->kd != d->kh || d->kh != d->kw || (d->kd != 3 && d->kd != 5)) return 0;
+  if (d->sd != 1 || d->sh != 1 || d->sw != 1) return 0;
+  const int r = (d->kd - 1) / 2;
+  if (d->pd != r || d->ph != r || d->pw != r) return 0;
+  return d->kd;
+}
+
 extern "C" {
 
 int rehr_conv3d_march_supported(const rehr_conv_desc* d, int cin, int cout) {
-  if (!d) return 0;
-  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd != 1 || d->ph != 1 || d->pw != 1)
-    return 0;
-  return march_ct(cin, cout) > 0 ? 1 : 0;
+  const int ks = march_ks_of(d);
+  if (ks == 0) return 0;
+  return march_ct(cin, cout, ks) > 0 ? 1 : 0;
 }
 
-size_t rehr_conv3d_march_weight_bytes(int cin, int cout) {
-  return march_ct(cin, cout) > 0 ? (size_t)27 * cin * cout * 2 : 0;
+size_t rehr_conv3d_march_weight_bytes(int cin, int cout, int ks) {
+  return march_ct(cin, cout, ks) > 0 ? (size_t)ks * ks * ks * cin * pad16(cout) * 2 : 0;
 }
 
-int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, long long s_co, long long s_ci, int flip,
+int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
                            rehr_stream stream) {
   if (!src || !dst_bf16) return REHR_BAD_SHAPE;
-  const int ct = march_ct(cin, cout);
+  const int ct = march_ct(cin, cout, ks);
   if (ct == 0) return REHR_UNSUPPORTED;
-  const long long total = (long long)cout * cin * 27;
+  const long long total = (long long)pad16(cout) * cin * ks * ks * ks;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  pack_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, cin, ct,
-                                                             std::min(cin, 64), s_co, s_ci, flip);
+  pack_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, pad16(cout), cin, ct,
+                                                             std::min(cin, 64), ks, s_co, s_ci, flip);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
 
-int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y) {
+int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y, int ks) {
   if (!x || !y) return 0;
-  return march_stats_tiles(*x, *y);
+  return march_stats_tiles(*x, *y, ks);
 }
 
-int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int y_is_f32,
+int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int ks, int y_is_f32,
                           int act, float slope, float* stats, rehr_stream stream) {
   if (!x || !y || !x->ptr || !y->ptr || !w_march) return REHR_BAD_SHAPE;
-  return launch_march(*x, w_march, bias, *y, y_is_f32, act, slope, stats, (cudaStream_t)stream);
+  return launch_march(*x, w_march, bias, *y, ks, y_is_f32, act, slope, stats, (cudaStream_t)stream);
 }
 
 }  // extern "C"

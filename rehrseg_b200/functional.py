@@ -113,11 +113,13 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor
     if w.dtype != torch.float32:
         w = w.float()
     if kind == "march_fwd":      # conv A<-B, marching-kernel layout
-        out = torch.empty((A * B * T,), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), A, B, B * T, T, 0, stream_ptr()), "pack_weight_march")
+        ks = int(weight.shape[2])
+        out = torch.empty((lib().rehr_conv3d_march_weight_bytes(B, A, ks) // 2,), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), A, B, ks, B * T, T, 0, stream_ptr()), "pack_weight_march")
     elif kind == "march_dgrad":  # its input-gradient B<-A (transposed, taps flipped)
-        out = torch.empty((A * B * T,), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, T, B * T, 1, stream_ptr()), "pack_weight_march")
+        ks = int(weight.shape[2])
+        out = torch.empty((lib().rehr_conv3d_march_weight_bytes(A, B, ks) // 2,), dtype=torch.bfloat16, device=w.device)
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, ks, T, B * T, 1, stream_ptr()), "pack_weight_march")
     elif kind == "tconv_fused":  # ConvTranspose weight [Cin=A][Cout=B][T] -> [T][Cout][Cin]
         out = torch.empty((T, B, A), dtype=torch.bfloat16, device=w.device)
         check(lib().rehr_pack_weight(ptr(w), ptr(out), T, A, B, 1, B * T, T, stream_ptr()), "pack_weight")
@@ -189,11 +191,11 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), cin, cout):
         xt = rt(x)
         if want_stats:
-            tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt))
+            tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt), int(kernel[0]))
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
         wp = _packed(weight, "march_fwd")
         with _timed("conv_march_kernel", flops, tag):
-            check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
+            check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(kernel[0]), int(out_f32), act,
                                               float(slope), ptr(stats), stream_ptr()), "conv3d_march_fwd")
         _count()
         return out, stats, tiles
@@ -233,7 +235,7 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
         wp = _packed(weight, "march_dgrad", cache)
         dyt, dxt = rt(dy), rt(dx)
         with _timed("conv_march_kernel", flops, tag):
-            check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0, None,
+            check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), int(kernel[0]), 0, ACT_NONE, 0.0, None,
                                               stream_ptr()), "conv3d_march_dgrad")
         _count()
         return dx

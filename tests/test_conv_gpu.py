@@ -58,6 +58,11 @@ FWD_CASES = [
     (1, 64, 128, (5, 20, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 16, 16, (3, 5, 5), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 32, 16, (1, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    # 5x5x5 marching variant (sr_head.2, models/seg_model.py:199) and output-channel counts that do not fill a tile
+    (1, 16, 16, (9, 20, 12), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
+    (2, 16, 2, (24, 16, 8), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
+    (1, 32, 2, (6, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 16, 40, (5, 9, 9), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
 ]
 
 
