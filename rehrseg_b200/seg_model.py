@@ -195,16 +195,34 @@ class LazyNCDHW(Sequence):
         return self._cl[i]
 
 
-def segmodel_forward(model: nn.Module, x: torch.Tensor, return_inetermediate_feature: bool = False):
-    """SegModel.forward (models/seg_model.py:201-210); the kwarg spelling is the reference's."""
+def segmodel_forward(model: nn.Module, x: torch.Tensor, return_inetermediate_feature: bool = False, want_hr: bool = True):
+    """SegModel.forward (models/seg_model.py:201-210); the kwarg spelling is the reference's.  `want_hr=False` (not in the
+    reference, whose forward has no switch) skips the x`upscale` SR head and returns None in its place: the LR logits do
+    not depend on it, and the sliding-window evaluation only reads output 0 (utils/seg_utils.py:753)."""
     if not x.is_cuda:
         raise RehrError("rehrseg_b200 runs on CUDA (sm_100a) only; there is no CPU path")
     skips = encoder_forward(model.encoder, x)
     out, features = decoder_forward(model.decoder, skips)
-    out_up = sr_head_forward(model.sr_head, features, model.upscale)
+    out_up = sr_head_forward(model.sr_head, features, model.upscale) if want_hr else None
     if return_inetermediate_feature:
         return out, out_up, LazyNCDHW(skips)
     return out, out_up
+
+
+class LRHeadOnly(nn.Module):
+    """View of a SegModel whose forward skips the SR head: returns (out, None).  Used by the sliding-window driver when only
+    output 0 is consumed."""
+
+    def __init__(self, model: nn.Module):
+        super().__init__()
+        self.model = model
+
+    @property
+    def decoder(self):
+        return self.model.decoder
+
+    def forward(self, x):
+        return segmodel_forward(self.model, x, want_hr=False)
 
 
 class _EngineForward:

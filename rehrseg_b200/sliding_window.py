@@ -175,9 +175,12 @@ INF_MESSAGE = ('Encountered inf in predicted array. Aborting... If this problem 
 def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, network, do_on_device=True, out_idx=None,
                                                    slice_seperation=1, patch_size=[14, 320, 384], use_gaussian=False,
                                                    deep_supervision=True, accum_dtype: Optional[torch.dtype] = torch.float16,
-                                                   tile_filter: Optional[Callable[[int], bool]] = None, finalize: bool = True):
+                                                   tile_filter: Optional[Callable[[int], bool]] = None, finalize: bool = True,
+                                                   cuda_graph: bool = True):
     """utils/seg_utils.py:240-287.  `data` [C_in, X, Y, Z]; returns fp16 logits [2, X*slice_seperation, Y, Z].
-    `tile_filter(i)` / `finalize=False` are the hooks the sharded driver uses (returns (logits, n_predictions) then)."""
+    `tile_filter(i)` / `finalize=False` are the hooks the sharded driver uses (returns (logits, n_predictions) then).
+    `cuda_graph`: when gradients are off and `network` is an nn.Module, its tile forward is captured once in a CUDA graph
+    and replayed for the 8 x n_tiles identically shaped calls (rehrseg_b200/graphs.py)."""
     if not do_on_device:
         raise RehrError("rehrseg_b200 blends on the GPU only (do_on_device=True); there is no CPU path")
     dev = data.device if data.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -185,6 +188,13 @@ def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, 
     predicted_logits = torch.zeros((2, data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
     n_predictions = torch.zeros((data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
     gaussian = compute_gaussian(tuple(patch_size), sigma_scale=1. / 8, value_scaling_factor=10, device=dev) if use_gaussian else 1
+    if out_idx == 0 and isinstance(network, torch.nn.Module) and hasattr(network, "sr_head") and hasattr(network, "upscale"):
+        from .seg_model import LRHeadOnly, _EngineForward, SegModel
+        if isinstance(network, (SegModel, _EngineForward)):
+            network = LRHeadOnly(network)   # output 1 (the x`upscale` SR head) is never read on this path: do not compute it
+    if cuda_graph and len(slicers) > 0 and isinstance(network, torch.nn.Module) and not torch.is_grad_enabled():
+        from .graphs import GraphedForward
+        network = GraphedForward(network, data[slicers[0]][None])
     for i, sl in enumerate(slicers):
         if tile_filter is not None and not tile_filter(i):
             continue

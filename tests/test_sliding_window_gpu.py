@@ -105,3 +105,20 @@ def test_sliding_window_segmodel_vs_oracle():
     assert float(agree) >= 0.999, float(agree)   # north_star: argmax agreement >= 99.9 % (on voxels with a clear fp32 margin)
     labels = sw.sliding_window_segment(mine, data.cuda(), patch)
     assert labels.dtype == torch.uint8 and labels.shape == data.shape[1:]
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """The captured-and-replayed tile forward must give exactly the logits of the eager launches."""
+    from rehrseg_b200 import seg_model as sm, sliding_window as sw
+    from oracle import seg_model as ref_seg
+    torch.manual_seed(3)
+    mine = sm.SegModel(**ref_seg.plan_kwargs("tiny")).cuda().eval()
+    data = torch.randn((1, 24, 40, 32), generator=torch.Generator().manual_seed(5)).cuda()
+    patch = [16, 32, 32]
+    sl = sw._internal_get_sliding_window_slicers(data.shape[1:], patch)
+    with torch.no_grad():
+        a = sw._internal_predict_sliding_window_return_logits(data, sl, mine, True, 0, 1, patch, use_gaussian=True, deep_supervision=False,
+                                                              cuda_graph=False)
+        b = sw._internal_predict_sliding_window_return_logits(data, sl, mine, True, 0, 1, patch, use_gaussian=True, deep_supervision=False,
+                                                              cuda_graph=True)
+    assert torch.equal(a, b)
