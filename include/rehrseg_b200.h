@@ -127,12 +127,14 @@ int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y, in
 int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int ks, int y_is_f32,
                           int act, float slope, float* stats, rehr_stream stream);
 
-/* Marching weight-gradient kernel for k=(3,3,3), stride 1, pad 1 (csrc/wgrad_march.cu): both activations are TMA-loaded once
- * per plane, the 27 taps are UMMA descriptor offsets / a kd-fused N = 96 MMA, accumulators live in TMEM for the whole CTA.
- * Same call site as rehr_conv3d_wgrad (dW f32 [Cout][Cin][3][3][3]); needs cin, cout multiples of 32. */
+/* Marching weight-gradient kernel for cubic kernels ks = 3 or 5, stride 1, pad (ks-1)/2 (csrc/wgrad_march.cu): both
+ * activations are TMA-loaded once per plane, the ks^3 taps are UMMA descriptor offsets / a kd-fused N = ks*PC MMA,
+ * accumulators live in TMEM for the whole CTA.  Same call site as rehr_conv3d_wgrad.  dw = f32 [cout][x->c][ks^3] with
+ * cout <= dy->c (dy may be zero-padded to a multiple of 16 channels).  ks = 3: channel counts multiples of 32 on one side
+ * and of 16 on the other; ks = 5: 16 channels each (sr_head.2, models/seg_model.py:199). */
 int rehr_conv3d_wgrad_march_supported(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
-size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy);
-int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate, void* ws,
+size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy, int ks);
+int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks, int cout, float* dw, int accumulate, void* ws,
                             size_t ws_bytes, rehr_stream stream);
 
 /* Direct convolution for tiny input-channel counts (Cin <= 4: the 1-channel nnU-Net stem, the 2-channel

@@ -83,8 +83,8 @@ def _declare(L: C.CDLL) -> None:
         "rehr_conv3d_march_stats_tiles": (i, [T, T, i]),
         "rehr_conv3d_march_fwd": (i, [T, vp, vp, T, i, i, i, f, vp, vp]),
         "rehr_conv3d_wgrad_march_supported": (i, [D, T, T]),
-        "rehr_conv3d_wgrad_march_workspace": (sz, [T, T]),
-        "rehr_conv3d_wgrad_march": (i, [T, T, vp, i, vp, sz, vp]),
+        "rehr_conv3d_wgrad_march_workspace": (sz, [T, T, i]),
+        "rehr_conv3d_wgrad_march": (i, [T, T, i, i, vp, i, vp, sz, vp]),
         "rehr_conv3d_smallcin_fwd": (i, [D, vp, i, i, i, i, i, vp, vp, T, i, f, vp, vp]),
         "rehr_conv3d_smallcin_wgrad": (i, [D, vp, i, i, i, i, i, T, vp, i, vp, sz, vp]),
         "rehr_conv3d_smallcin_wgrad_workspace": (sz, [D, i, T]),

@@ -40,35 +40,48 @@ int encode_tiled_bf16(CUtensorMap* m, const void* base, int rank, const unsigned
 
 static constexpr int kWgmThreads = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 TMEM zero / final drain
 static constexpr int kWTileH = 16, kWTileW = 8;
-static constexpr int kWHaloH = 18, kWHaloW = 10, kWHaloRows = kWHaloH * kWHaloW;
 static constexpr int kHStages = 4;        // halo-plane ring
-static constexpr int kPRing = 6;          // plain-plane ring (+2 mirrored positions)
-static constexpr int kPC = 32;            // channels per plain-operand piece
-static constexpr uint32_t kPSlotBytes = kWTileH * kWTileW * kPC * 2;  // 8192
 
 struct alignas(64) WgmParams {
-  CUtensorMap h_map;  // 5-D NDHWC, box (CH, 10, 18, 1, 1)
-  CUtensorMap p_map;  // 5-D NDHWC, box (32, 8, 16, 1, 1)
+  CUtensorMap h_map;  // 5-D NDHWC, box (CH, 8 + KS - 1, 16 + KS - 1, 1, 1)
+  CUtensorMap p_map;  // 5-D NDHWC, box (PC, 8, 16, 1, 1)
   int N, D, H, W;
   int tiles_h, tiles_w, Ds, n_seg;
   int n_hs, n_ps, n_combo, ctas_per_combo, items_per_combo;
   uint32_t h_stride;  // bytes per halo stage (1024-aligned)
-  float* ws;          // [cta][group][128][96]
+  float* ws;          // [cta][group][128][KS * PC]
   int* err;
 };
 
-template <int CH>
+// Geometry of one (CH halo channels, PC plain channels, KS kernel size) variant.
+//   * plain planes: KS consecutive ones (q - R .. q + R) are fused along N (= KS * PC); ring of KS + 3 slots with the
+//     first KS - 1 mirrored behind the last one so that the KS-tuple is always contiguous in shared memory;
+//   * halo tile: the KS in-plane offsets of one kernel row (kh) are consecutive tile rows, so they are stacked along M through
+//     LBO = one row; 128 / CH of them fit one MMA ("part"); for CH = 64, KS = 3 the 9 offsets are paired freely instead
+//     (any two rows form an arithmetic progression), which needs 5 MMAs instead of 6.
+template <int CH, int PC, int KS>
 struct WgmCfg {
-  static constexpr int kGroups = CH == 32 ? 3 : 5;
+  static constexpr int R = (KS - 1) / 2;
+  static constexpr int kHaloH = kWTileH + KS - 1, kHaloW = kWTileW + KS - 1, kHaloRows = kHaloH * kHaloW;
+  static constexpr int kApm = 128 / CH;                   // atoms (in-plane offsets) per MMA
+  static constexpr int kParts = (KS + kApm - 1) / kApm;   // MMAs per kernel row
+  static constexpr bool kPaired = (CH == 64 && KS == 3);
+  static constexpr int kGroups = kPaired ? 5 : KS * kParts;
+  static constexpr int kN = KS * PC;                      // accumulator columns per group
   static constexpr uint32_t kRowB = CH * 2;
-  static constexpr uint32_t kLayout = kRowB == 128 ? 2u : 4u;
-  // halo-tile row of atom 0 of group g, and the row distance (LBO) to the next atom
-  __host__ __device__ static constexpr int row0(int g) { return CH == 32 ? g * kWHaloW : ((2 * g) / 3) * kWHaloW + (2 * g) % 3; }
+  static constexpr uint32_t kLayout = kRowB == 128 ? 2u : (kRowB == 64 ? 4u : 6u);
+  static constexpr uint32_t kPRowB = PC * 2;
+  static constexpr uint32_t kPLayout = kPRowB == 64 ? 4u : 6u;
+  static constexpr uint32_t kPSlotBytes = kWTileH * kWTileW * PC * 2;
+  static constexpr int kPRing = KS + 3, kMirror = KS - 1;
+  static_assert(kGroups * kN <= 512, "accumulators must fit TMEM");
+  __host__ __device__ static constexpr int row0(int g) {
+    return kPaired ? ((2 * g) / 3) * kHaloW + (2 * g) % 3 : (g / kParts) * kHaloW + (g % kParts) * kApm;
+  }
   __host__ __device__ static constexpr int lbo_rows(int g) {
-    if (CH == 32) return 1;          // (oh, 0), (oh, 1), (oh, 2), (oh, 3 = discarded)
-    if (g == 4) return 1;            // (2, 2) and its right neighbour; the latter is discarded
+    if (!kPaired || g == 4) return 1;
     const int a0 = 2 * g, a1 = 2 * g + 1;
-    return ((a1 / 3) * kWHaloW + a1 % 3) - ((a0 / 3) * kWHaloW + a0 % 3);
+    return ((a1 / 3) * kHaloW + a1 % 3) - ((a0 / 3) * kHaloW + a0 % 3);
   }
 };
 
@@ -92,13 +105,16 @@ __device__ __forceinline__ WgmItem wgm_decode(const WgmParams& p, int item) {
   return c;
 }
 
-template <int CH>
+template <int CH, int PC, int KS>
 __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __grid_constant__ WgmParams p) {
-  using Cfg = WgmCfg<CH>;
+  using Cfg = WgmCfg<CH, PC, KS>;
+  constexpr int R = Cfg::R;
+  constexpr int kPRing = Cfg::kPRing;
+  constexpr uint32_t kPSlotBytes = Cfg::kPSlotBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_p = smem;                                          // (kPRing + 2) x 8 KB
-  uint8_t* s_h = smem + (size_t)(kPRing + 2) * kPSlotBytes;     // kHStages x h_stride
+  uint8_t* s_p = smem;                                                    // (kPRing + kMirror) plain-plane slots
+  uint8_t* s_h = smem + (((size_t)(kPRing + Cfg::kMirror) * kPSlotBytes + 1023) & ~size_t(1023));  // kHStages x h_stride
   uint8_t* tail = s_h + (size_t)kHStages * p.h_stride;
   uint64_t* full_h = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_h = full_h + kHStages;
@@ -143,25 +159,26 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
       for (int item = rank; item < p.items_per_combo; item += p.ctas_per_combo) {
         const WgmItem c = wgm_decode(p, item);
         const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
-        const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
+        const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
         const int h0 = c.th * kWTileH, w0 = c.tw * kWTileW;
         int next_p = pa;
         for (int q = d0; q < d1; ++q) {
-          const int need = min(q + 1, pb);
+          const int need = min(q + R, pb);
           while (next_p <= need) {
             const uint32_t slot = kp % kPRing;
+            const bool mirrored = slot < (uint32_t)Cfg::kMirror;
             mbar_wait(&empty_p[slot], ((kp / kPRing) & 1u) ^ 1u, p.err, 51);
-            mbar_arrive_expect_tx(&full_p[slot], slot < 2 ? 2 * kPSlotBytes : kPSlotBytes);
-            tma_load_5d(&p.p_map, &full_p[slot], s_p + (size_t)slot * kPSlotBytes, ps * kPC, w0, h0, next_p, c.n);
-            if (slot < 2)
-              tma_load_5d(&p.p_map, &full_p[slot], s_p + (size_t)(slot + kPRing) * kPSlotBytes, ps * kPC, w0, h0, next_p, c.n);
+            mbar_arrive_expect_tx(&full_p[slot], mirrored ? 2 * kPSlotBytes : kPSlotBytes);
+            tma_load_5d(&p.p_map, &full_p[slot], s_p + (size_t)slot * kPSlotBytes, ps * PC, w0, h0, next_p, c.n);
+            if (mirrored)
+              tma_load_5d(&p.p_map, &full_p[slot], s_p + (size_t)(slot + kPRing) * kPSlotBytes, ps * PC, w0, h0, next_p, c.n);
             ++kp;
             ++next_p;
           }
           const uint32_t st = kh % kHStages;
           mbar_wait(&empty_h[st], ((kh / kHStages) & 1u) ^ 1u, p.err, 52);
-          mbar_arrive_expect_tx(&full_h[st], kWHaloRows * Cfg::kRowB);
-          tma_load_5d(&p.h_map, &full_h[st], s_h + (size_t)st * p.h_stride, hs * CH, w0 - 1, h0 - 1, q, c.n);
+          mbar_arrive_expect_tx(&full_h[st], Cfg::kHaloRows * Cfg::kRowB);
+          tma_load_5d(&p.h_map, &full_h[st], s_h + (size_t)st * p.h_stride, hs * CH, w0 - R, h0 - R, q, c.n);
           ++kh;
         }
       }
@@ -169,8 +186,8 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     // descriptor high words: SBO (bits 32..45) = pitch between 8-voxel groups, version 1 (bit 46), swizzle (61..63)
-    constexpr uint32_t kAHi = ((kWHaloW * Cfg::kRowB) >> 4) | (1u << 14) | (Cfg::kLayout << 29);
-    constexpr uint32_t kBHi = ((8u * kPC * 2u) >> 4) | (1u << 14) | (4u << 29);
+    constexpr uint32_t kAHi = ((Cfg::kHaloW * Cfg::kRowB) >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+    constexpr uint32_t kBHi = ((8u * Cfg::kPRowB) >> 4) | (1u << 14) | (Cfg::kPLayout << 29);
     constexpr uint32_t kBLoLbo = (kPSlotBytes >> 4) << 16;
     const uint32_t sp_lo = smem_u32(s_p) >> 4, sh_lo = smem_u32(s_h) >> 4;
     const uint32_t hstride_lo = p.h_stride >> 4;
@@ -180,11 +197,11 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
     for (int item = rank; item < p.items_per_combo; item += p.ctas_per_combo) {
       const WgmItem c = wgm_decode(p, item);
       const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
-      const int pa = max(d0 - 1, 0), pb = min(d1, p.D - 1);
+      const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
       const uint32_t cnt0 = kp;  // counter of plane pa
       int waited = pa - 1;
       for (int q = d0; q < d1; ++q) {
-        const int need = min(q + 1, pb);
+        const int need = min(q + R, pb);
         while (waited < need) {
           ++waited;
           const uint32_t cc = cnt0 + (uint32_t)(waited - pa);
@@ -193,30 +210,31 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
         const uint32_t st = kh % kHStages;
         mbar_wait(&full_h[st], (kh / kHStages) & 1u, p.err, 63);
         tc_fence_after();
-        const int jlo = q == 0 ? 1 : 0, jhi = q == p.D - 1 ? 1 : 2;
-        const uint32_t cbase = cnt0 + (uint32_t)(q - 1 + jlo - pa);
+        // plain planes q - R + j, j in [jlo, jhi], exist inside the volume
+        const int jlo = max(0, R - q), jhi = min(KS - 1, p.D - 1 - q + R);
+        const uint32_t cbase = cnt0 + (uint32_t)(q - R + jlo - pa);
         const uint32_t s0 = cbase % kPRing;
-        const uint32_t idesc = make_idesc_bf16(128, (jhi - jlo + 1) * kPC, 1, 1);
+        const uint32_t idesc = make_idesc_bf16(128, (jhi - jlo + 1) * PC, 1, 1);
         const uint32_t a_lo = sh_lo + st * hstride_lo;
         const uint32_t b_lo = (sp_lo + s0 * (kPSlotBytes >> 4)) | kBLoLbo;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(jlo * kPC);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(jlo * PC);
         if (wgm_elect()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(b_lo + (uint32_t)((ks * 16 * kPC * 2) >> 4));
+            const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(b_lo + (uint32_t)((ks * 16 * Cfg::kPRowB) >> 4));
 #pragma unroll
             for (int g = 0; g < Cfg::kGroups; ++g) {
-              const uint32_t a_off = (uint32_t)(((2 * ks * kWHaloW + Cfg::row0(g)) * Cfg::kRowB) >> 4) |
+              const uint32_t a_off = (uint32_t)(((2 * ks * Cfg::kHaloW + Cfg::row0(g)) * Cfg::kRowB) >> 4) |
                                      ((uint32_t)((Cfg::lbo_rows(g) * Cfg::kRowB) >> 4) << 16);
               const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(a_lo + a_off);
-              umma_bf16(d_tmem + (uint32_t)(g * 3 * kPC), ad, bd, idesc, 1u);
+              umma_bf16(d_tmem + (uint32_t)(g * Cfg::kN), ad, bd, idesc, 1u);
             }
           }
           umma_commit(&empty_h[st]);
           // plain planes whose last reader is this step
-          if (q - 1 >= pa) umma_commit(&empty_p[(cnt0 + (uint32_t)(q - 1 - pa)) % kPRing]);
+          if (q - R >= pa) umma_commit(&empty_p[(cnt0 + (uint32_t)(q - R - pa)) % kPRing]);
           if (q == d1 - 1) {
-            for (int r = max(q, pa); r <= pb; ++r) umma_commit(&empty_p[(cnt0 + (uint32_t)(r - pa)) % kPRing]);
+            for (int r = max(q - R + 1, pa); r <= pb; ++r) umma_commit(&empty_p[(cnt0 + (uint32_t)(r - pa)) % kPRing]);
           }
         }
         __syncwarp();
@@ -243,16 +261,16 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
     mbar_wait(done_bar, 0, p.err, 71);
     tc_fence_after();
     const int row = q4 * 32 + lane;
-    float* dst = p.ws + ((size_t)blockIdx.x * Cfg::kGroups * 128 + row) * 96;
+    float* dst = p.ws + ((size_t)blockIdx.x * Cfg::kGroups * 128 + row) * Cfg::kN;
     for (int g = 0; g < Cfg::kGroups; ++g) {
 #pragma unroll
-      for (int c0 = 0; c0 < 96; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)(g * 96 + c0), v);
+      for (int c0 = 0; c0 < Cfg::kN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + (uint32_t)(g * Cfg::kN + c0), v);
         tmem_ld_wait();
-        float4* o = reinterpret_cast<float4*>(dst + (size_t)g * 128 * 96 + c0);
+        float4* o = reinterpret_cast<float4*>(dst + (size_t)g * 128 * Cfg::kN + c0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
           o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                              __uint_as_float(v[4 * i + 3]));
       }
@@ -268,53 +286,64 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
-// partial sums -> dW (PyTorch layout [co][ci][27], fp32)
+// partial sums -> dW (PyTorch layout [co][ci][KS^3], fp32)
 // ------------------------------------------------------------------------------------------------
 struct WgmReduceParams {
   const float* ws;
   float* dw;
-  int CH, groups, n_hs, n_ps, n_combo, ctas_per_combo;
+  int CH, PC, KS, groups, apm, parts, paired;
+  int n_hs, n_ps, n_combo, ctas_per_combo;
   int role;  // 0: Hh = X (ch = ci, cp = co), 1: Hh = dY (ch = co, cp = ci)
-  int Ci, Co;
+  int Ci, Co;        // channels of the dW tensor (Co may be smaller than the padded dY the kernel saw)
   int accumulate;
 };
 
-// block = 32 (cp within piece) x 8 (slices of the partial list); grid.x enumerates (hs, ps, a, j, ch)
+// block = PC (cp within piece) x 256/PC (slices of the partial list); grid.x enumerates (hs, ps, a, j, ch)
 __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduceParams p) {
-  __shared__ float red[8][33];
-  const int cpl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  __shared__ float red[16][33];
+  const int cpl = threadIdx.x % p.PC, slice = threadIdx.x / p.PC;
+  const int nslice = 256 / p.PC;
   int idx = blockIdx.x;
   const int ch = idx % p.CH;
   idx /= p.CH;
-  const int j = idx % 3;
-  idx /= 3;
-  const int a = idx % 9;
-  idx /= 9;
+  const int j = idx % p.KS;
+  idx /= p.KS;
+  const int a = idx % (p.KS * p.KS);
+  idx /= p.KS * p.KS;
   const int ps = idx % p.n_ps;
   const int hs = idx / p.n_ps;
-  const int vpg = p.CH == 32 ? 3 : 2;  // in-plane offsets kept per MMA group (the 4th atom of a 32-channel group is discarded)
-  const int g = a / vpg, m = (a % vpg) * p.CH + ch;
+  const int oh = a / p.KS, ow = a % p.KS;
+  int g, at;
+  if (p.paired) {
+    g = a / 2;
+    at = a % 2;
+  } else {
+    g = oh * p.parts + ow / p.apm;
+    at = ow % p.apm;
+  }
+  const int m = at * p.CH + ch;
+  const int kn = p.KS * p.PC;
   const int combo = hs * p.n_ps + ps;
-  const size_t per_cta = (size_t)p.groups * 128 * 96;
-  const size_t off = ((size_t)g * 128 + m) * 96 + j * 32 + cpl;
+  const size_t per_cta = (size_t)p.groups * 128 * kn;
+  const size_t off = ((size_t)g * 128 + m) * kn + j * p.PC + cpl;
   float acc = 0.f;
-  for (int k = slice; k < p.ctas_per_combo; k += 8) acc += p.ws[(size_t)(k * p.n_combo + combo) * per_cta + off];
+  for (int k = slice; k < p.ctas_per_combo; k += nslice) acc += p.ws[(size_t)(k * p.n_combo + combo) * per_cta + off];
   red[slice][cpl] = acc;
   __syncthreads();
   if (slice == 0) {
     float t = 0.f;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) t += red[s][cpl];
-    const int chH = hs * p.CH + ch, chP = ps * 32 + cpl;
-    const int oh = a / 3, ow = a % 3;
+    for (int s = 0; s < nslice; ++s) t += red[s][cpl];
+    const int chH = hs * p.CH + ch, chP = ps * p.PC + cpl;
     int co, ci, kd, kh, kw;
     if (p.role == 0) {
-      ci = chH; co = chP; kh = oh; kw = ow; kd = 2 - j;
+      ci = chH; co = chP; kh = oh; kw = ow; kd = p.KS - 1 - j;
     } else {
-      co = chH; ci = chP; kh = 2 - oh; kw = 2 - ow; kd = j;
+      co = chH; ci = chP; kh = p.KS - 1 - oh; kw = p.KS - 1 - ow; kd = j;
     }
-    float* d = p.dw + ((size_t)co * p.Ci + ci) * 27 + (kd * 3 + kh) * 3 + kw;
-    *d = p.accumulate ? (*d + t) : t;
+    if (co < p.Co && ci < p.Ci) {
+      float* d = p.dw + ((size_t)co * p.Ci + ci) * (p.KS * p.KS * p.KS) + (kd * p.KS + kh) * p.KS + kw;
+      *d = p.accumulate ? (*d + t) : t;
+    }
   }
 }
 
@@ -323,48 +352,65 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
 // ------------------------------------------------------------------------------------------------
 struct WgmPlan {
   WgmParams p;
-  int CH, role, grid;
+  int CH, PC, KS, role, grid, groups;
   size_t smem, ws_bytes;
 };
 
-static int wgm_groups(int ch) { return ch == 32 ? 3 : 5; }
+static int wgm_groups(int ch, int ks) {
+  if (ch == 64 && ks == 3) return 5;
+  const int apm = 128 / ch;
+  return ks * ((ks + apm - 1) / apm);
+}
+
+// instantiated (CH, PC, KS) variants
+static bool wgm_variant_ok(int ch, int pc, int ks) {
+  if (ks == 3) return (ch == 32 || ch == 64) && (pc == 32 || pc == 16);
+  if (ks == 5) return ch == 16 && pc == 16;
+  return false;
+}
 
 // pick the role / piece sizes with the fewest MMAs per voxel tile; 0 = unsupported
-static int wgm_choose(int ci, int co, int* role, int* CH) {
+static int wgm_choose(int ci, int co, int ks, int* role, int* CH, int* PC) {
   int best = 0;
   for (int r = 0; r < 2; ++r) {
     const int chh = r == 0 ? ci : co, chp = r == 0 ? co : ci;
-    if (chp % 32 != 0) continue;
-    for (int ch : {64, 32}) {
+    for (int ch : {64, 32, 16}) {
       if (chh % ch != 0) continue;
-      const int cost = (chh / ch) * (chp / 32) * wgm_groups(ch);
-      if (best == 0 || cost < best) {
-        best = cost;
-        *role = r;
-        *CH = ch;
+      for (int pc : {32, 16}) {
+        if (chp % pc != 0 || !wgm_variant_ok(ch, pc, ks)) continue;
+        if (wgm_groups(ch, ks) * ks * pc > 512) continue;
+        const int cost = (chh / ch) * (chp / pc) * wgm_groups(ch, ks) * (pc == 32 ? 4 : 3);  // N = ks*32 costs ~4/3 of ks*16
+        if (best == 0 || cost < best) {
+          best = cost;
+          *role = r;
+          *CH = ch;
+          *PC = pc;
+        }
       }
-      break;
     }
   }
   return best;
 }
 
-static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, WgmPlan* out) {
+static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks, WgmPlan* out) {
   WgmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   if (x.n != dy.n || x.d != dy.d || x.h != dy.h || x.w != dy.w) return REHR_BAD_SHAPE;
-  int role = 0, CH = 0;
-  if (wgm_choose(x.c, dy.c, &role, &CH) == 0) return REHR_UNSUPPORTED;
+  int role = 0, CH = 0, PC = 0;
+  if (wgm_choose(x.c, dy.c, ks, &role, &CH, &PC) == 0) return REHR_UNSUPPORTED;
   const rehr_tensor& hh = role == 0 ? x : dy;
   const rehr_tensor& pp = role == 0 ? dy : x;
   if (hh.ld % 8 != 0 || pp.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
   out->CH = CH;
+  out->PC = PC;
+  out->KS = ks;
   out->role = role;
+  out->groups = wgm_groups(CH, ks);
   p.N = x.n; p.D = x.d; p.H = x.h; p.W = x.w;
   p.tiles_h = (p.H + kWTileH - 1) / kWTileH;
   p.tiles_w = (p.W + kWTileW - 1) / kWTileW;
   p.n_hs = hh.c / CH;
-  p.n_ps = pp.c / kPC;
+  p.n_ps = pp.c / PC;
   p.n_combo = p.n_hs * p.n_ps;
   const int sms = sm_count();
   if (p.n_combo > sms) return REHR_UNSUPPORTED;
@@ -380,23 +426,25 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, WgmPlan* out) {
   // too little work to amortise the per-CTA partial dW and its reduction (measured on B200: the generic split-K kernel
   // wins at 16^3 and below, this one from 32^3 up): leave small volumes to conv_wgrad_kernel
   if (cols * p.D < 256) return REHR_UNSUPPORTED;
-  p.h_stride = ((uint32_t)(kWHaloRows + 2) * CH * 2 + 1023u) & ~1023u;
+  const int halo_rows = (kWTileH + ks - 1) * (kWTileW + ks - 1);
+  p.h_stride = ((uint32_t)(halo_rows + 16) * CH * 2 + 1023u) & ~1023u;  // + slack rows read by discarded atoms
   out->grid = p.n_combo * p.ctas_per_combo;
-  const size_t tailb = (2 * kHStages + 2 * kPRing + 2) * 8 + 16;
-  out->smem = 1024 + (size_t)(kPRing + 2) * kPSlotBytes + (size_t)kHStages * p.h_stride + tailb;
-  out->ws_bytes = (size_t)out->grid * wgm_groups(CH) * 128 * 96 * sizeof(float);
+  const size_t pslot = (size_t)kWTileH * kWTileW * PC * 2;
+  const size_t tailb = (2 * kHStages + 2 * (ks + 3) + 2) * 8 + 16;
+  out->smem = 1024 + (((size_t)(ks + 3 + ks - 1) * pslot + 1023) & ~size_t(1023)) + (size_t)kHStages * p.h_stride + tailb;
+  out->ws_bytes = (size_t)out->grid * out->groups * 128 * ks * PC * sizeof(float);
   return REHR_OK;
 }
 
-template <int CH>
+template <int CH, int PC, int KS>
 static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
   static cudaError_t attr_err =
-      cudaFuncSetAttribute(wgrad_march_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(wgrad_march_kernel<CH, PC, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr_err != cudaSuccess) {
     g_last_cuda_error = (int)attr_err;
     return REHR_CUDA_ERROR;
   }
-  wgrad_march_kernel<CH><<<pl.grid, kWgmThreads, pl.smem, stream>>>(pl.p);
+  wgrad_march_kernel<CH, PC, KS><<<pl.grid, kWgmThreads, pl.smem, stream>>>(pl.p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -405,29 +453,39 @@ static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
 
 using namespace rehr;
 
+static int wgm_ks_of(const rehr_conv_desc* d) {
+  if (!d) return 0;
+  if (d->kd != d->kh || d->kh != d->kw || (d->kd != 3 && d->kd != 5)) return 0;
+  if (d->sd != 1 || d->sh != 1 || d->sw != 1) return 0;
+  const int r = (d->kd - 1) / 2;
+  if (d->pd != r || d->ph != r || d->pw != r) return 0;
+  return d->kd;
+}
+
 extern "C" {
 
 int rehr_conv3d_wgrad_march_supported(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy) {
-  if (!d || !x || !dy) return 0;
-  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd != 1 || d->ph != 1 || d->pw != 1)
-    return 0;
+  if (!x || !dy) return 0;
+  const int ks = wgm_ks_of(d);
+  if (ks == 0) return 0;
   WgmPlan pl;
-  return plan_wgm(*x, *dy, &pl) == REHR_OK ? 1 : 0;
+  return plan_wgm(*x, *dy, ks, &pl) == REHR_OK ? 1 : 0;
 }
 
-size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy) {
+size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy, int ks) {
   if (!x || !dy) return 0;
   WgmPlan pl;
-  if (plan_wgm(*x, *dy, &pl) != REHR_OK) return 0;
+  if (plan_wgm(*x, *dy, ks, &pl) != REHR_OK) return 0;
   return pl.ws_bytes;
 }
 
-int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
-                            rehr_stream stream_) {
-  if (!x || !dy || !x->ptr || !dy->ptr || !dw) return REHR_BAD_SHAPE;
+// dw: f32 [cout][x->c][ks^3]; `cout` <= dy->c lets the caller pass a dy zero-padded to a multiple of 16 channels.
+int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks, int cout, float* dw, int accumulate, void* ws,
+                            size_t ws_bytes, rehr_stream stream_) {
+  if (!x || !dy || !x->ptr || !dy->ptr || !dw || cout <= 0 || cout > dy->c) return REHR_BAD_SHAPE;
   cudaStream_t stream = (cudaStream_t)stream_;
   WgmPlan pl;
-  int rc = plan_wgm(*x, *dy, &pl);
+  int rc = plan_wgm(*x, *dy, ks, &pl);
   if (rc != REHR_OK) return rc;
   if (!ws || ws_bytes < pl.ws_bytes) return REHR_WORKSPACE;
   WgmParams& p = pl.p;
@@ -440,7 +498,7 @@ int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, float* 
                                         (unsigned long long)hh.d, (unsigned long long)hh.n};
     const unsigned long long pitch = (unsigned long long)hh.ld * 2;
     const unsigned long long gstr[4] = {pitch, pitch * hh.w, pitch * hh.w * hh.h, pitch * hh.w * hh.h * hh.d};
-    const unsigned box[5] = {(unsigned)pl.CH, (unsigned)kWHaloW, (unsigned)kWHaloH, 1u, 1u};
+    const unsigned box[5] = {(unsigned)pl.CH, (unsigned)(kWTileW + ks - 1), (unsigned)(kWTileH + ks - 1), 1u, 1u};
     rc = encode_tiled_bf16(&p.h_map, hh.ptr, 5, gdim, gstr, box, pl.CH * 2);
     if (rc != REHR_OK) return rc;
   }
@@ -449,26 +507,36 @@ int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, float* 
                                         (unsigned long long)pp.d, (unsigned long long)pp.n};
     const unsigned long long pitch = (unsigned long long)pp.ld * 2;
     const unsigned long long gstr[4] = {pitch, pitch * pp.w, pitch * pp.w * pp.h, pitch * pp.w * pp.h * pp.d};
-    const unsigned box[5] = {(unsigned)kPC, (unsigned)kWTileW, (unsigned)kWTileH, 1u, 1u};
-    rc = encode_tiled_bf16(&p.p_map, pp.ptr, 5, gdim, gstr, box, kPC * 2);
+    const unsigned box[5] = {(unsigned)pl.PC, (unsigned)kWTileW, (unsigned)kWTileH, 1u, 1u};
+    rc = encode_tiled_bf16(&p.p_map, pp.ptr, 5, gdim, gstr, box, pl.PC * 2);
     if (rc != REHR_OK) return rc;
   }
-  rc = pl.CH == 32 ? launch_wgm<32>(pl, stream) : launch_wgm<64>(pl, stream);
+  rc = REHR_UNSUPPORTED;
+  if (ks == 3 && pl.CH == 32 && pl.PC == 32) rc = launch_wgm<32, 32, 3>(pl, stream);
+  else if (ks == 3 && pl.CH == 64 && pl.PC == 32) rc = launch_wgm<64, 32, 3>(pl, stream);
+  else if (ks == 3 && pl.CH == 32 && pl.PC == 16) rc = launch_wgm<32, 16, 3>(pl, stream);
+  else if (ks == 3 && pl.CH == 64 && pl.PC == 16) rc = launch_wgm<64, 16, 3>(pl, stream);
+  else if (ks == 5 && pl.CH == 16 && pl.PC == 16) rc = launch_wgm<16, 16, 5>(pl, stream);
   if (rc != REHR_OK) return rc;
   WgmReduceParams r;
   r.ws = p.ws;
   r.dw = dw;
   r.CH = pl.CH;
-  r.groups = pl.CH == 32 ? 3 : 5;
+  r.PC = pl.PC;
+  r.KS = ks;
+  r.groups = pl.groups;
+  r.apm = 128 / pl.CH;
+  r.parts = (ks + r.apm - 1) / r.apm;
+  r.paired = (pl.CH == 64 && ks == 3) ? 1 : 0;
   r.n_hs = p.n_hs;
   r.n_ps = p.n_ps;
   r.n_combo = p.n_combo;
   r.ctas_per_combo = p.ctas_per_combo;
   r.role = pl.role;
   r.Ci = x->c;
-  r.Co = dy->c;
+  r.Co = cout;
   r.accumulate = accumulate;
-  const int blocks = p.n_hs * p.n_ps * 9 * 3 * pl.CH;
+  const int blocks = p.n_hs * p.n_ps * ks * ks * ks * pl.CH;
   wgrad_march_reduce_kernel<<<blocks, 256, 0, stream>>>(r);
   REHR_CHECK_LAUNCH();
   return REHR_OK;

@@ -257,11 +257,11 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * x.shape[4] * kernel[0] * kernel[1] * kernel[2]
     tag = f"wgrad {x.shape[4]}->{dy.shape[4]} in{x.shape[1]}x{x.shape[2]}x{x.shape[3]} k{kernel} s{stride}" if _ktimer is not None else ""
     if USE_MARCH and lib().rehr_conv3d_wgrad_march_supported(C.byref(desc), C.byref(xt), C.byref(dyt)):
-        need = lib().rehr_conv3d_wgrad_march_workspace(C.byref(xt), C.byref(dyt))
+        need = lib().rehr_conv3d_wgrad_march_workspace(C.byref(xt), C.byref(dyt), int(kernel[0]))
         ws = _ws(need, x.device)
         with _timed("wgrad_march_kernel", flops, tag):
-            check(lib().rehr_conv3d_wgrad_march(C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
-                  "conv3d_wgrad_march")
+            check(lib().rehr_conv3d_wgrad_march(C.byref(xt), C.byref(dyt), int(kernel[0]), int(wshape[0]), ptr(dw), 0, ptr(ws), need,
+                                                stream_ptr()), "conv3d_wgrad_march")
         _count(2)
         return dw
     need = lib().rehr_conv3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))

@@ -133,6 +133,11 @@ WGRAD_MARCH_CASES = [
     (1, 64, 96, (4, 16, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 32, 32, (1, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 256, 320, (4, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    # sr_head shapes: 32 -> 16 k3 (16-channel plain pieces) and 16 -> 16 k5 (16-channel halo pieces, N = 5 x 16)
+    (1, 32, 16, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 16, (30, 40, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 16, 16, (32, 32, 32), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
+    (2, 16, 16, (13, 24, 40), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
 ]
 
 
@@ -159,7 +164,10 @@ def test_wgrad_march_routing():
     import ctypes as C
     from rehrseg_b200 import _lib as L
     desc = L.conv_desc((3, 3, 3), (1, 1, 1), (1, 1, 1))
-    for (n, ci, co, dhw), want in [((2, 32, 32, (16, 32, 32)), 1), ((1, 64, 32, (32, 64, 64)), 1), ((1, 128, 64, (32, 32, 32)), 1),
+    d5 = L.conv_desc((5, 5, 5), (1, 1, 1), (2, 2, 2))
+    x5, y5 = L.RehrTensor(16, 1, 32, 32, 32, 16, 16), L.RehrTensor(16, 1, 32, 32, 32, 16, 16)
+    assert L.lib().rehr_conv3d_wgrad_march_supported(C.byref(d5), C.byref(x5), C.byref(y5)) == 1
+    for (n, ci, co, dhw), want in [((2, 32, 32, (16, 32, 32)), 1), ((1, 32, 16, (32, 32, 32)), 1), ((1, 64, 32, (32, 64, 64)), 1), ((1, 128, 64, (32, 32, 32)), 1),
                                    ((2, 32, 32, (128, 128, 128)), 1), ((2, 320, 320, (4, 4, 4)), 0), ((1, 16, 16, (32, 32, 32)), 0)]:
         x = L.RehrTensor(16, n, *dhw, ci, ci)
         dy = L.RehrTensor(16, n, *dhw, co, co)
