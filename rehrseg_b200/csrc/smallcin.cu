@@ -289,6 +289,93 @@ static int launch_smallcin_wgrad_k3(const SmallCinWgradArgs& a, cudaStream_t str
   return REHR_OK;
 }
 
+// General row-staged variant for larger in-plane kernels / strides (the FLAVR stem k(3,7,7) s(1,2,2), resnet_3D.py:42-50):
+// one launch covers all (ci, kz) pairs through blockIdx.z, each CTA stages the (7*SH + KH) input rows that 8 output rows need
+// for that (ci, kz) into shared memory, lane = output channel, KH*KW register accumulators per thread, 4 output voxels per
+// inner iteration.  Partials: ws[block][(ci*KD + kz)*KH*KW + ky*KW + kx][cout].
+template <int KH, int KW, int SH, int SW>
+__global__ void __launch_bounds__(256) smallcin_wgrad_rows_kernel(const SmallCinWgradArgs a) {
+  extern __shared__ float sx[];  // [7*SH + KH][Wa], then reused as red[8][KH*KW][32]
+  constexpr int T2 = KH * KW;
+  constexpr int ROWS = 7 * SH + KH;
+  constexpr int SPAN = 3 * SW + KW;  // input columns touched by 4 consecutive output voxels
+  const int Wa = a.wd + 2 * a.pw + SPAN + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co = blockIdx.y * 32 + lane;
+  const bool cok = co < a.cout;
+  const int ci = blockIdx.z / a.kd, kz = blockIdx.z % a.kd;
+  float acc[T2];
+#pragma unroll
+  for (int i = 0; i < T2; ++i) acc[i] = 0.f;
+  const int ytiles = (a.oh + 7) / 8;
+  const long long tiles = (long long)a.n * a.od * ytiles;
+  const long long in_plane = (long long)a.h * a.wd, in_vol = in_plane * a.d;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int yt = (int)(tile % ytiles);
+    long long r = tile / ytiles;
+    const int oz = (int)(r % a.od);
+    const int nn = (int)(r / a.od);
+    const int oy0 = yt * 8;
+    const int iz = oz * a.sd + kz - a.pd;
+    if (iz < 0 || iz >= a.d) continue;  // whole (tile, kz) reads padding: contributes nothing (uniform across the CTA)
+    __syncthreads();
+    const float* xp = a.x + ((long long)nn * a.cin + ci) * in_vol + (long long)iz * in_plane;
+    for (int i = threadIdx.x; i < ROWS * Wa; i += 256) {
+      const int xx = i % Wa, rr = i / Wa;
+      const int iy = oy0 * SH + rr - a.ph, ix = xx - a.pw;
+      sx[i] = (iy >= 0 && iy < a.h && ix >= 0 && ix < a.wd) ? __ldg(xp + (long long)iy * a.wd + ix) : 0.f;
+    }
+    __syncthreads();
+    const int oy = oy0 + warp;
+    if (oy < a.oh) {
+      const __nv_bfloat16* dyrow = a.dy + ((((long long)nn * a.od + oz) * a.oh + oy) * a.ow) * a.lddy + co;
+      for (int ox0 = 0; ox0 < a.ow; ox0 += 4) {
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = (cok && ox0 + j < a.ow) ? __bfloat162float(dyrow[(long long)(ox0 + j) * a.lddy]) : 0.f;
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+          const float* xr = sx + (warp * SH + ky) * Wa + ox0 * SW;
+          float xv[SPAN];
+#pragma unroll
+          for (int j = 0; j < SPAN; ++j) xv[j] = xr[j];
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[ky * KW + kx] = fmaf(g[j], xv[j * SW + kx], acc[ky * KW + kx]);
+        }
+      }
+    }
+  }
+  float* red = sx;  // [8][T2][32]
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < T2; ++t) red[(warp * T2 + t) * 32 + lane] = acc[t];
+  __syncthreads();
+  const int KT = a.cin * a.kd * T2;
+  for (int i = threadIdx.x; i < T2 * 32; i += 256) {
+    const int t = i / 32, l = i % 32;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[(w * T2 + t) * 32 + l];
+    if (blockIdx.y * 32 + l < a.cout)
+      a.ws[((long long)blockIdx.x * KT + (long long)blockIdx.z * T2 + t) * a.cout + blockIdx.y * 32 + l] = sum;
+  }
+}
+
+// ws[block][k][cout] -> dw[co][k]  (k = (ci*KD + kz)*KH*KW + t2 is exactly PyTorch's [ci][kz][ky][kx] order)
+__global__ void smallcin_wgrad_rows_reduce_kernel(const float* ws, int blocks, int KT, int cout, float* dw, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KT * cout) return;
+  const int co = i % cout, k = i / cout;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += ws[((long long)b * KT + k) * cout + co];
+  float* d = dw + (long long)co * KT + k;
+  *d = accumulate ? *d + s : s;
+}
+
+static constexpr int kWgRowsBlocks = 296;  // 2 x 148 CTAs per (channel block, (ci, kz)) slice
+
 __global__ void smallcin_wgrad_reduce_kernel(const float* ws, int blocks, int passes, int KT, int cout, float* dw,
                                              int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,11 +490,17 @@ int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, i
   return REHR_OK;
 }
 
+static bool smallcin_rows_variant(const rehr_conv_desc* d) {
+  return d->kh == 7 && d->kw == 7 && d->sh == 2 && d->sw == 2;
+}
+
 size_t rehr_conv3d_smallcin_wgrad_workspace(const rehr_conv_desc* desc, int cin, const rehr_tensor* dy) {
   if (!desc || !dy || cin <= 0 || cin > kScMaxCin) return 0;
   const int KT = cin * desc->kd * desc->kh * desc->kw;
   const int passes = (KT + kWgAcc - 1) / kWgAcc;
-  return (size_t)passes * kWgBlocks * kWgAcc * dy->c * sizeof(float);
+  const size_t generic = (size_t)passes * kWgBlocks * kWgAcc * dy->c * sizeof(float);
+  const size_t rows = smallcin_rows_variant(desc) ? (size_t)kWgRowsBlocks * KT * dy->c * sizeof(float) : 0;
+  return std::max(generic, rows);
 }
 
 int rehr_conv3d_smallcin_wgrad(const rehr_conv_desc* desc, const float* x_ncdhw, int n, int cin, int d, int h, int w,
@@ -440,6 +533,30 @@ int rehr_conv3d_smallcin_wgrad(const rehr_conv_desc* desc, const float* x_ncdhw,
       default: break;
     }
     if (rc != REHR_OK && rc != REHR_UNSUPPORTED) return rc;
+  }
+  if (rc == REHR_UNSUPPORTED && smallcin_rows_variant(desc)) {
+    constexpr int ROWS = 7 * 2 + 7, SPAN = 3 * 2 + 7;
+    const int Wa = w + 2 * desc->pw + SPAN + 4;
+    const size_t smem = std::max<size_t>((size_t)ROWS * Wa * sizeof(float), (size_t)8 * 49 * 32 * sizeof(float));
+    if (smem <= 200 * 1024) {
+      static size_t attr_smem = 0;
+      if (smem > 48 * 1024 && smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(smallcin_wgrad_rows_kernel<7, 7, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+          g_last_cuda_error = (int)e;
+          return REHR_CUDA_ERROR;
+        }
+        attr_smem = smem;
+      }
+      dim3 grid(kWgRowsBlocks, (dy->c + 31) / 32, cin * desc->kd);
+      smallcin_wgrad_rows_kernel<7, 7, 2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+      REHR_CHECK_LAUNCH();
+      const int total = KT * dy->c;
+      smallcin_wgrad_rows_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a.ws, kWgRowsBlocks, KT, dy->c, dw,
+                                                                                             accumulate);
+      REHR_CHECK_LAUNCH();
+      return REHR_OK;
+    }
   }
   if (rc == REHR_UNSUPPORTED) {
     dim3 grid(kWgBlocks, passes);
