@@ -911,7 +911,7 @@ struct WgradReduceParams {
   int widx[kMaxTaps];
 };
 
-__global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
+__global__ void wgrad_reduce_serial_kernel(const WgradReduceParams p) {
   const long long total = (long long)p.num_groups * 128 * p.CN;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cn = (int)(i % p.CN);
@@ -932,6 +932,45 @@ __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
     for (int s = 0; s < p.splits; ++s) acc += p.ws[((long long)s * p.num_groups * 128 + gr) * p.CN + cn];
     float* d = p.dw + cn * p.s_n + cm * p.s_m + p.widx[tap] * p.s_t;
     *d = p.accumulate ? (*d + acc) : acc;
+  }
+}
+
+// Long split lists (few accumulator groups => hundreds of split-K partials, e.g. the stride-2 32->64 layer):
+// block = 32 (consecutive cn) x 8 (slices of the split list): the partial list of an output element is summed by 8 threads in
+// an interleaved, fixed order and combined through shared memory (deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceParams p) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long total = (long long)p.num_groups * 128 * p.CN;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  bool live = i < total;
+  int cn = 0, tap = 0, cm = 0;
+  if (live) {
+    cn = (int)(i % p.CN);
+    const long long gr = i / p.CN;
+    const int m = (int)(gr % 128);
+    const int g = (int)(gr / 128);
+    if (p.cm_tiles > 1) {
+      tap = g / p.cm_tiles;
+      cm = (g % p.cm_tiles) * 128 + m;
+    } else {
+      tap = g * p.tpg + m / p.cmt;
+      cm = m % p.cmt;
+      if (m / p.cmt >= p.tpg) live = false;
+    }
+    if (tap >= p.num_taps || cm >= p.CM) live = false;
+    if (live)
+      for (int s = slice; s < p.splits; s += 8) acc += p.ws[((long long)s * p.num_groups * 128 + gr) * p.CN + cn];
+  }
+  red[slice][lane] = acc;
+  __syncthreads();
+  if (slice == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) t += red[s][lane];
+    float* d = p.dw + cn * p.s_n + cm * p.s_m + p.widx[tap] * p.s_t;
+    *d = p.accumulate ? (*d + t) : t;
   }
 }
 
@@ -1090,8 +1129,12 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
   r.accumulate = accumulate;
   for (int j = 0; j < plan.num_taps; ++j) r.widx[j] = plan.taps[j].widx;
   const long long total = (long long)r.num_groups * 128 * r.CN;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(r);
+  if (r.splits >= 24) {
+    wgrad_reduce_kernel<<<(int)((total + 31) / 32), 256, 0, stream>>>(r);
+  } else {
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    wgrad_reduce_serial_kernel<<<blocks, 256, 0, stream>>>(r);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
@@ -1115,12 +1158,43 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
   }
 }
 
+// st == 1 (the T taps of one (r, c) pair are contiguous in src): block = (r, 64 consecutive c); the 64 runs of T floats are
+// read coalesced into shared memory and written back transposed as 64 consecutive bf16 per tap.
+static constexpr int kPackC = 64;
+__global__ void __launch_bounds__(256) pack_weight_runs_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R,
+                                                               int C, int T, long long sr, long long sc) {
+  extern __shared__ float tile[];  // [kPackC][T + 1]
+  const int r = blockIdx.y, c0 = blockIdx.x * kPackC;
+  const int nc = min(kPackC, C - c0);
+  for (int i = threadIdx.x; i < nc * T; i += 256) {
+    const int cl = i / T, t = i % T;
+    tile[cl * (T + 1) + t] = src[r * sr + (long long)(c0 + cl) * sc + t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc * T; i += 256) {
+    const int t = i / nc, cl = i % nc;
+    dst[((long long)r * T + t) * C + c0 + cl] = __float2bfloat16(tile[cl * (T + 1) + t]);
+  }
+}
+
 int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long long sr, long long sc, long long st,
                        cudaStream_t stream) {
   const long long total = (long long)R * T * C;
   if (total == 0) return REHR_OK;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, T, sr, sc, st);
+  if (st == 1 && T <= 343 && R <= 65535) {
+    dim3 grid((C + kPackC - 1) / kPackC, R);
+    const size_t smem = (size_t)kPackC * (T + 1) * sizeof(float);
+    static bool attr = false;
+    if (smem > 48 * 1024 && !attr) {
+      if (cudaFuncSetAttribute(pack_weight_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+        return REHR_CUDA_ERROR;
+      attr = true;
+    }
+    pack_weight_runs_kernel<<<grid, 256, smem, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, T, sr, sc);
+  } else {
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, T, sr, sc, st);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;

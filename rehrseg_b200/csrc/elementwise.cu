@@ -376,9 +376,10 @@ static int launch_in_apply(const ApplyArgs& a, int N, cudaStream_t st) {
 // =================================================================================================
 // 1x1x1 conv to a few channels (segmentation head), NDHWC bf16 -> NCDHW f32
 // =================================================================================================
-static constexpr int kPwMaxCout = 8;
+static constexpr int kPwCoutLimit = 8;
 static constexpr int kPwMaxCin = 128;
 
+template <int kPwMaxCout>  // compile-time bound on cout (2 / 4 / 8): keeps the accumulators in a few registers
 __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16* x, long long ld, const float* w,
                                                             const float* bias, float* y, int N, long long V, int cin,
                                                             int cout) {
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16*
 }
 
 // dx[v, ci] = sum_co dy[co, v] w[co][ci]; per-block partials of dw[co][ci] and dbias[co] into ws.
+template <int kPwMaxCout>
 __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16* x, long long ldx, const float* dy,
                                                             const float* w, __nv_bfloat16* dx, long long lddx, float* ws,
                                                             int N, long long V, int cin, int cout) {
@@ -467,23 +469,33 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
   for (int i = threadIdx.x; i < cout * (cin + 1); i += blockDim.x) ws[(long long)blockIdx.x * cout * (cin + 1) + i] = sacc[i];
 }
 
-__global__ void pointwise_bwd_reduce_kernel(const float* ws, int blocks, int cin, int cout, float* dw, float* dbias,
-                                            int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cout * (cin + 1)) return;
+// one block per output element: 256 threads stride through the per-block partials, shared-memory tree (double)
+__global__ void __launch_bounds__(256) pointwise_bwd_reduce_kernel(const float* ws, int blocks, int cin, int cout, float* dw,
+                                                                    float* dbias, int accumulate) {
+  __shared__ double red[256];
+  const int i = blockIdx.x;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)ws[(long long)b * cout * (cin + 1) + i];
-  const int o = i / (cin + 1), c = i % (cin + 1);
-  if (c < cin) {
-    if (dw) dw[o * cin + c] = accumulate ? dw[o * cin + c] + (float)s : (float)s;
-  } else {
-    if (dbias) dbias[o] = accumulate ? dbias[o] + (float)s : (float)s;
+  for (int b = threadIdx.x; b < blocks; b += 256) s += (double)ws[(long long)b * cout * (cin + 1) + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float t = (float)red[0];
+    const int o = i / (cin + 1), c = i % (cin + 1);
+    if (c < cin) {
+      if (dw) dw[o * cin + c] = accumulate ? dw[o * cin + c] + t : t;
+    } else {
+      if (dbias) dbias[o] = accumulate ? dbias[o] + t : t;
+    }
   }
 }
 
 static int pointwise_bwd_blocks(const rehr_tensor* x) {
   const long long items = (long long)x->n * voxels_per_sample(x) * (x->c / 8);
-  return grid_for(items, 256, 4);
+  return grid_for(items, 256, 8);
 }
 
 // per-channel sum over all voxels (bias gradient): per-block partials + reduce
@@ -1009,10 +1021,16 @@ int rehr_instnorm_lrelu_bwd_apply(const rehr_tensor* y, const rehr_tensor* da1, 
 
 int rehr_pointwise_fwd(const rehr_tensor* x, const float* w, const float* bias, float* y_ncdhw, int cout, rehr_stream stream) {
   if (!bf16_tensor_ok(x) || !w || !y_ncdhw) return REHR_BAD_SHAPE;
-  if (cout > kPwMaxCout || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
+  if (cout > kPwCoutLimit || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
   const long long V = voxels_per_sample(x);
-  pointwise_fwd_kernel<<<grid_for((long long)x->n * V, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+  const int grid = grid_for((long long)x->n * V, 256, 8);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
+  if (cout <= 2)
+    pointwise_fwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+  else if (cout <= 4)
+    pointwise_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+  else
+    pointwise_fwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -1025,17 +1043,24 @@ size_t rehr_pointwise_bwd_workspace(const rehr_tensor* x, int cout) {
 int rehr_pointwise_bwd(const rehr_tensor* x, const float* dy_ncdhw, const float* w, int cout, const rehr_tensor* dx, float* dw,
                        float* dbias, int accumulate, void* ws, size_t ws_bytes, rehr_stream stream) {
   if (!bf16_tensor_ok(x) || !dy_ncdhw || !w || (dx && !bf16_tensor_ok(dx))) return REHR_BAD_SHAPE;
-  if (cout > kPwMaxCout || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
+  if (cout > kPwCoutLimit || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
   if (ws_bytes < rehr_pointwise_bwd_workspace(x, cout) || !ws) return REHR_WORKSPACE;
   const long long V = voxels_per_sample(x);
   const int blocks = pointwise_bwd_blocks(x);
-  pointwise_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, dy_ncdhw, w, dx ? reinterpret_cast<__nv_bfloat16*>(dx->ptr) : nullptr,
-      dx ? dx->ld : 0, reinterpret_cast<float*>(ws), x->n, V, x->c, cout);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
+  __nv_bfloat16* dxp = dx ? reinterpret_cast<__nv_bfloat16*>(dx->ptr) : nullptr;
+  const long long lddx = dx ? dx->ld : 0;
+  float* wsp = reinterpret_cast<float*>(ws);
+  if (cout <= 2)
+    pointwise_bwd_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, x->n, V, x->c, cout);
+  else if (cout <= 4)
+    pointwise_bwd_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, x->n, V, x->c, cout);
+  else
+    pointwise_bwd_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, x->n, V, x->c, cout);
   REHR_CHECK_LAUNCH();
   const int outs = cout * (x->c + 1);
-  pointwise_bwd_reduce_kernel<<<(outs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c,
-                                                                                cout, dw, dbias, accumulate);
+  pointwise_bwd_reduce_kernel<<<outs, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c, cout, dw,
+                                                                     dbias, accumulate);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
