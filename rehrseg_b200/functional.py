@@ -159,6 +159,14 @@ def _alias(storage_of: torch.Tensor, offset: int, size, stride) -> torch.Tensor:
     return t.set_(storage_of.untyped_storage(), offset, tuple(size), tuple(stride))
 
 
+# Second gradient source of an encoder skip activation.  A skip `a` feeds the next encoder stage AND the decoder concat; autograd
+# would add the two gradients with an extra full-tensor pass.  The InstanceNorm backward kernels take two gradient operands
+# (da1, da2), so ConvTranspose.backward parks the concat-buffer half here (keyed by the skip's storage) instead of returning it,
+# and the ConvNormAct.backward that produced the skip picks it up.  Autograd runs a node only after every consumer's backward,
+# so the entry is always there in time; it is popped on use.
+_skip_grads: dict = {}
+
+
 def concat_room_of(t: torch.Tensor):
     """(total_channels, channel_offset) if `t` was produced inside a wider concat buffer (see conv_norm_act), else None."""
     return getattr(t, "_rehr_cat", None)
@@ -346,6 +354,7 @@ class ConvNormAct(torch.autograd.Function):
         _count(2)
         ctx.save_for_backward(x_saved, weight, gamma, beta, y, mean, rstd)
         ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None)
+        ctx.skip_key = (a.untyped_storage().data_ptr(), a.storage_offset()) if cat_room else None
         return a
 
     @staticmethod
@@ -357,11 +366,14 @@ class ConvNormAct(torch.autograd.Function):
         n, cout = y.shape[0], y.shape[4]
         vox = y.shape[1] * y.shape[2] * y.shape[3]
         yt, dat = rt(y), rt(da)
+        da2 = _skip_grads.pop(ctx.skip_key, None) if ctx.skip_key is not None else None
+        da2t = rt(da2) if da2 is not None else None
+        da2p = C.byref(da2t) if da2t is not None else None
         g32 = _f32(gamma) if gamma is not None else None
         b32 = _f32(beta) if beta is not None else None
         tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
         partial = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
-        check(lib().rehr_instnorm_lrelu_bwd_reduce(C.byref(yt), C.byref(dat), None, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
+        check(lib().rehr_instnorm_lrelu_bwd_reduce(C.byref(yt), C.byref(dat), da2p, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
                                                    float(slope), ptr(partial), stream_ptr()), "instnorm_bwd_reduce")
         sums = torch.empty((n, cout, 2), dtype=torch.float32, device=dev)
         dgamma = torch.empty((cout,), dtype=torch.float32, device=dev)
@@ -370,7 +382,7 @@ class ConvNormAct(torch.autograd.Function):
                                                      0, stream_ptr()), "instnorm_bwd_finalize")
         dy = torch.empty_like(y)
         dyt = rt(dy)
-        check(lib().rehr_instnorm_lrelu_bwd_apply(C.byref(yt), C.byref(dat), None, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
+        check(lib().rehr_instnorm_lrelu_bwd_apply(C.byref(yt), C.byref(dat), da2p, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
                                                   float(slope), ptr(sums), C.byref(dyt), stream_ptr()), "instnorm_bwd_apply")
         _count(3)
         desc = conv_desc(kernel, stride, padding)
@@ -605,8 +617,10 @@ class ConvTranspose(torch.autograd.Function):
         od, oh, ow = ((i - 1) * s - 2 * p + k for i, k, s, p in zip((d, h, w), kernel, stride, padding))
         desc = conv_desc(kernel, stride, padding)
         ctx.cat = skip is not None
+        ctx.skip_key = None
         if skip is not None:
             tot, off = skip._rehr_cat
+            ctx.skip_key = (skip.untyped_storage().data_ptr(), skip.storage_offset())
             if tot != 2 * cout or off != cout or tuple(skip.shape) != (n, od, oh, ow, cout):
                 raise L.RehrError("conv_transpose: skip does not sit in a matching [up | skip] concat buffer")
             full = _alias(skip, skip.storage_offset() - off, (n, od, oh, ow, tot),
@@ -640,6 +654,9 @@ class ConvTranspose(torch.autograd.Function):
             da = as_cl(da)
             dskip = da[..., cout:]
             da = da[..., :cout]
+            if ctx.skip_key is not None and ctx.needs_input_grad[3]:
+                _skip_grads[ctx.skip_key] = dskip   # picked up by the skip producer's backward as its second gradient operand
+                dskip = None
         dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
         desc = conv_desc(kernel, stride, padding)
         dyt, xt = rt(dy), rt(x)
