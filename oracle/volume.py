@@ -178,3 +178,13 @@ def zscore_normalization(image):
     image -= mu
     image /= max(sd, 1e-8)
     return image
+
+
+def sr_volume_orientations(model, image, angles=(0,), pred_out_idx=0):
+    """utils/sr_utils.py:157-173: rotate, permute to (hr, C, lr, hr), window sweep, permute back, un-rotate, mean."""
+    preds = []
+    for angle in angles:
+        rot = rotate_vol_2d(image, angle).permute(0, 3, 2, 1)
+        res = apply_to_vol_flavr(model, rot, pred_out_idx).permute(0, 3, 1, 2)
+        preds.append(rotate_vol_2d(res, -angle))
+    return torch.mean(torch.stack(preds), dim=0)

@@ -406,3 +406,45 @@ def get_intermediate_features(model_sr, img_lr: torch.Tensor, label_lr: torch.Te
         last = f[-1:, :, :, 2]                                      # slice 2 of the last window
         out[i] = torch.cat([mid, last], dim=0).permute(1, 2, 0, 3, 4).contiguous()   # [B, C, D, h, w]
     return out
+
+
+def sr_volume_orientations(model, image: torch.Tensor, angles=(0,), pred_out_idx=0, fuse="mean", group=None, max_batch: int = 8):
+    """The tensor part of `inference_flavr` (utils/sr_utils.py:157-175): for every in-plane angle rotate `image`
+    [hr, hr, lr, C] with rotate_vol_2d, move the axes to (hr, C, lr, hr), sweep the 4-slice windows through the network
+    (apply_to_vol_flavr), move the axes back, undo the rotation, then fuse the orientations -- "mean" (what the reference
+    runs, torch.mean(torch.stack(...))) or "fba_inf" / "fba_<p>" (utils/fba.py).  The reference ships angles = [0]; the SMORE
+    lineage uses [0, 90].  With a torch.distributed `group` the angles are dealt round-robin over the ranks (one process per
+    GPU) and the per-orientation volumes are all-gathered before the (replicated) fusion."""
+    from . import volume_ops as vo
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if (group is not None or dist.is_initialized()) and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = image.device if image.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    image = image.to(dev)
+    mine = {}
+    for i, angle in enumerate(angles):
+        if i % world != rank:
+            continue
+        rot = vo.rotate_vol_2d(image, angle).permute(0, 3, 2, 1)
+        res = apply_to_vol_flavr(model, rot, pred_out_idx, max_batch=max_batch).permute(0, 3, 1, 2)
+        mine[i] = vo.rotate_vol_2d(res.contiguous(), -angle)
+    if world > 1:
+        shape = None
+        for v in mine.values():
+            shape = v.shape
+        # every orientation comes back in the un-rotated frame, so all ranks hold equally shaped volumes
+        shp = torch.tensor(list(shape) if shape is not None else [0, 0, 0, 0], device=dev)
+        dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=group)
+        preds = []
+        for i in range(len(angles)):
+            buf = mine[i].contiguous() if i in mine else torch.empty(tuple(int(s) for s in shp), dtype=torch.float32, device=dev)
+            dist.broadcast(buf, src=dist.get_global_rank(group, i % world) if group is not None else i % world, group=group)
+            preds.append(buf)
+    else:
+        preds = [mine[i] for i in range(len(angles))]
+    if fuse == "mean":
+        return vo.mean_fuse(preds)
+    if fuse.startswith("fba"):
+        p = fuse.split("_", 1)[1] if "_" in fuse else "infinity"
+        return vo.fba(preds, "infinity" if p in ("inf", "infinity") else float(p))
+    raise RehrError(f"unknown fusion {fuse!r}")

@@ -119,3 +119,16 @@ def test_convert_reference_shaped_flavr():
         got = m(x.clone().cuda())
     assert rel(got, want) <= 1e-2
     assert m.calc_out_patch_size([4, 32, 32]) == [16, 32, 32] if hasattr(m, "calc_out_patch_size") else True
+
+
+def test_sr_volume_orientations_vs_oracle():
+    """Tensor part of inference_flavr (utils/sr_utils.py:157-175) with two orientations (0 and 180 degrees: the reference un-rotates over the OUTPUT dims (0, 1), so only shape-preserving angles can be stacked), mean fusion."""
+    from oracle import volume as ov
+    from rehrseg_b200 import flavr
+    ref, mine = _pair(False, seed=13)
+    img = torch.rand((7, 7, 20, 2), generator=torch.Generator().manual_seed(8))    # (hr, hr, lr, C), square in-plane
+    with torch.no_grad():
+        want = ov.sr_volume_orientations(ref, img.clone(), angles=(0, 180))
+        got = flavr.sr_volume_orientations(mine, img.clone().cuda(), angles=(0, 180), max_batch=3)
+    assert got.shape == want.shape
+    assert rel(got, want) <= 1e-2
