@@ -795,24 +795,41 @@ static constexpr int kBlurMaxTaps = 65;
 struct BlurTaps {
   float t[kBlurMaxTaps];
 };
-__global__ void __launch_bounds__(256) blur1d_kernel(const float* x, float* y, const float* taps, int L, long long Z, int X,
+// Tile = kBlurRows output rows (along X) x 128 columns (along Y, the contiguous axis): the kBlurRows + L - 1 input rows are
+// staged once in shared memory with coalesced 512 B row reads, every thread then slides down its column (bank-conflict free),
+// so each input element is read from HBM ~(1 + (L-1)/kBlurRows) times instead of L times through L2.
+static constexpr int kBlurRows = 64;
+__global__ void __launch_bounds__(128) blur1d_kernel(const float* x, float* y, const float* taps, int L, long long Z, int X,
                                                      int Y) {
+  extern __shared__ float tile[];  // [kBlurRows + L - 1][128]
   __shared__ float st[kBlurMaxTaps];
   for (int i = threadIdx.x; i < L; i += blockDim.x) st[i] = taps[i];
-  __syncthreads();
   const int left = (L - 1) / 2;
-  const long long total = Z * (long long)X * Y;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int yy = (int)(i % Y);
-    const int xx = (int)((i / Y) % X);
-    const long long z = i / ((long long)Y * X);
-    const float* base = x + z * (long long)X * Y + yy;
-    float acc = 0.f;
-    for (int l = 0; l < L; ++l) {
-      const int xs = xx + l - left;
-      if (xs >= 0 && xs < X) acc += st[l] * base[(long long)xs * Y];
+  const int ytiles = (Y + 127) / 128, xtiles = (X + kBlurRows - 1) / kBlurRows;
+  const long long total = Z * (long long)xtiles * ytiles;
+  const int rows_in = kBlurRows + L - 1;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int yt = (int)(t % ytiles);
+    const int xt = (int)((t / ytiles) % xtiles);
+    const long long z = t / ((long long)ytiles * xtiles);
+    const int yy = yt * 128 + threadIdx.x;
+    const int x0 = xt * kBlurRows;
+    const float* base = x + z * (long long)X * Y;
+    __syncthreads();
+    for (int r = 0; r < rows_in; ++r) {
+      const int xs = x0 + r - left;
+      tile[r * 128 + threadIdx.x] = (xs >= 0 && xs < X && yy < Y) ? base[(long long)xs * Y + yy] : 0.f;
     }
-    y[i] = acc;
+    __syncthreads();
+    if (yy < Y) {
+      float* out = y + z * (long long)X * Y;
+      const int nrows = min(kBlurRows, X - x0);
+      for (int r = 0; r < nrows; ++r) {
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l) acc += st[l] * tile[(r + l) * 128 + threadIdx.x];
+        out[(long long)(x0 + r) * Y + yy] = acc;
+      }
+    }
   }
 }
 
@@ -1200,7 +1217,20 @@ int rehr_sw_finalize(void* logits_f16, const void* npred_f16, int C, long long v
 int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z, int X, int Y, rehr_stream stream) {
   if (!x || !taps || !y || L <= 0) return REHR_BAD_SHAPE;
   if (L > kBlurMaxTaps) return REHR_UNSUPPORTED;
-  blur1d_kernel<<<grid_for(Z * (long long)X * Y, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  const size_t smem = (size_t)(kBlurRows + L - 1) * 128 * sizeof(float);
+  static bool attr = false;
+  if (smem > 48 * 1024 && !attr) {
+    cudaError_t e = cudaFuncSetAttribute(blur1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((kBlurRows + kBlurMaxTaps) * 128 * sizeof(float)));
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+    attr = true;
+  }
+  const long long tiles = Z * (long long)((X + kBlurRows - 1) / kBlurRows) * ((Y + 127) / 128);
+  const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 6));
+  blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
