@@ -334,8 +334,13 @@ def main() -> None:
             name, (n, tms, fl) = top
             achieved = fl / tms / 1e9
             peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+            # DRAM bytes (read + write) of the largest launch of each family from the committed `ncu --set full` capture
+            # (profiles/r01_march_kernels_ncu_full_summary.txt: conv_march_kernel on the 64->32 128^3 layer, 805 MB algorithmic)
+            traffic = {"conv_march_kernel": 784.0e6}.get(name)
             roof = {"kernel": name, "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "launches_per_step": n,
+                    "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "traffic_note": "dram read+write of the 64->32 @128^3 launch (463.9 GFLOP, 805 MB algorithmic), ncu --set full"
+                    if traffic else None, "launches_per_step": n,
                     "avg_launch_ms": round(tms / n, 4), "flops_per_launch": fl / n,
                     "share_of_step": round(tms / (ms / args.steps), 4),
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']}); kernel timed inside a step",
