@@ -298,14 +298,24 @@ struct WgmReduceParams {
   int accumulate;
 };
 
-// block = PC (cp within piece) x 256/PC (slices of the partial list); grid.x enumerates (hs, ps, a, j, ch)
+// Two thread layouts over the same index space (hs, ps, a, j, ch, cpl):
+//   SLICED = true : block = PC (cpl) x 256/PC slices of a LONG partial list (one (.., ch) per block, shared-memory combine);
+//   SLICED = false: block = PC (cpl) x 256/PC consecutive ch, every thread walks its SHORT partial list alone.
+template <bool SLICED>
 __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduceParams p) {
   __shared__ float red[16][33];
-  const int cpl = threadIdx.x % p.PC, slice = threadIdx.x / p.PC;
-  const int nslice = 256 / p.PC;
+  const int cpl = threadIdx.x % p.PC, sub = threadIdx.x / p.PC;
+  const int nsub = 256 / p.PC;
   int idx = blockIdx.x;
-  const int ch = idx % p.CH;
-  idx /= p.CH;
+  int ch;
+  if (SLICED) {
+    ch = idx % p.CH;
+    idx /= p.CH;
+  } else {
+    const int chb = (p.CH + nsub - 1) / nsub;  // channel blocks per (.., j)
+    ch = (idx % chb) * nsub + sub;
+    idx /= chb;
+  }
   const int j = idx % p.KS;
   idx /= p.KS;
   const int a = idx % (p.KS * p.KS);
@@ -321,29 +331,34 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
     g = oh * p.parts + ow / p.apm;
     at = ow % p.apm;
   }
-  const int m = at * p.CH + ch;
+  const bool chok = ch < p.CH;
+  const int m = at * p.CH + (chok ? ch : 0);
   const int kn = p.KS * p.PC;
   const int combo = hs * p.n_ps + ps;
   const size_t per_cta = (size_t)p.groups * 128 * kn;
   const size_t off = ((size_t)g * 128 + m) * kn + j * p.PC + cpl;
-  float acc = 0.f;
-  for (int k = slice; k < p.ctas_per_combo; k += nslice) acc += p.ws[(size_t)(k * p.n_combo + combo) * per_cta + off];
-  red[slice][cpl] = acc;
-  __syncthreads();
-  if (slice == 0) {
-    float t = 0.f;
-    for (int s = 0; s < nslice; ++s) t += red[s][cpl];
-    const int chH = hs * p.CH + ch, chP = ps * p.PC + cpl;
-    int co, ci, kd, kh, kw;
-    if (p.role == 0) {
-      ci = chH; co = chP; kh = oh; kw = ow; kd = p.KS - 1 - j;
-    } else {
-      co = chH; ci = chP; kh = p.KS - 1 - oh; kw = p.KS - 1 - ow; kd = j;
-    }
-    if (co < p.Co && ci < p.Ci) {
-      float* d = p.dw + ((size_t)co * p.Ci + ci) * (p.KS * p.KS * p.KS) + (kd * p.KS + kh) * p.KS + kw;
-      *d = p.accumulate ? (*d + t) : t;
-    }
+  float t = 0.f;
+  if (SLICED) {
+    float acc = 0.f;
+    for (int k = sub; k < p.ctas_per_combo; k += nsub) acc += p.ws[(size_t)(k * p.n_combo + combo) * per_cta + off];
+    red[sub][cpl] = acc;
+    __syncthreads();
+    if (sub != 0) return;
+    for (int s = 0; s < nsub; ++s) t += red[s][cpl];
+  } else {
+    if (!chok) return;
+    for (int k = 0; k < p.ctas_per_combo; ++k) t += p.ws[(size_t)(k * p.n_combo + combo) * per_cta + off];
+  }
+  const int chH = hs * p.CH + ch, chP = ps * p.PC + cpl;
+  int co, ci, kd, kh, kw;
+  if (p.role == 0) {
+    ci = chH; co = chP; kh = oh; kw = ow; kd = p.KS - 1 - j;
+  } else {
+    co = chH; ci = chP; kh = p.KS - 1 - oh; kw = p.KS - 1 - ow; kd = j;
+  }
+  if (co < p.Co && ci < p.Ci) {
+    float* d = p.dw + ((size_t)co * p.Ci + ci) * (p.KS * p.KS * p.KS) + (kd * p.KS + kh) * p.KS + kw;
+    *d = p.accumulate ? (*d + t) : t;
   }
 }
 
@@ -536,8 +551,15 @@ int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks,
   r.Ci = x->c;
   r.Co = cout;
   r.accumulate = accumulate;
-  const int blocks = p.n_hs * p.n_ps * ks * ks * ks * pl.CH;
-  wgrad_march_reduce_kernel<<<blocks, 256, 0, stream>>>(r);
+  if (p.ctas_per_combo >= 24) {
+    const int blocks = p.n_hs * p.n_ps * ks * ks * ks * pl.CH;
+    wgrad_march_reduce_kernel<true><<<blocks, 256, 0, stream>>>(r);
+  } else {
+    const int nsub = 256 / pl.PC;
+    const int chb = (pl.CH + nsub - 1) / nsub;
+    const int blocks = p.n_hs * p.n_ps * ks * ks * ks * chb;
+    wgrad_march_reduce_kernel<false><<<blocks, 256, 0, stream>>>(r);
+  }
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
