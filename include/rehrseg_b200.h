@@ -220,7 +220,7 @@ int rehr_act_bwd(const rehr_tensor* a, const rehr_tensor* da, int act, float slo
  *   logits[c, sl] += pred[c] * gauss ;  n_pred[sl] += gauss     (rehr_sw_accumulate)
  *   logits /= n_pred ; *inf_flag |= any(isinf(logits))          (rehr_sw_finalize)
  * logits [C][VD][VH][VW] f16, n_pred [VD][VH][VW] f16, pred [C][TD][TH][TW] f16 (or f32), gauss [TD][TH][TW] f16
- * (NULL = the reference's `gaussian = 1`).
+ * (NULL = the reference's `gaussian = 1`).  npred_f16 may be NULL (blend the logits only).
  * ---------------------------------------------------------------------------------------------- */
 int rehr_sw_accumulate(void* logits_f16, void* npred_f16, const void* pred, int pred_is_f32, const void* gauss_f16,
                        int C, int VD, int VH, int VW, int TD, int TH, int TW, int od, int oh, int ow,

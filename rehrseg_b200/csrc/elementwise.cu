@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(256) sw_accumulate_kernel(__half* logits, __ha
         prod = __half2float(__float2half(__half2float(reinterpret_cast<const __half*>(pred)[c * tv + i]) * g));
       logits[c * vv + vi] = __float2half(__half2float(logits[c * vv + vi]) + prod);
     }
-    npred[vi] = __float2half(__half2float(npred[vi]) + g);
+    if (npred) npred[vi] = __float2half(__half2float(npred[vi]) + g);
   }
 }
 __global__ void __launch_bounds__(256) sw_finalize_kernel(__half* logits, const __half* npred, int C, long long vv,
@@ -1196,7 +1196,7 @@ int rehr_segate_bwd_apply(const rehr_tensor* y, const rehr_tensor* dy, int act, 
 
 int rehr_sw_accumulate(void* logits_f16, void* npred_f16, const void* pred, int pred_is_f32, const void* gauss_f16, int C, int VD,
                        int VH, int VW, int TD, int TH, int TW, int od, int oh, int ow, rehr_stream stream) {
-  if (!logits_f16 || !npred_f16 || !pred) return REHR_BAD_SHAPE;
+  if (!logits_f16 || !pred) return REHR_BAD_SHAPE;  // npred_f16 may be NULL: blend the logits only
   if (od < 0 || oh < 0 || ow < 0 || od + TD > VD || oh + TH > VH || ow + TW > VW) return REHR_BAD_SHAPE;
   const long long tv = (long long)TD * TH * TW;
   sw_accumulate_kernel<<<grid_for(tv, 256, 8), 256, 0, (cudaStream_t)stream>>>(

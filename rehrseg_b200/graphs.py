@@ -7,7 +7,11 @@ captured once and replayed with new input contents.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
+
+_graph_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # module -> (signature, GraphedForward)
 
 
 class GraphedForward:
@@ -36,3 +40,17 @@ class GraphedForward:
         self.static_in.copy_(x)
         self.graph.replay()
         return self.static_out
+
+
+def graphed(module, example: torch.Tensor) -> GraphedForward:
+    """Cached GraphedForward for (module, input shape).  The capture bakes in the packed bf16 copies of the weights, so it is
+    reused only while every parameter still has the version and storage it had at capture time (an optimiser step or a
+    load_state_dict invalidates it)."""
+    params = list(module.parameters())
+    sig = (tuple(example.shape), example.dtype, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+    hit = _graph_cache.get(module)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    g = GraphedForward(module, example)
+    _graph_cache[module] = (sig, g)   # kept outside the module so state_dict / pickling of the model are unaffected
+    return g

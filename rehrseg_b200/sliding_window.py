@@ -130,17 +130,18 @@ def _internal_maybe_mirror_and_predict(model, x, out_idx=None, deep_supervision=
 # ----------------------------------------------------------------------------------------------------------------
 # blend
 # ----------------------------------------------------------------------------------------------------------------
-def sw_accumulate(predicted_logits: torch.Tensor, n_predictions: torch.Tensor, prediction: torch.Tensor, gaussian,
+def sw_accumulate(predicted_logits: torch.Tensor, n_predictions: Optional[torch.Tensor], prediction: torch.Tensor, gaussian,
                   origin: Sequence[int]) -> None:
-    """logits[:, o:o+t] += prediction * gaussian ; n[o:o+t] += gaussian  (utils/seg_utils.py:275-276), fp16 accumulators."""
-    if predicted_logits.dtype != torch.float16 or n_predictions.dtype != torch.float16:
+    """logits[:, o:o+t] += prediction * gaussian ; n[o:o+t] += gaussian  (utils/seg_utils.py:275-276), fp16 accumulators.
+    `n_predictions=None` blends the logits only."""
+    if predicted_logits.dtype != torch.float16 or (n_predictions is not None and n_predictions.dtype != torch.float16):
         raise RehrError("sliding-window accumulators are fp16 as in the reference (utils/seg_utils.py:256-259)")
     cch, vd, vh, vw = predicted_logits.shape
     prediction = prediction.contiguous()
     if prediction.dtype not in (torch.float16, torch.float32):
         prediction = prediction.float()
     c2, td, th, tw = prediction.shape
-    if c2 != cch or tuple(n_predictions.shape) != (vd, vh, vw):
+    if c2 != cch or (n_predictions is not None and tuple(n_predictions.shape) != (vd, vh, vw)):
         raise RehrError("sw_accumulate: shape mismatch")
     od, oh, ow = (int(v) for v in origin)
     if od < 0 or oh < 0 or ow < 0 or od + td > vd or oh + th > vh or ow + tw > vw:
@@ -191,10 +192,15 @@ def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, 
     if out_idx == 0 and isinstance(network, torch.nn.Module) and hasattr(network, "sr_head") and hasattr(network, "upscale"):
         from .seg_model import LRHeadOnly, _EngineForward, SegModel
         if isinstance(network, (SegModel, _EngineForward)):
-            network = LRHeadOnly(network)   # output 1 (the x`upscale` SR head) is never read on this path: do not compute it
+            # output 1 (the x`upscale` SR head) is never read on this path: do not compute it
+            wrapper = network.__dict__.get("_rehr_lr_only")  # kept on the model (not a registered sub-module) so the
+            if wrapper is None:                               # captured CUDA graph of the view is reused across calls
+                wrapper = LRHeadOnly(network)
+                object.__setattr__(network, "_rehr_lr_only", wrapper)
+            network = wrapper
     if cuda_graph and len(slicers) > 0 and isinstance(network, torch.nn.Module) and not torch.is_grad_enabled():
-        from .graphs import GraphedForward
-        network = GraphedForward(network, data[slicers[0]][None])
+        from .graphs import graphed
+        network = graphed(network, data[slicers[0]][None])
     for i, sl in enumerate(slicers):
         if tile_filter is not None and not tile_filter(i):
             continue
@@ -215,20 +221,27 @@ def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, 
 
 def predict_sliding_window_sharded(data: torch.Tensor, slicers, network, group=None, out_idx=None, slice_seperation=1,
                                    patch_size=[14, 320, 384], use_gaussian=True, deep_supervision=True,
-                                   accumulate_fn=None):
-    """Tiles dealt round-robin over the ranks of `group` (one process per GPU); every rank blends its own tiles into
-    full-volume buffers exactly as the single-GPU path does, the buffers are summed with ONE all-reduce (fp32 on the wire:
-    the reference's fp16 running sums depend on tile order, so the N-rank result matches at tolerance, not bit for bit)
-    and every rank finalises locally.  `accumulate_fn` lets the CPU/gloo test substitute the blend."""
+                                   accumulate_fn=None, shard_mirrors: bool = True):
+    """N-GPU sliding window (one process per GPU).  The independent units are the (tile, mirror variant) forwards
+    (27 x 8 = 216 for config 3): unit u = 8 * tile + variant runs on rank u % world, so the load is balanced even when the
+    tile count is not a multiple of the rank count (`shard_mirrors=False` deals whole tiles instead).  The variants of a
+    tile are summed on the tile's owner rank (tile % world) with one small fp32 reduce, the owner blends the mean exactly
+    like the single-GPU path (fp16 prediction, fp16 accumulators, utils/seg_utils.py:256-276), and ONE all-reduce merges the
+    per-rank buffers (fp32 on the wire: the reference's fp16 running sums depend on tile order, so the N-rank result matches
+    at tolerance, not bit for bit) before every rank finalises locally.  `accumulate_fn` lets the CPU/gloo test substitute
+    the blend."""
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if accumulate_fn is None:
+    if accumulate_fn is not None:
+        logits, npred = accumulate_fn(data, [(i, sl) for i, sl in enumerate(slicers) if i % world == rank])
+    elif world == 1 or not shard_mirrors:
         logits, npred = _internal_predict_sliding_window_return_logits(
             data, slicers, network, True, out_idx, slice_seperation, patch_size, use_gaussian, deep_supervision,
             tile_filter=lambda i: i % world == rank, finalize=False)
     else:
-        logits, npred = accumulate_fn(data, [(i, sl) for i, sl in enumerate(slicers) if i % world == rank])
+        logits, npred = _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch_size, use_gaussian,
+                                            deep_supervision, rank, world, group)
     if world > 1:
         l32, n32 = logits.float(), npred.float()
         dist.all_reduce(l32, group=group)
@@ -239,6 +252,47 @@ def predict_sliding_window_sharded(data: torch.Tensor, slicers, network, group=N
     if torch.any(torch.isinf(out)):
         raise RuntimeError(INF_MESSAGE)
     return out.to(torch.float16)
+
+
+def _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch_size, use_gaussian, deep_supervision, rank, world,
+                        group):
+    """This rank's share of the (tile, mirror variant) units; tiles it owns are blended into its fp16 full-volume buffers."""
+    import torch.distributed as dist
+    if not torch.is_grad_enabled() and isinstance(network, torch.nn.Module):
+        if out_idx == 0 and hasattr(network, "sr_head") and hasattr(network, "upscale"):
+            from .seg_model import LRHeadOnly, _EngineForward, SegModel
+            if isinstance(network, (SegModel, _EngineForward)):
+                wrapper = network.__dict__.get("_rehr_lr_only")
+                if wrapper is None:
+                    wrapper = LRHeadOnly(network)
+                    object.__setattr__(network, "_rehr_lr_only", wrapper)
+                network = wrapper
+        from .graphs import graphed
+        if len(slicers) > 0:
+            network = graphed(network, data[slicers[0]][None])
+    dev = data.device
+    logits = torch.zeros((2, data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
+    npred = torch.zeros((data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
+    gaussian = compute_gaussian(tuple(patch_size), sigma_scale=1. / 8, value_scaling_factor=10, device=dev) if use_gaussian else 1
+    variants = [()] + mirror_axes_combinations()
+    for i, sl in enumerate(slicers):
+        mine = [v for v in range(len(variants)) if (i * len(variants) + v) % world == rank]
+        owner = i % world
+        workon = data[sl][None]
+        part = None
+        for v in mine:
+            axes = variants[v]
+            p = _select(network(torch.flip(workon, axes) if axes else workon), out_idx, deep_supervision)
+            p = (torch.flip(p, axes) if axes else p).float()
+            part = p.clone() if part is None else part + p
+        if part is None:  # no variant of this tile landed here: contribute zeros to the tile's reduce
+            part = torch.zeros((1, logits.shape[0], *[s.stop - s.start for s in sl[1:]]), dtype=torch.float32, device=dev)
+            part = part if slice_seperation == 1 else part.repeat_interleave(slice_seperation, dim=2)
+        dist.reduce(part, dst=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        if rank == owner:
+            pred = (part[0] / len(variants)).to(torch.float16)
+            sw_accumulate(logits, npred, pred, gaussian, (sl[1].start * slice_seperation, sl[2].start, sl[3].start))
+    return logits, npred
 
 
 def sliding_window_segment(model, lr_data, patch_size, slice_separation=1, out_idx=0, use_gaussian=True):
