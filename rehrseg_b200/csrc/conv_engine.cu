@@ -299,6 +299,26 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// One K block = KSTEPS tcgen05.mma with compile-time descriptor increments.  Issued from warp-uniform control flow by an
+// elected lane so that the descriptors stay in uniform registers: with `if (lane == 0)` and run-time descriptor arithmetic a
+// single thread needs 120-280 clk per MMA (tools/umma_rate2.cu), which bounds every N <= 256 tile of this kernel.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                             uint32_t idesc, bool first, uint32_t a_step, uint32_t b_step) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)k * a_step);
+    const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)k * b_step);
+    umma_bf16(d_tmem, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+  }
+}
+
 __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment of the dynamic window is required by the 128B swizzle atoms.
@@ -381,6 +401,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     const uint32_t layout = swizzle_layout_for_bytes((int)row_bytes);
     const uint32_t sbo = 8u * row_bytes;
+    const uint32_t desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);  // SBO, version 1, swizzle mode
+    const uint32_t smem_lo = smem_u32(smem) >> 4, stage_lo = stage_bytes >> 4, a_lo_bytes = a_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
@@ -393,15 +415,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full_bar[stage], phase, p.err, 3);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          const int ksteps = p.BK / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_smem_desc(sa + (uint32_t)k * 32u, 0, sbo, layout);
-            const uint64_t bd = make_smem_desc(sb + (uint32_t)k * 32u, 0, sbo, layout);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+        const uint32_t sa_lo = smem_lo + (uint32_t)stage * stage_lo;
+        const uint32_t sb_lo = sa_lo + a_lo_bytes;
+        if (elect_one()) {
+          if (p.BK == 64) issue_kblock<4>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == 0, 2u, 2u);
+          else if (p.BK == 32) issue_kblock<2>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == 0, 2u, 2u);
+          else issue_kblock<1>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == 0, 2u, 2u);
           umma_commit(&empty_bar[stage]);
           if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
         }
@@ -831,24 +850,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_wgrad_kernel(const __grid
     const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
     const uint32_t x_row = (uint32_t)p.xa * 2u, y_row = (uint32_t)p.ya * 2u;
     const uint32_t x_layout = swizzle_layout_for_bytes((int)x_row), y_layout = swizzle_layout_for_bytes((int)y_row);
+    // MN-major descriptors: LBO (bits 16..29 of the low word) = pitch between channel atoms, SBO = pitch between 8-voxel groups
+    const uint32_t a_hi = (((8u * x_row) >> 4) & 0x3FFFu) | (1u << 14) | (x_layout << 29);
+    const uint32_t b_hi = (((8u * y_row) >> 4) & 0x3FFFu) | (1u << 14) | (y_layout << 29);
+    const uint32_t a_lbo = ((x_atom_bytes >> 4) & 0x3FFFu) << 16, b_lbo = ((y_atom_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_step = (16u * x_row) >> 4, b_step = (16u * y_row) >> 4;
+    const uint32_t smem_lo = smem_u32(smem) >> 4, stage_lo = stage_bytes >> 4, y_lo = y_bytes >> 4, xg_lo = x_group_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
     for (int kt = kt0; kt < kt1; ++kt) {
       mbar_wait(&full_bar[stage], phase, p.err, 12);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sy = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sx = sy + y_bytes;
-        const int ksteps = p.BKV / 16;
+      const uint32_t sy_lo = smem_lo + (uint32_t)stage * stage_lo;
+      if (elect_one()) {
         for (int g = 0; g < ng; ++g) {
-          const uint32_t sg = sx + (uint32_t)g * x_group_bytes;
+          const uint32_t sg_lo = (sy_lo + y_lo + (uint32_t)g * xg_lo) | a_lbo;
           const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.BN);
-          for (int k = 0; k < ksteps; ++k) {
-            // MN-major: LBO = pitch between channel atoms, SBO = pitch between 8-voxel groups
-            const uint64_t ad = make_smem_desc(sg + (uint32_t)k * 16u * x_row, x_atom_bytes, 8u * x_row, x_layout);
-            const uint64_t bd = make_smem_desc(sy + (uint32_t)k * 16u * y_row, y_atom_bytes, 8u * y_row, y_layout);
-            umma_bf16(d_tmem, ad, bd, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
-          }
+          if (p.BKV == 128) issue_kblock<8>(d_tmem, sg_lo, sy_lo | b_lbo, a_hi, b_hi, idesc, kt == kt0, a_step, b_step);
+          else if (p.BKV == 64) issue_kblock<4>(d_tmem, sg_lo, sy_lo | b_lbo, a_hi, b_hi, idesc, kt == kt0, a_step, b_step);
+          else issue_kblock<2>(d_tmem, sg_lo, sy_lo | b_lbo, a_hi, b_hi, idesc, kt == kt0, a_step, b_step);
         }
         umma_commit(&empty_bar[stage]);
         if (kt == kt1 - 1) umma_commit(&done_bar[0]);
