@@ -57,7 +57,7 @@ typedef enum { REHR_ACT_NONE = 0, REHR_ACT_RELU = 1, REHR_ACT_LRELU = 2 } rehr_a
 
 const char* rehr_strerror(int status);
 int rehr_last_cuda_error(void);     /* cudaError_t of the last failing CUDA call on this thread */
-int rehr_version(void);             /* ABI version, currently 2 */
+int rehr_version(void);             /* ABI version, currently 3 */
 int rehr_device_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -90,6 +90,19 @@ int rehr_conv3d_stats_tiles(const rehr_tensor* y);
 int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed,
                       const float* bias, const rehr_tensor* dx, int dx_is_f32, int act, float slope,
                       rehr_stream stream);
+
+/* Split-K variants of the two calls above for layers with fewer output tiles than SMs (the <= 8^3 bottleneck stages would
+ * otherwise stream megabytes of weights and taps through one or two SMs): the K loop is shared by several CTAs through an
+ * fp32 scratch buffer and a second small kernel sums the partials and runs the epilogue.  rehr_conv3d_splitk_workspace(desc,
+ * src, w_packed, dst, is_dgrad) returns the scratch bytes (0 = the layer does not split; then ws may be NULL). */
+size_t rehr_conv3d_splitk_workspace(const rehr_conv_desc* desc, const rehr_tensor* src, const void* w_packed,
+                                    const rehr_tensor* dst, int is_dgrad);
+int rehr_conv3d_fwd_ws(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                       const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats, void* ws, size_t ws_bytes,
+                       rehr_stream stream);
+int rehr_conv3d_dgrad_ws(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
+                         const rehr_tensor* dx, int dx_is_f32, int act, float slope, void* ws, size_t ws_bytes,
+                         rehr_stream stream);
 
 /* dW[A][B][T] (f32, PyTorch layout) = sum_o dy[o,A] (x) x[o*s+k-p, B].  Split-K partials go to `ws`. */
 size_t rehr_conv3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);

@@ -69,6 +69,9 @@ def _declare(L: C.CDLL) -> None:
         "rehr_conv3d_fwd": (i, [D, T, vp, vp, T, i, i, f, vp, vp]),
         "rehr_conv3d_stats_tiles": (i, [T]),
         "rehr_conv3d_dgrad": (i, [D, T, vp, vp, T, i, i, f, vp]),
+        "rehr_conv3d_splitk_workspace": (sz, [D, T, vp, T, i]),
+        "rehr_conv3d_fwd_ws": (i, [D, T, vp, vp, T, i, i, f, vp, vp, sz, vp]),
+        "rehr_conv3d_dgrad_ws": (i, [D, T, vp, vp, T, i, i, f, vp, sz, vp]),
         "rehr_conv3d_wgrad_workspace": (sz, [D, T, T]),
         "rehr_conv3d_wgrad": (i, [D, T, T, vp, i, vp, sz, vp]),
         "rehr_convtranspose3d_fwd": (i, [D, T, vp, vp, T, i, f, vp]),

@@ -59,7 +59,7 @@ const char* rehr_strerror(int status) {
   }
 }
 int rehr_last_cuda_error(void) { return g_last_cuda_error; }
-int rehr_version(void) { return 2; }
+int rehr_version(void) { return 3; }
 int rehr_device_sm_count(void) { return sm_count(); }
 
 int rehr_pack_weight(const float* src, void* dst_bf16, int R, int C, int T, long long sr, long long sc, long long st,
@@ -76,21 +76,26 @@ int rehr_conv3d_stats_tiles(const rehr_tensor* y) {
   return ((y->w + box[0] - 1) / box[0]) * ((y->h + box[1] - 1) / box[1]) * ((y->d + box[2] - 1) / box[2]);
 }
 
-int rehr_conv3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
-                    const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats, rehr_stream stream) {
+// ws / ws_bytes: optional split-K scratch (see rehr_conv3d_splitk_workspace); need != nullptr => planning query only.
+static int conv_fwd_impl(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                         const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats, rehr_stream stream, void* ws,
+                         size_t ws_bytes, size_t* need) {
   if (!conv_shapes_ok(desc, x, y) || !w_packed) return REHR_BAD_SHAPE;
   TapPlan plan;
   int rc = build_fwd_taps(*desc, *x, &plan);
   if (rc != REHR_OK) return rc;
   const int O[4] = {y->w, y->h, y->d, y->n};
   const int os[3] = {1, 1, 1}, oo[3] = {0, 0, 0};
-  return launch_tapped_gemm(plan, *x, w_packed, y->c, bias, *y, y_is_f32, O, os, oo, act, slope, stats, (cudaStream_t)stream);
+  return launch_tapped_gemm(plan, *x, w_packed, y->c, bias, *y, y_is_f32, O, os, oo, act, slope, stats, (cudaStream_t)stream, nullptr,
+                            ws, ws_bytes, need);
 }
 
-int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
-                      const rehr_tensor* dx, int dx_is_f32, int act, float slope, rehr_stream stream) {
+static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
+                           const rehr_tensor* dx, int dx_is_f32, int act, float slope, rehr_stream stream, void* ws, size_t ws_bytes,
+                           size_t* need) {
   // shapes: dy is the conv output grid, dx the conv input grid
   if (!conv_shapes_ok(desc, dx, dy) || !w_packed) return REHR_BAD_SHAPE;
+  if (need) *need = 0;
   const int s[3] = {desc->sw, desc->sh, desc->sd};
   const int isz[3] = {dx->w, dx->h, dx->d};
   for (int cd = 0; cd < s[2]; ++cd)
@@ -109,6 +114,7 @@ int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const v
         int rc = build_dgrad_taps(*desc, cls, &plan);
         if (rc != REHR_OK) return rc;
         if (plan.num_taps == 0) {
+          if (need) continue;
           const long long total = (long long)O[0] * O[1] * O[2] * O[3] * dx->c;
           const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
           fill_class_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dx->ptr, dx_is_f32, dx->ld, dx->c, bias, act, slope, O[0], O[1],
@@ -116,11 +122,42 @@ int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const v
           REHR_CHECK_LAUNCH();
           continue;
         }
+        size_t cls_need = 0;
         rc = launch_tapped_gemm(plan, *dy, w_packed, dx->c, bias, *dx, dx_is_f32, O, s, cls, act, slope, nullptr,
-                                (cudaStream_t)stream);
+                                (cudaStream_t)stream, nullptr, ws, ws_bytes, need ? &cls_need : nullptr);
         if (rc != REHR_OK) return rc;
+        if (need && cls_need > *need) *need = cls_need;  // the classes run back to back on one stream: they share the scratch
       }
   return REHR_OK;
+}
+
+int rehr_conv3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                    const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats, rehr_stream stream) {
+  return conv_fwd_impl(desc, x, w_packed, bias, y, y_is_f32, act, slope, stats, stream, nullptr, 0, nullptr);
+}
+
+int rehr_conv3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
+                      const rehr_tensor* dx, int dx_is_f32, int act, float slope, rehr_stream stream) {
+  return conv_dgrad_impl(desc, dy, w_packed, bias, dx, dx_is_f32, act, slope, stream, nullptr, 0, nullptr);
+}
+
+// Split-K variants: layers with fewer output tiles than SMs (the <= 8^3 bottleneck stages) share their K loop over several CTAs
+// through an fp32 scratch buffer.  rehr_conv3d_splitk_workspace returns the bytes needed (0 = the layer does not split).
+size_t rehr_conv3d_splitk_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const rehr_tensor* y,
+                                    int is_dgrad) {
+  size_t need = 0;
+  int rc = is_dgrad ? conv_dgrad_impl(desc, x, w_packed, nullptr, y, 0, REHR_ACT_NONE, 0.f, nullptr, nullptr, 0, &need)
+                    : conv_fwd_impl(desc, x, w_packed, nullptr, y, 0, REHR_ACT_NONE, 0.f, nullptr, nullptr, nullptr, 0, &need);
+  return rc == REHR_OK ? need : 0;
+}
+int rehr_conv3d_fwd_ws(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                       const rehr_tensor* y, int y_is_f32, int act, float slope, float* stats, void* ws, size_t ws_bytes,
+                       rehr_stream stream) {
+  return conv_fwd_impl(desc, x, w_packed, bias, y, y_is_f32, act, slope, stats, stream, ws, ws_bytes, nullptr);
+}
+int rehr_conv3d_dgrad_ws(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
+                         const rehr_tensor* dx, int dx_is_f32, int act, float slope, void* ws, size_t ws_bytes, rehr_stream stream) {
+  return conv_dgrad_impl(desc, dy, w_packed, bias, dx, dx_is_f32, act, slope, stream, ws, ws_bytes, nullptr);
 }
 
 size_t rehr_conv3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy) {

@@ -290,6 +290,11 @@ struct alignas(64) FwdParams {
   // column block (cls, co) of row (input voxel i) is output voxel i*s + r(cls), channel co.  0 = off.
   int sc_cout;
   int sc_s[3];     // stride per dim (w h d)
+  // split-K for layers with fewer output tiles than SMs (the <= 8^3 bottleneck stages stream 2-5 MB of weights and taps
+  // through ONE or TWO SMs otherwise): work item = (tile, split); a split accumulates its share of the (tap, Cin-chunk)
+  // K blocks and stores raw fp32 partials [split][tile][128][BN]; conv_splitk_finish_kernel sums them and runs the epilogue.
+  int ksplit;
+  float* partial;
   int* err;
 };
 
@@ -298,6 +303,10 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == REHR_ACT_LRELU) return v > 0.f ? v : v * slope;
   return v;
 }
+
+// bias + InstanceNorm partial sums + activation + store of one 16-column chunk of one accumulator row (non-scatter epilogue)
+__device__ __forceinline__ void finish_chunk(const FwdParams& p, float (&f)[16], bool valid, long long vox, int nbase, int c0,
+                                             int lane, float* mypart);
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -316,6 +325,64 @@ __device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_lo, uin
     const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)k * a_step);
     const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)k * b_step);
     umma_bf16(d_tmem, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+  }
+}
+
+__device__ __forceinline__ void finish_chunk(const FwdParams& p, float (&f)[16], bool valid, long long vox, int nbase, int c0,
+                                             int lane, float* mypart) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = nbase + c0 + i;
+    if (p.bias != nullptr && c < p.cout) f[i] += __ldg(p.bias + c);
+  }
+  if (p.stats != nullptr) {
+    float s1[16], s2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float x = valid ? f[i] : 0.f;
+      s1[i] = x;
+      s2[i] = x * x;
+    }
+    warp_colsum16(s1, lane);
+    warp_colsum16(s2, lane);
+    if ((lane & 1) == 0) {
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      mypart[c0 + col] = s1[0];
+      mypart[256 + c0 + col] = s2[0];
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
+    const int cbase = nbase + c0;
+    if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cbase;
+      if (cbase + 16 <= p.cout && (p.out_ld & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (cbase + i < p.cout) o[i] = f[i];
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cbase;
+      if (cbase + 16 <= p.cout && (p.out_ld & 7) == 0) {
+        uint4 lo, hi;
+        lo.x = pack_bf16x2(f[0], f[1]);
+        lo.y = pack_bf16x2(f[2], f[3]);
+        lo.z = pack_bf16x2(f[4], f[5]);
+        lo.w = pack_bf16x2(f[6], f[7]);
+        hi.x = pack_bf16x2(f[8], f[9]);
+        hi.y = pack_bf16x2(f[10], f[11]);
+        hi.z = pack_bf16x2(f[12], f[13]);
+        hi.w = pack_bf16x2(f[14], f[15]);
+        reinterpret_cast<uint4*>(o)[0] = lo;
+        reinterpret_cast<uint4*>(o)[1] = hi;
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (cbase + i < p.cout) o[i] = __float2bfloat16(f[i]);
+      }
+    }
   }
 }
 
@@ -359,6 +426,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
 
   const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
   const int total_tiles = m_tiles * p.n_tiles;
+  const int total_work = total_tiles * p.ksplit;
   const int kblocks = p.num_taps * p.cin_chunks;
 
   if (warp == 0) {
@@ -366,7 +434,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work / p.ksplit, split = work - tile * p.ksplit;
+        const int kb0 = (int)(((long long)kblocks * split) / p.ksplit), kb1 = (int)(((long long)kblocks * (split + 1)) / p.ksplit);
         const int n_tile = tile % p.n_tiles;
         int mt = tile / p.n_tiles;
         const int tw = mt % p.tiles[0];
@@ -376,21 +446,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
         const int td = mt % p.tiles[2];
         const int tn = mt / p.tiles[2];
         const int w0 = tw * p.box[0], h0 = th * p.box[1], d0 = td * p.box[2], n0 = tn * p.box[3];
-        for (int j = 0; j < p.num_taps; ++j) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int j = kb / p.cin_chunks, cc = kb - j * p.cin_chunks;
           const int2 t = p.taps[j];
           const int map_id = t.x & 0xff;
           const int dw = ((t.x >> 8) & 0xff) - 128, dh = ((t.x >> 16) & 0xff) - 128, dd = ((t.x >> 24) & 0xff) - 128;
           const int kbase = t.y * p.cin;
-          for (int cc = 0; cc < p.cin_chunks; ++cc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            tma_load_5d(&p.a_map[map_id], &full_bar[stage], sa, cc * p.BK, w0 + dw, h0 + dh, d0 + dd, n0);
-            tma_load_2d(&p.b_map, &full_bar[stage], sa + a_bytes, kbase + cc * p.BK, n_tile * p.BN);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_5d(&p.a_map[map_id], &full_bar[stage], sa, cc * p.BK, w0 + dw, h0 + dh, d0 + dd, n0);
+          tma_load_2d(&p.b_map, &full_bar[stage], sa + a_bytes, kbase + cc * p.BK, n_tile * p.BN);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -406,23 +475,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
+      const int split = work % p.ksplit;
+      const int kb0 = (int)(((long long)kblocks * split) / p.ksplit), kb1 = (int)(((long long)kblocks * (split + 1)) / p.ksplit);
       const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, p.err, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, p.err, 3);
         tc_fence_after();
         const uint32_t sa_lo = smem_lo + (uint32_t)stage * stage_lo;
         const uint32_t sb_lo = sa_lo + a_lo_bytes;
         if (elect_one()) {
-          if (p.BK == 64) issue_kblock<4>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == 0, 2u, 2u);
-          else if (p.BK == 32) issue_kblock<2>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == 0, 2u, 2u);
-          else issue_kblock<1>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == 0, 2u, 2u);
+          if (p.BK == 64) issue_kblock<4>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == kb0, 2u, 2u);
+          else if (p.BK == 32) issue_kblock<2>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == kb0, 2u, 2u);
+          else issue_kblock<1>(d_tmem, sa_lo, sb_lo, desc_hi, desc_hi, idesc, kb == kb0, 2u, 2u);
           umma_commit(&empty_bar[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -437,7 +508,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
     const int row = q * 32 + lane;   // accumulator row = voxel within the box
     const int et = threadIdx.x - 64; // 0..127
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
+      const int tile = work / p.ksplit, split = work - tile * p.ksplit;
       const int acc = iter & 1;
       const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
       const int n_tile = tile % p.n_tiles;
@@ -501,68 +573,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
           }
           continue;
         }
+        if (p.partial != nullptr) {  // split-K: raw fp32 partial, finished by conv_splitk_finish_kernel
+          float4* o = reinterpret_cast<float4*>(p.partial + (((size_t)split * total_tiles + tile) * 128 + row) * p.BN + c0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = nbase + c0 + i;
-          float x = __uint_as_float(v[i]);
-          if (p.bias != nullptr && c < p.cout) x += __ldg(p.bias + c);
-          f[i] = x;
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+          continue;
         }
-        if (p.stats != nullptr) {
-          float s1[16], s2[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x = valid ? f[i] : 0.f;
-            s1[i] = x;
-            s2[i] = x * x;
-          }
-          warp_colsum16(s1, lane);
-          warp_colsum16(s2, lane);
-          if ((lane & 1) == 0) {
-            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            mypart[c0 + col] = s1[0];
-            mypart[256 + c0 + col] = s2[0];
-          }
-        }
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
-          const int cbase = nbase + c0;
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cbase;
-            if (cbase + 16 <= p.cout && (p.out_ld & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-              for (int i = 0; i < 16; ++i)
-                if (cbase + i < p.cout) o[i] = f[i];
-            }
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cbase;
-            if (cbase + 16 <= p.cout && (p.out_ld & 7) == 0) {
-              uint4 lo, hi;
-              lo.x = pack_bf16x2(f[0], f[1]);
-              lo.y = pack_bf16x2(f[2], f[3]);
-              lo.z = pack_bf16x2(f[4], f[5]);
-              lo.w = pack_bf16x2(f[6], f[7]);
-              hi.x = pack_bf16x2(f[8], f[9]);
-              hi.y = pack_bf16x2(f[10], f[11]);
-              hi.z = pack_bf16x2(f[12], f[13]);
-              hi.w = pack_bf16x2(f[14], f[15]);
-              reinterpret_cast<uint4*>(o)[0] = lo;
-              reinterpret_cast<uint4*>(o)[1] = hi;
-            } else {
-              for (int i = 0; i < 16; ++i)
-                if (cbase + i < p.cout) o[i] = __float2bfloat16(f[i]);
-            }
-          }
-        }
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        finish_chunk(p, f, valid, vox, nbase, c0, lane, mypart);
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (p.stats != nullptr) {
+      if (p.stats != nullptr && p.partial == nullptr) {
         named_bar_sync(1, 128);
         for (int c = et; c < p.BN; c += 128) {
           if (nbase + c < p.cout) {
@@ -589,6 +616,69 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
   }
 }
 
+// Second stage of split-K: one CTA of 128 threads per (output tile, 16-column chunk); thread = accumulator row; sums the `ksplit`
+// raw partials and runs the same per-chunk epilogue (bias, InstanceNorm partial sums, activation, store) as the fused path.
+__global__ void __launch_bounds__(128) conv_splitk_finish_kernel(const __grid_constant__ FwdParams p) {
+  __shared__ float part[4 * 2 * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int c0 = blockIdx.y * 16;
+  const int total_tiles = gridDim.x;
+  const int n_tile = tile % p.n_tiles;
+  const int m_tile = tile / p.n_tiles;
+  int mt = m_tile;
+  const int tw = mt % p.tiles[0];
+  mt /= p.tiles[0];
+  const int th = mt % p.tiles[1];
+  mt /= p.tiles[1];
+  const int td = mt % p.tiles[2];
+  const int tn = mt / p.tiles[2];
+  int r = row;
+  const int ow = tw * p.box[0] + r % p.box[0];
+  r /= p.box[0];
+  const int oh = th * p.box[1] + r % p.box[1];
+  r /= p.box[1];
+  const int od = td * p.box[2] + r % p.box[2];
+  r /= p.box[2];
+  const int on = tn * p.box[3] + r;
+  const bool valid = ow < p.O[0] && oh < p.O[1] && od < p.O[2] && on < p.O[3];
+  const long long vox = (((long long)on * p.AO[2] + (od * p.os[2] + p.oo[2])) * p.AO[1] + (oh * p.os[1] + p.oo[1])) * p.AO[0] +
+                        (ow * p.os[0] + p.oo[0]);
+  const int nbase = n_tile * p.BN;
+  float* mypart = part + (warp * 2) * 256;
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = 0.f;
+  const float* src0 = p.partial + ((size_t)tile * 128 + row) * p.BN + c0;
+  const size_t sstride = (size_t)total_tiles * 128 * p.BN;
+#pragma unroll 4
+  for (int s = 0; s < p.ksplit; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(src0 + (size_t)s * sstride);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = src[i];
+      f[4 * i] += v.x; f[4 * i + 1] += v.y; f[4 * i + 2] += v.z; f[4 * i + 3] += v.w;
+    }
+  }
+  finish_chunk(p, f, valid, vox, nbase, c0, lane, mypart);
+  if (p.stats != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 16 && nbase + c0 + threadIdx.x < p.cout) {
+      const int c = c0 + threadIdx.x;
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        a += part[(w * 2) * 256 + c];
+        b += part[(w * 2 + 1) * 256 + c];
+      }
+      float* dst = p.stats + ((long long)m_tile * p.cout + nbase + c) * 2;
+      dst[0] = a;
+      dst[1] = b;
+    }
+  }
+}
+
 static size_t fwd_smem_tail_bytes() { return (2 * kMaxStages + 4) * 8 + 16 + 2 * 4 * 2 * 256 * 4; }
 
 // Launch one tapped GEMM:  out(class) = act(sum_taps T_j(in) Wp + bias).
@@ -596,7 +686,8 @@ static size_t fwd_smem_tail_bytes() { return (2 * kMaxStages + 4) * 8 + 16 + 2 *
 // transform (os, oo); AO = actual output extents.
 int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w_packed, int w_rows,
                        const float* bias, const rehr_tensor& out, int out_f32, const int O[4], const int os[3],
-                       const int oo[3], int act, float slope, float* stats, cudaStream_t stream, const int* scatter_s) {
+                       const int oo[3], int act, float slope, float* stats, cudaStream_t stream, const int* scatter_s, void* ws,
+                       size_t ws_bytes, size_t* ws_need) {
   const int cin = in.c;
   const int ncls = scatter_s ? scatter_s[0] * scatter_s[1] * scatter_s[2] : 1;
   const int cout = out.c * ncls;  // GEMM N: all parity classes side by side in scatter mode
@@ -699,12 +790,35 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
     attr_set = true;
   }
   const int total_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3] * p.n_tiles;
-  const int grid = std::min(total_tiles, sm_count());
+  // split-K when the output tiles cannot fill the machine and there is a long K loop to share
+  const int kblocks = p.num_taps * p.cin_chunks;
+  int ksplit = 1;
+  if (!scatter_s && total_tiles * 4 <= sm_count() && kblocks >= 16) {
+    ksplit = std::min(std::min(kblocks / 8, sm_count() / total_tiles), 32);
+    if (ksplit < 2) ksplit = 1;
+  }
+  const size_t need = ksplit > 1 ? (size_t)ksplit * total_tiles * 128 * BN * sizeof(float) : 0;
+  if (ws_need) {  // planning query only
+    *ws_need = need;
+    return REHR_OK;
+  }
+  if (ksplit > 1 && (ws == nullptr || ws_bytes < need)) ksplit = 1;  // no scratch supplied: single pass
+  p.ksplit = ksplit;
+  p.partial = ksplit > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+  const int grid = std::min(total_tiles * ksplit, sm_count());
   conv_tapped_gemm_kernel<<<grid, kFwdThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return REHR_CUDA_ERROR;
+  }
+  if (ksplit > 1) {
+    conv_splitk_finish_kernel<<<dim3(total_tiles, BN / 16), 128, 0, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
   }
   return REHR_OK;
 }

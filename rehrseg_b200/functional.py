@@ -213,10 +213,12 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
     wp = _packed(weight, "fwd")
     xt = rt(x)
+    need = lib().rehr_conv3d_splitk_workspace(C.byref(desc), C.byref(xt), ptr(wp), C.byref(yt), 0)
+    ws = _ws(need, x.device) if need else None
     with _timed("conv_tapped_gemm_kernel", flops, tag):
-        check(lib().rehr_conv3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
-                                    float(slope), ptr(stats), stream_ptr()), "conv3d_fwd")
-    _count()
+        check(lib().rehr_conv3d_fwd_ws(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(out_f32), act,
+                                       float(slope), ptr(stats), ptr(ws), need, stream_ptr()), "conv3d_fwd")
+    _count(2 if need else 1)
     if want_stats and stats is None:
         stats, tiles = instnorm_stats_raw(out)
     return out, stats, tiles
@@ -249,10 +251,12 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
         return dx
     wp = _packed(weight, "dgrad", cache)
     dyt, dxt = rt(dy), rt(dx)
+    need = lib().rehr_conv3d_splitk_workspace(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), 1)
+    ws = _ws(need, dy.device) if need else None
     with _timed("conv_tapped_gemm_kernel", flops, tag):
-        check(lib().rehr_conv3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0,
-                                      stream_ptr()), "conv3d_dgrad")
-    _count(stride[0] * stride[1] * stride[2])
+        check(lib().rehr_conv3d_dgrad_ws(C.byref(desc), C.byref(dyt), ptr(wp), None, C.byref(dxt), 0, ACT_NONE, 0.0, ptr(ws), need,
+                                         stream_ptr()), "conv3d_dgrad")
+    _count(stride[0] * stride[1] * stride[2] * (2 if need else 1))
     return dx
 
 
