@@ -119,6 +119,116 @@ __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const SmallCinArgs a)
   }
 }
 
+// Fast forward path for k = 3x3x3, stride 1, pad 1, Cout = 32 (the nnU-Net stem at the C1 size: 4.2 M voxels): a CTA stages the
+// CIN x 3 x 10 x (W+2) fp32 input rows that 8 output rows (one per warp) need plus the 27*CIN x 32 weights in shared memory; a
+// thread owns one output voxel and all 32 channels, so the inner loop is fully unrolled (no bounds tests, no index arithmetic),
+// every x value is one conflict-free shared load, weights are float4 broadcasts, and a warp writes 2 KB of contiguous NDHWC bf16.
+template <int CIN>
+__global__ void __launch_bounds__(256) smallcin_fwd_k3c32_kernel(const SmallCinArgs a) {
+  extern __shared__ float sm[];  // [CIN*27][32] weights, then [CIN][3][10][Wa] input rows
+  const int Wa = a.wd + 2;
+  float* sw = sm;
+  float* sx = sm + CIN * 27 * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < CIN * 27 * 32; i += 256) {
+    const int co = i % 32, k = i / 32;  // k = ci*27 + t
+    sw[i] = a.w[(long long)co * CIN * 27 + k];
+  }
+  float bias[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) bias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+  const int ytiles = (a.oh + 7) / 8;
+  const long long tiles = (long long)a.n * a.od * ytiles;
+  const long long in_plane = (long long)a.h * a.wd, in_vol = in_plane * a.d;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int yt = (int)(tile % ytiles);
+    long long r = tile / ytiles;
+    const int oz = (int)(r % a.od);
+    const int nn = (int)(r / a.od);
+    const int oy0 = yt * 8;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CIN * 30 * Wa; i += 256) {
+      const int xx = i % Wa;
+      int q = i / Wa;
+      const int yy = q % 10;
+      q /= 10;
+      const int kz = q % 3, ci = q / 3;
+      const int iz = oz + kz - 1, iy = oy0 + yy - 1, ix = xx - 1;
+      float v = 0.f;
+      if (iz >= 0 && iz < a.d && iy >= 0 && iy < a.h && ix >= 0 && ix < a.wd)
+        v = __ldg(a.x + ((long long)nn * CIN + ci) * in_vol + iz * in_plane + (long long)iy * a.wd + ix);
+      sx[i] = v;
+    }
+    __syncthreads();
+    const int oy = oy0 + warp;
+    if (oy >= a.oh) continue;
+    for (int ox = lane; ox < a.ow; ox += 32) {
+      // compiler barrier: without it the 27*CIN*32 loop-invariant weight loads are hoisted out of this loop into 864+
+      // "registers" that ptxas spills to local memory (9.6 KB stack frame, 6x slower)
+      asm volatile("" ::: "memory");
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = bias[i];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const float* xr = sx + ((ci * 3 + kz) * 10 + warp + ky) * Wa + ox;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float xv = xr[kx];
+              const float4* wp = reinterpret_cast<const float4*>(sw + (ci * 27 + (kz * 3 + ky) * 3 + kx) * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 w4 = wp[i];
+                acc[4 * i] = fmaf(xv, w4.x, acc[4 * i]);
+                acc[4 * i + 1] = fmaf(xv, w4.y, acc[4 * i + 1]);
+                acc[4 * i + 2] = fmaf(xv, w4.z, acc[4 * i + 2]);
+                acc[4 * i + 3] = fmaf(xv, w4.w, acc[4 * i + 3]);
+              }
+            }
+          }
+      const long long v = (((long long)nn * a.od + oz) * a.oh + oy) * a.ow + ox;
+      uint4* o = reinterpret_cast<uint4*>(a.y + v * a.ldy);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float z0 = acc[8 * j + 2 * i], z1 = acc[8 * j + 2 * i + 1];
+          if (a.act == REHR_ACT_RELU) { z0 = z0 > 0.f ? z0 : 0.f; z1 = z1 > 0.f ? z1 : 0.f; }
+          if (a.act == REHR_ACT_LRELU) { z0 = z0 > 0.f ? z0 : z0 * a.slope; z1 = z1 > 0.f ? z1 : z1 * a.slope; }
+          h2[i] = __floats2bfloat162_rn(z0, z1);
+        }
+        o[j] = u;
+      }
+    }
+  }
+}
+
+template <int CIN>
+static int launch_smallcin_fwd_k3c32(const SmallCinArgs& a, cudaStream_t stream) {
+  const size_t smem = ((size_t)CIN * 27 * 32 + (size_t)CIN * 30 * (a.wd + 2)) * sizeof(float);
+  if (smem > 200 * 1024) return REHR_UNSUPPORTED;
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(smallcin_fwd_k3c32_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      return REHR_CUDA_ERROR;
+    }
+    attr_smem = smem;
+  }
+  const long long tiles = (long long)a.n * a.od * ((a.oh + 7) / 8);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 4));
+  smallcin_fwd_k3c32_kernel<CIN><<<blocks, 256, smem, stream>>>(a);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight gradient: dw[co][ci][t] = sum_o dy[o, co] * x[ci, o*s + t - p].
 // Warp = a run of output voxels, lane = output channel (coalesced 64 B dy rows); each lane keeps kWgAcc
@@ -479,10 +589,19 @@ int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, i
   a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
   a.act = act;
   a.slope = slope;
-  const long long items = (long long)n * y->d * y->h * y->w * ((y->c + kScCoutPerThread - 1) / kScCoutPerThread);
-  const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)sm_count() * 8));
-  smallcin_fwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(a);
-  REHR_CHECK_LAUNCH();
+  const bool k3 = desc->kd == 3 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
+                  desc->pd == 1 && desc->ph == 1 && desc->pw == 1;
+  int rc = REHR_UNSUPPORTED;
+  if (k3 && y->c == 32 && cin <= 2) {
+    rc = cin == 1 ? launch_smallcin_fwd_k3c32<1>(a, (cudaStream_t)stream) : launch_smallcin_fwd_k3c32<2>(a, (cudaStream_t)stream);
+    if (rc != REHR_OK && rc != REHR_UNSUPPORTED) return rc;
+  }
+  if (rc == REHR_UNSUPPORTED) {
+    const long long items = (long long)n * y->d * y->h * y->w * ((y->c + kScCoutPerThread - 1) / kScCoutPerThread);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)sm_count() * 8));
+    smallcin_fwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(a);
+    REHR_CHECK_LAUNCH();
+  }
   if (stats) {
     if (act != REHR_ACT_NONE) return REHR_UNSUPPORTED;  // statistics are defined on the pre-activation output
     return rehr_instnorm_stats(y, stats, stream);
