@@ -37,8 +37,8 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
     # weights the two class logits are nearly tied almost everywhere, so raw agreement measures the tie density, not
     # the kernels (torch's own bf16 autocast path scores the same 99.6-99.7 % -- see `autocast_*` below and DESIGN.md).
     om, orr = out_m.float().cpu(), out_r.float()
-    margin = (orr[:, 0] - orr[:, 1]).abs()
-    tau = 4.0 * float((om - orr).pow(2).mean().sqrt())
+    margin = (orr[:, 0] - orr[:, 1]).detach().abs()
+    tau = 4.0 * float((om - orr).detach().pow(2).mean().sqrt())
     sel = margin > tau
     res["argmax_agreement_clear_margin"] = float((om.argmax(1) == orr.argmax(1))[sel].double().mean()) if bool(sel.any()) else 1.0
     res["clear_margin_fraction"] = float(sel.double().mean())
