@@ -140,6 +140,16 @@ int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y, in
 int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int ks, int y_is_f32,
                           int act, float slope, float* stats, rehr_stream stream);
 
+/* Input gradient of a k3 / pad 1 conv with strides in {1, 2} (the nnU-Net stage-entry convs) through the marching kernel:
+ * every output parity class of dx is a stride-1 correlation over dy with 1 or 2 taps per strided dimension, written in place
+ * at (2i + r).  w = conv weight f32 [Cout][Cin][27]; cin / cout are the CONV's channel counts. */
+int rehr_conv3d_march_s2dgrad_supported(const rehr_conv_desc* desc, int cin, int cout);
+size_t rehr_conv3d_march_s2dgrad_weight_bytes(const rehr_conv_desc* desc, int cin, int cout);
+int rehr_pack_weight_march_s2dgrad(const rehr_conv_desc* desc, const float* w, void* dst_bf16, int cin, int cout,
+                                   rehr_stream stream);
+int rehr_conv3d_march_s2dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const rehr_tensor* dx,
+                              rehr_stream stream);
+
 /* Marching weight-gradient kernel for cubic kernels ks = 3 or 5, stride 1, pad (ks-1)/2 (csrc/wgrad_march.cu): both
  * activations are TMA-loaded once per plane, the ks^3 taps are UMMA descriptor offsets / a kd-fused N = ks*PC MMA,
  * accumulators live in TMEM for the whole CTA.  Same call site as rehr_conv3d_wgrad.  dw = f32 [cout][x->c][ks^3] with

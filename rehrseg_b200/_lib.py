@@ -85,6 +85,10 @@ def _declare(L: C.CDLL) -> None:
         "rehr_pack_weight_march": (i, [vp, vp, i, i, i, ll, ll, i, vp]),
         "rehr_conv3d_march_stats_tiles": (i, [T, T, i]),
         "rehr_conv3d_march_fwd": (i, [T, vp, vp, T, i, i, i, f, vp, vp]),
+        "rehr_conv3d_march_s2dgrad_supported": (i, [D, i, i]),
+        "rehr_conv3d_march_s2dgrad_weight_bytes": (sz, [D, i, i]),
+        "rehr_pack_weight_march_s2dgrad": (i, [D, vp, vp, i, i, vp]),
+        "rehr_conv3d_march_s2dgrad": (i, [D, T, vp, T, vp]),
         "rehr_conv3d_wgrad_march_supported": (i, [D, T, T]),
         "rehr_conv3d_wgrad_march_workspace": (sz, [T, T, i]),
         "rehr_conv3d_wgrad_march": (i, [T, T, i, i, vp, i, vp, sz, vp]),

@@ -50,6 +50,13 @@ struct alignas(64) MarchParams {
   CUtensorMap w_map;  // 2-D [n_ct*9*chunks*3Ct rows][BK], box (BK, 3Ct)
   int N, D, H, W, Cin, Cout;
   int ks;  // 3 or 5
+  // tap-index ranges actually present (the rest of the packed weights are zero and are skipped): whole kernel by default; the
+  // parity classes of a stride-2 input gradient use 1 or 2 of the 3 taps per dimension (see rehr_conv3d_march_s2dgrad)
+  int kd_lo, kd_hi, kh_lo, kh_hi, kw_lo, kw_hi;
+  // output addressing: element offset = n*o_pn + d*o_pd + h*o_ph + w*o_pw (dense NDHWC by default; a parity class of a
+  // larger tensor otherwise) and the extents that really exist (<= D, H, W)
+  long long o_pn, o_pd, o_ph, o_pw;
+  int OD, OH, OW;
   int Ct, n_ct, BK, chunks;
   int tiles_h, tiles_w, Ds, n_seg;
   int ring, slots;
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
             tma_load_2d(&p.w_map, wfull_bar, s_w + (size_t)t * p.wtile_bytes, 0, (c.ct * tiles + t) * KS * p.Ct);
         }
         const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
-        const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
+        const int pa = max(d0 + p.kd_lo - R, 0), pb = min(d1 - 1 + p.kd_hi - R, p.D - 1);
         const int h0 = c.th * kTileH - R, w0 = c.tw * kTileW - R;
         for (int pl = pa; pl <= pb; ++pl) {
           const long long tp0 = clock64();
@@ -213,10 +220,11 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         tc_fence_after();
       }
       const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
-      const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
+      const int pa = max(d0 + p.kd_lo - R, 0), pb = min(d1 - 1 + p.kd_hi - R, p.D - 1);
       int next_open = d0;
       for (int pl = pa; pl <= pb; ++pl) {
-        const int qa = max(pl - R, d0), qb = min(pl + R, d1 - 1);
+        // input plane pl feeds output plane q through depth tap kd = pl - q + R, kd in [kd_lo, kd_hi]
+        const int qa = max(pl - p.kd_hi + R, d0), qb = min(pl - p.kd_lo + R, d1 - 1);
         const long long tm0 = clock64();
         while (next_open <= qb) {  // first touch of an output plane's TMEM slot: wait until it was drained + zeroed
           const int s = (next_open - d0) & kSlotMask;
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           if (!(p.debug & 4) && elect_one_sync()) {
 #pragma unroll
             for (int khw = 0; khw < KS * KS; ++khw) {
+              if (khw / KS < p.kh_lo || khw / KS > p.kh_hi || khw % KS < p.kw_lo || khw % KS > p.kw_hi) continue;  // zero taps
 #pragma unroll
               for (int ch = 0; ch < CHUNKS; ++ch) {
                 const uint32_t a_t = a_lo + (uint32_t)((((khw / KS) * kHaloW + (khw % KS)) * kRowB) >> 4) + (uint32_t)ch * chunk_lo;
@@ -259,9 +268,11 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         if (elect_one_sync()) {
           umma_commit(&empty_bar[stage]);
           // finished output planes
-          if (pl - R >= d0) umma_commit(&tfull_bar[(pl - R - d0) & kSlotMask]);
+          // output plane q is complete once its last contributing input plane q + kd_hi - R has been issued
+          const int qdone = pl - p.kd_hi + R;
+          if (qdone >= d0 && qdone <= d1 - 1) umma_commit(&tfull_bar[(qdone - d0) & kSlotMask]);
           if (pl == pb) {
-            for (int q = max(pl - R + 1, d0); q <= d1 - 1; ++q) umma_commit(&tfull_bar[(q - d0) & kSlotMask]);
+            for (int q = max(qdone + 1, d0); q <= d1 - 1; ++q) umma_commit(&tfull_bar[(q - d0) & kSlotMask]);
           }
         }
         __syncwarp();
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
       const ItemCoord c = decode_item(p, item);
       const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
       const int oh = c.th * kTileH + hl, ow = c.tw * kTileW + wl;
-      const bool valid = oh < p.H && ow < p.W;
+      const bool valid_hw = oh < p.OH && ow < p.OW;
       const int cbase = c.ct * CT;
       // per-thread running column sums of this item (this thread's output row, all planes of the segment)
       float s1[CT], s2[CT];
@@ -320,7 +331,8 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         tc_fence_after();
         const long long te1 = clock64();
         const uint32_t taddr = lane_addr + (uint32_t)(s * CT);
-        const long long vox = (((long long)c.n * p.D + q) * p.H + oh) * p.W + ow;
+        const bool valid = valid_hw && q < p.OD;
+        const long long obase = (long long)c.n * p.o_pn + (long long)q * p.o_pd + (long long)oh * p.o_ph + (long long)ow * p.o_pw;
 #pragma unroll
         for (int c0 = 0; c0 < CT; c0 += kW) {
           if (p.debug & 2) break;
@@ -357,18 +369,18 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
             const int cc = cbase + c0;
             if (nvalid < kW) {
               if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cc;
+                float* o = reinterpret_cast<float*>(p.out) + obase + cc;
 #pragma unroll
                 for (int i = 0; i < kW; ++i)
                   if (i < nvalid) o[i] = f[i];
               } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cc;
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
 #pragma unroll
                 for (int i = 0; i < kW; ++i)
                   if (i < nvalid) o[i] = __float2bfloat16(f[i]);
               }
             } else if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + vox * p.out_ld + cc;
+              float* o = reinterpret_cast<float*>(p.out) + obase + cc;
               if ((p.out_ld & 3) == 0) {
 #pragma unroll
                 for (int i = 0; i < kW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
                 for (int i = 0; i < kW; ++i) o[i] = f[i];
               }
             } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cc;
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
               if ((p.out_ld & 7) == 0) {
 #pragma unroll
                 for (int i = 0; i < kW; i += 8) {
@@ -492,6 +504,9 @@ static int plan_march(const rehr_tensor& x, const rehr_tensor& y, int ks, MarchP
   if (x.n != y.n || x.d != y.d || x.h != y.h || x.w != y.w) return REHR_BAD_SHAPE;
   p.N = x.n; p.D = x.d; p.H = x.h; p.W = x.w; p.Cin = x.c; p.Cout = y.c;
   p.ks = ks;
+  p.kd_lo = p.kh_lo = p.kw_lo = 0;
+  p.kd_hi = p.kh_hi = p.kw_hi = ks - 1;
+  p.OD = p.D; p.OH = p.H; p.OW = p.W;
   p.Ct = ct;
   p.n_ct = pad16(y.c) / ct;
   p.BK = std::min(x.c, 64);
@@ -533,8 +548,15 @@ int march_stats_tiles(const rehr_tensor& x, const rehr_tensor& y, int ks) {
 
 static int dispatch_march(const MarchPlan& pl, cudaStream_t stream);
 
+// Optional: restrict the taps and write one parity class of a larger tensor (stride-2 input gradients).
+struct MarchExt {
+  int lo[3], hi[3];            // tap ranges (d h w)
+  long long pn, pd, ph, pw;    // output pitches in elements
+  int OD, OH, OW;              // extents of the class that exist
+};
+
 int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int ks, int y_is_f32, int act,
-                 float slope, float* stats, cudaStream_t stream) {
+                 float slope, float* stats, cudaStream_t stream, const MarchExt* ext = nullptr) {
   MarchPlan pl;
   int rc = plan_march(x, y, ks, &pl, 0);
   if (rc != REHR_OK) return rc;
@@ -543,6 +565,21 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
   p.out = y.ptr;
   p.out_f32 = y_is_f32;
   p.out_ld = y.ld;
+  p.o_pw = y.ld;
+  p.o_ph = (long long)y.w * y.ld;
+  p.o_pd = (long long)y.h * p.o_ph;
+  p.o_pn = (long long)y.d * p.o_pd;
+  if (ext) {
+    const int R = (ks - 1) / 2;
+    for (int a = 0; a < 3; ++a)
+      if (ext->lo[a] > R || ext->hi[a] < R || ext->lo[a] < 0 || ext->hi[a] > ks - 1) return REHR_UNSUPPORTED;  // centre tap must exist
+    p.kd_lo = ext->lo[0]; p.kd_hi = ext->hi[0];
+    p.kh_lo = ext->lo[1]; p.kh_hi = ext->hi[1];
+    p.kw_lo = ext->lo[2]; p.kw_hi = ext->hi[2];
+    p.o_pn = ext->pn; p.o_pd = ext->pd; p.o_ph = ext->ph; p.o_pw = ext->pw;
+    p.OD = ext->OD; p.OH = ext->OH; p.OW = ext->OW;
+    if ((p.o_pw | p.o_ph | p.o_pd | p.o_pn) & 7) return REHR_BAD_ALIGNMENT;
+  }
   p.bias = bias;
   p.act = act;
   p.slope = slope;
@@ -645,6 +682,46 @@ __global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* 
   }
 }
 
+// Packed weights of the 8 (or 4 / 2) output parity classes of the input gradient of a k3 / pad 1 conv with strides in {1, 2}:
+// class r of a stride-2 dimension sees a stride-1 correlation over dy with tap u (offset u - 1): r = 0 -> {u=1: k=1};
+// r = 1 -> {u=1: k=2, u=2: k=0}; a stride-1 dimension has the ordinary flipped taps u -> k = 2 - u.  Taps a class does not
+// use are zero (and skipped by the kernel through its tap ranges).  src = conv weight W[A][B][27] (A = conv Cout = channels
+// of dy, B = conv Cin = channels of dx); marching "cin" = A, "cout" = B.  dst = [class][ct][khw][chunk][j*Ct + col][BK].
+__global__ void pack_march_s2dgrad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int A, int B, int Bpad,
+                                          int Ct, int BK, int sd, int sh, int sw) {
+  const int chunks = A / BK;
+  const long long per_cls = (long long)Bpad * A * 27;
+  const int ncls = sd * sh * sw;
+  const long long total = per_cls * ncls;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += (long long)gridDim.x * blockDim.x) {
+    const int cls = (int)(i0 / per_cls);
+    long long i = i0 % per_cls;
+    const int rw = cls % sw, rh = (cls / sw) % sh, rd = cls / (sw * sh);
+    const int k = (int)(i % BK);
+    long long r = i / BK;
+    const int rowi = (int)(r % (3 * Ct));
+    r /= 3 * Ct;
+    const int chunk = (int)(r % chunks);
+    r /= chunks;
+    const int khw = (int)(r % 9);
+    const int ct = (int)(r / 9);
+    const int j = rowi / Ct, col = rowi % Ct;
+    const int u[3] = {2 - j, khw / 3, khw % 3};
+    const int st[3] = {sd, sh, sw}, rr[3] = {rd, rh, rw};
+    int kk[3];
+    bool ok = true;
+    for (int a = 0; a < 3; ++a) {
+      if (st[a] == 1) kk[a] = 2 - u[a];
+      else if (rr[a] == 0) { kk[a] = 1; ok = ok && u[a] == 1; }
+      else { kk[a] = u[a] == 1 ? 2 : 0; ok = ok && u[a] >= 1; }
+    }
+    const int b = ct * Ct + col, a_ch = chunk * BK + k;
+    float v = 0.f;
+    if (ok && b < B) v = src[((long long)a_ch * B + b) * 27 + (kk[0] * 3 + kk[1]) * 3 + kk[2]];
+    dst[i0] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace rehr
 
 using namespace rehr;
@@ -692,6 +769,72 @@ int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float
                           int act, float slope, float* stats, rehr_stream stream) {
   if (!x || !y || !x->ptr || !y->ptr || !w_march) return REHR_BAD_SHAPE;
   return launch_march(*x, w_march, bias, *y, ks, y_is_f32, act, slope, stats, (cudaStream_t)stream);
+}
+
+// ---- stride-2 (per dimension 1 or 2) input gradient of a k3 / pad 1 conv through the marching kernel, one launch per parity class
+static bool s2dgrad_desc_ok(const rehr_conv_desc* d) {
+  if (!d) return false;
+  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->pd != 1 || d->ph != 1 || d->pw != 1) return false;
+  if ((d->sd != 1 && d->sd != 2) || (d->sh != 1 && d->sh != 2) || (d->sw != 1 && d->sw != 2)) return false;
+  return d->sd * d->sh * d->sw > 1;
+}
+int rehr_conv3d_march_s2dgrad_supported(const rehr_conv_desc* d, int cin, int cout) {
+  return s2dgrad_desc_ok(d) && march_ct(cout, cin, 3) > 0 ? 1 : 0;  // marching cin = conv Cout (dy), cout = conv Cin (dx)
+}
+size_t rehr_conv3d_march_s2dgrad_weight_bytes(const rehr_conv_desc* d, int cin, int cout) {
+  if (!rehr_conv3d_march_s2dgrad_supported(d, cin, cout)) return 0;
+  return (size_t)d->sd * d->sh * d->sw * 27 * cout * pad16(cin) * 2;
+}
+int rehr_pack_weight_march_s2dgrad(const rehr_conv_desc* d, const float* w, void* dst_bf16, int cin, int cout, rehr_stream stream) {
+  if (!w || !dst_bf16) return REHR_BAD_SHAPE;
+  if (!rehr_conv3d_march_s2dgrad_supported(d, cin, cout)) return REHR_UNSUPPORTED;
+  const int ct = march_ct(cout, cin, 3);
+  const long long total = (long long)d->sd * d->sh * d->sw * 27 * cout * pad16(cin);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  pack_march_s2dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, cin, pad16(cin),
+                                                                      ct, std::min(cout, 64), d->sd, d->sh, d->sw);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+int rehr_conv3d_march_s2dgrad(const rehr_conv_desc* d, const rehr_tensor* dy, const void* w_packed, const rehr_tensor* dx,
+                              rehr_stream stream) {
+  if (!dy || !dx || !dy->ptr || !dx->ptr || !w_packed) return REHR_BAD_SHAPE;
+  if (!rehr_conv3d_march_s2dgrad_supported(d, dx->c, dy->c)) return REHR_UNSUPPORTED;
+  const int s[3] = {d->sd, d->sh, d->sw};
+  const int in[3] = {dx->d, dx->h, dx->w}, out[3] = {dy->d, dy->h, dy->w};
+  for (int a = 0; a < 3; ++a)
+    if (out[a] != (in[a] + 2 - 3) / s[a] + 1) return REHR_BAD_SHAPE;
+  if (dx->n != dy->n || dx->ld % 8 != 0) return REHR_BAD_SHAPE;
+  const size_t per_cls = (size_t)27 * dy->c * pad16(dx->c) * 2;
+  const long long pw = dx->ld, ph = (long long)dx->w * pw, pd = (long long)dx->h * ph, pn = (long long)dx->d * pd;
+  int cls = 0;
+  for (int rd = 0; rd < s[0]; ++rd)
+    for (int rh = 0; rh < s[1]; ++rh)
+      for (int rw = 0; rw < s[2]; ++rw, ++cls) {
+        const int r[3] = {rd, rh, rw};
+        MarchExt e;
+        int ext[3];
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+          ext[a] = (in[a] - r[a] + s[a] - 1) / s[a];
+          if (ext[a] <= 0) empty = true;
+          if (s[a] == 1) { e.lo[a] = 0; e.hi[a] = 2; }
+          else if (r[a] == 0) { e.lo[a] = 1; e.hi[a] = 1; }
+          else { e.lo[a] = 1; e.hi[a] = 2; }
+        }
+        if (empty) continue;
+        e.pn = pn; e.pd = pd * s[0]; e.ph = ph * s[1]; e.pw = pw * s[2];
+        e.OD = ext[0]; e.OH = ext[1]; e.OW = ext[2];
+        // the class is computed on the dy grid; its rows are written at (2i + r) of dx
+        rehr_tensor yv = *dy;  // output "tensor" of the marching conv: dy grid, dx channels, class base pointer
+        yv.c = dx->c;
+        yv.ld = dx->ld;
+        yv.ptr = reinterpret_cast<__nv_bfloat16*>(dx->ptr) + rd * pd + rh * ph + rw * pw;
+        int rc = launch_march(*dy, reinterpret_cast<const uint8_t*>(w_packed) + cls * per_cls, nullptr, yv, 3, 0, REHR_ACT_NONE, 0.f,
+                              nullptr, (cudaStream_t)stream, &e);
+        if (rc != REHR_OK) return rc;
+      }
+  return REHR_OK;
 }
 
 }  // extern "C"

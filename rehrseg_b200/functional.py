@@ -249,6 +249,29 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
                                               stream_ptr()), "conv3d_march_dgrad")
         _count()
         return dx
+    if USE_MARCH and lib().rehr_conv3d_march_s2dgrad_supported(C.byref(desc), cin, dy.shape[4]) \
+            and dy.shape[1] * dy.shape[2] * dy.shape[3] >= 4096 and dy.shape[4] <= 64:
+        # stride-2 stage-entry conv: one marching launch per output parity class (small volumes stay on the split-K path;
+        # with more than 64 dy channels the resident-weight tile shrinks to 16 columns and the tapped kernel is faster)
+        key = (id(weight), "s2dgrad", tuple(stride))
+        hit = _wcache.get(key) if cache else None
+        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
+            wp = hit[2]
+        else:
+            w32 = _f32(weight)
+            wp = torch.empty((lib().rehr_conv3d_march_s2dgrad_weight_bytes(C.byref(desc), cin, dy.shape[4]) // 2,),
+                             dtype=torch.bfloat16, device=dy.device)
+            check(lib().rehr_pack_weight_march_s2dgrad(C.byref(desc), ptr(w32), ptr(wp), cin, dy.shape[4], stream_ptr()),
+                  "pack_weight_march_s2dgrad")
+            _count()
+            if cache:
+                _wcache[key] = (weakref.ref(weight), weight._version, wp)
+        dyt, dxt = rt(dy), rt(dx)
+        with _timed("conv_march_kernel", flops, tag):
+            check(lib().rehr_conv3d_march_s2dgrad(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), stream_ptr()),
+                  "conv3d_march_s2dgrad")
+        _count(stride[0] * stride[1] * stride[2])
+        return dx
     wp = _packed(weight, "dgrad", cache)
     dyt, dxt = rt(dy), rt(dx)
     need = lib().rehr_conv3d_splitk_workspace(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), 1)

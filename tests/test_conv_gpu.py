@@ -58,6 +58,11 @@ FWD_CASES = [
     (1, 64, 128, (5, 20, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 16, 16, (3, 5, 5), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 32, 16, (1, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    # stride-2 stage-entry convs big enough for the per-parity-class marching input gradient (even, odd and anisotropic)
+    (1, 32, 64, (32, 32, 32), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (1, 32, 64, (33, 31, 35), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (1, 64, 128, (8, 64, 64), (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+    (2, 64, 32, (20, 32, 34), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     # 5x5x5 marching variant (sr_head.2, models/seg_model.py:199) and output-channel counts that do not fill a tile
     (1, 16, 16, (9, 20, 12), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
     (2, 16, 2, (24, 16, 8), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
