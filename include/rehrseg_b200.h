@@ -160,6 +160,13 @@ size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor
 int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks, int cout, float* dw, int accumulate, void* ws,
                             size_t ws_bytes, rehr_stream stream);
 
+/* Weight gradient of a k3 / pad 1 conv with strides in {1, 2}: one marching pass per parity class of X (a strided TMA view),
+ * restricted to the 1-2 offsets per strided dimension that class contributes to; dw f32 [Cout][Cin][27]. */
+int rehr_conv3d_wgrad_march_s2_supported(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
+size_t rehr_conv3d_wgrad_march_s2_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
+int rehr_conv3d_wgrad_march_s2(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate,
+                               void* ws, size_t ws_bytes, rehr_stream stream);
+
 /* Direct convolution for tiny input-channel counts (Cin <= 4: the 1-channel nnU-Net stem, the 2-channel
  * FLAVR stem k(3,7,7)); x is NCDHW f32 exactly as the caller hands it (train_all.py:524), y NDHWC bf16.
  * w is the PyTorch f32 weight [Cout][Cin][kd][kh][kw]. */

@@ -92,6 +92,9 @@ def _declare(L: C.CDLL) -> None:
         "rehr_conv3d_wgrad_march_supported": (i, [D, T, T]),
         "rehr_conv3d_wgrad_march_workspace": (sz, [T, T, i]),
         "rehr_conv3d_wgrad_march": (i, [T, T, i, i, vp, i, vp, sz, vp]),
+        "rehr_conv3d_wgrad_march_s2_supported": (i, [D, T, T]),
+        "rehr_conv3d_wgrad_march_s2_workspace": (sz, [D, T, T]),
+        "rehr_conv3d_wgrad_march_s2": (i, [D, T, T, vp, i, vp, sz, vp]),
         "rehr_conv3d_smallcin_fwd": (i, [D, vp, i, i, i, i, i, vp, vp, T, i, f, vp, vp]),
         "rehr_conv3d_smallcin_wgrad": (i, [D, vp, i, i, i, i, i, T, vp, i, vp, sz, vp]),
         "rehr_conv3d_smallcin_wgrad_workspace": (sz, [D, i, T]),

@@ -49,6 +49,9 @@ struct alignas(64) WgmParams {
   int tiles_h, tiles_w, Ds, n_seg;
   int n_hs, n_ps, n_combo, ctas_per_combo, items_per_combo;
   uint32_t h_stride;  // bytes per halo stage (1024-aligned)
+  // sub-setting for the parity classes of a stride-2 conv (rehr_conv3d_wgrad_march_s2): which MMA groups (in-plane offset rows)
+  // and which of the fused depth planes j are needed; everything else would multiply zeros
+  int g_mask, j_min, j_max;
   float* ws;          // [cta][group][128][KS * PC]
   int* err;
 };
@@ -211,23 +214,26 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
         mbar_wait(&full_h[st], (kh / kHStages) & 1u, p.err, 63);
         tc_fence_after();
         // plain planes q - R + j, j in [jlo, jhi], exist inside the volume
-        const int jlo = max(0, R - q), jhi = min(KS - 1, p.D - 1 - q + R);
+        const int jlo = max(max(0, R - q), p.j_min), jhi = min(min(KS - 1, p.D - 1 - q + R), p.j_max);
         const uint32_t cbase = cnt0 + (uint32_t)(q - R + jlo - pa);
         const uint32_t s0 = cbase % kPRing;
-        const uint32_t idesc = make_idesc_bf16(128, (jhi - jlo + 1) * PC, 1, 1);
+        const uint32_t idesc = make_idesc_bf16(128, max(jhi - jlo + 1, 1) * PC, 1, 1);
         const uint32_t a_lo = sh_lo + st * hstride_lo;
         const uint32_t b_lo = (sp_lo + s0 * (kPSlotBytes >> 4)) | kBLoLbo;
         const uint32_t d_tmem = tmem_base + (uint32_t)(jlo * PC);
         if (wgm_elect()) {
+          if (jlo <= jhi) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(b_lo + (uint32_t)((ks * 16 * Cfg::kPRowB) >> 4));
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(b_lo + (uint32_t)((ks * 16 * Cfg::kPRowB) >> 4));
 #pragma unroll
-            for (int g = 0; g < Cfg::kGroups; ++g) {
-              const uint32_t a_off = (uint32_t)(((2 * ks * Cfg::kHaloW + Cfg::row0(g)) * Cfg::kRowB) >> 4) |
-                                     ((uint32_t)((Cfg::lbo_rows(g) * Cfg::kRowB) >> 4) << 16);
-              const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(a_lo + a_off);
-              umma_bf16(d_tmem + (uint32_t)(g * Cfg::kN), ad, bd, idesc, 1u);
+              for (int g = 0; g < Cfg::kGroups; ++g) {
+                if (!((p.g_mask >> g) & 1)) continue;
+                const uint32_t a_off = (uint32_t)(((2 * ks * Cfg::kHaloW + Cfg::row0(g)) * Cfg::kRowB) >> 4) |
+                                       ((uint32_t)((Cfg::lbo_rows(g) * Cfg::kRowB) >> 4) << 16);
+                const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(a_lo + a_off);
+                umma_bf16(d_tmem + (uint32_t)(g * Cfg::kN), ad, bd, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty_h[st]);
@@ -296,6 +302,9 @@ struct WgmReduceParams {
   int role;  // 0: Hh = X (ch = ci, cp = co), 1: Hh = dY (ch = co, cp = ci)
   int Ci, Co;        // channels of the dW tensor (Co may be smaller than the padded dY the kernel saw)
   int accumulate;
+  // stride-2 parity class (rehr_conv3d_wgrad_march_s2): per dim (d h w) stride s and class r; offset e = k_stride1 - 1 maps
+  // to the conv tap 2e + r + 1 (s = 2) or e + 1 (s = 1); offsets that give no tap in [0, 3) are dropped
+  int cls_s[3], cls_r[3];
 };
 
 // Two thread layouts over the same index space (hs, ps, a, j, ch, cpl):
@@ -356,6 +365,16 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
   } else {
     co = chH; ci = chP; kh = p.KS - 1 - oh; kw = p.KS - 1 - ow; kd = j;
   }
+  if (p.cls_s[0] > 0) {
+    int kk[3] = {kd, kh, kw};
+    for (int a3 = 0; a3 < 3; ++a3) {
+      const int e = kk[a3] - 1;
+      const int t = p.cls_s[a3] == 2 ? 2 * e + p.cls_r[a3] + 1 : e + 1;
+      if (t < 0 || t > 2) return;
+      kk[a3] = t;
+    }
+    kd = kk[0]; kh = kk[1]; kw = kk[2];
+  }
   if (co < p.Co && ci < p.Ci) {
     float* d = p.dw + ((size_t)co * p.Ci + ci) * (p.KS * p.KS * p.KS) + (kd * p.KS + kh) * p.KS + kw;
     *d = p.accumulate ? (*d + t) : t;
@@ -407,12 +426,22 @@ static int wgm_choose(int ci, int co, int ks, int* role, int* CH, int* PC) {
   return best;
 }
 
-static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks, WgmPlan* out) {
+static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks, WgmPlan* out, int force_role = -1) {
   WgmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   if (x.n != dy.n || x.d != dy.d || x.h != dy.h || x.w != dy.w) return REHR_BAD_SHAPE;
   int role = 0, CH = 0, PC = 0;
   if (wgm_choose(x.c, dy.c, ks, &role, &CH, &PC) == 0) return REHR_UNSUPPORTED;
+  if (force_role >= 0 && role != force_role) {  // the caller needs a fixed operand assignment: re-pick the pieces for it
+    const int chh = force_role == 0 ? x.c : dy.c, chp = force_role == 0 ? dy.c : x.c;
+    CH = chh % 64 == 0 ? 64 : (chh % 32 == 0 ? 32 : 0);
+    PC = chp % 32 == 0 ? 32 : (chp % 16 == 0 ? 16 : 0);
+    if (CH == 0 || PC == 0 || !wgm_variant_ok(CH, PC, ks)) return REHR_UNSUPPORTED;
+    role = force_role;
+  }
+  p.g_mask = 0xffff;
+  p.j_min = 0;
+  p.j_max = ks - 1;
   const rehr_tensor& hh = role == 0 ? x : dy;
   const rehr_tensor& pp = role == 0 ? dy : x;
   if (hh.ld % 8 != 0 || pp.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
@@ -467,6 +496,56 @@ static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
 }  // namespace rehr
 
 using namespace rehr;
+
+// launch the variant + its reduction (cls_s / cls_r: parity-class tap mapping of a stride-2 conv, or null)
+static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate, const int* cls_s, const int* cls_r,
+                   cudaStream_t stream) {
+  const WgmParams& p = pl.p;
+  const int ks = pl.KS;
+  int rc = REHR_UNSUPPORTED;
+  if (ks == 3 && pl.CH == 32 && pl.PC == 32) rc = launch_wgm<32, 32, 3>(pl, stream);
+  else if (ks == 3 && pl.CH == 64 && pl.PC == 32) rc = launch_wgm<64, 32, 3>(pl, stream);
+  else if (ks == 3 && pl.CH == 32 && pl.PC == 16) rc = launch_wgm<32, 16, 3>(pl, stream);
+  else if (ks == 3 && pl.CH == 64 && pl.PC == 16) rc = launch_wgm<64, 16, 3>(pl, stream);
+  else if (ks == 5 && pl.CH == 16 && pl.PC == 16) rc = launch_wgm<16, 16, 5>(pl, stream);
+  if (rc != REHR_OK) return rc;
+  WgmReduceParams r;
+  memset(&r, 0, sizeof(r));
+  r.ws = p.ws;
+  r.dw = dw;
+  r.CH = pl.CH;
+  r.PC = pl.PC;
+  r.KS = ks;
+  r.groups = pl.groups;
+  r.apm = 128 / pl.CH;
+  r.parts = (ks + r.apm - 1) / r.apm;
+  r.paired = (pl.CH == 64 && ks == 3) ? 1 : 0;
+  r.n_hs = p.n_hs;
+  r.n_ps = p.n_ps;
+  r.n_combo = p.n_combo;
+  r.ctas_per_combo = p.ctas_per_combo;
+  r.role = pl.role;
+  r.Ci = Ci;
+  r.Co = Co;
+  r.accumulate = accumulate;
+  if (cls_s) {
+    for (int a = 0; a < 3; ++a) {
+      r.cls_s[a] = cls_s[a];
+      r.cls_r[a] = cls_r[a];
+    }
+  }
+  if (p.ctas_per_combo >= 24) {
+    const int blocks = p.n_hs * p.n_ps * ks * ks * ks * pl.CH;
+    wgrad_march_reduce_kernel<true><<<blocks, 256, 0, stream>>>(r);
+  } else {
+    const int nsub = 256 / pl.PC;
+    const int chb = (pl.CH + nsub - 1) / nsub;
+    const int blocks = p.n_hs * p.n_ps * ks * ks * ks * chb;
+    wgrad_march_reduce_kernel<false><<<blocks, 256, 0, stream>>>(r);
+  }
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
 
 static int wgm_ks_of(const rehr_conv_desc* d) {
   if (!d) return 0;
@@ -526,41 +605,102 @@ int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks,
     rc = encode_tiled_bf16(&p.p_map, pp.ptr, 5, gdim, gstr, box, pl.PC * 2);
     if (rc != REHR_OK) return rc;
   }
-  rc = REHR_UNSUPPORTED;
-  if (ks == 3 && pl.CH == 32 && pl.PC == 32) rc = launch_wgm<32, 32, 3>(pl, stream);
-  else if (ks == 3 && pl.CH == 64 && pl.PC == 32) rc = launch_wgm<64, 32, 3>(pl, stream);
-  else if (ks == 3 && pl.CH == 32 && pl.PC == 16) rc = launch_wgm<32, 16, 3>(pl, stream);
-  else if (ks == 3 && pl.CH == 64 && pl.PC == 16) rc = launch_wgm<64, 16, 3>(pl, stream);
-  else if (ks == 5 && pl.CH == 16 && pl.PC == 16) rc = launch_wgm<16, 16, 5>(pl, stream);
+  return wgm_run(pl, x->c, cout, dw, accumulate, nullptr, nullptr, stream);
+}
+
+// ---- weight gradient of a k3 / pad 1 conv with strides in {1, 2}: one marching pass per parity class of X -------------------
+static bool wgm_s2_desc_ok(const rehr_conv_desc* d) {
+  if (!d) return false;
+  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->pd != 1 || d->ph != 1 || d->pw != 1) return false;
+  if ((d->sd != 1 && d->sd != 2) || (d->sh != 1 && d->sh != 2) || (d->sw != 1 && d->sw != 2)) return false;
+  return d->sd * d->sh * d->sw > 1;
+}
+
+static int wgm_s2_plan(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy, WgmPlan* pl) {
+  if (!wgm_s2_desc_ok(d) || !x || !dy) return REHR_UNSUPPORTED;
+  const int s[3] = {d->sd, d->sh, d->sw};
+  const int in[3] = {x->d, x->h, x->w}, out[3] = {dy->d, dy->h, dy->w};
+  for (int a = 0; a < 3; ++a)
+    if (out[a] != (in[a] + 2 - 3) / s[a] + 1) return REHR_BAD_SHAPE;
+  if (x->n != dy->n) return REHR_BAD_SHAPE;
+  rehr_tensor xv = *dy;  // the iteration space is the dy grid; the halo operand is a parity class of X with X's channels
+  xv.c = x->c;
+  xv.ld = x->ld;
+  return plan_wgm(xv, *dy, 3, pl, 0);
+}
+
+int rehr_conv3d_wgrad_march_s2_supported(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy) {
+  WgmPlan pl;
+  return wgm_s2_plan(d, x, dy, &pl) == REHR_OK ? 1 : 0;
+}
+size_t rehr_conv3d_wgrad_march_s2_workspace(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy) {
+  WgmPlan pl;
+  if (wgm_s2_plan(d, x, dy, &pl) != REHR_OK) return 0;
+  return pl.ws_bytes;
+}
+int rehr_conv3d_wgrad_march_s2(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy, float* dw, int accumulate,
+                               void* ws, size_t ws_bytes, rehr_stream stream_) {
+  if (!x || !dy || !x->ptr || !dy->ptr || !dw) return REHR_BAD_SHAPE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  WgmPlan pl;
+  int rc = wgm_s2_plan(d, x, dy, &pl);
   if (rc != REHR_OK) return rc;
-  WgmReduceParams r;
-  r.ws = p.ws;
-  r.dw = dw;
-  r.CH = pl.CH;
-  r.PC = pl.PC;
-  r.KS = ks;
-  r.groups = pl.groups;
-  r.apm = 128 / pl.CH;
-  r.parts = (ks + r.apm - 1) / r.apm;
-  r.paired = (pl.CH == 64 && ks == 3) ? 1 : 0;
-  r.n_hs = p.n_hs;
-  r.n_ps = p.n_ps;
-  r.n_combo = p.n_combo;
-  r.ctas_per_combo = p.ctas_per_combo;
-  r.role = pl.role;
-  r.Ci = x->c;
-  r.Co = cout;
-  r.accumulate = accumulate;
-  if (p.ctas_per_combo >= 24) {
-    const int blocks = p.n_hs * p.n_ps * ks * ks * ks * pl.CH;
-    wgrad_march_reduce_kernel<true><<<blocks, 256, 0, stream>>>(r);
-  } else {
-    const int nsub = 256 / pl.PC;
-    const int chb = (pl.CH + nsub - 1) / nsub;
-    const int blocks = p.n_hs * p.n_ps * ks * ks * ks * chb;
-    wgrad_march_reduce_kernel<false><<<blocks, 256, 0, stream>>>(r);
+  if (!ws || ws_bytes < pl.ws_bytes) return REHR_WORKSPACE;
+  const int s[3] = {d->sd, d->sh, d->sw};
+  const int in[3] = {x->d, x->h, x->w};
+  const unsigned long long pitch = (unsigned long long)x->ld * 2;  // bytes
+  const unsigned long long xpw = pitch, xph = pitch * x->w, xpd = xph * x->h, xpn = xpd * x->d;
+  {
+    const unsigned long long gdim[5] = {(unsigned long long)dy->c, (unsigned long long)dy->w, (unsigned long long)dy->h,
+                                        (unsigned long long)dy->d, (unsigned long long)dy->n};
+    const unsigned long long dp = (unsigned long long)dy->ld * 2;
+    const unsigned long long gstr[4] = {dp, dp * dy->w, dp * dy->w * dy->h, dp * dy->w * dy->h * dy->d};
+    const unsigned box[5] = {(unsigned)pl.PC, (unsigned)kWTileW, (unsigned)kWTileH, 1u, 1u};
+    rc = encode_tiled_bf16(&pl.p.p_map, dy->ptr, 5, gdim, gstr, box, pl.PC * 2);
+    if (rc != REHR_OK) return rc;
   }
-  REHR_CHECK_LAUNCH();
+  pl.p.ws = reinterpret_cast<float*>(ws);
+  pl.p.err = nullptr;
+  for (int rd = 0; rd < s[0]; ++rd)
+    for (int rh = 0; rh < s[1]; ++rh)
+      for (int rw = 0; rw < s[2]; ++rw) {
+        const int r[3] = {rd, rh, rw};
+        int ext[3];
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+          ext[a] = (in[a] - r[a] + s[a] - 1) / s[a];
+          if (ext[a] <= 0) empty = true;
+        }
+        if (empty) continue;
+        // halo operand = class view of X: extents ext, doubled pitches, base offset r
+        const unsigned long long gdim[5] = {(unsigned long long)x->c, (unsigned long long)ext[2], (unsigned long long)ext[1],
+                                            (unsigned long long)ext[0], (unsigned long long)x->n};
+        const unsigned long long gstr[4] = {xpw * s[2], xph * s[1], xpd * s[0], xpn};
+        const unsigned box[5] = {(unsigned)pl.CH, (unsigned)(kWTileW + 2), (unsigned)(kWTileH + 2), 1u, 1u};
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(x->ptr) + rd * xpd + rh * xph + rw * xpw;
+        rc = encode_tiled_bf16(&pl.p.h_map, base, 5, gdim, gstr, box, pl.CH * 2);
+        if (rc != REHR_OK) return rc;
+        // offsets e needed per dim: stride 1 -> {-1, 0, 1}; stride 2: r = 0 -> {0}; r = 1 -> {-1, 0}
+        int elo[3], ehi[3];
+        for (int a = 0; a < 3; ++a) {
+          if (s[a] == 1) { elo[a] = -1; ehi[a] = 1; }
+          else if (r[a] == 0) { elo[a] = 0; ehi[a] = 0; }
+          else { elo[a] = -1; ehi[a] = 0; }
+        }
+        // depth: e_d = 1 - j  ->  j in [1 - ehi, 1 - elo];  in-plane: offset index oh = e_h + 1, ow = e_w + 1
+        pl.p.j_min = 1 - ehi[0];
+        pl.p.j_max = 1 - elo[0];
+        int gmask = 0;
+        for (int oh = elo[1] + 1; oh <= ehi[1] + 1; ++oh)
+          for (int ow = elo[2] + 1; ow <= ehi[2] + 1; ++ow) {
+            const int a = oh * 3 + ow;
+            gmask |= 1 << (pl.CH == 64 ? a / 2 : oh);
+          }
+        pl.p.g_mask = gmask;
+        const int cs[3] = {s[0], s[1], s[2]};
+        rc = wgm_run(pl, x->c, dy->c, dw, accumulate, cs, r, stream);
+        if (rc != REHR_OK) return rc;
+      }
   return REHR_OK;
 }
 

@@ -94,6 +94,7 @@ class _timed:
 # --------------------------------------------------------------------------------------------------
 _wcache: dict = {}
 USE_MARCH = True  # route eligible k3/s1/p1 layers through the halo-resident marching kernel (csrc/conv_march.cu)
+S2_WGRAD_MARCH_MIN_VOXELS = 262144  # dy voxels from which the per-parity-class marching wgrad of a stride-2 conv wins
 
 
 def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor:
@@ -298,6 +299,17 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
             check(lib().rehr_conv3d_wgrad_march(C.byref(xt), C.byref(dyt), int(kernel[0]), int(wshape[0]), ptr(dw), 0, ptr(ws), need,
                                                 stream_ptr()), "conv3d_wgrad_march")
         _count(2)
+        return dw
+    if USE_MARCH and dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] >= S2_WGRAD_MARCH_MIN_VOXELS \
+            and lib().rehr_conv3d_wgrad_march_s2_supported(C.byref(desc), C.byref(xt), C.byref(dyt)):
+        # one marching pass per parity class of x; its fixed cost (TMEM drain + partial reduction per class) only pays off on
+        # the full-resolution stage-entry conv (measured: 32->64 @128^3 0.86 -> 0.57 ms, 64->128 @64^3 0.14 -> 0.48 ms)
+        need = lib().rehr_conv3d_wgrad_march_s2_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
+        ws = _ws(need, x.device)
+        with _timed("wgrad_march_kernel", flops, tag):
+            check(lib().rehr_conv3d_wgrad_march_s2(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
+                  "conv3d_wgrad_march_s2")
+        _count(2 * stride[0] * stride[1] * stride[2])
         return dw
     need = lib().rehr_conv3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
     if need == 0:

@@ -310,3 +310,28 @@ def test_flavr_stem_smallcin_raw():
     torch.cuda.synchronize()
     assert rel_l2(dw, rdw) < 1e-3
     assert rel_l2(dx, rdx) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(1, 32, 64, (16, 128, 128), (2, 2, 2)), (1, 64, 32, (15, 130, 126), (2, 2, 2)),
+                                  (1, 32, 32, (8, 128, 128), (1, 2, 2))])
+def test_wgrad_march_stride2(case):
+    """Per-parity-class marching weight gradient of the stride-2 stage-entry convs (strided TMA views of x, offset masks),
+    forced on for these mid-size shapes, against torch autograd."""
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, s = case
+    x, w, _ = _mk(n, cin, cout, dhw, (3, 3, 3), seed=11)
+    w.requires_grad_(True)
+    y = F.conv3d(bf16r(x), w, None, stride=s, padding=1)
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(12)).cuda()
+    (ref,) = torch.autograd.grad(y, w, bf16r(g))
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    gcl = g.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    old = Fn.S2_WGRAD_MARCH_MIN_VOXELS
+    Fn.S2_WGRAD_MARCH_MIN_VOXELS = 0
+    try:
+        with Fn.kernel_timer() as kt:
+            dw = Fn.conv3d_wgrad_raw(xcl, gcl, w.shape, (3, 3, 3), s, (1, 1, 1))
+        assert [r[0] for r in kt.rows()] == ["wgrad_march_kernel"]   # really took the marching path
+    finally:
+        Fn.S2_WGRAD_MARCH_MIN_VOXELS = old
+    assert rel_l2(dw, ref) < 1e-3, (case, rel_l2(dw, ref))
