@@ -34,8 +34,45 @@ def conv_net(seed=7, half=False):
     return (lambda x: conv(x).half()) if half else conv, conv
 
 
+def joint_fixture() -> None:
+    """The reference's own Distiller (models/seg_model.py:115-151) and _build_loss (utils/seg_utils.py:355-372) on seeded inputs."""
+    sm = refimport.load("models.seg_model")
+    seg_utils = refimport.load("utils.seg_utils")
+    g = torch.Generator().manual_seed(21)
+    fs = torch.randn((2, 64, 3, 12, 10), generator=g, requires_grad=True)
+    ft = torch.randn((2, 64, 3, 12, 10), generator=g)
+    arrs = {"feat_s": fs.detach().numpy(), "feat_t": ft.numpy()}
+    for tag, lam in (("cos_struct", (0.0, 1.0, 1.0)), ("all", (0.5, 1.0, 2.0))):
+        torch.manual_seed(77)
+        d = sm.Distiller(64, 64, *lam)
+        arrs[f"distill_keys"] = np.array(list(d.state_dict().keys()))
+        arrs[f"distill_w"], arrs[f"distill_b"] = d.distill.weight.detach().numpy(), d.distill.bias.detach().numpy()
+        fs.grad = None
+        loss = d(fs, ft)
+        loss.backward()
+        arrs[f"distill_{tag}_loss"] = loss.detach().numpy()
+        arrs[f"distill_{tag}_dfeat"] = fs.grad.numpy().copy()
+        arrs[f"distill_{tag}_dw"] = d.distill.weight.grad.numpy().copy()
+    logits = torch.randn((2, 2, 3, 8, 8), generator=g, requires_grad=True)
+    target = (torch.rand((2, 1, 3, 8, 8), generator=g) > 0.7).float()
+    unc = torch.rand((2, 1, 3, 8, 8), generator=g) * 0.99 + 0.01
+    arrs.update(logits=logits.detach().numpy(), target=target.numpy(), unc=unc.numpy())
+    for tag, wd, u in (("lr_unc", 0, unc), ("hr", 1, None), ("lr_nounc", 1, "omit")):
+        obj = seg_utils._build_loss(enable_deep_supervision=False, weight_dice=wd)
+        logits.grad = None
+        loss = obj(logits, target) if isinstance(u, str) else obj(logits, target, u)
+        loss.backward()
+        arrs[f"loss_{tag}"] = loss.detach().numpy()
+        arrs[f"loss_{tag}_dlogits"] = logits.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "joint_step.npz"), **arrs)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
+    import sys
+    if "--only-joint" in sys.argv:
+        joint_fixture()
+        return
     seg_utils = refimport.load("utils.seg_utils")
     patch_ops = refimport.load("utils.patch_ops")
     pad = refimport.load("utils.pad")
@@ -143,6 +180,7 @@ def main() -> None:
     fl["gif_f1"], fl["gif_f3"] = feats[1].numpy(), feats[3].numpy()
     np.savez_compressed(os.path.join(OUT, "flavr_small.npz"), **fl)
 
+    joint_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 
