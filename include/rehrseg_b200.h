@@ -131,7 +131,10 @@ int rehr_convtranspose3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x,
  *   rehr_pack_weight_march: dst bf16 (rehr_conv3d_march_weight_bytes) from fp32 src[co*s_co + ci*s_ci + t], T = ks^3:
  *     forward of W[Cout][Cin][T]: cout, cin, s_co = Cin*T, s_ci = T, flip = 0
  *     input-gradient dx[B] <- dy[A] of W[A][B][T]: cout := B, cin := A, s_co = T, s_ci = B*T, flip = 1
- *   rehr_conv3d_march_fwd: y = act(conv(x) + bias); stats (optional) = f32 [n][rehr_conv3d_march_stats_tiles][cout][2]. */
+ *   rehr_conv3d_march_fwd: y = act(conv(x) + bias); stats (optional) = f32 [n][rehr_conv3d_march_stats_tiles][cout][2].
+ * Planar layers -- k = (1,3,3), stride 1, pad (0,1,1): the thick-slice stages of anisotropic nnU-Net plans (the kernel_sizes
+ * argument of SegModel, models/seg_model.py:154-173) -- run through the same kernel restricted to the centre depth tap; they are
+ * selected by passing the kernel's DEPTH extent ks = 1 to the functions below (T = 9, weights W[Cout][Cin][9]). */
 int rehr_conv3d_march_supported(const rehr_conv_desc* desc, int cin, int cout);
 size_t rehr_conv3d_march_weight_bytes(int cin, int cout, int ks);
 int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
@@ -154,7 +157,8 @@ int rehr_conv3d_march_s2dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy,
  * activations are TMA-loaded once per plane, the ks^3 taps are UMMA descriptor offsets / a kd-fused N = ks*PC MMA,
  * accumulators live in TMEM for the whole CTA.  Same call site as rehr_conv3d_wgrad.  dw = f32 [cout][x->c][ks^3] with
  * cout <= dy->c (dy may be zero-padded to a multiple of 16 channels).  ks = 3: channel counts multiples of 32 on one side
- * and of 16 on the other; ks = 5: 16 channels each (sr_head.2, models/seg_model.py:199). */
+ * and of 16 on the other; ks = 5: 16 channels each (sr_head.2, models/seg_model.py:199).  ks = 1 selects the planar k = (1,3,3),
+ * pad (0,1,1) layer (only the centre depth offset is accumulated; dw = f32 [cout][x->c][9]). */
 int rehr_conv3d_wgrad_march_supported(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);
 size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor* dy, int ks);
 int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks, int cout, float* dw, int accumulate, void* ws,

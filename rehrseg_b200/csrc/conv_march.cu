@@ -49,7 +49,11 @@ struct alignas(64) MarchParams {
   CUtensorMap x_map;  // 5-D NDHWC, box (BK, 10, 18, 1, 1)
   CUtensorMap w_map;  // 2-D [n_ct*9*chunks*3Ct rows][BK], box (BK, 3Ct)
   int N, D, H, W, Cin, Cout;
-  int ks;  // 3 or 5
+  int ks;  // 3 or 5 (in-plane extent; the depth extent is 1 for the planar k(1,3,3) layers, see kd_off)
+  // planar layers (k = (1,3,3), pad (0,1,1): the thick-slice stages of anisotropic nnU-Net plans) run as the centre depth tap
+  // only (kd_lo = kd_hi = R) and store just that tap: wrows = weight rows per (kh,kw,chunk) tile (= Ct instead of KS*Ct),
+  // kd_off = index of the first stored depth tap (R instead of 0)
+  int wrows, kd_off;
   // tap-index ranges actually present (the rest of the packed weights are zero and are skipped): whole kernel by default; the
   // parity classes of a stride-2 input gradient use 1 or 2 of the 3 taps per dimension (see rehr_conv3d_march_s2dgrad)
   int kd_lo, kd_hi, kh_lo, kh_hi, kw_lo, kw_hi;
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           mbar_arrive_expect_tx(wfull_bar, p.w_bytes);
           const int tiles = KS * KS * p.chunks;
           for (int t = 0; t < tiles; ++t)
-            tma_load_2d(&p.w_map, wfull_bar, s_w + (size_t)t * p.wtile_bytes, 0, (c.ct * tiles + t) * KS * p.Ct);
+            tma_load_2d(&p.w_map, wfull_bar, s_w + (size_t)t * p.wtile_bytes, 0, (c.ct * tiles + t) * p.wrows);
         }
         const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
         const int pa = max(d0 + p.kd_lo - R, 0), pb = min(d1 - 1 + p.kd_hi - R, p.D - 1);
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
           int rb = ra;
           while (rb < qb && ((rb + 1 - d0) & kSlotMask) != 0) ++rb;
           const uint32_t idesc = make_idesc_bf16(128, (rb - ra + 1) * CT, 0, 0);
-          const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + R) * CT) * kRowB) >> 4);
+          const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + R - p.kd_off) * CT) * kRowB) >> 4);
           const uint32_t d_tmem = tmem_base + (uint32_t)(((ra - d0) & kSlotMask) * CT);
           if (!(p.debug & 4) && elect_one_sync()) {
 #pragma unroll
@@ -473,17 +477,19 @@ static const size_t kMarchWeightBudget = 112 * 1024;
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 
 // output-channel tile for a (cin, cout, ks) layer; 0 = not supported by the marching kernel
-int march_ct(int cin, int cout, int ks) {
+int march_ct(int cin, int cout, int ks, bool planar) {
   if (ks != 3 && ks != 5) return 0;
+  if (planar && ks != 3) return 0;
+  const int kdn = planar ? 1 : ks;  // stored depth taps
   if (cin % 16 != 0 || cout <= 0) return 0;
   if (cin != 16 && cin != 32 && cin != 64 && cin != 128) return 0;  // instantiated (BK, chunks) variants
   if (ks == 5 && cin != 16) return 0;                               // instantiated k5 variant: sr_head.2 (models/seg_model.py:199)
   const int cp = pad16(cout);
   for (int ct : {64, 32, 16}) {
     if (cp % ct != 0) continue;
-    if (ks * ct > 256) continue;  // kd-fused N and the weight TMA box are limited to 256 rows
+    if (kdn * ct > 256) continue;  // kd-fused N and the weight TMA box are limited to 256 rows
     if (ks == 5 && ct != 16) continue;
-    if ((size_t)ks * ks * ks * cin * ct * 2 <= kMarchWeightBudget) return ct;
+    if ((size_t)kdn * ks * ks * cin * ct * 2 <= kMarchWeightBudget) return ct;
   }
   return 0;
 }
@@ -496,16 +502,22 @@ struct MarchPlan {
 
 static size_t march_tail_bytes() { return (2 * kMaxRing + 2 * kMaxSlots + 2) * 8 + 16 + 4 * 2 * 64 * 4; }
 
-static int plan_march(const rehr_tensor& x, const rehr_tensor& y, int ks, MarchPlan* out, int ds_override) {
+static int plan_march(const rehr_tensor& x, const rehr_tensor& y, int ks_code, MarchPlan* out, int ds_override) {
   MarchParams& p = out->p;
   memset(&p, 0, sizeof(p));
-  const int ct = march_ct(x.c, y.c, ks);
+  const bool planar = ks_code == 1;  // k(1,3,3)
+  const int ks = planar ? 3 : ks_code;
+  const int kdn = planar ? 1 : ks;
+  const int ct = march_ct(x.c, y.c, ks, planar);
   if (ct == 0) return REHR_UNSUPPORTED;
   if (x.n != y.n || x.d != y.d || x.h != y.h || x.w != y.w) return REHR_BAD_SHAPE;
   p.N = x.n; p.D = x.d; p.H = x.h; p.W = x.w; p.Cin = x.c; p.Cout = y.c;
   p.ks = ks;
   p.kd_lo = p.kh_lo = p.kw_lo = 0;
   p.kd_hi = p.kh_hi = p.kw_hi = ks - 1;
+  if (planar) p.kd_lo = p.kd_hi = (ks - 1) / 2;
+  p.kd_off = planar ? (ks - 1) / 2 : 0;
+  p.wrows = kdn * ct;
   p.OD = p.D; p.OH = p.H; p.OW = p.W;
   p.Ct = ct;
   p.n_ct = pad16(y.c) / ct;
@@ -516,7 +528,7 @@ static int plan_march(const rehr_tensor& x, const rehr_tensor& y, int ks, MarchP
   p.slots = std::min(kMaxSlots, 512 / ct);
   const uint32_t rowb = p.BK * 2;
   const int halo_rows = (kTileH + ks - 1) * (kTileW + ks - 1);
-  p.wtile_bytes = ks * ct * rowb;
+  p.wtile_bytes = kdn * ct * rowb;
   p.w_bytes = ks * ks * p.chunks * p.wtile_bytes;
   p.chunk_stride = (halo_rows * rowb + 1023u) & ~1023u;
   p.slot_stride = p.chunks * p.chunk_stride;
@@ -555,12 +567,14 @@ struct MarchExt {
   int OD, OH, OW;              // extents of the class that exist
 };
 
-int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int ks, int y_is_f32, int act,
+int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int ks_code, int y_is_f32, int act,
                  float slope, float* stats, cudaStream_t stream, const MarchExt* ext = nullptr) {
   MarchPlan pl;
-  int rc = plan_march(x, y, ks, &pl, 0);
+  int rc = plan_march(x, y, ks_code, &pl, 0);
   if (rc != REHR_OK) return rc;
   MarchParams& p = pl.p;
+  const int ks = p.ks;
+  if (ext && ks_code == 1) return REHR_UNSUPPORTED;
   if (x.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
   p.out = y.ptr;
   p.out_f32 = y_is_f32;
@@ -609,10 +623,10 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
     if (rc != REHR_OK) return rc;
   }
   {
-    const unsigned long long rows = (unsigned long long)p.n_ct * ks * ks * p.chunks * ks * p.Ct;
+    const unsigned long long rows = (unsigned long long)p.n_ct * ks * ks * p.chunks * p.wrows;
     const unsigned long long gdim[2] = {(unsigned long long)p.BK, rows};
     const unsigned long long gstr[1] = {(unsigned long long)p.BK * 2};
-    const unsigned box[2] = {(unsigned)p.BK, (unsigned)(ks * p.Ct)};
+    const unsigned box[2] = {(unsigned)p.BK, (unsigned)p.wrows};
     rc = encode_tiled_bf16(&p.w_map, w_march, 2, gdim, gstr, box, p.BK * 2);
     if (rc != REHR_OK) return rc;
   }
@@ -649,6 +663,8 @@ static int dispatch_march(const MarchPlan& pl, cudaStream_t stream) {
   REHR_MARCH_CASE(64, 1, 16)
   REHR_MARCH_CASE(64, 1, 32)
   REHR_MARCH_CASE(64, 2, 16)
+  REHR_MARCH_CASE(64, 1, 64)  // planar 64 -> 64
+  REHR_MARCH_CASE(64, 2, 32)  // planar 128 -> 64
 #undef REHR_MARCH_CASE
   return REHR_UNSUPPORTED;
 }
@@ -661,21 +677,22 @@ static int dispatch_march(const MarchPlan& pl, cudaStream_t stream) {
 // input-gradient (dx[B] from dy[A]) of W[A][B][T]: cout := B, cin := A, s_co = T, s_ci = B*T, flip = 1.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int cout, int cout_pad, int cin,
-                                  int Ct, int BK, int ks, long long s_co, long long s_ci, int flip) {
+                                  int Ct, int BK, int ks, int kdn, long long s_co, long long s_ci, int flip) {
+  // kdn = stored depth taps: ks (cubic kernel) or 1 (planar k(1,ks,ks): source taps t = kh*ks + kw)
   const int chunks = cin / BK;
-  const int T = ks * ks * ks;
+  const int T = kdn * ks * ks;
   const long long total = (long long)cout_pad * cin * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % BK);
     long long r = i / BK;
-    const int rowi = (int)(r % (ks * Ct));
-    r /= ks * Ct;
+    const int rowi = (int)(r % (kdn * Ct));
+    r /= kdn * Ct;
     const int chunk = (int)(r % chunks);
     r /= chunks;
     const int khw = (int)(r % (ks * ks));
     const int ct = (int)(r / (ks * ks));
     const int j = rowi / Ct, col = rowi % Ct;
-    const int kd = ks - 1 - j, kh = khw / ks, kw = khw % ks;
+    const int kd = kdn - 1 - j, kh = khw / ks, kw = khw % ks;
     const int t = (kd * ks + kh) * ks + kw;
     const int co = ct * Ct + col, ci = chunk * BK + k;
     dst[i] = co < cout ? __float2bfloat16(src[co * s_co + ci * s_ci + (flip ? T - 1 - t : t)]) : __float2bfloat16(0.f);
@@ -726,8 +743,10 @@ __global__ void pack_march_s2dgrad_kernel(const float* __restrict__ src, __nv_bf
 
 using namespace rehr;
 
+// 3 / 5: cubic kernel; 1: planar k(1,3,3) pad (0,1,1); 0: not a marching layer
 static int march_ks_of(const rehr_conv_desc* d) {
   if (!d) return 0;
+  if (d->kd == 1 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == 0 && d->ph == 1 && d->pw == 1) return 1;
   if (d->kd != d->kh || d->kh != d->kw || (d->kd != 3 && d->kd != 5)) return 0;
   if (d->sd != 1 || d->sh != 1 || d->sw != 1) return 0;
   const int r = (d->kd - 1) / 2;
@@ -740,22 +759,27 @@ extern "C" {
 int rehr_conv3d_march_supported(const rehr_conv_desc* d, int cin, int cout) {
   const int ks = march_ks_of(d);
   if (ks == 0) return 0;
-  return march_ct(cin, cout, ks) > 0 ? 1 : 0;
+  return march_ct(cin, cout, ks == 1 ? 3 : ks, ks == 1) > 0 ? 1 : 0;
 }
 
+// ks: 3 / 5 = cubic kernel, 1 = planar k(1,3,3) (the kernel's depth extent, as in the other marching entry points)
 size_t rehr_conv3d_march_weight_bytes(int cin, int cout, int ks) {
-  return march_ct(cin, cout, ks) > 0 ? (size_t)ks * ks * ks * cin * pad16(cout) * 2 : 0;
+  if (ks == 1) return march_ct(cin, cout, 3, true) > 0 ? (size_t)9 * cin * pad16(cout) * 2 : 0;
+  return march_ct(cin, cout, ks, false) > 0 ? (size_t)ks * ks * ks * cin * pad16(cout) * 2 : 0;
 }
 
 int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
                            rehr_stream stream) {
   if (!src || !dst_bf16) return REHR_BAD_SHAPE;
-  const int ct = march_ct(cin, cout, ks);
+  const bool planar = ks == 1;
+  if (planar) ks = 3;
+  const int kdn = planar ? 1 : ks;
+  const int ct = march_ct(cin, cout, ks, planar);
   if (ct == 0) return REHR_UNSUPPORTED;
-  const long long total = (long long)pad16(cout) * cin * ks * ks * ks;
+  const long long total = (long long)pad16(cout) * cin * kdn * ks * ks;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   pack_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, pad16(cout), cin, ct,
-                                                             std::min(cin, 64), ks, s_co, s_ci, flip);
+                                                             std::min(cin, 64), ks, kdn, s_co, s_ci, flip);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -779,7 +803,7 @@ static bool s2dgrad_desc_ok(const rehr_conv_desc* d) {
   return d->sd * d->sh * d->sw > 1;
 }
 int rehr_conv3d_march_s2dgrad_supported(const rehr_conv_desc* d, int cin, int cout) {
-  return s2dgrad_desc_ok(d) && march_ct(cout, cin, 3) > 0 ? 1 : 0;  // marching cin = conv Cout (dy), cout = conv Cin (dx)
+  return s2dgrad_desc_ok(d) && march_ct(cout, cin, 3, false) > 0 ? 1 : 0;  // marching cin = conv Cout (dy), cout = conv Cin (dx)
 }
 size_t rehr_conv3d_march_s2dgrad_weight_bytes(const rehr_conv_desc* d, int cin, int cout) {
   if (!rehr_conv3d_march_s2dgrad_supported(d, cin, cout)) return 0;
@@ -788,7 +812,7 @@ size_t rehr_conv3d_march_s2dgrad_weight_bytes(const rehr_conv_desc* d, int cin, 
 int rehr_pack_weight_march_s2dgrad(const rehr_conv_desc* d, const float* w, void* dst_bf16, int cin, int cout, rehr_stream stream) {
   if (!w || !dst_bf16) return REHR_BAD_SHAPE;
   if (!rehr_conv3d_march_s2dgrad_supported(d, cin, cout)) return REHR_UNSUPPORTED;
-  const int ct = march_ct(cout, cin, 3);
+  const int ct = march_ct(cout, cin, 3, false);
   const long long total = (long long)d->sd * d->sh * d->sw * 27 * cout * pad16(cin);
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   pack_march_s2dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, cin, pad16(cin),

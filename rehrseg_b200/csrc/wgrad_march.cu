@@ -305,6 +305,8 @@ struct WgmReduceParams {
   // stride-2 parity class (rehr_conv3d_wgrad_march_s2): per dim (d h w) stride s and class r; offset e = k_stride1 - 1 maps
   // to the conv tap 2e + r + 1 (s = 2) or e + 1 (s = 1); offsets that give no tap in [0, 3) are dropped
   int cls_s[3], cls_r[3];
+  // planar k(1,3,3) layer: only the centre depth offset was accumulated (j_min = j_max = 1); dW is [co][ci][9]
+  int planar;
 };
 
 // Two thread layouts over the same index space (hs, ps, a, j, ch, cpl):
@@ -375,6 +377,14 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
     }
     kd = kk[0]; kh = kk[1]; kw = kk[2];
   }
+  if (p.planar) {
+    if (kd != 1) return;
+    if (co < p.Co && ci < p.Ci) {
+      float* d = p.dw + ((size_t)co * p.Ci + ci) * 9 + kh * 3 + kw;
+      *d = p.accumulate ? (*d + t) : t;
+    }
+    return;
+  }
   if (co < p.Co && ci < p.Ci) {
     float* d = p.dw + ((size_t)co * p.Ci + ci) * (p.KS * p.KS * p.KS) + (kd * p.KS + kh) * p.KS + kw;
     *d = p.accumulate ? (*d + t) : t;
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
 // ------------------------------------------------------------------------------------------------
 struct WgmPlan {
   WgmParams p;
-  int CH, PC, KS, role, grid, groups;
+  int CH, PC, KS, role, grid, groups, planar;
   size_t smem, ws_bytes;
 };
 
@@ -426,9 +436,12 @@ static int wgm_choose(int ci, int co, int ks, int* role, int* CH, int* PC) {
   return best;
 }
 
-static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks, WgmPlan* out, int force_role = -1) {
+// ks_code: 3 / 5 = cubic kernel; 1 = planar k(1,3,3), pad (0,1,1): the k3 machinery restricted to the centre depth offset
+static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, WgmPlan* out, int force_role = -1) {
   WgmParams& p = out->p;
   memset(&p, 0, sizeof(p));
+  const int ks = ks_code == 1 ? 3 : ks_code;
+  out->planar = ks_code == 1 ? 1 : 0;
   if (x.n != dy.n || x.d != dy.d || x.h != dy.h || x.w != dy.w) return REHR_BAD_SHAPE;
   int role = 0, CH = 0, PC = 0;
   if (wgm_choose(x.c, dy.c, ks, &role, &CH, &PC) == 0) return REHR_UNSUPPORTED;
@@ -442,6 +455,7 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks, WgmPlan
   p.g_mask = 0xffff;
   p.j_min = 0;
   p.j_max = ks - 1;
+  if (out->planar) p.j_min = p.j_max = 1;
   const rehr_tensor& hh = role == 0 ? x : dy;
   const rehr_tensor& pp = role == 0 ? dy : x;
   if (hh.ld % 8 != 0 || pp.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
@@ -528,6 +542,7 @@ static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate,
   r.Ci = Ci;
   r.Co = Co;
   r.accumulate = accumulate;
+  r.planar = pl.planar;
   if (cls_s) {
     for (int a = 0; a < 3; ++a) {
       r.cls_s[a] = cls_s[a];
@@ -549,6 +564,7 @@ static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate,
 
 static int wgm_ks_of(const rehr_conv_desc* d) {
   if (!d) return 0;
+  if (d->kd == 1 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == 0 && d->ph == 1 && d->pw == 1) return 1;
   if (d->kd != d->kh || d->kh != d->kw || (d->kd != 3 && d->kd != 5)) return 0;
   if (d->sd != 1 || d->sh != 1 || d->sw != 1) return 0;
   const int r = (d->kd - 1) / 2;
@@ -573,7 +589,7 @@ size_t rehr_conv3d_wgrad_march_workspace(const rehr_tensor* x, const rehr_tensor
   return pl.ws_bytes;
 }
 
-// dw: f32 [cout][x->c][ks^3]; `cout` <= dy->c lets the caller pass a dy zero-padded to a multiple of 16 channels.
+// dw: f32 [cout][x->c][ks^3] (ks = 1: planar k(1,3,3) layer, dw [cout][x->c][9]); `cout` <= dy->c lets the caller pass a dy zero-padded to a multiple of 16 channels.
 int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks, int cout, float* dw, int accumulate, void* ws,
                             size_t ws_bytes, rehr_stream stream_) {
   if (!x || !dy || !x->ptr || !dy->ptr || !dw || cout <= 0 || cout > dy->c) return REHR_BAD_SHAPE;
@@ -592,7 +608,7 @@ int rehr_conv3d_wgrad_march(const rehr_tensor* x, const rehr_tensor* dy, int ks,
                                         (unsigned long long)hh.d, (unsigned long long)hh.n};
     const unsigned long long pitch = (unsigned long long)hh.ld * 2;
     const unsigned long long gstr[4] = {pitch, pitch * hh.w, pitch * hh.w * hh.h, pitch * hh.w * hh.h * hh.d};
-    const unsigned box[5] = {(unsigned)pl.CH, (unsigned)(kWTileW + ks - 1), (unsigned)(kWTileH + ks - 1), 1u, 1u};
+    const unsigned box[5] = {(unsigned)pl.CH, (unsigned)(kWTileW + pl.KS - 1), (unsigned)(kWTileH + pl.KS - 1), 1u, 1u};
     rc = encode_tiled_bf16(&p.h_map, hh.ptr, 5, gdim, gstr, box, pl.CH * 2);
     if (rc != REHR_OK) return rc;
   }

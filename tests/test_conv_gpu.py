@@ -68,6 +68,13 @@ FWD_CASES = [
     (2, 16, 2, (24, 16, 8), (5, 5, 5), (1, 1, 1), (2, 2, 2)),
     (1, 32, 2, (6, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     (1, 16, 40, (5, 9, 9), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    # planar k(1,3,3) layers of anisotropic plans through the marching kernels (centre depth tap only): channel chunks,
+    # Cout tiling, ragged tiles, several depth segments, big enough for the marching weight gradient
+    (2, 64, 32, (5, 20, 12), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 128, 64, (3, 16, 16), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 32, 48, (20, 9, 11), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (2, 32, 32, (16, 64, 64), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 64, 64, (9, 40, 24), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
 ]
 
 
@@ -177,6 +184,18 @@ def test_wgrad_march_routing():
         x = L.RehrTensor(16, n, *dhw, ci, ci)
         dy = L.RehrTensor(16, n, *dhw, co, co)
         assert L.lib().rehr_conv3d_wgrad_march_supported(C.byref(desc), C.byref(x), C.byref(dy)) == want, (n, ci, co, dhw)
+
+
+def test_planar_layers_take_the_marching_kernels():
+    """k(1,3,3) / pad (0,1,1) layers must really be routed to conv_march_kernel / wgrad_march_kernel."""
+    from rehrseg_b200 import functional as Fn
+    x, w, b = _mk(2, 32, 32, (16, 64, 64), (1, 3, 3), seed=8)
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    with Fn.kernel_timer() as kt:
+        y, _, _ = Fn.conv3d_raw(xcl, w, b, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+        Fn.conv3d_dgrad_raw(y, w, tuple(xcl.shape), (1, 3, 3), (1, 1, 1), (0, 1, 1), cache=False)
+        Fn.conv3d_wgrad_raw(xcl, y, w.shape, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    assert [r[0] for r in kt.rows()] == ["conv_march_kernel", "conv_march_kernel", "wgrad_march_kernel"]
 
 
 TCONV_CASES = [

@@ -4,13 +4,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rehrseg_b200 import seg_model as sm, functional as Fn
 torch.manual_seed(0)
-m = sm.plainconv_unet_3d_fullres().cuda()
-x = torch.randn(2, 1, 128, 128, 128, device='cuda')
+ANISO = "--aniso" in sys.argv   # config 4 student: anisotropic SegModel (x4 SR head) on [2,1,16,256,256]
+if ANISO:
+    kw = sm.fullres_kwargs()
+    kw.update(kernel_sizes=[[1, 3, 3], [1, 3, 3]] + [[3, 3, 3]] * 4, strides=[[1, 1, 1], [1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2], [1, 2, 2]])
+    m = sm.SegModel(upscale=4, **kw).cuda()
+    x = torch.randn(2, 1, 16, 256, 256, device='cuda')
+else:
+    m = sm.plainconv_unet_3d_fullres().cuda()
+    x = torch.randn(2, 1, 128, 128, 128, device='cuda')
 def step():
     for p in m.parameters():
         p.grad = None
     out = m(x)
-    out.float().mean().backward()
+    if ANISO:
+        (out[0].float().mean() + out[1].float().mean()).backward()
+    else:
+        out.float().mean().backward()
 for i in range(3):
     step()
 torch.cuda.synchronize()
