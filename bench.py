@@ -221,6 +221,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="b200 arm: replay the step from one CUDA graph (rehrseg_b200.graphs.GraphedTrainStep) or launch it from Python")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -257,17 +259,31 @@ def main() -> None:
     x_dev, g_dev = x_host.to(dev), g_host.to(dev)
     dp = {"flat": None, "active": None}  # gradient bucket, sized after the first backward (unused seg layers get no grad)
 
-    def fwd_bwd(x, g):
-        for p in params:
-            p.grad = None
-        if args.impl == "b200":
-            Fn.clear_weight_cache()  # bf16 operand copies are re-derived every step, as after an optimiser update
-            out = model(x)
+    def loss_fn(out, g):
+        return torch.dot(out.float().reshape(-1), g.reshape(-1)) / out.numel()  # <logits, g> / numel
+
+    use_graph = args.impl == "b200" and args.launch == "graph"
+    gstep = None
+    if use_graph:
+        from rehrseg_b200.graphs import GraphedTrainStep
+        # the whole step (weight re-pack, forward, loss, backward) captured once; replays re-read the live parameters
+        gstep = GraphedTrainStep(model, loss_fn, (x_dev, g_dev))
+        x_dev, g_dev = gstep.static_inputs       # "resident" steps run on the static inputs without any copy
+
+    def fwd_bwd(x, g, eager=False):
+        if use_graph and not eager:
+            loss = gstep(x, g)                   # device->device copy into the static inputs unless x, g already are them
         else:
-            with torch.autocast("cuda", dtype=torch.bfloat16):
+            for p in params:
+                p.grad = None
+            if args.impl == "b200":
+                Fn.clear_weight_cache()  # bf16 operand copies are re-derived every step, as after an optimiser update
                 out = model(x)
-        loss = torch.dot(out.float().reshape(-1), g.reshape(-1)) / out.numel()  # <logits, g> / numel
-        loss.backward()
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = model(x)
+            loss = loss_fn(out, g)
+            loss.backward()
         if world > 1:  # data-parallel gradient mean over NVLink (one flat bucket)
             if dp["active"] is None:
                 dp["active"] = [p for p in params if p.grad is not None]
@@ -344,9 +360,12 @@ def main() -> None:
     kernels = {}
     if args.impl == "b200":
         torch.cuda.synchronize()
+        l0 = Fn.launches()
         with Fn.kernel_timer() as kt:
             torch.cuda._sleep(200_000_000)  # let the host run ahead so launch latency stays out of the event pairs
-            step_resident()
+            fwd_bwd(x_dev, g_dev, eager=True)   # launched from Python so that every conv-engine launch gets its event pair
+        if use_graph:
+            launches = (Fn.launches() - l0) * args.steps   # a replay issues the same kernels as the eager step it captured
         summ = kt.summary()
         peaks = measured_peaks()
         for name, (n, tms, fl) in summ.items():
@@ -382,7 +401,8 @@ def main() -> None:
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "patch": list(PATCH),
                        "parallelism": f"dp{world}" if world > 1 else "single", "cache": "per-step working set ~8 GB >> 126 MB L2",
-                       "weights_repacked_each_step": True, "algorithmic_tflop_per_step": round(flops["fwd_bwd"] / 1e12, 4)},
+                       "weights_repacked_each_step": True,
+                       "launch": ("one CUDA graph per step (rehrseg_b200.graphs.GraphedTrainStep)" if use_graph else "python"), "algorithmic_tflop_per_step": round(flops["fwd_bwd"] / 1e12, 4)},
             "conv_tflops_per_gpu": round(tfl, 1), "frac_bf16_peak_burst": round(tfl / float(peaks["bf16_tflops"]), 4),
             "frac_bf16_peak_sustained": round(tfl / float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), 4),
             "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": world * (x_host.numel() + g_host.numel()) * 4,

@@ -54,3 +54,72 @@ def graphed(module, example: torch.Tensor) -> GraphedForward:
     g = GraphedForward(module, example)
     _graph_cache[module] = (sig, g)   # kept outside the module so state_dict / pickling of the model are unaffected
     return g
+
+
+class GraphedTrainStep:
+    """Forward + loss + backward of a fixed-shape training step captured into ONE CUDA graph and replayed.
+
+    A PlainConvUNet step is ~360 kernel launches of 5-400 us; issued from Python the launch latency of the small bottleneck
+    layers is exposed (15.06 ms eager vs 14.20 ms replayed for the 2x1x128^3 step on one B200).  Everything the engine does
+    is stream-ordered and allocation-free (tensor maps travel by value, workspaces come from PyTorch's caching allocator, no
+    host synchronisation), so the whole step -- including the bf16 re-pack of every weight, which reads the CURRENT parameter
+    values on every replay -- captures cleanly.
+
+        step = GraphedTrainStep(model, loss_fn, (x, target))      # loss_fn(model(x), target) -> scalar
+        for x, target in loader:
+            loss = step(x, target)          # copies the batch into the static inputs (host or device source), replays
+            opt.step()                      # parameters are updated in place; the .grad tensors are static, overwritten by
+                                            # every replay and re-attached to the parameters after it
+
+    The first input is the network input; all inputs must keep their shapes.  `loss` is a static tensor, valid until the next call.
+    """
+
+    def __init__(self, model, loss_fn, example_inputs, warmup: int = 2, before_step=None):
+        self.model, self.loss_fn, self.before_step = model, loss_fn, before_step
+        self.static_inputs = tuple(t.detach().clone() if t.is_cuda else t.detach().to(next(model.parameters()).device)
+                                   for t in example_inputs)
+        dev = self.static_inputs[0].device
+        self.params = list(model.parameters())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in self.params:
+            p.grad = None                    # gradients are (re)created inside the capture: static addresses, plain assignment
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+        self.grads = [p.grad for p in self.params]     # static gradient tensors (None for parameters the loss does not reach)
+
+    def _eager(self):
+        from . import functional as Fn
+        # the bf16 operand copies must be re-derived INSIDE the captured step (a cache hit at capture time would bake stale
+        # weights into the graph): drop the cache so every pack kernel is part of the graph and re-reads the live parameters
+        Fn.clear_weight_cache()
+        if self.before_step is not None:
+            self.before_step()
+        for p in self.params:
+            p.grad = None
+        out = self.model(self.static_inputs[0])
+        loss = self.loss_fn(out, *self.static_inputs[1:])
+        loss.backward()
+        return loss.detach()
+
+    def load(self, *inputs, non_blocking: bool = True):
+        """Copy a batch (pinned host or device tensors) into the static input buffers on the current stream."""
+        for dst, src in zip(self.static_inputs, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):      # re-attach the static gradients (zero_grad(set_to_none=True) or an
+            p.grad = g                                 # eager step in between may have replaced them)
+        return self.loss
+
+    def __call__(self, *inputs):
+        self.load(*inputs)
+        return self.replay()

@@ -66,3 +66,46 @@ def test_convert_reference_shaped_model_shares_parameters():
     assert (out.float().cpu() - want).norm() / want.norm() <= 1e-2
     assert (up.float().cpu() - want_up).norm() / want_up.norm() <= 1e-2
     assert skips[1].shape == (1, 64, 8, 16, 16) and skips[1].dtype == torch.float32
+
+
+def test_graphed_train_step_matches_eager_and_tracks_weight_updates():
+    """rehrseg_b200.graphs.GraphedTrainStep: the replayed step gives the eager step's loss and gradients, and -- because the
+    bf16 weight re-pack is part of the graph -- a replay after an in-place optimiser update equals an eager step on the
+    updated weights."""
+    from oracle import seg_model as ref_seg
+    from rehrseg_b200 import seg_model as sm
+    from rehrseg_b200.graphs import GraphedTrainStep
+    torch.manual_seed(3)
+    model = sm.PlainConvUNet(**{k: v for k, v in ref_seg.plan_kwargs("tiny").items() if k != "upscale"}).cuda()
+    params = [p for p in model.parameters()]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 1, 16, 32, 32), generator=g).cuda()
+    t = torch.randn((2, 2, 16, 32, 32), generator=g).cuda()
+
+    def loss_fn(out, tgt):
+        return (out.float() * tgt).mean()
+
+    def eager(xx, tt):
+        for p in params:
+            p.grad = None
+        loss = loss_fn(model(xx), tt)
+        loss.backward()
+        return float(loss.detach()), [p.grad.clone() for p in params if p.grad is not None]
+
+    l0, g0 = eager(x, t)
+    step = GraphedTrainStep(model, loss_fn, (x, t))
+    x2 = torch.randn(x.shape, generator=g)               # a new batch, from (unpinned) host memory
+    t2 = torch.randn(t.shape, generator=g).cuda()
+    for xx, tt, in ((x, t), (x2, t2)):
+        got = float(step(xx, tt))
+        torch.cuda.synchronize()
+        grads = [p.grad.clone() for p in params if p.grad is not None]
+        want, wgrads = eager(xx.cuda(), tt)
+        assert abs(got - want) <= 1e-6 * max(1.0, abs(want))
+        assert len(grads) == len(wgrads) and all(torch.allclose(a, b, rtol=1e-4, atol=1e-7) for a, b in zip(grads, wgrads))
+    with torch.no_grad():
+        for p in params:
+            p.add_(0.05 * torch.randn_like(p))            # in-place update, as an optimiser does
+    got = float(step(x, t))
+    want, _ = eager(x, t)
+    assert abs(got - want) <= 1e-6 * max(1.0, abs(want)) and abs(want - l0) > 1e-6
