@@ -192,6 +192,7 @@ int rehr_convtranspose3d_fused_supported(const rehr_conv_desc* d, int cin, int c
   if (!d) return 0;
   if (d->kd != d->sd || d->kh != d->sh || d->kw != d->sw || d->pd || d->ph || d->pw) return 0;
   if (cout % 16 != 0 || cin % 16 != 0) return 0;
+  if (d->sd * d->sh * d->sw > 8) return 0;  // class offset table of the scatter epilogue
   return 1;
 }
 int rehr_convtranspose3d_fused_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,

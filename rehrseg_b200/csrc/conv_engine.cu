@@ -257,7 +257,12 @@ static int chunk_for_channels(int c) {
 // ------------------------------------------------------------------------------------------------
 // Device: forward / dgrad kernel
 // ------------------------------------------------------------------------------------------------
-static constexpr int kFwdThreads = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+// warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue: two warps per TMEM lane quarter (warp % 4), taking alternate 16-column
+// chunks.  With one epilogue warp per scheduler every instruction latency of the drain was exposed (ncu: IPC 0.15, 2.2k clk per
+// chunk) and small-K tiles (transposed convs, stride-2 stage entries) were bound by it.
+static constexpr int kFwdThreads = 320;
+static constexpr int kFwdEpiThreads = 256;
+static constexpr int kWgradThreads = 192;  // conv_wgrad_kernel: warp0 TMA, warp1 MMA, warps 2..5 drain
 static constexpr int kMaxStages = 8;
 
 struct alignas(64) FwdParams {
@@ -290,6 +295,7 @@ struct alignas(64) FwdParams {
   // column block (cls, co) of row (input voxel i) is output voxel i*s + r(cls), channel co.  0 = off.
   int sc_cout;
   int sc_s[3];     // stride per dim (w h d)
+  long long sc_off[8];  // output voxel offset of class cls = (rd * AO[1] + rh) * AO[0] + rw (at most 8 classes)
   // split-K for layers with fewer output tiles than SMs (the <= 8^3 bottleneck stages stream 2-5 MB of weights and taps
   // through ONE or TWO SMs otherwise): work item = (tile, split); a split accumulates its share of the (tap, Cin-chunk)
   // K blocks and stores raw fp32 partials [split][tile][128][BN]; conv_splitk_finish_kernel sums them and runs the epilogue.
@@ -330,10 +336,20 @@ __device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a_lo, uin
 
 __device__ __forceinline__ void finish_chunk(const FwdParams& p, float (&f)[16], bool valid, long long vox, int nbase, int c0,
                                              int lane, float* mypart) {
+  if (p.bias != nullptr) {
+    if (nbase + c0 + 16 <= p.cout && ((nbase + c0) & 3) == 0) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = nbase + c0 + i;
-    if (p.bias != nullptr && c < p.cout) f[i] += __ldg(p.bias + c);
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + c0 + i));
+        f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = nbase + c0 + i;
+        if (c < p.cout) f[i] += __ldg(p.bias + c);
+      }
+    }
   }
   if (p.stats != nullptr) {
     float s1[16], s2[16];
@@ -412,7 +428,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kFwdEpiThreads / 32);
     }
     fence_mbar_init();
   } else if (warp == 1) {
@@ -503,10 +519,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 16-column chunks
     const int row = q * 32 + lane;   // accumulator row = voxel within the box
-    const int et = threadIdx.x - 64; // 0..127
+    const int et = threadIdx.x - 64; // 0..255
     int iter = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
       const int tile = work / p.ksplit, split = work - tile * p.ksplit;
@@ -538,26 +555,42 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
       mbar_wait(&tfull_bar[acc], acc_phase, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      // scatter epilogue bookkeeping without per-chunk divisions: class / channel of this warp's first chunk, then +32 columns
+      int sc_cls = 0, sc_co0 = 0;
+      long long sc_ov0 = 0;
+      if (p.sc_cout > 0) {
+        const int col0 = nbase + half * 16;
+        sc_cls = col0 / p.sc_cout;
+        sc_co0 = col0 - sc_cls * p.sc_cout;
+        sc_ov0 = (((long long)on * p.AO[2] + od * p.sc_s[2]) * p.AO[1] + oh * p.sc_s[1]) * p.AO[0] + ow * p.sc_s[0];
+      }
+      const int sc_ncls = p.sc_s[0] * p.sc_s[1] * p.sc_s[2];
+      for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
         float f[16];
         if (p.sc_cout > 0) {
           // scatter epilogue: this 16-column chunk belongs to one output parity class
-          const int col = nbase + c0;
-          const int cls = col / p.sc_cout, co0 = col - cls * p.sc_cout;
-          const int ncls = p.sc_s[0] * p.sc_s[1] * p.sc_s[2];
-          if (valid && cls < ncls) {
-            const int rw = cls % p.sc_s[0], rh = (cls / p.sc_s[0]) % p.sc_s[1], rd = cls / (p.sc_s[0] * p.sc_s[1]);
-            const long long ov = (((long long)on * p.AO[2] + (od * p.sc_s[2] + rd)) * p.AO[1] + (oh * p.sc_s[1] + rh)) * p.AO[0] +
-                                 (ow * p.sc_s[0] + rw);
+          const int cls = sc_cls, co0 = sc_co0;
+          sc_co0 += 32;
+          while (sc_co0 >= p.sc_cout) {
+            sc_co0 -= p.sc_cout;
+            ++sc_cls;
+          }
+          if (valid && cls < sc_ncls) {
+            const long long ov = sc_ov0 + p.sc_off[cls];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(v[i]);
-              if (p.bias != nullptr) x += __ldg(p.bias + co0 + i);
-              f[i] = apply_act(x, p.act, p.slope);
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + i));
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ov * p.out_ld + co0;
             uint4 lo, hi;
             lo.x = pack_bf16x2(f[0], f[1]);
@@ -590,8 +623,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (p.stats != nullptr && p.partial == nullptr) {
-        named_bar_sync(1, 128);
-        for (int c = et; c < p.BN; c += 128) {
+        named_bar_sync(1, kFwdEpiThreads);
+        for (int c = et; c < p.BN; c += kFwdEpiThreads) {
           if (nbase + c < p.cout) {
             float a = 0.f, b = 0.f;
 #pragma unroll
@@ -733,8 +766,13 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
   p.stats = stats;
   p.err = nullptr;
   if (scatter_s) {
+    if (ncls > 8) return REHR_UNSUPPORTED;
     p.sc_cout = out.c;
     for (int a = 0; a < 3; ++a) p.sc_s[a] = scatter_s[a];
+    for (int cls = 0; cls < ncls; ++cls) {
+      const int rw = cls % scatter_s[0], rh = (cls / scatter_s[0]) % scatter_s[1], rd = cls / (scatter_s[0] * scatter_s[1]);
+      p.sc_off[cls] = ((long long)rd * out.h + rh) * out.w + rw;
+    }
   }
   int tc = 32;
   while (tc < 2 * BN) tc <<= 1;
@@ -852,7 +890,7 @@ struct alignas(64) WgradParams {
   int* err;
 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1240,7 +1278,7 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
     }
     attr_set = true;
   }
-  conv_wgrad_kernel<<<wp.grid, kFwdThreads, wp.smem, stream>>>(wp.p);
+  conv_wgrad_kernel<<<wp.grid, kWgradThreads, wp.smem, stream>>>(wp.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;

@@ -528,12 +528,22 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* x
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) ws[(long long)blockIdx.x * C + i] = sh[i];
 }
-__global__ void channel_sum_reduce_kernel(const float* ws, int blocks, int C, float* out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// block = 32 channels x 8 slices of the partial list (fixed summation order -> deterministic)
+__global__ void __launch_bounds__(256) channel_sum_reduce_kernel(const float* ws, int blocks, int C, float* out, int accumulate) {
+  __shared__ double red[8][33];
+  const int cl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)ws[(long long)b * C + c];
-  out[c] = accumulate ? out[c] + (float)s : (float)s;
+  if (c < C)
+    for (int b = slice; b < blocks; b += 8) s += (double)ws[(long long)b * C + c];
+  red[slice][cl] = s;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cl];
+    out[c] = accumulate ? out[c] + (float)t : (float)t;
+  }
 }
 static int channel_sum_blocks(const rehr_tensor* x) {
   const long long items = (long long)x->n * voxels_per_sample(x) * (x->c / 8);
@@ -1093,7 +1103,7 @@ int rehr_channel_sum(const rehr_tensor* x, float* out, int accumulate, void* ws,
   channel_sum_kernel<<<blocks, 256, x->c * sizeof(float), (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, (long long)x->n * voxels_per_sample(x), x->c, reinterpret_cast<float*>(ws));
   REHR_CHECK_LAUNCH();
-  channel_sum_reduce_kernel<<<(x->c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c, out,
+  channel_sum_reduce_kernel<<<(x->c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c, out,
                                                                              accumulate);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
