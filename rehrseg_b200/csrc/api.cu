@@ -2,6 +2,9 @@
 // kernels live in conv_engine.cu / smallcin.cu / elementwise.cu.
 #include "engine.h"
 
+#include <algorithm>
+#include <cstdint>
+
 #include <cuda_bf16.h>
 
 using namespace rehr;
@@ -90,6 +93,33 @@ static int conv_fwd_impl(const rehr_conv_desc* desc, const rehr_tensor* x, const
                             ws, ws_bytes, need);
 }
 
+// Fork / join helper for the parity classes of a small strided input gradient: each class is its own launch with a handful of
+// CTAs (e.g. 2 of 148 for the 8^3 -> 4^3 stage entry), so the classes are issued on side streams and run side by side.  The
+// fork / join is expressed with events only (no host synchronisation), which is also the pattern CUDA-graph capture accepts.
+namespace {
+struct ClassStreams {
+  static constexpr int kSide = 7;
+  cudaStream_t side[kSide];
+  cudaEvent_t fork, join[kSide];
+  bool ok = false;
+};
+ClassStreams* class_streams() {
+  static thread_local ClassStreams per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  ClassStreams& cs = per_dev[dev];
+  if (!cs.ok) {
+    if (cudaEventCreateWithFlags(&cs.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int i = 0; i < ClassStreams::kSide; ++i) {
+      if (cudaStreamCreateWithFlags(&cs.side[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&cs.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    cs.ok = true;
+  }
+  return &cs;
+}
+}  // namespace
+
 static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed, const float* bias,
                            const rehr_tensor* dx, int dx_is_f32, int act, float slope, rehr_stream stream, void* ws, size_t ws_bytes,
                            size_t* need) {
@@ -98,6 +128,25 @@ static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, co
   if (need) *need = 0;
   const int s[3] = {desc->sw, desc->sh, desc->sd};
   const int isz[3] = {dx->w, dx->h, dx->d};
+  // classes side by side when each of them fills less than half the machine (a function of the shapes only, so that the
+  // workspace query and the launch agree): every class then owns a slice of the split-K scratch
+  const int ncls = s[0] * s[1] * s[2];
+  bool parallel = false;
+  if (ncls > 1) {
+    long long vox = dx->n;
+    for (int a = 0; a < 3; ++a) vox *= (isz[a] + s[a] - 1) / s[a];
+    const long long tiles_cls = ((vox + 127) / 128) * ((dx->c + 255) / 256);
+    parallel = tiles_cls * 2 <= sm_count();
+  }
+  ClassStreams* cs = (parallel && !need) ? class_streams() : nullptr;
+  if (parallel && !need && cs == nullptr) parallel = false;
+  const size_t slice = parallel && ws && ws_bytes ? (ws_bytes / ncls) & ~size_t(255) : 0;
+  int launched = 0;
+  if (cs) {
+    cudaError_t e = cudaEventRecord(cs->fork, (cudaStream_t)stream);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return REHR_CUDA_ERROR; }
+  }
+  int ci = -1;
   for (int cd = 0; cd < s[2]; ++cd)
     for (int ch = 0; ch < s[1]; ++ch)
       for (int cw = 0; cw < s[0]; ++cw) {
@@ -109,25 +158,50 @@ static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, co
           if (O[a] <= 0) empty = true;
         }
         O[3] = dx->n;
+        ++ci;
         if (empty) continue;
         TapPlan plan;
         int rc = build_dgrad_taps(*desc, cls, &plan);
         if (rc != REHR_OK) return rc;
+        // class 0 stays on the caller's stream, the others go to side streams that wait for the fork event
+        cudaStream_t cstream = (cudaStream_t)stream;
+        if (cs && ci > 0) {
+          cstream = cs->side[(ci - 1) % ClassStreams::kSide];
+          if (!((launched >> ((ci - 1) % ClassStreams::kSide)) & 1)) {
+            cudaError_t e = cudaStreamWaitEvent(cstream, cs->fork, 0);
+            if (e != cudaSuccess) { g_last_cuda_error = (int)e; return REHR_CUDA_ERROR; }
+            launched |= 1 << ((ci - 1) % ClassStreams::kSide);
+          }
+        }
         if (plan.num_taps == 0) {
           if (need) continue;
           const long long total = (long long)O[0] * O[1] * O[2] * O[3] * dx->c;
           const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-          fill_class_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dx->ptr, dx_is_f32, dx->ld, dx->c, bias, act, slope, O[0], O[1],
+          fill_class_kernel<<<blocks, 256, 0, cstream>>>(dx->ptr, dx_is_f32, dx->ld, dx->c, bias, act, slope, O[0], O[1],
                                                                      O[2], O[3], s[0], s[1], s[2], cw, ch, cd, dx->w, dx->h, dx->d);
           REHR_CHECK_LAUNCH();
           continue;
         }
         size_t cls_need = 0;
-        rc = launch_tapped_gemm(plan, *dy, w_packed, dx->c, bias, *dx, dx_is_f32, O, s, cls, act, slope, nullptr,
-                                (cudaStream_t)stream, nullptr, ws, ws_bytes, need ? &cls_need : nullptr);
+        void* cws = parallel ? (slice ? reinterpret_cast<uint8_t*>(ws) + (size_t)ci * slice : nullptr) : ws;
+        rc = launch_tapped_gemm(plan, *dy, w_packed, dx->c, bias, *dx, dx_is_f32, O, s, cls, act, slope, nullptr, cstream, nullptr, cws,
+                                parallel ? slice : ws_bytes, need ? &cls_need : nullptr);
         if (rc != REHR_OK) return rc;
-        if (need && cls_need > *need) *need = cls_need;  // the classes run back to back on one stream: they share the scratch
+        // back to back on one stream the classes share the scratch; side by side each class gets its own slice
+        if (need) {
+          cls_need = (cls_need + 255) & ~size_t(255);
+          if (parallel) *need = std::max(*need, cls_need * (size_t)ncls);
+          else if (cls_need > *need) *need = cls_need;
+        }
       }
+  if (cs) {  // join: the caller's stream continues after every side stream that was used
+    for (int i = 0; i < ClassStreams::kSide; ++i)
+      if ((launched >> i) & 1) {
+        cudaError_t e = cudaEventRecord(cs->join[i], cs->side[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, cs->join[i], 0);
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return REHR_CUDA_ERROR; }
+      }
+  }
   return REHR_OK;
 }
 

@@ -1146,6 +1146,44 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReducePara
   }
 }
 
+// PyTorch-layout outputs (s_t == 1, s_m == T: the T taps of one (cn, cm) pair are contiguous): block = 32 cn x 8 cm.  Reads stay
+// coalesced over cn; the sums go through a shared-memory tile so that every cn row is written as one contiguous run of 8*T floats
+// (the element-per-thread kernels above write 4 bytes per 32-byte sector).  Fixed summation order -> deterministic.
+__global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const WgradReduceParams p, int T) {
+  extern __shared__ float sm[];  // [32][8*T + 1], then T present-flags
+  const int rowlen = 8 * T + 1;
+  int* present = reinterpret_cast<int*>(sm + 32 * rowlen);
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < T; t += 256) present[t] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < p.num_taps; j += 256) present[p.widx[j]] = 1;
+  const int cn = blockIdx.x * 32 + lane;
+  const int cm = blockIdx.y * 8 + wy;
+  if (cn < p.CN && cm < p.CM) {
+    const long long split_stride = (long long)p.num_groups * 128 * p.CN;
+    for (int j = 0; j < p.num_taps; ++j) {
+      long long gr;
+      if (p.cm_tiles > 1) gr = ((long long)j * p.cm_tiles + cm / 128) * 128 + (cm % 128);
+      else gr = (long long)(j / p.tpg) * 128 + (j % p.tpg) * p.cmt + cm;
+      const float* src = p.ws + gr * p.CN + cn;
+      float acc = 0.f;
+      for (int sp = 0; sp < p.splits; ++sp) acc += src[sp * split_stride];
+      sm[lane * rowlen + wy * T + p.widx[j]] = acc;
+    }
+  }
+  __syncthreads();
+  const int cm0 = blockIdx.y * 8;
+  for (int idx = threadIdx.x; idx < 32 * 8 * T; idx += 256) {
+    const int cnl = idx / (8 * T), off = idx - cnl * (8 * T);
+    const int cml = off / T, t = off - cml * T;
+    const int c_n = blockIdx.x * 32 + cnl;
+    if (c_n >= p.CN || cm0 + cml >= p.CM || !present[t]) continue;
+    float* d = p.dw + c_n * p.s_n + (long long)cm0 * T + off;
+    const float v = sm[cnl * rowlen + off];
+    *d = p.accumulate ? (*d + v) : v;
+  }
+}
+
 struct WgradPlan {
   WgradParams p;
   size_t ws_bytes;
@@ -1301,7 +1339,13 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
   r.accumulate = accumulate;
   for (int j = 0; j < plan.num_taps; ++j) r.widx[j] = plan.taps[j].widx;
   const long long total = (long long)r.num_groups * 128 * r.CN;
-  if (r.splits >= 24) {
+  const int T = (int)s_m;
+  bool tiled = s_t == 1 && T >= plan.num_taps && T <= 32 && r.splits < 24 && (r.cm_tiles > 1 || r.cmt >= r.CM);
+  for (int j = 0; j < plan.num_taps && tiled; ++j) tiled = r.widx[j] >= 0 && r.widx[j] < T;
+  if (tiled) {
+    const size_t smem = (size_t)32 * (8 * T + 1) * sizeof(float) + (size_t)T * sizeof(int);
+    wgrad_reduce_tiled_kernel<<<dim3((r.CN + 31) / 32, (r.CM + 7) / 8), 256, smem, stream>>>(r, T);
+  } else if (r.splits >= 24) {
     wgrad_reduce_kernel<<<(int)((total + 31) / 32), 256, 0, stream>>>(r);
   } else {
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);

@@ -379,34 +379,55 @@ static int launch_in_apply(const ApplyArgs& a, int N, cudaStream_t st) {
 static constexpr int kPwCoutLimit = 8;
 static constexpr int kPwMaxCin = 128;
 
-template <int kPwMaxCout>  // compile-time bound on cout (2 / 4 / 8): keeps the accumulators in a few registers
+// kPwMaxCout: compile-time bound on cout (2 / 4 / 8) -- keeps the accumulators in a few registers.  CIN > 0: compile-time
+// channel count (all 16-byte loads of a voxel are issued before the arithmetic); CIN = 0: run-time cin.  grid = (blocks, N):
+// the sample index comes from blockIdx.y, so the voxel loop carries no 64-bit division.
+template <int kPwMaxCout, int CIN>
 __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16* x, long long ld, const float* w,
-                                                            const float* bias, float* y, int N, long long V, int cin,
-                                                            int cout) {
+                                                            const float* bias, float* y, long long V, int cin_rt, int cout) {
+  const int cin = CIN > 0 ? CIN : cin_rt;
   __shared__ float sw[kPwMaxCout * kPwMaxCin + kPwMaxCout];
   for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[kPwMaxCout * kPwMaxCin + i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const long long total = (long long)N * V;
-  for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < total; vox += (long long)gridDim.x * blockDim.x) {
+  const int n = blockIdx.y;
+  const __nv_bfloat16* xs = x + (long long)n * V * ld;
+  float* ys = y + (long long)n * cout * V;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
     float acc[kPwMaxCout];
 #pragma unroll
     for (int o = 0; o < kPwMaxCout; ++o) acc[o] = sw[kPwMaxCout * kPwMaxCin + o];
-    const __nv_bfloat16* xp = x + vox * ld;
-    for (int c0 = 0; c0 < cin; c0 += 8) {
-      float f[8];
-      bf16x8_to_float(*reinterpret_cast<const uint4*>(xp + c0), f);
+    const __nv_bfloat16* xp = xs + v * ld;
+    if constexpr (CIN > 0) {
+      uint4 raw[CIN / 8];
 #pragma unroll
-      for (int o = 0; o < kPwMaxCout; ++o)
-        if (o < cout) {
+      for (int c = 0; c < CIN / 8; ++c) raw[c] = __ldcs(reinterpret_cast<const uint4*>(xp) + c);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[o] += f[i] * sw[o * cin + c0 + i];
-        }
+      for (int c = 0; c < CIN / 8; ++c) {
+        float f[8];
+        bf16x8_to_float(raw[c], f);
+#pragma unroll
+        for (int o = 0; o < kPwMaxCout; ++o)
+          if (o < cout) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[o] = fmaf(f[i], sw[o * CIN + c * 8 + i], acc[o]);
+          }
+      }
+    } else {
+      for (int c0 = 0; c0 < cin; c0 += 8) {
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(xp + c0), f);
+#pragma unroll
+        for (int o = 0; o < kPwMaxCout; ++o)
+          if (o < cout) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[o] += f[i] * sw[o * cin + c0 + i];
+          }
+      }
     }
-    const long long n = vox / V, v = vox % V;
 #pragma unroll
     for (int o = 0; o < kPwMaxCout; ++o)
-      if (o < cout) y[(n * cout + o) * V + v] = acc[o];
+      if (o < cout) __stcs(ys + (long long)o * V + v, acc[o]);
   }
 }
 
@@ -414,14 +435,17 @@ __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16*
 template <int kPwMaxCout>
 __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16* x, long long ldx, const float* dy,
                                                             const float* w, __nv_bfloat16* dx, long long lddx, float* ws,
-                                                            int N, long long V, int cin, int cout) {
+                                                            long long V, int cin, int cout) {
   __shared__ float sw[kPwMaxCout * kPwMaxCin];
   __shared__ float sacc[kPwMaxCout * (kPwMaxCin + 1)];
   for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < cout * (cin + 1); i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int groups = cin / 8;
-  const long long items = (long long)N * V * groups;
+  const int n = blockIdx.y;  // sample: no 64-bit division in the voxel loop
+  x += (long long)n * V * ldx;
+  dy += (long long)n * cout * V;
+  if (dx) dx += (long long)n * V * lddx;
   // thread = (voxel, channel group): keeps dw partials for its 8 channels x cout in registers
   float pw[kPwMaxCout][8];
   float pb[kPwMaxCout];
@@ -437,17 +461,16 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
   const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(gtid % groups);
   const long long vlane = gtid / groups;
-  (void)items;
-  for (long long vox = vlane; vlane < vlanes && vox < (long long)N * V; vox += vlanes) {
-    const long long n = vox / V, v = vox % V;
+  for (long long vox = vlane; vlane < vlanes && vox < V; vox += vlanes) {
+    const long long v = vox;
     float f[8], d[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + vox * ldx + g * 8), f);
+    bf16x8_to_float(__ldcs(reinterpret_cast<const uint4*>(x + vox * ldx + g * 8)), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = 0.f;
 #pragma unroll
     for (int o = 0; o < kPwMaxCout; ++o)
       if (o < cout) {
-        const float gy = dy[(n * cout + o) * V + v];
+        const float gy = dy[(long long)o * V + v];
         if (g == 0) pb[o] += gy;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -455,7 +478,7 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
           pw[o][i] += gy * f[i];
         }
       }
-    if (dx) *reinterpret_cast<uint4*>(dx + vox * lddx + g * 8) = float_to_bf16x8(d);
+    if (dx) __stcs(reinterpret_cast<uint4*>(dx + vox * lddx + g * 8), float_to_bf16x8(d));
   }
   if (vlane < vlanes)
 #pragma unroll
@@ -466,7 +489,8 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
       if (g == 0) atomicAdd(&sacc[o * (cin + 1) + cin], pb[o]);
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < cout * (cin + 1); i += blockDim.x) ws[(long long)blockIdx.x * cout * (cin + 1) + i] = sacc[i];
+  const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int i = threadIdx.x; i < cout * (cin + 1); i += blockDim.x) ws[blk * cout * (cin + 1) + i] = sacc[i];
 }
 
 // one block per output element: 256 threads stride through the per-block partials, shared-memory tree (double)
@@ -493,9 +517,9 @@ __global__ void __launch_bounds__(256) pointwise_bwd_reduce_kernel(const float* 
   }
 }
 
-static int pointwise_bwd_blocks(const rehr_tensor* x) {
-  const long long items = (long long)x->n * voxels_per_sample(x) * (x->c / 8);
-  return grid_for(items, 256, 8);
+static int pointwise_bwd_blocks(const rehr_tensor* x) {  // per sample (grid.x); the launch uses grid.y = N
+  const long long items = voxels_per_sample(x) * (x->c / 8);
+  return std::max(1, grid_for(items, 256, 8) / std::max(1, x->n));
 }
 
 // per-channel sum over all voxels (bias gradient): per-block partials + reduce
@@ -1050,21 +1074,23 @@ int rehr_pointwise_fwd(const rehr_tensor* x, const float* w, const float* bias, 
   if (!bf16_tensor_ok(x) || !w || !y_ncdhw) return REHR_BAD_SHAPE;
   if (cout > kPwCoutLimit || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
   const long long V = voxels_per_sample(x);
-  const int grid = grid_for((long long)x->n * V, 256, 8);
+  const dim3 grid((unsigned)std::max(1, grid_for(V, 256, 8)), (unsigned)x->n);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
-  if (cout <= 2)
-    pointwise_fwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+  if (cout <= 2 && x->c == 32)  // the nnU-Net segmentation head (decoder.seg_layers[-1], models/seg_model.py:44)
+    pointwise_fwd_kernel<2, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
+  else if (cout <= 2)
+    pointwise_fwd_kernel<2, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
   else if (cout <= 4)
-    pointwise_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+    pointwise_fwd_kernel<4, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
   else
-    pointwise_fwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, x->n, V, x->c, cout);
+    pointwise_fwd_kernel<8, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
 
 size_t rehr_pointwise_bwd_workspace(const rehr_tensor* x, int cout) {
   if (!x) return 0;
-  return (size_t)pointwise_bwd_blocks(x) * cout * (x->c + 1) * sizeof(float);
+  return (size_t)pointwise_bwd_blocks(x) * x->n * cout * (x->c + 1) * sizeof(float);
 }
 
 int rehr_pointwise_bwd(const rehr_tensor* x, const float* dy_ncdhw, const float* w, int cout, const rehr_tensor* dx, float* dw,
@@ -1073,17 +1099,19 @@ int rehr_pointwise_bwd(const rehr_tensor* x, const float* dy_ncdhw, const float*
   if (cout > kPwCoutLimit || x->c > kPwMaxCin) return REHR_UNSUPPORTED;
   if (ws_bytes < rehr_pointwise_bwd_workspace(x, cout) || !ws) return REHR_WORKSPACE;
   const long long V = voxels_per_sample(x);
-  const int blocks = pointwise_bwd_blocks(x);
+  const int bx = pointwise_bwd_blocks(x);
+  const int blocks = bx * x->n;
+  const dim3 grid((unsigned)bx, (unsigned)x->n);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
   __nv_bfloat16* dxp = dx ? reinterpret_cast<__nv_bfloat16*>(dx->ptr) : nullptr;
   const long long lddx = dx ? dx->ld : 0;
   float* wsp = reinterpret_cast<float*>(ws);
   if (cout <= 2)
-    pointwise_bwd_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, x->n, V, x->c, cout);
+    pointwise_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout);
   else if (cout <= 4)
-    pointwise_bwd_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, x->n, V, x->c, cout);
+    pointwise_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout);
   else
-    pointwise_bwd_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, x->n, V, x->c, cout);
+    pointwise_bwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout);
   REHR_CHECK_LAUNCH();
   const int outs = cout * (x->c + 1);
   pointwise_bwd_reduce_kernel<<<outs, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c, cout, dw,
