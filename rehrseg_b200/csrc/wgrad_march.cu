@@ -54,6 +54,13 @@ struct alignas(64) WgmParams {
   int g_mask, j_min, j_max;
   float* ws;          // [cta][group][128][KS * PC]
   int* err;
+  // fused parity classes (n_cls > 0): CTAs [cls_begin[c], cls_begin[c + 1]) work on class c -- halo operand h_maps[c], its own
+  // group mask / depth-plane range -- all inside ONE launch, so the TMEM drain and the partial-dW reduction are paid once per CTA
+  // instead of once per class pass, and the 8 classes share the dY tiles through L2
+  int n_cls;
+  int cls_begin[9];
+  int cls_gmask[8], cls_jmin[8], cls_jmax[8];
+  CUtensorMap h_maps[8];
 };
 
 // Geometry of one (CH halo channels, PC plain channels, KS kernel size) variant.
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.h_map);
+    if (p.n_cls == 0) tma_prefetch_desc(&p.h_map);
     tma_prefetch_desc(&p.p_map);
     for (int i = 0; i < kHStages; ++i) {
       mbar_init(&full_h[i], 1);
@@ -151,15 +158,29 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int combo = blockIdx.x % p.n_combo;
-  const int rank = blockIdx.x / p.n_combo;
+  // class (fused stride-2 passes) -> CTA range, halo map, masks; a single class otherwise
+  int cta = blockIdx.x, ctas_per_combo = p.ctas_per_combo;
+  int g_mask = p.g_mask, j_min = p.j_min, j_max = p.j_max;
+  const CUtensorMap* h_map = &p.h_map;
+  if (p.n_cls > 0) {
+    int cls = 0;
+    while (cls + 1 < p.n_cls && (int)blockIdx.x >= p.cls_begin[cls + 1]) ++cls;
+    cta = blockIdx.x - p.cls_begin[cls];
+    ctas_per_combo = (p.cls_begin[cls + 1] - p.cls_begin[cls]) / p.n_combo;
+    g_mask = p.cls_gmask[cls];
+    j_min = p.cls_jmin[cls];
+    j_max = p.cls_jmax[cls];
+    h_map = &p.h_maps[cls];
+  }
+  const int combo = cta % p.n_combo;
+  const int rank = cta / p.n_combo;
   const int hs = combo / p.n_ps, ps = combo % p.n_ps;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       uint32_t kh = 0, kp = 0;  // running plane counters (ring position = counter % ring, parity = (counter / ring) & 1)
-      for (int item = rank; item < p.items_per_combo; item += p.ctas_per_combo) {
+      for (int item = rank; item < p.items_per_combo; item += ctas_per_combo) {
         const WgmItem c = wgm_decode(p, item);
         const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
         const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
           const uint32_t st = kh % kHStages;
           mbar_wait(&empty_h[st], ((kh / kHStages) & 1u) ^ 1u, p.err, 52);
           mbar_arrive_expect_tx(&full_h[st], Cfg::kHaloRows * Cfg::kRowB);
-          tma_load_5d(&p.h_map, &full_h[st], s_h + (size_t)st * p.h_stride, hs * CH, w0 - R, h0 - R, q, c.n);
+          tma_load_5d(h_map, &full_h[st], s_h + (size_t)st * p.h_stride, hs * CH, w0 - R, h0 - R, q, c.n);
           ++kh;
         }
       }
@@ -197,7 +218,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
     mbar_wait(zero_bar, 0, p.err, 61);  // accumulators zeroed by the drain warps
     tc_fence_after();
     uint32_t kh = 0, kp = 0;
-    for (int item = rank; item < p.items_per_combo; item += p.ctas_per_combo) {
+    for (int item = rank; item < p.items_per_combo; item += ctas_per_combo) {
       const WgmItem c = wgm_decode(p, item);
       const int d0 = c.seg * p.Ds, d1 = min(p.D, d0 + p.Ds);
       const int pa = max(d0 - R, 0), pb = min(d1 - 1 + R, p.D - 1);
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
         mbar_wait(&full_h[st], (kh / kHStages) & 1u, p.err, 63);
         tc_fence_after();
         // plain planes q - R + j, j in [jlo, jhi], exist inside the volume
-        const int jlo = max(max(0, R - q), p.j_min), jhi = min(min(KS - 1, p.D - 1 - q + R), p.j_max);
+        const int jlo = max(max(0, R - q), j_min), jhi = min(min(KS - 1, p.D - 1 - q + R), j_max);
         const uint32_t cbase = cnt0 + (uint32_t)(q - R + jlo - pa);
         const uint32_t s0 = cbase % kPRing;
         const uint32_t idesc = make_idesc_bf16(128, max(jhi - jlo + 1, 1) * PC, 1, 1);
@@ -228,7 +249,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
               const uint64_t bd = ((uint64_t)kBHi << 32) | (uint64_t)(b_lo + (uint32_t)((ks * 16 * Cfg::kPRowB) >> 4));
 #pragma unroll
               for (int g = 0; g < Cfg::kGroups; ++g) {
-                if (!((p.g_mask >> g) & 1)) continue;
+                if (!((g_mask >> g) & 1)) continue;
                 const uint32_t a_off = (uint32_t)(((2 * ks * Cfg::kHaloW + Cfg::row0(g)) * Cfg::kRowB) >> 4) |
                                        ((uint32_t)((Cfg::lbo_rows(g) * Cfg::kRowB) >> 4) << 16);
                 const uint64_t ad = ((uint64_t)kAHi << 32) | (uint64_t)(a_lo + a_off);
@@ -512,9 +533,7 @@ static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
 using namespace rehr;
 
 // launch the variant + its reduction (cls_s / cls_r: parity-class tap mapping of a stride-2 conv, or null)
-static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate, const int* cls_s, const int* cls_r,
-                   cudaStream_t stream) {
-  const WgmParams& p = pl.p;
+static int wgm_launch_kernel(const WgmPlan& pl, cudaStream_t stream) {
   const int ks = pl.KS;
   int rc = REHR_UNSUPPORTED;
   if (ks == 3 && pl.CH == 32 && pl.PC == 32) rc = launch_wgm<32, 32, 3>(pl, stream);
@@ -522,10 +541,17 @@ static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate,
   else if (ks == 3 && pl.CH == 32 && pl.PC == 16) rc = launch_wgm<32, 16, 3>(pl, stream);
   else if (ks == 3 && pl.CH == 64 && pl.PC == 16) rc = launch_wgm<64, 16, 3>(pl, stream);
   else if (ks == 5 && pl.CH == 16 && pl.PC == 16) rc = launch_wgm<16, 16, 5>(pl, stream);
-  if (rc != REHR_OK) return rc;
+  return rc;
+}
+
+// sum the partial dW of `ctas_per_combo` x n_combo consecutive CTAs starting at `ws` into dw
+static int wgm_reduce(const WgmPlan& pl, const float* ws, int ctas_per_combo, int Ci, int Co, float* dw, int accumulate,
+                      const int* cls_s, const int* cls_r, cudaStream_t stream) {
+  const WgmParams& p = pl.p;
+  const int ks = pl.KS;
   WgmReduceParams r;
   memset(&r, 0, sizeof(r));
-  r.ws = p.ws;
+  r.ws = ws;
   r.dw = dw;
   r.CH = pl.CH;
   r.PC = pl.PC;
@@ -537,7 +563,7 @@ static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate,
   r.n_hs = p.n_hs;
   r.n_ps = p.n_ps;
   r.n_combo = p.n_combo;
-  r.ctas_per_combo = p.ctas_per_combo;
+  r.ctas_per_combo = ctas_per_combo;
   r.role = pl.role;
   r.Ci = Ci;
   r.Co = Co;
@@ -549,7 +575,7 @@ static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate,
       r.cls_r[a] = cls_r[a];
     }
   }
-  if (p.ctas_per_combo >= 24) {
+  if (ctas_per_combo >= 24) {
     const int blocks = p.n_hs * p.n_ps * ks * ks * ks * pl.CH;
     wgrad_march_reduce_kernel<true><<<blocks, 256, 0, stream>>>(r);
   } else {
@@ -560,6 +586,13 @@ static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate,
   }
   REHR_CHECK_LAUNCH();
   return REHR_OK;
+}
+
+static int wgm_run(const WgmPlan& pl, int Ci, int Co, float* dw, int accumulate, const int* cls_s, const int* cls_r,
+                   cudaStream_t stream) {
+  int rc = wgm_launch_kernel(pl, stream);
+  if (rc != REHR_OK) return rc;
+  return wgm_reduce(pl, pl.p.ws, pl.p.ctas_per_combo, Ci, Co, dw, accumulate, cls_s, cls_r, stream);
 }
 
 static int wgm_ks_of(const rehr_conv_desc* d) {
@@ -677,6 +710,9 @@ int rehr_conv3d_wgrad_march_s2(const rehr_conv_desc* d, const rehr_tensor* x, co
   }
   pl.p.ws = reinterpret_cast<float*>(ws);
   pl.p.err = nullptr;
+  // all parity classes in ONE launch: class c owns the CTAs [cls_begin[c], cls_begin[c + 1]), sized by its MMA count
+  WgmParams& p = pl.p;
+  int n_cls = 0, cost[8], cls_r[8][3];
   for (int rd = 0; rd < s[0]; ++rd)
     for (int rh = 0; rh < s[1]; ++rh)
       for (int rw = 0; rw < s[2]; ++rw) {
@@ -694,7 +730,7 @@ int rehr_conv3d_wgrad_march_s2(const rehr_conv_desc* d, const rehr_tensor* x, co
         const unsigned long long gstr[4] = {xpw * s[2], xph * s[1], xpd * s[0], xpn};
         const unsigned box[5] = {(unsigned)pl.CH, (unsigned)(kWTileW + 2), (unsigned)(kWTileH + 2), 1u, 1u};
         const uint8_t* base = reinterpret_cast<const uint8_t*>(x->ptr) + rd * xpd + rh * xph + rw * xpw;
-        rc = encode_tiled_bf16(&pl.p.h_map, base, 5, gdim, gstr, box, pl.CH * 2);
+        rc = encode_tiled_bf16(&p.h_maps[n_cls], base, 5, gdim, gstr, box, pl.CH * 2);
         if (rc != REHR_OK) return rc;
         // offsets e needed per dim: stride 1 -> {-1, 0, 1}; stride 2: r = 0 -> {0}; r = 1 -> {-1, 0}
         int elo[3], ehi[3];
@@ -704,19 +740,44 @@ int rehr_conv3d_wgrad_march_s2(const rehr_conv_desc* d, const rehr_tensor* x, co
           else { elo[a] = -1; ehi[a] = 0; }
         }
         // depth: e_d = 1 - j  ->  j in [1 - ehi, 1 - elo];  in-plane: offset index oh = e_h + 1, ow = e_w + 1
-        pl.p.j_min = 1 - ehi[0];
-        pl.p.j_max = 1 - elo[0];
+        p.cls_jmin[n_cls] = 1 - ehi[0];
+        p.cls_jmax[n_cls] = 1 - elo[0];
         int gmask = 0;
         for (int oh = elo[1] + 1; oh <= ehi[1] + 1; ++oh)
           for (int ow = elo[2] + 1; ow <= ehi[2] + 1; ++ow) {
             const int a = oh * 3 + ow;
             gmask |= 1 << (pl.CH == 64 ? a / 2 : oh);
           }
-        pl.p.g_mask = gmask;
-        const int cs[3] = {s[0], s[1], s[2]};
-        rc = wgm_run(pl, x->c, dy->c, dw, accumulate, cs, r, stream);
-        if (rc != REHR_OK) return rc;
+        p.cls_gmask[n_cls] = gmask;
+        cost[n_cls] = __builtin_popcount(gmask);
+        for (int a = 0; a < 3; ++a) cls_r[n_cls][a] = r[a];
+        ++n_cls;
       }
+  if (n_cls == 0) return REHR_OK;
+  // CTA shares proportional to the MMA groups a class issues per plane; multiples of n_combo, at least one combo set each
+  const int budget = pl.grid / p.n_combo;  // combo sets available (<= SMs)
+  if (budget < n_cls) return REHR_UNSUPPORTED;
+  int total_cost = 0, share[8], used = 0;
+  for (int c = 0; c < n_cls; ++c) total_cost += cost[c];
+  for (int c = 0; c < n_cls; ++c) {
+    share[c] = std::max(1, (int)((long long)budget * cost[c] / total_cost));
+    share[c] = std::min(share[c], p.items_per_combo);
+    used += share[c];
+  }
+  for (int c = 0; used > budget; c = (c + 1) % n_cls)
+    if (share[c] > 1) { --share[c]; --used; }
+  p.n_cls = n_cls;
+  p.cls_begin[0] = 0;
+  for (int c = 0; c < n_cls; ++c) p.cls_begin[c + 1] = p.cls_begin[c] + share[c] * p.n_combo;
+  pl.grid = p.cls_begin[n_cls];
+  rc = wgm_launch_kernel(pl, stream);
+  if (rc != REHR_OK) return rc;
+  const size_t per_cta = (size_t)pl.groups * 128 * pl.KS * pl.PC;
+  const int cs[3] = {s[0], s[1], s[2]};
+  for (int c = 0; c < n_cls; ++c) {
+    rc = wgm_reduce(pl, p.ws + (size_t)p.cls_begin[c] * per_cta, share[c], x->c, dy->c, dw, accumulate, cs, cls_r[c], stream);
+    if (rc != REHR_OK) return rc;
+  }
   return REHR_OK;
 }
 

@@ -298,6 +298,40 @@ def test_smallcin_stem_block():
     assert rel_l2(dbeta, rdb) < 6e-2
 
 
+@pytest.mark.parametrize("dhw", [(5, 11, 20), (3, 16, 128), (4, 9, 33)])
+def test_stem_tensor_core_kernels_keep_fp32_accuracy(dhw):
+    """1 -> 32 k3 stem through the mma.sync kernels (csrc/stem_mma.cu): the fp32 image and weights are split into bf16 hi + lo
+    parts, so forward and weight gradient must match fp32 torch far below bf16 resolution (output only rounded once to bf16)."""
+    import ctypes as C
+    from rehrseg_b200 import _lib as L
+    g = torch.Generator().manual_seed(21)
+    d, h, w_ = dhw
+    x = torch.randn((2, 1, d, h, w_), generator=g).cuda()
+    w = (torch.randn((32, 1, 3, 3, 3), generator=g) / 27 ** 0.5).cuda()
+    b = torch.randn((32,), generator=g).cuda()
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv3d(x, wr, b, padding=1)
+    desc = L.conv_desc((3, 3, 3), (1, 1, 1), (1, 1, 1))
+    y = torch.empty((2, d, h, w_, 32), dtype=torch.bfloat16, device="cuda")
+    yt = L.rt(y)
+    L.check(L.lib().rehr_conv3d_smallcin_fwd(C.byref(desc), L.ptr(x), 2, 1, d, h, w_, L.ptr(w), L.ptr(b), C.byref(yt),
+                                             L.ACT_NONE, 0.0, None, L.stream_ptr()))
+    got = y.float().permute(0, 4, 1, 2, 3)
+    assert float((got - bf16r(ref)).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())      # <= 1 bf16 ulp anywhere
+    assert rel_l2(got, bf16r(ref)) < 5e-4                                                    # and almost always 0 ulp
+    go = torch.randn(ref.shape, generator=g).cuda()
+    (rdw,) = torch.autograd.grad(ref, wr, bf16r(go))
+    gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    gt = L.rt(gcl)
+    need = L.lib().rehr_conv3d_smallcin_wgrad_workspace(C.byref(desc), 1, C.byref(gt))
+    ws = torch.empty((need,), dtype=torch.uint8, device="cuda")
+    dw = torch.empty_like(w)
+    L.check(L.lib().rehr_conv3d_smallcin_wgrad(C.byref(desc), L.ptr(x), 2, 1, d, h, w_, C.byref(gt), L.ptr(dw), 0, L.ptr(ws), need,
+                                               L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(dw, rdw) < 1e-4, rel_l2(dw, rdw)
+
+
 def test_flavr_stem_smallcin_raw():
     """2-channel FLAVR stem k(3,7,7) s(1,2,2) p(1,3,3) + ReLU (resnet_3D.py:42-50) forward / wgrad / dgrad."""
     import ctypes as C

@@ -12,6 +12,8 @@ LAYERS = [  # name, cin, cout, spatial (of the INPUT), stride
     ("dec0.0", 640, 320, 8, 1), ("dec1.0", 512, 256, 16, 1), ("dec2.0", 256, 128, 32, 1), ("dec3.0", 128, 64, 64, 1),
     ("dec4.0", 64, 32, 128, 1),
 ]
+if os.environ.get("S2_WGRAD_MIN") is not None:
+    Fn.S2_WGRAD_MARCH_MIN_VOXELS = int(os.environ["S2_WGRAD_MIN"])
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
 
@@ -27,7 +29,7 @@ def timeit(fn, iters=3):
     return min(ts)
 
 
-only = sys.argv[1:] 
+only = sys.argv[1:]
 rows = []
 for name, cin, cout, sp, st in LAYERS:
     if only and name not in only:
