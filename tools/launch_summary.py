@@ -1,5 +1,6 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: the last N launches (the measured step of
-tools/one_step.py) grouped by kernel.  usage: launch_summary.py launches.csv N [--list]"""
+tools/one_step.py) grouped by kernel.  usage: launch_summary.py launches.csv N [--list]; N = 0 takes the launches between the last two occurrences of
+the step's first kernel (the stem forward), i.e. exactly one steady-state step including the ATen kernels of the loss."""
 import csv, sys, re, collections
 
 path, n = sys.argv[1], int(sys.argv[2])
@@ -14,7 +15,11 @@ for r in csv.DictReader(lines):
     us = v / 1000.0 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1000.0)
     name = re.sub(r"\(.*", "", r["Kernel Name"])
     rows.append((name, us, r["Grid Size"], r["Block Size"]))
-rows = rows[-n:]
+if n == 0:
+    marks = [i for i, r in enumerate(rows) if "stem_fwd" in r[0] or "smallcin_fwd" in r[0]]
+    rows = rows[marks[-2]:marks[-1]]
+else:
+    rows = rows[-n:]
 tot = sum(r[1] for r in rows)
 print(f"# launches in the measured step: {len(rows)}   sum of durations: {tot / 1000:.3f} ms")
 if "--list" in sys.argv:
