@@ -1161,14 +1161,22 @@ __global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const WgradRedu
   const int cm = blockIdx.y * 8 + wy;
   if (cn < p.CN && cm < p.CM) {
     const long long split_stride = (long long)p.num_groups * 128 * p.CN;
+#pragma unroll 3
     for (int j = 0; j < p.num_taps; ++j) {
       long long gr;
       if (p.cm_tiles > 1) gr = ((long long)j * p.cm_tiles + cm / 128) * 128 + (cm % 128);
       else gr = (long long)(j / p.tpg) * 128 + (j % p.tpg) * p.cmt + cm;
       const float* src = p.ws + gr * p.CN + cn;
-      float acc = 0.f;
-      for (int sp = 0; sp < p.splits; ++sp) acc += src[sp * split_stride];
-      sm[lane * rowlen + wy * T + p.widx[j]] = acc;
+      // four independent partial sums: the loads of a tap's split list are in flight together (the chain was latency bound)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int sp = 0;
+      for (; sp + 4 <= p.splits; sp += 4) {
+        const float v0 = src[(sp + 0) * split_stride], v1 = src[(sp + 1) * split_stride];
+        const float v2 = src[(sp + 2) * split_stride], v3 = src[(sp + 3) * split_stride];
+        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+      }
+      for (; sp < p.splits; ++sp) a0 += src[sp * split_stride];
+      sm[lane * rowlen + wy * T + p.widx[j]] = (a0 + a1) + (a2 + a3);
     }
   }
   __syncthreads();

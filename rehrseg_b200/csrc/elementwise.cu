@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(32 * kFinLanes) in_finalize_kernel(const float
   double s1 = 0.0, s2 = 0.0;
   if (c < C) {
     const float2* p = reinterpret_cast<const float2*>(partial) + (long long)n * tiles * C + c;
-#pragma unroll 4
+#pragma unroll 8
     for (int t = tl; t < tiles; t += kFinLanes) {
       const float2 v = p[(long long)t * C];
       s1 += (double)v.x;
@@ -237,32 +237,41 @@ __global__ void __launch_bounds__(32 * kFinLanes) in_bwd_finalize_kernel(const f
   const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double g = 0.0, b = 0.0;
-  for (int n = 0; n < N; ++n) {
-    double s1 = 0.0, s2 = 0.0;
+  // two samples per pass: their partial lists are independent, so twice as many loads are in flight per round trip
+  for (int n0 = 0; n0 < N; n0 += 2) {
+    const bool two = n0 + 1 < N;
+    double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
     if (c < C) {
-      const float2* p = reinterpret_cast<const float2*>(partial) + (long long)n * tiles * C + c;
-#pragma unroll 4
+      const float2* pa = reinterpret_cast<const float2*>(partial) + (long long)n0 * tiles * C + c;
+      const float2* pb = pa + (two ? (long long)tiles * C : 0);
+#pragma unroll 8
       for (int t = tl; t < tiles; t += kFinLanes) {
-        const float2 v = p[(long long)t * C];
-        s1 += (double)v.x;
-        s2 += (double)v.y;
+        const float2 va = pa[(long long)t * C];
+        const float2 vb = pb[(long long)t * C];
+        s1a += (double)va.x;
+        s2a += (double)va.y;
+        s1b += (double)vb.x;
+        s2b += (double)vb.y;
       }
     }
-    __syncthreads();
-    sh1[tl][cl] = s1;
-    sh2[tl][cl] = s2;
-    __syncthreads();
-    if (tl == 0 && c < C) {
-      double a1 = 0.0, a2 = 0.0;
+    for (int k = 0; k < (two ? 2 : 1); ++k) {
+      __syncthreads();
+      sh1[tl][cl] = k == 0 ? s1a : s1b;
+      sh2[tl][cl] = k == 0 ? s2a : s2b;
+      __syncthreads();
+      if (tl == 0 && c < C) {
+        double a1 = 0.0, a2 = 0.0;
 #pragma unroll
-      for (int l = 0; l < kFinLanes; ++l) {
-        a1 += sh1[l][cl];
-        a2 += sh2[l][cl];
+        for (int l = 0; l < kFinLanes; ++l) {
+          a1 += sh1[l][cl];
+          a2 += sh2[l][cl];
+        }
+        const int n = n0 + k;
+        sums[((long long)n * C + c) * 2] = (float)a1;
+        sums[((long long)n * C + c) * 2 + 1] = (float)a2;
+        b += a1;
+        g += a2;
       }
-      sums[((long long)n * C + c) * 2] = (float)a1;
-      sums[((long long)n * C + c) * 2 + 1] = (float)a2;
-      b += a1;
-      g += a2;
     }
   }
   if (tl == 0 && c < C) {
@@ -461,24 +470,40 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
   const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(gtid % groups);
   const long long vlane = gtid / groups;
-  for (long long vox = vlane; vlane < vlanes && vox < V; vox += vlanes) {
-    const long long v = vox;
-    float f[8], d[8];
-    bf16x8_to_float(__ldcs(reinterpret_cast<const uint4*>(x + vox * ldx + g * 8)), f);
+  // two voxels per iteration: both x loads and both dy rows are issued before the arithmetic
+  for (long long vox = vlane; vlane < vlanes && vox < V; vox += 2 * vlanes) {
+    const long long v1 = vox + vlanes;
+    const bool has1 = v1 < V;
+    const uint4 r0 = __ldcs(reinterpret_cast<const uint4*>(x + vox * ldx + g * 8));
+    const uint4 r1 = has1 ? __ldcs(reinterpret_cast<const uint4*>(x + v1 * ldx + g * 8)) : make_uint4(0, 0, 0, 0);
+    float gy0[kPwMaxCout], gy1[kPwMaxCout];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = 0.f;
+    for (int o = 0; o < kPwMaxCout; ++o) {
+      gy0[o] = o < cout ? dy[(long long)o * V + vox] : 0.f;
+      gy1[o] = (o < cout && has1) ? dy[(long long)o * V + v1] : 0.f;
+    }
+    float f0[8], f1[8], d0[8], d1[8];
+    bf16x8_to_float(r0, f0);
+    bf16x8_to_float(r1, f1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d0[i] = d1[i] = 0.f;
 #pragma unroll
     for (int o = 0; o < kPwMaxCout; ++o)
       if (o < cout) {
-        const float gy = dy[(long long)o * V + v];
-        if (g == 0) pb[o] += gy;
+        if (g == 0) pb[o] += gy0[o] + gy1[o];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          d[i] += gy * sw[o * cin + g * 8 + i];
-          pw[o][i] += gy * f[i];
+          const float wv = sw[o * cin + g * 8 + i];
+          d0[i] = fmaf(gy0[o], wv, d0[i]);
+          d1[i] = fmaf(gy1[o], wv, d1[i]);
+          pw[o][i] = fmaf(gy0[o], f0[i], pw[o][i]);
+          pw[o][i] = fmaf(gy1[o], f1[i], pw[o][i]);
         }
       }
-    if (dx) __stcs(reinterpret_cast<uint4*>(dx + vox * lddx + g * 8), float_to_bf16x8(d));
+    if (dx) {
+      __stcs(reinterpret_cast<uint4*>(dx + vox * lddx + g * 8), float_to_bf16x8(d0));
+      if (has1) __stcs(reinterpret_cast<uint4*>(dx + v1 * lddx + g * 8), float_to_bf16x8(d1));
+    }
   }
   if (vlane < vlanes)
 #pragma unroll
