@@ -173,6 +173,58 @@ def concat_room_of(t: torch.Tensor):
     return getattr(t, "_rehr_cat", None)
 
 
+# Small layers (<= 32^3): the weight gradient and the input gradient of a conv are independent consumers of dy and each is a
+# latency-bound launch chain (GEMM + partial reduction) on a handful of CTAs, so the weight-gradient chain is forked onto a side
+# stream and joined after the input gradient has been issued (events only: the fork/join is captured as two parallel branches by
+# graphs.GraphedTrainStep).  Large layers fill the machine on their own and stay on one stream.
+WGRAD_SIDE_STREAM = True
+WGRAD_SIDE_MAX_VOXELS = 2 * 32 ** 3
+_side_streams: dict = {}
+
+
+class _fork:
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        side = _side_streams.get(key)
+        if side is None:
+            side = _side_streams[key] = torch.cuda.Stream(device=device)
+        self.side = side
+        self.ctx = None
+
+    def __enter__(self):
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        self.main.wait_event(ev)
+
+
+def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bool, cache: bool = True):
+    """(dx or None, dw) of a conv; the two chains run side by side for small layers (see WGRAD_SIDE_STREAM)."""
+    voxels = dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3]
+    if need_dx and WGRAD_SIDE_STREAM and _ktimer is None and voxels <= WGRAD_SIDE_MAX_VOXELS:
+        dw = torch.empty(tuple(wshape), dtype=torch.float32, device=dy.device)   # owned by the main stream's pool
+        fk = _fork(dy.device)
+        with fk:
+            conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw)
+        dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache)
+        fk.join()
+        return dx, dw
+    dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache) if need_dx else None
+    return dx, conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
 
@@ -285,9 +337,9 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
 
 
 def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], kernel: Triple, stride: Triple,
-                     padding: Triple) -> torch.Tensor:
+                     padding: Triple, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x, dy = as_cl(x), as_cl(dy)
-    dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)
     desc = conv_desc(kernel, stride, padding)
     xt, dyt = rt(x), rt(dy)
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * x.shape[4] * kernel[0] * kernel[1] * kernel[2]
@@ -322,10 +374,11 @@ def conv3d_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape: Sequence[int], k
     return dw
 
 
-def channel_sum_raw(x: torch.Tensor) -> torch.Tensor:
+def channel_sum_raw(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = as_cl(x)
     xt = rt(x)
-    out = torch.empty((x.shape[4],), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((x.shape[4],), dtype=torch.float32, device=x.device)
     need = lib().rehr_channel_sum_workspace(C.byref(xt))
     ws = _ws(need, x.device)
     check(lib().rehr_channel_sum(C.byref(xt), ptr(out), 0, ptr(ws), need, stream_ptr()), "channel_sum")
@@ -440,9 +493,7 @@ class ConvNormAct(torch.autograd.Function):
                                                        stream_ptr()), "smallcin_dgrad")
                 _count()
         else:
-            if ctx.needs_input_grad[0]:
-                dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding)
-            dw = conv3d_wgrad_raw(x, dy, weight.shape, kernel, stride, padding)
+            dx, dw = _dgrad_and_wgrad(x, dy, weight, weight.shape, kernel, stride, padding, ctx.needs_input_grad[0])
         # A per-channel constant added before InstanceNorm is removed by the mean subtraction: d(loss)/d(bias) == 0
         # exactly (PyTorch's value is rounding noise of the same sum).
         dbias = torch.zeros((cout,), dtype=torch.float32, device=dev) if has_bias else None
@@ -506,8 +557,7 @@ class ConvAct(torch.autograd.Function):
             dw = conv3d_wgrad_raw(x, dyp, wpad.shape, kernel, stride, padding)[:cout]
             dy = dyp
         else:
-            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding) if ctx.needs_input_grad[0] else None
-            dw = conv3d_wgrad_raw(x, dy, weight.shape, kernel, stride, padding)
+            dx, dw = _dgrad_and_wgrad(x, dy, weight, weight.shape, kernel, stride, padding, ctx.needs_input_grad[0])
         db = channel_sum_raw(dy)[:cout] if has_bias else None
         return dx, dw.to(weight.dtype), db, None, None, None, None, None, None, None
 
@@ -699,6 +749,26 @@ class ConvTranspose(torch.autograd.Function):
         dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
         desc = conv_desc(kernel, stride, padding)
         dyt, xt = rt(dy), rt(x)
+        need = lib().rehr_convtranspose3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
+        if need == 0:
+            raise L.RehrError("convtranspose3d_wgrad: unsupported configuration")
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+        db = torch.empty((weight.shape[1],), dtype=torch.float32, device=x.device) if has_bias else None
+
+        def weight_and_bias_grads():
+            ws = _ws(need, x.device)
+            check(lib().rehr_convtranspose3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
+                  "convtranspose3d_wgrad")
+            _count(2)
+            if has_bias:
+                channel_sum_raw(dy, out=db)
+
+        voxels = dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3]
+        fk = None
+        if ctx.needs_input_grad[0] and WGRAD_SIDE_STREAM and _ktimer is None and voxels <= WGRAD_SIDE_MAX_VOXELS:
+            fk = _fork(x.device)          # small layer: weight / bias gradients side by side with the input gradient
+            with fk:
+                weight_and_bias_grads()
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
@@ -707,15 +777,10 @@ class ConvTranspose(torch.autograd.Function):
             check(lib().rehr_convtranspose3d_dgrad(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), stream_ptr()),
                   "convtranspose3d_dgrad")
             _count()
-        need = lib().rehr_convtranspose3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
-        if need == 0:
-            raise L.RehrError("convtranspose3d_wgrad: unsupported configuration")
-        ws = _ws(need, x.device)
-        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-        check(lib().rehr_convtranspose3d_wgrad(C.byref(desc), C.byref(xt), C.byref(dyt), ptr(dw), 0, ptr(ws), need, stream_ptr()),
-              "convtranspose3d_wgrad")
-        _count(2)
-        db = channel_sum_raw(dy) if has_bias else None
+        if fk is not None:
+            fk.join()
+        else:
+            weight_and_bias_grads()
         return dx, dw.to(weight.dtype), db, dskip, None, None, None, None, None
 
 

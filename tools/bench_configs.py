@@ -11,7 +11,7 @@ a = ap.parse_args()
 what = a.what.split(",")
 
 
-def timeit(fn, iters=3, warm=2):
+def timeit(fn, iters=5, warm=4):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
