@@ -17,9 +17,9 @@ namespace rehr {
 bool stem_mma_supported(int cin, int cout, int wd);
 size_t stem_mma_wgrad_workspace();
 int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_bfloat16* y, long long ldy, int n, int d, int h, int wd,
-                        int act, float slope, cudaStream_t stream);
+                        int act, float slope, int planar, cudaStream_t stream);
 int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long lddy, int n, int d, int h, int wd, float* dw, int accumulate,
-                          float* ws, cudaStream_t stream);
+                          float* ws, int planar, cudaStream_t stream);
 
 static constexpr int kScMaxCin = 4;
 static constexpr int kScCoutPerThread = 16;
@@ -599,9 +599,12 @@ int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, i
   a.slope = slope;
   const bool k3 = desc->kd == 3 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
                   desc->pd == 1 && desc->ph == 1 && desc->pw == 1;
+  // planar stem of anisotropic plans: k = (1,3,3), stride 1, pad (0,1,1)
+  const bool k133 = desc->kd == 1 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
+                    desc->pd == 0 && desc->ph == 1 && desc->pw == 1;
   int rc = REHR_UNSUPPORTED;
-  if (k3 && stem_mma_supported(cin, y->c, w) && y->ld % 8 == 0) {
-    rc = launch_stem_fwd_mma(x_ncdhw, weight, bias, a.y, a.ldy, n, d, h, w, act, slope, (cudaStream_t)stream);
+  if ((k3 || k133) && stem_mma_supported(cin, y->c, w) && y->ld % 8 == 0) {
+    rc = launch_stem_fwd_mma(x_ncdhw, weight, bias, a.y, a.ldy, n, d, h, w, act, slope, k133 ? 1 : 0, (cudaStream_t)stream);
     if (rc != REHR_OK && rc != REHR_UNSUPPORTED) return rc;
   }
   if (rc == REHR_UNSUPPORTED && k3 && y->c == 32 && cin <= 2) {
@@ -654,9 +657,11 @@ int rehr_conv3d_smallcin_wgrad(const rehr_conv_desc* desc, const float* x_ncdhw,
   a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
   const bool k3 = desc->kd == 3 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
                   desc->pd == 1 && desc->ph == 1 && desc->pw == 1;
+  const bool k133 = desc->kd == 1 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
+                    desc->pd == 0 && desc->ph == 1 && desc->pw == 1;
   int rc = REHR_UNSUPPORTED;
-  if (k3 && stem_mma_supported(cin, dy->c, w) && dy->ld % 8 == 0 && ws_bytes >= stem_mma_wgrad_workspace())
-    return launch_stem_wgrad_mma(x_ncdhw, a.dy, a.lddy, n, d, h, w, dw, accumulate, a.ws, (cudaStream_t)stream);
+  if ((k3 || k133) && stem_mma_supported(cin, dy->c, w) && dy->ld % 8 == 0 && ws_bytes >= stem_mma_wgrad_workspace())
+    return launch_stem_wgrad_mma(x_ncdhw, a.dy, a.lddy, n, d, h, w, dw, accumulate, a.ws, k133 ? 1 : 0, (cudaStream_t)stream);
   if (k3) {
     switch (cin) {
       case 1: rc = launch_smallcin_wgrad_k3<1>(a, (cudaStream_t)stream); break;

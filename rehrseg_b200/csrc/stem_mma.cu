@@ -31,6 +31,7 @@ struct StemArgs {
   int n, d, h, wd;
   int act;
   float slope;
+  int planar;           // 1: k = (1,3,3), pad (0,1,1) (the stem of anisotropic plans): 9 taps, one staged plane
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -52,11 +53,12 @@ static constexpr int kStemRowPad = 80;  // bytes per staged 32-channel bf16 voxe
 // stage the rows oz-1..oz+1 x oy0-1..oy0+8 of sample nn, columns -1 .. Wp (zero outside the volume); Wa = Wp + 2
 __device__ __forceinline__ void stem_stage_rows(const StemArgs& a, float* sx, int Wa, int nn, int oz, int oy0) {
   const long long in_plane = (long long)a.h * a.wd, in_vol = in_plane * a.d;
-  for (int i = threadIdx.x; i < 30 * Wa; i += blockDim.x) {
+  const int rows = a.planar ? 10 : 30;
+  for (int i = threadIdx.x; i < rows * Wa; i += blockDim.x) {
     const int xx = i % Wa;
     const int q = i / Wa;
     const int yy = q % 10, kz = q / 10;
-    const int iz = oz + kz - 1, iy = oy0 + yy - 1, ix = xx - 1;
+    const int iz = a.planar ? oz : oz + kz - 1, iy = oy0 + yy - 1, ix = xx - 1;
     float v = 0.f;
     if (iz >= 0 && iz < a.d && iy >= 0 && iy < a.h && ix >= 0 && ix < a.wd)
       v = __ldg(a.x + (long long)nn * in_vol + iz * in_plane + (long long)iy * a.wd + ix);
@@ -66,8 +68,8 @@ __device__ __forceinline__ void stem_stage_rows(const StemArgs& a, float* sx, in
 
 // offset of tap k = (kz*3 + ky)*3 + kx inside the staged rows (relative to the row of this warp and the voxel column); taps >= 27
 // are the zero padding of K: they read a valid address and are multiplied by a zero weight / masked
-__device__ __forceinline__ int stem_tap_offset(int k, int Wa) {
-  if (k >= 27) return 0;
+__device__ __forceinline__ int stem_tap_offset(int k, int Wa, int planar) {
+  if (k >= (planar ? 9 : 27)) return 0;
   const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
   return (kz * 10 + ky) * Wa + kx;
 }
@@ -83,6 +85,8 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
   uint8_t* sout = smem_raw + (((size_t)30 * Wa * sizeof(float) + 15) & ~size_t(15));  // [8 warps][16 rows][kStemRowPad]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const int ntaps = a.planar ? 9 : 27;
+  const int ksteps = a.planar ? 1 : 2;  // K = taps padded to 16 / 32
 
   // B fragments: B[k = tap][n = co] = W[co][tap], hi / lo split; b0 = (k = 2t, 2t+1), b1 = (k = 2t+8, 2t+9), n = g
   uint32_t bhi[2][4][2], blo[2][4][2];
@@ -93,14 +97,14 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int k0 = ks * 16 + h * 8 + 2 * t, co = nt * 8 + g;
-        const float w0 = k0 < 27 ? __ldg(a.w + co * 27 + k0) : 0.f;
-        const float w1 = k0 + 1 < 27 ? __ldg(a.w + co * 27 + k0 + 1) : 0.f;
+        const float w0 = k0 < ntaps ? __ldg(a.w + co * ntaps + k0) : 0.f;
+        const float w1 = k0 + 1 < ntaps ? __ldg(a.w + co * ntaps + k0 + 1) : 0.f;
         split_bf16x2(w0, w1, bhi[ks][nt][h], blo[ks][nt][h]);
       }
   // this thread's 8 tap offsets: index (ks, h, j) -> k = ks*16 + h*8 + 2t + j
   int koff[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) koff[i] = stem_tap_offset((i >> 2) * 16 + ((i >> 1) & 1) * 8 + 2 * t + (i & 1), Wa);
+  for (int i = 0; i < 8; ++i) koff[i] = stem_tap_offset((i >> 2) * 16 + ((i >> 1) & 1) * 8 + 2 * t + (i & 1), Wa, a.planar);
   float bias[4][2];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -143,13 +147,15 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
         acc[nt][1] = acc[nt][3] = bias[nt][1];
       }
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks >= ksteps) break;  // warp-uniform
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           mma_bf16_16816(acc[nt], ahi[ks], bhi[ks][nt][0], bhi[ks][nt][1]);
           mma_bf16_16816(acc[nt], alo[ks], bhi[ks][nt][0], bhi[ks][nt][1]);
           mma_bf16_16816(acc[nt], ahi[ks], blo[ks][nt][0], blo[ks][nt][1]);
         }
+      }
       // activation, bf16, transpose through shared memory so that a thread writes 16 contiguous bytes (8 channels of a voxel)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -196,9 +202,11 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
   int toff[4];     // staged-row offsets of the taps g, g+8, g+16, g+24
   float tmask[4];  // 0 for the padding taps >= 27
 #pragma unroll
+  const int ntaps = a.planar ? 9 : 27;
+  const int mtiles = a.planar ? 1 : 2;  // taps padded to 16 / 32
   for (int i = 0; i < 4; ++i) {
-    toff[i] = stem_tap_offset(g + 8 * i, Wa);
-    tmask[i] = (g + 8 * i) < 27 ? 1.f : 0.f;
+    toff[i] = stem_tap_offset(g + 8 * i, Wa, a.planar);
+    tmask[i] = (g + 8 * i) < ntaps ? 1.f : 0.f;
   }
   float acc[2][4][4];
 #pragma unroll
@@ -255,6 +263,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
       // A fragments (im2col of the fp32 rows, hi / lo)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
+        if (mt >= mtiles) break;  // warp-uniform
         uint32_t ahi[4], alo[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
       red[(warp * 32 + tap + 8) * 33 + co + 1] = acc[mt][nt][3];
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+  for (int i = threadIdx.x; i < ntaps * 32; i += 256) {
     const int tap = i / 32, co = i % 32;
     float sum = 0.f;
 #pragma unroll
@@ -296,8 +305,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
   }
 }
 
-// ws [blocks][27][32] -> dw [32][27]; block = one tap: 32 channels x 8 slices of the partial list, fixed order
-__global__ void __launch_bounds__(256) stem_wgrad_reduce_kernel(const float* ws, int blocks, float* dw, int accumulate) {
+// ws [blocks][27][32] -> dw [32][ntaps]; block = one tap: 32 channels x 8 slices of the partial list, fixed order
+__global__ void __launch_bounds__(256) stem_wgrad_reduce_kernel(const float* ws, int blocks, float* dw, int accumulate, int ntaps) {
   __shared__ float red[8][33];
   const int co = threadIdx.x & 31, slice = threadIdx.x >> 5, tap = blockIdx.x;
   float s = 0.f;
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_reduce_kernel(const float* ws,
     float tsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tsum += red[k][co];
-    float* d = dw + co * 27 + tap;
+    float* d = dw + co * ntaps + tap;
     *d = accumulate ? *d + tsum : tsum;
   }
 }
@@ -340,8 +349,9 @@ bool stem_mma_supported(int cin, int cout, int wd) { return cin == 1 && cout == 
 size_t stem_mma_wgrad_workspace() { return (size_t)kStemWgradBlocks * 27 * 32 * sizeof(float); }
 
 int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_bfloat16* y, long long ldy, int n, int d, int h, int wd,
-                        int act, float slope, cudaStream_t stream) {
+                        int act, float slope, int planar, cudaStream_t stream) {
   StemArgs a;
+  a.planar = planar;
   a.x = x; a.w = w; a.bias = bias; a.y = y; a.ldy = ldy; a.ws = nullptr;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = act; a.slope = slope;
   const size_t smem = stem_smem_bytes(wd, false);
@@ -356,8 +366,9 @@ int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_
 }
 
 int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long lddy, int n, int d, int h, int wd, float* dw, int accumulate,
-                          float* ws, cudaStream_t stream) {
+                          float* ws, int planar, cudaStream_t stream) {
   StemArgs a;
+  a.planar = planar;
   a.x = x; a.w = nullptr; a.bias = nullptr; a.y = const_cast<__nv_bfloat16*>(dy); a.ldy = lddy; a.ws = ws;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = 0; a.slope = 0.f;
   const size_t smem = stem_smem_bytes(wd, true);
@@ -368,7 +379,7 @@ int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long ldd
   const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)kStemWgradBlocks));
   stem_wgrad_mma_kernel<<<blocks, 256, smem, stream>>>(a);
   REHR_CHECK_LAUNCH();
-  stem_wgrad_reduce_kernel<<<27, 256, 0, stream>>>(ws, blocks, dw, accumulate);
+  stem_wgrad_reduce_kernel<<<planar ? 9 : 27, 256, 0, stream>>>(ws, blocks, dw, accumulate, planar ? 9 : 27);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -298,8 +298,9 @@ def test_smallcin_stem_block():
     assert rel_l2(dbeta, rdb) < 6e-2
 
 
+@pytest.mark.parametrize("planar", [False, True])
 @pytest.mark.parametrize("dhw", [(5, 11, 20), (3, 16, 128), (4, 9, 33)])
-def test_stem_tensor_core_kernels_keep_fp32_accuracy(dhw):
+def test_stem_tensor_core_kernels_keep_fp32_accuracy(dhw, planar):
     """1 -> 32 k3 stem through the mma.sync kernels (csrc/stem_mma.cu): the fp32 image and weights are split into bf16 hi + lo
     parts, so forward and weight gradient must match fp32 torch far below bf16 resolution (output only rounded once to bf16)."""
     import ctypes as C
@@ -307,11 +308,12 @@ def test_stem_tensor_core_kernels_keep_fp32_accuracy(dhw):
     g = torch.Generator().manual_seed(21)
     d, h, w_ = dhw
     x = torch.randn((2, 1, d, h, w_), generator=g).cuda()
-    w = (torch.randn((32, 1, 3, 3, 3), generator=g) / 27 ** 0.5).cuda()
+    kern, pad = ((1, 3, 3), (0, 1, 1)) if planar else ((3, 3, 3), (1, 1, 1))   # planar: the stem of anisotropic plans
+    w = (torch.randn((32, 1, *kern), generator=g) / 27 ** 0.5).cuda()
     b = torch.randn((32,), generator=g).cuda()
     wr = w.clone().requires_grad_(True)
-    ref = F.conv3d(x, wr, b, padding=1)
-    desc = L.conv_desc((3, 3, 3), (1, 1, 1), (1, 1, 1))
+    ref = F.conv3d(x, wr, b, padding=pad)
+    desc = L.conv_desc(kern, (1, 1, 1), pad)
     y = torch.empty((2, d, h, w_, 32), dtype=torch.bfloat16, device="cuda")
     yt = L.rt(y)
     L.check(L.lib().rehr_conv3d_smallcin_fwd(C.byref(desc), L.ptr(x), 2, 1, d, h, w_, L.ptr(w), L.ptr(b), C.byref(yt),
