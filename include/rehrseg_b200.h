@@ -278,6 +278,33 @@ int rehr_fba_combine(const void* const* spectra_dev_ptrs, int K, float p, void* 
 /* mean over K volumes (utils/sr_utils.py:65,173,217) */
 int rehr_mean_stack(const float* const* vols_dev_ptrs, int K, float* out, long long n, rehr_stream stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Fused loss reductions of the stage-2 step (csrc/loss_ops.cu): every forward entry point makes ONE pass over the fp32 NCDHW
+ * tensor the caller holds and writes per-block partial sums (the caller adds the `rehr_loss_blocks(V)` partials of a sample and
+ * forms the few loss scalars); every backward entry point turns the gradients of those sums into the dense gradient.
+ *   rehr_seg_loss_sums      DC_and_weighted_CE_loss (utils/seg_utils.py:305-353): logits [B][C][V], target [B][V] (class index as
+ *                           f32), weight [V] or NULL (multiplies the CE map of every sample -- the reference's uncertainty
+ *                           broadcast); partial [B][blocks][1 + 3C] = {sum w*ce, then per class sum p*[y=c], sum p, sum [y=c]}
+ *   rehr_seg_loss_bwd       g_ce [B], g_int [B][C], g_pred [B][C] -> dlogits [B][C][V]
+ *   rehr_cosine_sums        cosine_distance_loss (models/seg_model.py:60-78): a, b [B][C][V]; partial [B][blocks][3][C] =
+ *                           voxel sums of ahat*bhat, ahat^2, bhat^2 with xhat = x / max(||x[:, v]||, 1e-12)
+ *   rehr_cosine_sums_bwd    g_ab, g_aa [B][C] -> da [B][C][V]  (b carries no gradient: the teacher is detached)
+ *   rehr_plane_maxpool      CriterionPairWiseforWholeFeatAfterPool (models/seg_model.py:95-113): x [N][C][S][H][W], windows ph x pw,
+ *                           stride = window, ceil mode -> out, idx [N][S][C][OH][OW] (idx = first arg-max inside the H*W plane)
+ *   rehr_plane_maxpool_bwd  g, idx -> scatter into the caller-zeroed dx [N][C][S][H][W]
+ * ---------------------------------------------------------------------------------------------- */
+int rehr_loss_blocks(long long voxels);
+int rehr_seg_loss_sums(const float* logits, const float* target, const float* weight, int B, int C, long long V, float* partial,
+                       rehr_stream stream);
+int rehr_seg_loss_bwd(const float* logits, const float* target, const float* weight, int B, int C, long long V, const float* g_ce,
+                      const float* g_int, const float* g_pred, float* dlogits, rehr_stream stream);
+int rehr_cosine_sums(const float* a, const float* b, int B, int C, long long V, float* partial, rehr_stream stream);
+int rehr_cosine_sums_bwd(const float* a, const float* b, int B, int C, long long V, const float* g_ab, const float* g_aa, float* da,
+                         rehr_stream stream);
+int rehr_plane_maxpool(const float* x, int N, int C, int S, int H, int W, int ph, int pw, float* out, int* idx, rehr_stream stream);
+int rehr_plane_maxpool_bwd(const float* g, const int* idx, int N, int C, int S, int H, int W, int ph, int pw, float* dx_zeroed,
+                           rehr_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,13 @@ def _declare(L: C.CDLL) -> None:
         "rehr_rot90": (i, [vp, vp, i, i, ll, i, vp]),
         "rehr_fba_combine": (i, [vp, i, f, vp, ll, vp]),
         "rehr_mean_stack": (i, [vp, i, vp, ll, vp]),
+        "rehr_loss_blocks": (i, [ll]),
+        "rehr_seg_loss_sums": (i, [vp, vp, vp, i, i, ll, vp, vp]),
+        "rehr_seg_loss_bwd": (i, [vp, vp, vp, i, i, ll, vp, vp, vp, vp, vp]),
+        "rehr_cosine_sums": (i, [vp, vp, i, i, ll, vp, vp]),
+        "rehr_cosine_sums_bwd": (i, [vp, vp, i, i, ll, vp, vp, vp, vp]),
+        "rehr_plane_maxpool": (i, [vp, i, i, i, i, i, i, i, vp, vp, vp]),
+        "rehr_plane_maxpool_bwd": (i, [vp, vp, i, i, i, i, i, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

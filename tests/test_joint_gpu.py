@@ -21,9 +21,11 @@ def _batch(seed, b, d, hw, up=4):
     return img, label_lr, label, unc
 
 
-def test_joint_step_vs_oracle():
+@pytest.mark.parametrize("fused", [False, True])
+def test_joint_step_vs_oracle(fused):
+    """fused=True: Distiller / losses on the fused CUDA reductions (rehrseg_b200/loss_ops.py) instead of the plain-PyTorch mirrors"""
     from oracle import flavr as of, joint as oj, seg_model as ref_seg
-    from rehrseg_b200 import flavr, seg_model as sm, train_step as ts
+    from rehrseg_b200 import flavr, loss_ops, seg_model as sm, train_step as ts
 
     ref_student = ref_seg.build("anisotropic")
     student = sm.SegModel(**ref_seg.plan_kwargs("anisotropic"))
@@ -34,14 +36,15 @@ def test_joint_step_vs_oracle():
     teacher = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).cuda().eval()
     torch.manual_seed(5)
     ref_dist = oj.RefDistiller(64, 64, 0.0, 1.0, 1.0)
-    dist_mod = ts.Distiller(64, 64, 0.0, 1.0, 1.0)
+    dist_mod = (loss_ops.FusedDistiller if fused else ts.Distiller)(64, 64, 0.0, 1.0, 1.0)
     dist_mod.load_state_dict(ref_dist.state_dict())
     dist_mod = dist_mod.cuda()
 
     batch = _batch(4, b=2, d=8, hw=64)
     want = oj.ref_joint_step(ref_student, tuple(t.clone() for t in batch), ref_teacher, ref_dist)
     gpu_batch = tuple(t.clone().cuda() for t in batch)
-    got = ts.joint_train_step(student, gpu_batch, ts.build_loss(False, 0), ts.build_loss(False, 1), None, teacher, dist_mod)
+    build = loss_ops.build_fused_loss if fused else ts.build_loss
+    got = ts.joint_train_step(student, gpu_batch, build(False, 0), build(False, 1), None, teacher, dist_mod)
     torch.cuda.synchronize()
     print({k: (float(got[k]), float(want[k])) for k in want})
     # scalar losses: means over >= 65k voxels of bf16-perturbed logits

@@ -11,13 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from rehrseg_b200 import flavr, functional as Fn, seg_model as sm, train_step as ts
+from rehrseg_b200 import flavr, functional as Fn, loss_ops, seg_model as sm, train_step as ts
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--no-distill", action="store_true")
 ap.add_argument("--breakdown", action="store_true")
+ap.add_argument("--plain-losses", action="store_true", help="plain-PyTorch Distiller / losses instead of the fused kernels")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -37,11 +38,12 @@ ANISO = dict(input_channels=1, n_stages=6, features_per_stage=[32, 64, 128, 256,
 torch.manual_seed(1234)
 student = sm.SegModel(**ANISO).to(dev)
 teacher = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).to(dev).eval()
-distiller = ts.Distiller(64, 64, 0.0, 1.0, 1.0).to(dev)
+distiller = (ts.Distiller if a.plain_losses else loss_ops.FusedDistiller)(64, 64, 0.0, 1.0, 1.0).to(dev)
 import itertools
 opt = torch.optim.SGD(itertools.chain(student.parameters(), distiller.parameters()), lr=1e-3, momentum=0.99, nesterov=True,
                       weight_decay=3e-5)
-lr_obj, hr_obj = ts.build_loss(False, 0), ts.build_loss(False, 1)
+build = ts.build_loss if a.plain_losses else loss_ops.build_fused_loss
+lr_obj, hr_obj = build(False, 0), build(False, 1)
 
 g = torch.Generator().manual_seed(4 + rank)
 B, D, HW = 2, 16, 256
@@ -78,6 +80,7 @@ ms = float(t)
 res = {"config": "C4 joint SR+seg step, student anisotropic SegModel [2,1,16,256,256] x4 SR head, UASR FLAVR teacher sweep (15 windows), "
                  "Distiller(64,64,0,1,1), SGD; batch 2 per GPU", "n_gpus": world, "ms_per_step": round(ms, 3),
        "samples_per_s": round(world * B / ms * 1e3, 2), "steps": a.steps, "warmup": a.warmup, "distill": not a.no_distill,
+       "losses": "plain PyTorch (train_step.py)" if a.plain_losses else "fused CUDA reductions (loss_ops.py)",
        "engine_launches_per_step": (Fn.launches() - l0) // a.steps, "loss": {k: round(float(v), 5) for k, v in out.items()},
        "algorithmic_tflop_per_gpu_step": None if a.no_distill else 15.5}
 if not a.no_distill:
