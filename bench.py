@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 PATCH = (128, 128, 128)
