@@ -35,6 +35,12 @@ def test_no_cpu_fallback():
     with pytest.raises(NotImplementedError):
         vo.rotate_vol_2d(torch.zeros(2, 2, 2), 45)
     assert vo.rotate_vol_2d(torch.zeros(2, 2, 2), 0).shape == (2, 2, 2)  # identity never touches the device
+    # the fused loss reductions are CUDA kernels only (the plain-PyTorch mirrors in train_step.py are separate, explicit classes)
+    from rehrseg_b200 import loss_ops
+    with pytest.raises(_lib.RehrError):
+        loss_ops.build_fused_loss(False, 1)(torch.zeros(1, 2, 2, 4, 4), torch.zeros(1, 1, 2, 4, 4))
+    with pytest.raises(_lib.RehrError):
+        loss_ops.FusedDistiller(4, 4, 0.0, 1.0, 1.0)(torch.zeros(1, 4, 2, 4, 4), torch.zeros(1, 4, 2, 4, 4))
 
 
 def test_index_math_matches_reference_fixtures():
