@@ -132,12 +132,22 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor
         check(lib().rehr_pack_weight(ptr(w), ptr(out), B, A, T, T, B * T, 1, stream_ptr()), "pack_weight")
     _count()
     if cache:
-        _wcache[key] = (weakref.ref(weight), ver, out)
+        _cache_put(key, weight, out)
     return out
 
 
 def clear_weight_cache() -> None:
     _wcache.clear()
+
+
+def _cache_put(key, weight: torch.Tensor, out: torch.Tensor) -> None:
+    """Insert an operand copy.  Backward passes look their weights up through autograd's saved tensors, which are fresh Python
+    objects every step: their entries die with them (the weak reference clears) and would otherwise pile up in a training loop that
+    never calls clear_weight_cache(), each holding a packed bf16 copy -- so dead entries are dropped once the table grows."""
+    if len(_wcache) >= 256:
+        for k in [k for k, v in _wcache.items() if v[0]() is None]:
+            del _wcache[k]
+    _wcache[key] = (weakref.ref(weight), weight._version, out)
 
 
 def _out_size(i: int, k: int, s: int, p: int) -> int:
@@ -318,7 +328,7 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
                   "pack_weight_march_s2dgrad")
             _count()
             if cache:
-                _wcache[key] = (weakref.ref(weight), weight._version, wp)
+                _cache_put(key, weight, wp)
         dyt, dxt = rt(dy), rt(dx)
         with _timed("conv_march_kernel", flops, tag):
             check(lib().rehr_conv3d_march_s2dgrad(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), stream_ptr()),

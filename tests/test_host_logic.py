@@ -107,3 +107,20 @@ def test_rehr_tensor_descriptor_of_channel_slice():
     t = _lib.rt(a)
     assert (t.n, t.d, t.h, t.w, t.c, t.ld) == (1, 2, 3, 4, 32, 64) and t.ptr == buf.data_ptr() + 64
     assert not _lib.cl_strides_ok(buf.permute(0, 4, 1, 2, 3))
+
+
+def test_weight_cache_drops_dead_entries():
+    """Backward passes reach their weights through autograd's saved tensors (fresh objects every step): a training loop that never
+    calls clear_weight_cache() must not accumulate their packed copies."""
+    from rehrseg_b200 import functional as Fn
+    Fn.clear_weight_cache()
+    keep = []
+    for i in range(600):
+        w = torch.zeros(1)
+        if i % 20 == 0:
+            keep.append(w)
+        Fn._cache_put((id(w), "dgrad", i), w, torch.zeros(1))
+        del w
+    live = sum(1 for v in Fn._wcache.values() if v[0]() is not None)
+    assert live == len(keep) and len(Fn._wcache) <= 256 + len(keep)
+    Fn.clear_weight_cache()
