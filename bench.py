@@ -29,8 +29,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when NCCL_DEBUG is set) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Native libraries print there too (NCCL's "NCCL version ..." banner when NCCL_DEBUG is
+# set), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to a saved copy of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import torch  # noqa: E402
 
@@ -213,7 +220,7 @@ def reference_arm(args) -> None:
                        "(dynamic_network_architectures 0.3.1 restated; /root/reference is absent on the GPU box)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -416,7 +423,7 @@ def main() -> None:
         line["gpu_launches"] = None
     if world == 1 and args.impl == "b200" and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
