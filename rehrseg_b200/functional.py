@@ -183,12 +183,12 @@ def concat_room_of(t: torch.Tensor):
     return getattr(t, "_rehr_cat", None)
 
 
-# Small layers (<= 32^3): the weight gradient and the input gradient of a conv are independent consumers of dy and each is a
+# Small and mid-size layers (<= 64^3): the weight gradient and the input gradient of a conv are independent consumers of dy and each is a
 # latency-bound launch chain (GEMM + partial reduction) on a handful of CTAs, so the weight-gradient chain is forked onto a side
 # stream and joined after the input gradient has been issued (events only: the fork/join is captured as two parallel branches by
 # graphs.GraphedTrainStep).  Large layers fill the machine on their own and stay on one stream.
 WGRAD_SIDE_STREAM = True
-WGRAD_SIDE_MAX_VOXELS = 2 * 32 ** 3
+WGRAD_SIDE_MAX_VOXELS = 2 * 64 ** 3   # measured on the C1 step: 12.58 ms at 2 * 32^3, 12.46 ms at 2 * 64^3 and above
 _side_streams: dict = {}
 
 
