@@ -67,11 +67,67 @@ def joint_fixture() -> None:
     np.savez_compressed(os.path.join(OUT, "joint_step.npz"), **arrs)
 
 
+TINY_ANISO = dict(n_stages=3, features_per_stage=[32, 64, 128], kernel_sizes=[[1, 3, 3], [3, 3, 3], [3, 3, 3]],
+                  strides=[[1, 1, 1], [1, 2, 2], [1, 2, 2]], n_conv_per_stage=[2] * 3, n_conv_per_stage_decoder=[2] * 2)
+
+
+def joint_step_fixture() -> None:
+    """One whole stage-2 iteration executed with the reference's OWN objects -- SegModel, UNet_3D_3D teacher, Distiller, _build_loss,
+    train_all.get_intermediate_features -- following the loop body train_all.py:519-555 line by line (device = cpu, distillation and
+    uncertainty on).  Stores the batch, the loss terms and a few gradients; tests/test_joint_cpu.py replays it through
+    oracle.joint.ref_joint_step on oracle-built modules with the same default initialisation."""
+    sm = refimport.load("models.seg_model")
+    fa = refimport.load("models.FLAVR.FLAVR_arch")
+    ta = refimport.load("train_all")
+    seg_utils = refimport.load("utils.seg_utils")
+    kw = ref_seg.plan_kwargs("tiny")
+    kw.update(TINY_ANISO)
+    torch.manual_seed(1234)
+    model_seg = sm.SegModel(**kw)
+    torch.manual_seed(1234)
+    model_sr = fa.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).eval()
+    torch.manual_seed(5)
+    distiller = sm.Distiller(64, 64, 0.0, 1.0, 1.0)
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn((1, 1, 5, 32, 32), generator=g)
+    label_lr = (torch.rand((1, 1, 5, 32, 32), generator=g) > 0.8).float()
+    label = (torch.rand((1, 1, 20, 32, 32), generator=g) > 0.8).float()
+    uncertainty_lr = torch.rand((1, 1, 5, 32, 32), generator=g) * 0.99 + 0.01
+    arrs = {"img": img.numpy().copy(), "label_lr": label_lr.numpy(), "label": label.numpy(), "uncertainty_lr": uncertainty_lr.numpy()}
+    device = torch.device("cpu")
+    loss_obj_lr_seg = seg_utils._build_loss(enable_deep_supervision=False, weight_dice=0)      # enable_uncertainty = True
+    loss_obj_hr_seg = seg_utils._build_loss(enable_deep_supervision=False, weight_dice=1)
+    # ---- train_all.py:520-555 ----
+    model_seg.train()
+    pseudo_img_lr = img.to(device)
+    pseudo_label_lr = label_lr.to(device)
+    label_sr = label.to(device)
+    with torch.no_grad():
+        features_sr = ta.get_intermediate_features(model_sr, pseudo_img_lr, pseudo_label_lr, device)
+    pseudo_seg_lr, seg_sr, features_seg = model_seg(pseudo_img_lr, return_inetermediate_feature=True)
+    pseudo_uncertainty_lr = uncertainty_lr.to(device)
+    loss_lr_seg = loss_obj_lr_seg(pseudo_seg_lr, pseudo_label_lr, pseudo_uncertainty_lr)
+    loss_hr_seg = loss_obj_hr_seg(seg_sr, label_sr, None)
+    loss = loss_lr_seg + loss_hr_seg
+    distill_loss = 0
+    distill_loss += distiller(features_seg[1], features_sr[1])
+    loss += distill_loss
+    loss.backward()
+    # ------------------------------
+    arrs.update(loss=loss.detach().numpy(), loss_lr_seg=loss_lr_seg.detach().numpy(), loss_hr_seg=loss_hr_seg.detach().numpy(),
+                distill_loss=distill_loss.detach().numpy(), img_after=pseudo_img_lr.numpy(),
+                grad_stem=model_seg.encoder.stages[0][0].convs[0].conv.weight.grad.numpy(),
+                grad_sr_head0=model_seg.sr_head[0].weight.grad.numpy(), grad_distill=distiller.distill.weight.grad.numpy(),
+                grad_abs_sum=np.array(float(sum(p.grad.double().abs().sum() for p in model_seg.parameters() if p.grad is not None))))
+    np.savez_compressed(os.path.join(OUT, "joint_whole_step.npz"), **arrs)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     import sys
     if "--only-joint" in sys.argv:
         joint_fixture()
+        joint_step_fixture()
         return
     seg_utils = refimport.load("utils.seg_utils")
     patch_ops = refimport.load("utils.patch_ops")
@@ -181,6 +237,7 @@ def main() -> None:
     np.savez_compressed(os.path.join(OUT, "flavr_small.npz"), **fl)
 
     joint_fixture()
+    joint_step_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

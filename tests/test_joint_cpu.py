@@ -142,3 +142,40 @@ def test_joint_step_data_parallel_world2():
         oj.ref_joint_step(student, _batch(40 + rank, d=4, hw=16))
         local.append(torch.cat([p.grad.reshape(-1) for p in student.parameters() if p.grad is not None]))
     assert _rel(got[0][2], (local[0] + local[1]) / 2) < 1e-5
+
+
+def test_oracle_joint_step_reproduces_the_reference_loop_body():
+    """tests/golden/joint_whole_step.npz was produced by the reference's own SegModel / UNet_3D_3D / Distiller / _build_loss /
+    get_intermediate_features executing train_all.py:520-555 (oracle/make_golden.py:joint_step_fixture).  The oracle's modules have
+    the same default initialisation, so `ref_joint_step` must reproduce every loss term and gradient -- this pins the restated step."""
+    from oracle import flavr as ref_flavr
+    from oracle import seg_model as ref_seg
+    W = np.load(os.path.join(ROOT, "tests", "golden", "joint_whole_step.npz"))
+    kw = ref_seg.plan_kwargs("tiny")
+    kw.update(n_stages=3, features_per_stage=[32, 64, 128], kernel_sizes=[[1, 3, 3], [3, 3, 3], [3, 3, 3]],
+              strides=[[1, 1, 1], [1, 2, 2], [1, 2, 2]], n_conv_per_stage=[2] * 3, n_conv_per_stage_decoder=[2] * 2)
+    torch.manual_seed(1234)
+    student = ref_seg.RefSegModel(**kw)
+    teacher = ref_flavr.build(use_uncertainty=True, seed=1234).eval()
+    torch.manual_seed(5)
+    dist_mod = oj.RefDistiller(64, 64, 0.0, 1.0, 1.0)
+    batch = tuple(torch.from_numpy(W[k]).clone() for k in ("img", "label_lr", "label", "uncertainty_lr"))
+    out = oj.ref_joint_step(student, batch, teacher, dist_mod)
+    for k in ("loss", "loss_lr_seg", "loss_hr_seg", "distill_loss"):
+        assert abs(float(out[k]) - float(W[k])) <= 2e-6 * max(1.0, abs(float(W[k]))), (k, float(out[k]), float(W[k]))
+    assert _rel(batch[0], W["img_after"]) < 1e-6                       # in-place z-score of the caller's image
+    assert _rel(student.encoder.stages[0][0].convs[0].conv.weight.grad, W["grad_stem"]) < 1e-4
+    assert _rel(student.sr_head[0].weight.grad, W["grad_sr_head0"]) < 1e-4
+    assert _rel(dist_mod.distill.weight.grad, W["grad_distill"]) < 1e-4
+    tot = float(sum(p.grad.double().abs().sum() for p in student.parameters() if p.grad is not None))
+    assert abs(tot - float(W["grad_abs_sum"])) <= 1e-4 * float(W["grad_abs_sum"])
+    # the product-side mirror of the step on the same CPU stand-ins gives the same numbers
+    torch.manual_seed(1234)
+    student2 = ref_seg.RefSegModel(**kw)
+    torch.manual_seed(5)
+    dist2 = ts.Distiller(64, 64, 0.0, 1.0, 1.0)
+    batch2 = tuple(torch.from_numpy(W[k]).clone() for k in ("img", "label_lr", "label", "uncertainty_lr"))
+    got = ts.joint_train_step(student2, batch2, ts.build_loss(False, 0), ts.build_loss(False, 1), None, teacher, dist2,
+                              device=torch.device("cpu"))
+    for k in ("loss", "loss_lr_seg", "loss_hr_seg", "distill_loss"):
+        assert abs(float(got[k]) - float(W[k])) <= 2e-6 * max(1.0, abs(float(W[k]))), k
