@@ -122,12 +122,34 @@ def joint_step_fixture() -> None:
     np.savez_compressed(os.path.join(OUT, "joint_whole_step.npz"), **arrs)
 
 
+def sr_sweep_fixture() -> None:
+    """The reference's own `apply_to_vol_flavr` (utils/sr_utils.py:102-135) on its own UNet_3D_3D (plain head).  The function hard-codes
+    `.cuda()` for its zero padding, so `torch.Tensor.cuda` is made the identity while it runs on the CPU; nothing else is touched."""
+    fa = refimport.load("models.FLAVR.FLAVR_arch")
+    sr_utils = refimport.load("utils.sr_utils")
+    torch.manual_seed(1234)
+    net = fa.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=False).eval()
+    g = torch.Generator().manual_seed(6)
+    vol = torch.rand((5, 2, 20, 24), generator=g)          # [Z, C, X, Y]: ragged in-plane size -> zero-padded to 32 x 32
+    vol[:, 1] = (vol[:, 1] > 0.8).float()
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        out = sr_utils.apply_to_vol_flavr(net, vol.clone())
+    finally:
+        torch.Tensor.cuda = orig
+    np.savez_compressed(os.path.join(OUT, "sr_sweep.npz"), vol=vol.numpy(), out=out.numpy())
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     import sys
     if "--only-joint" in sys.argv:
         joint_fixture()
         joint_step_fixture()
+        return
+    if "--only-sweep" in sys.argv:
+        sr_sweep_fixture()
         return
     seg_utils = refimport.load("utils.seg_utils")
     patch_ops = refimport.load("utils.patch_ops")
@@ -238,6 +260,7 @@ def main() -> None:
 
     joint_fixture()
     joint_step_fixture()
+    sr_sweep_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

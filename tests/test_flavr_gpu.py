@@ -105,6 +105,18 @@ def test_get_intermediate_features_and_window_sweep():
     assert rel(got, want) <= 1e-2
 
 
+def test_window_sweep_vs_reference_function_fixture():
+    """Engine sweep against the output of the reference's OWN apply_to_vol_flavr on its own network (tests/golden/sr_sweep.npz,
+    oracle/make_golden.py:sr_sweep_fixture): same default-initialised weights, ragged 20 x 24 planes, 4 windows."""
+    from rehrseg_b200 import flavr
+    z = np.load(os.path.join(G, "sr_sweep.npz"))
+    _, mine = _pair(False, seed=1234)
+    got = flavr.apply_to_vol_flavr(mine, torch.from_numpy(z["vol"]).clone().cuda(), max_batch=3)
+    want = torch.from_numpy(z["out"])
+    assert got.shape == want.shape
+    assert rel(got, want) <= 1e-2
+
+
 def test_convert_reference_shaped_flavr():
     from oracle import flavr as of
     from rehrseg_b200 import flavr

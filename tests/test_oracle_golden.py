@@ -128,3 +128,16 @@ def test_oracle_flavr_matches_reference_flavr():
     for i, key in ((1, "gif_f1"), (3, "gif_f3")):
         ref = torch.from_numpy(z[key])
         assert feats[i].shape == ref.shape and float((feats[i] - ref).norm() / ref.norm()) <= 1e-5
+
+
+def test_oracle_sr_sweep_matches_reference_apply_to_vol_flavr():
+    """tests/golden/sr_sweep.npz: the reference's own apply_to_vol_flavr (utils/sr_utils.py:102-135) on its own UNet_3D_3D
+    (oracle/make_golden.py:sr_sweep_fixture) -- pad to a multiple of 16, Z-1 zero-padded windows, crop, transposed in-plane axes."""
+    from oracle import flavr as of
+    z = np.load(os.path.join(G, "sr_sweep.npz"))
+    net = of.build(False, seed=1234).eval()
+    with torch.no_grad():
+        got = ov.apply_to_vol_flavr(net, torch.from_numpy(z["vol"]).clone())
+    want = torch.from_numpy(z["out"])
+    assert got.shape == want.shape == (16, 2, 24, 20)
+    assert float((got - want).norm() / want.norm()) <= 1e-5
