@@ -3,7 +3,7 @@ and inputs.  Bounds from north_star: relative L2 <= 1e-2 on logits (bf16), argma
 
 Argmax: with RANDOM-INIT weights (the protocol north_star prescribes) the two class logits are tied to within the bf16
 noise floor on ~0.3 % of voxels, so raw agreement is ~99.7 % for ANY bf16 implementation -- torch's own autocast/cuDNN
-path scores 99.60-99.65 % on these inputs (tools/bf16_noise.py, profiles/r01_bf16_noise.log).  The tests therefore
+path scores 99.60-99.65 % on these inputs (tests/diag_bf16_noise.py, profiles/r01_bf16_noise.log).  The tests therefore
 assert (a) >= 99.9 % on every voxel whose fp32 decision margin is above 4x the RMS logit error, and (b) raw agreement
 no worse than the reference's own bf16 GPU path on the same inputs.  Gradients: bf16 back-propagation through 22
 InstanceNorm layers is noisy for both (12-16 % here vs 14-18 % for autocast); bounded against autocast the same way."""
