@@ -147,6 +147,9 @@ static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, co
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return REHR_CUDA_ERROR; }
   }
   int ci = -1;
+  // the class launches live in a lambda so that EVERY exit path -- also an error half-way through -- reaches the join below (a
+  // forked side stream that is never joined would poison an enclosing CUDA-graph capture)
+  auto run_classes = [&]() -> int {
   for (int cd = 0; cd < s[2]; ++cd)
     for (int ch = 0; ch < s[1]; ++ch)
       for (int cw = 0; cw < s[0]; ++cw) {
@@ -194,15 +197,18 @@ static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, co
           else if (cls_need > *need) *need = cls_need;
         }
       }
+  return REHR_OK;
+  };
+  int status = run_classes();
   if (cs) {  // join: the caller's stream continues after every side stream that was used
     for (int i = 0; i < ClassStreams::kSide; ++i)
       if ((launched >> i) & 1) {
         cudaError_t e = cudaEventRecord(cs->join[i], cs->side[i]);
         if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, cs->join[i], 0);
-        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return REHR_CUDA_ERROR; }
+        if (e != cudaSuccess && status == REHR_OK) { g_last_cuda_error = (int)e; status = REHR_CUDA_ERROR; }
       }
   }
-  return REHR_OK;
+  return status;
 }
 
 int rehr_conv3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
