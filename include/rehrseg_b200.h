@@ -37,10 +37,17 @@ typedef enum {
   REHR_BAD_ALIGNMENT = -5   /* pointer / pitch not aligned as required (16 B) */
 } rehr_status;
 
+/* 16-bit storage format of an activation tensor.  Gradients and FLAVR activations are bf16; the SegModel forward stores its
+ * activations and pre-normalisation conv outputs in fp16 (InstanceNorm bounds them; 3 more mantissa bits bring the logits from
+ * 9e-3 to 1e-3 of the fp32 reference at the same tensor-core rate), see DESIGN.md section 4.  A tcgen05.mma needs both operands
+ * in ONE format: the packed weights of a forward conv must be packed in the format of its input tensor. */
+typedef enum { REHR_BF16 = 0, REHR_F16 = 1 } rehr_dtype;
+
 typedef struct {
   void* ptr;
   int n, d, h, w, c;
   long long ld; /* voxel pitch in elements */
+  int dtype;    /* rehr_dtype of the 16-bit payload (ignored where an entry point says f32) */
 } rehr_tensor;
 
 /* A 3-D convolution "A <- B": weight Wc[A][B][kd][kh][kw], out[o] = sum_k Wc[k] . in[o*s + k - p].
@@ -57,7 +64,7 @@ typedef enum { REHR_ACT_NONE = 0, REHR_ACT_RELU = 1, REHR_ACT_LRELU = 2 } rehr_a
 
 const char* rehr_strerror(int status);
 int rehr_last_cuda_error(void);     /* cudaError_t of the last failing CUDA call on this thread */
-int rehr_version(void);             /* ABI version, currently 3 */
+int rehr_version(void);             /* ABI version, currently 4 (rehr_tensor.dtype, dtype arguments of the weight packers) */
 int rehr_device_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -69,11 +76,12 @@ int rehr_device_sm_count(void);
  *   models/FLAVR/FLAVR_arch.py:24-88).
  * ---------------------------------------------------------------------------------------------- */
 
-/* Repack fp32 weights src[(r*sr + c*sc + t*st)] into bf16 dst[r][t][c] (the K-major GEMM operand).
+/* Repack fp32 weights src[(r*sr + c*sc + t*st)] into 16-bit dst[r][t][c] (the K-major GEMM operand), dtype = rehr_dtype
+ * of the packed copy: it must equal the dtype of the activation tensor the GEMM contracts it with.
  *   fwd   of Wc[A][B][T]: R=A, C=B, sr=B*T, sc=T, st=1
  *   dgrad of Wc[A][B][T]: R=B, C=A, sr=T,   sc=B*T, st=1 */
-int rehr_pack_weight(const float* src, void* dst_bf16, int R, int C, int T, long long sr, long long sc,
-                     long long st, rehr_stream stream);
+int rehr_pack_weight(const float* src, void* dst16, int R, int C, int T, long long sr, long long sc,
+                     long long st, int dtype, rehr_stream stream);
 
 /* y[A] = act(conv(x[B]) + bias).  w_packed = bf16 [A][T][B].  bias may be NULL.  y may be bf16 or f32.
  * stats (optional, f32 [rehr_conv3d_stats_tiles()][A][2]) receives per-output-tile (sum, sum of squares)
@@ -137,8 +145,8 @@ int rehr_convtranspose3d_wgrad(const rehr_conv_desc* desc, const rehr_tensor* x,
  * selected by passing the kernel's DEPTH extent ks = 1 to the functions below (T = 9, weights W[Cout][Cin][9]). */
 int rehr_conv3d_march_supported(const rehr_conv_desc* desc, int cin, int cout);
 size_t rehr_conv3d_march_weight_bytes(int cin, int cout, int ks);
-int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
-                           rehr_stream stream);
+int rehr_pack_weight_march(const float* src, void* dst16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
+                           int dtype, rehr_stream stream);
 int rehr_conv3d_march_stats_tiles(const rehr_tensor* x, const rehr_tensor* y, int ks);
 int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float* bias, const rehr_tensor* y, int ks, int y_is_f32,
                           int act, float slope, float* stats, rehr_stream stream);
@@ -196,9 +204,11 @@ int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream
 /* partial [n][tiles][c][2] -> mean[n][c], rstd[n][c] (biased variance, double accumulation). */
 int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long long count, float eps,
                            float* mean, float* rstd, rehr_stream stream);
-/* a = lrelu(gamma * (y - mean) * rstd + beta)   (slope = 1 -> no activation) */
+/* a = lrelu(gamma * (y - mean) * rstd + beta)   (slope = 1 -> no activation).  a2 (optional, may be NULL): a second copy of
+ * the result in another 16-bit format / buffer, written in the same pass (the bf16 twin of an fp16 activation that the
+ * weight-gradient GEMM of the consumer contracts with bf16 gradients). */
 int rehr_instnorm_lrelu_apply(const rehr_tensor* y, const float* mean, const float* rstd, const float* gamma,
-                              const float* beta, float slope, const rehr_tensor* a, rehr_stream stream);
+                              const float* beta, float slope, const rehr_tensor* a, const rehr_tensor* a2, rehr_stream stream);
 /* Backward, two passes.  (1) reduce: partial[n][tiles][c][2] = (sum g, sum g*xhat), g = (da1 + da2) * lrelu'.
  * (2) apply: dy = gamma*rstd*(g - S1/V - xhat*S2/V).  da2 may be NULL (second gradient source of a skip). */
 int rehr_instnorm_lrelu_bwd_reduce(const rehr_tensor* y, const rehr_tensor* da1, const rehr_tensor* da2,
@@ -230,6 +240,8 @@ int rehr_upsample_linear_d_bwd(const rehr_tensor* dy, const rehr_tensor* dx, reh
 /* layout / dtype adapters at the model boundary (train_all.py:524 hands NCDHW f32) */
 int rehr_ncdhw_f32_to_ndhwc_bf16(const float* src, const rehr_tensor* dst, rehr_stream stream);
 int rehr_ndhwc_bf16_to_ncdhw_f32(const rehr_tensor* src, float* dst, rehr_stream stream);
+/* dst = src converted between the two 16-bit storage formats (rehr_tensor.dtype of each side; pitched channel slices allowed) */
+int rehr_convert16(const rehr_tensor* src, const rehr_tensor* dst, rehr_stream stream);
 /* elementwise helpers for FLAVR blocks (models/FLAVR/resnet_3D.py:100-151, FLAVR_arch.py:169-248) */
 int rehr_segate_scale_add_act(const rehr_tensor* x, const float* gate /*[n][c]*/, const rehr_tensor* residual,
                               int act, float slope, const rehr_tensor* y, rehr_stream stream);

@@ -12,7 +12,7 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda:0", backward=True, seed=0,
-                    threads: int | None = None, autocast_baseline: bool = False) -> dict:
+                    threads: int | None = None, autocast_baseline: bool = False, state_dict=None, runner=None) -> dict:
     """Run the oracle SegModel on CPU (fp32) and the B200 engine on `device` with identical weights and input
     (SURVEY.md section 8(d), config 1 protocol: x ~ N(0,1) seed 0; cotangent g ~ N(0,1) seed 1,
     loss = <logits, g>/numel + <hr_logits, g2>/numel)."""
@@ -21,13 +21,25 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
     if threads:
         torch.set_num_threads(threads)
     ref = ref_seg.build(plan)
+    if state_dict is not None:       # e.g. trained weights (separated logits) instead of the default random init
+        ref.load_state_dict(state_dict)
     mine = sm.SegModel(**ref_seg.plan_kwargs(plan))
     mine.load_state_dict(ref.state_dict())
     mine = mine.to(device)
     g = torch.Generator().manual_seed(seed)
     x = torch.randn((batch, 1, *patch), generator=g)
+    # keep the gradient of every up-sampled tensor of the oracle: yardstick for the transposed-conv bias gradients below
+    up_outs = []
+
+    def keep(_m, _i, o):
+        o.retain_grad()
+        up_outs.append(o)
+
+    hooks = [tc.register_forward_hook(keep) for tc in ref.decoder.transpconvs] if backward else []
     out_r, up_r = ref(x)
-    out_m, up_m = mine(x.to(device))
+    for h in hooks:
+        h.remove()
+    out_m, up_m = (runner or (lambda m, t: m(t)))(mine, x.to(device))
     res = {
         "rel_l2_logits": rel_l2(out_m, out_r),
         "rel_l2_hr_logits": rel_l2(up_m, up_r),
@@ -62,12 +74,28 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
         worst, worst_name = 0.0, ""
         num = den = 0.0
         pr = dict(ref.named_parameters())
+        missing = []
+        per_param = {}
+        tbias_ratio = 0.0
         for name, p in mine.named_parameters():
-            if p.grad is None or pr[name].grad is None:
+            if pr[name].grad is None:
+                continue
+            if p.grad is None:
+                missing.append(name)   # the reference has a gradient here and the engine produced none: a dropped path
                 continue
             a, b = p.grad.detach().double().cpu(), pr[name].grad.detach().double()
             if name.endswith("conv.bias") and ".convs." in name:
                 continue  # bias before InstanceNorm: exact gradient is 0, the reference's value is rounding noise
+            if name.startswith("decoder.transpconvs.") and name.endswith(".bias"):
+                # The up-sampled tensor feeds conv -> InstanceNorm, which removes a per-channel constant up to the zero-padding
+                # border effect, so this gradient is the (nearly cancelling) sum of V gradients: ill-conditioned.  It is judged
+                # against the rounding noise a sum of V bf16-rounded summands carries, sqrt(V) * rms_c * 2^-9, not against its
+                # own tiny norm (a dropped or truncated sum would miss by ~2^9 / sqrt(2) such units).
+                gup = up_outs[int(name.split(".")[2])].grad.detach().double()
+                noise = gup.pow(2).sum((0, 2, 3, 4)).sqrt() * 2.0 ** -9
+                tbias_ratio = max(tbias_ratio, float(((a - b).abs() / (noise + 1e-300)).max()))
+                continue
+            per_param[name] = float((a - b).norm() / (b.norm() + 1e-30))
             num += float((a - b).pow(2).sum())
             den += float(b.pow(2).sum())
             r = float((a - b).norm() / (b.norm() + 1e-30))
@@ -76,4 +104,7 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
         res["rel_l2_grads_global"] = (num / max(den, 1e-300)) ** 0.5
         res["rel_l2_grads_worst"] = worst
         res["worst_grad"] = worst_name
+        res["missing_grads"] = missing
+        res["tconv_bias_err_over_bf16_sum_noise"] = tbias_ratio
+        res["per_param_grad_rel_l2"] = per_param
     return res

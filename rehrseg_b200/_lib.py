@@ -22,7 +22,10 @@ class RehrTensor(C.Structure):
     """Mirror of ``rehr_tensor``: channels-last activation with a voxel pitch."""
 
     _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("d", C.c_int), ("h", C.c_int), ("w", C.c_int),
-                ("c", C.c_int), ("ld", C.c_longlong)]
+                ("c", C.c_int), ("ld", C.c_longlong), ("dtype", C.c_int)]
+
+
+BF16, F16 = 0, 1   # rehr_dtype
 
 
 class RehrConvDesc(C.Structure):
@@ -65,7 +68,7 @@ def _declare(L: C.CDLL) -> None:
         "rehr_last_cuda_error": (i, []),
         "rehr_version": (i, []),
         "rehr_device_sm_count": (i, []),
-        "rehr_pack_weight": (i, [vp, vp, i, i, i, ll, ll, ll, vp]),
+        "rehr_pack_weight": (i, [vp, vp, i, i, i, ll, ll, ll, i, vp]),
         "rehr_conv3d_fwd": (i, [D, T, vp, vp, T, i, i, f, vp, vp]),
         "rehr_conv3d_stats_tiles": (i, [T]),
         "rehr_conv3d_dgrad": (i, [D, T, vp, vp, T, i, i, f, vp]),
@@ -82,7 +85,7 @@ def _declare(L: C.CDLL) -> None:
         "rehr_convtranspose3d_wgrad": (i, [D, T, T, vp, i, vp, sz, vp]),
         "rehr_conv3d_march_supported": (i, [D, i, i]),
         "rehr_conv3d_march_weight_bytes": (sz, [i, i, i]),
-        "rehr_pack_weight_march": (i, [vp, vp, i, i, i, ll, ll, i, vp]),
+        "rehr_pack_weight_march": (i, [vp, vp, i, i, i, ll, ll, i, i, vp]),
         "rehr_conv3d_march_stats_tiles": (i, [T, T, i]),
         "rehr_conv3d_march_fwd": (i, [T, vp, vp, T, i, i, i, f, vp, vp]),
         "rehr_conv3d_march_s2dgrad_supported": (i, [D, i, i]),
@@ -102,7 +105,8 @@ def _declare(L: C.CDLL) -> None:
         "rehr_instnorm_stats_tiles": (i, [T]),
         "rehr_instnorm_stats": (i, [T, vp, vp]),
         "rehr_instnorm_finalize": (i, [vp, i, i, i, ll, f, vp, vp, vp]),
-        "rehr_instnorm_lrelu_apply": (i, [T, vp, vp, vp, vp, f, T, vp]),
+        "rehr_instnorm_lrelu_apply": (i, [T, vp, vp, vp, vp, f, T, T, vp]),
+        "rehr_convert16": (i, [T, T, vp]),
         "rehr_instnorm_lrelu_bwd_reduce": (i, [T, T, T, vp, vp, vp, vp, f, vp, vp]),
         "rehr_instnorm_lrelu_bwd_finalize": (i, [vp, i, i, i, vp, vp, vp, vp, i, vp]),
         "rehr_instnorm_lrelu_bwd_apply": (i, [T, T, T, vp, vp, vp, vp, f, vp, T, vp]),
@@ -192,10 +196,11 @@ def _pitch(t: torch.Tensor) -> int:
     return c
 
 
-def rt(t: torch.Tensor) -> RehrTensor:
-    """rehr_tensor descriptor of a channels-last [N,D,H,W,C] tensor (see as_cl)."""
+def rt(t: torch.Tensor, f16: bool = False) -> RehrTensor:
+    """rehr_tensor descriptor of a channels-last [N,D,H,W,C] tensor (see as_cl).  `f16`: the 16-bit payload is fp16 (the
+    forward activations of the SegModel path, see functional.is_h), not the tensor's nominal bf16."""
     n, d, h, w, c = t.shape
-    return RehrTensor(t.data_ptr(), n, d, h, w, c, _pitch(t))
+    return RehrTensor(t.data_ptr(), n, d, h, w, c, _pitch(t), F16 if f16 else BF16)
 
 
 def conv_desc(kernel, stride, padding) -> RehrConvDesc:

@@ -7,6 +7,8 @@
 
 #include <cuda_bf16.h>
 
+#include "ptx.cuh"
+
 using namespace rehr;
 
 namespace {
@@ -22,7 +24,7 @@ bool conv_shapes_ok(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_te
 }
 
 // out(class) = act(bias): used for output parity classes no tap reaches.
-__global__ void fill_class_kernel(void* out, int out_f32, long long ld, int cout, const float* bias, int act, float slope,
+__global__ void fill_class_kernel(void* out, int out_f32, int out_f16, long long ld, int cout, const float* bias, int act, float slope,
                                   int O0, int O1, int O2, int N, int s0, int s1, int s2, int o0, int o1, int o2, int A0, int A1,
                                   int A2) {
   const long long total = (long long)N * O2 * O1 * O0 * cout;
@@ -42,7 +44,7 @@ __global__ void fill_class_kernel(void* out, int out_f32, long long ld, int cout
     if (out_f32)
       reinterpret_cast<float*>(out)[vox * ld + c] = v;
     else
-      reinterpret_cast<__nv_bfloat16*>(out)[vox * ld + c] = __float2bfloat16(v);
+      reinterpret_cast<unsigned short*>(out)[vox * ld + c] = pack16(v, out_f16);
   }
 }
 
@@ -62,13 +64,13 @@ const char* rehr_strerror(int status) {
   }
 }
 int rehr_last_cuda_error(void) { return g_last_cuda_error; }
-int rehr_version(void) { return 3; }
+int rehr_version(void) { return 4; }
 int rehr_device_sm_count(void) { return sm_count(); }
 
-int rehr_pack_weight(const float* src, void* dst_bf16, int R, int C, int T, long long sr, long long sc, long long st,
+int rehr_pack_weight(const float* src, void* dst16, int R, int C, int T, long long sr, long long sc, long long st, int dtype,
                      rehr_stream stream) {
-  if (!src || !dst_bf16 || R <= 0 || C <= 0 || T <= 0) return REHR_BAD_SHAPE;
-  return launch_pack_weight(src, dst_bf16, R, C, T, sr, sc, st, (cudaStream_t)stream);
+  if (!src || !dst16 || R <= 0 || C <= 0 || T <= 0) return REHR_BAD_SHAPE;
+  return launch_pack_weight(src, dst16, R, C, T, sr, sc, st, (cudaStream_t)stream, dtype == REHR_F16);
 }
 
 int rehr_conv3d_stats_tiles(const rehr_tensor* y) {
@@ -180,7 +182,7 @@ static int conv_dgrad_impl(const rehr_conv_desc* desc, const rehr_tensor* dy, co
           if (need) continue;
           const long long total = (long long)O[0] * O[1] * O[2] * O[3] * dx->c;
           const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-          fill_class_kernel<<<blocks, 256, 0, cstream>>>(dx->ptr, dx_is_f32, dx->ld, dx->c, bias, act, slope, O[0], O[1],
+          fill_class_kernel<<<blocks, 256, 0, cstream>>>(dx->ptr, dx_is_f32, dx->dtype == REHR_F16, dx->ld, dx->c, bias, act, slope, O[0], O[1],
                                                                      O[2], O[3], s[0], s[1], s[2], cw, ch, cd, dx->w, dx->h, dx->d);
           REHR_CHECK_LAUNCH();
           continue;

@@ -282,6 +282,8 @@ struct alignas(64) FwdParams {
   // output
   void* out;
   int out_f32;
+  int out_f16;     // 16-bit output format (rehr_dtype of the output tensor) when !out_f32
+  int in_f16;      // operand format of the input tensor AND of the packed weights
   long long out_ld;
   int O[4];        // class-local output extents (w h d n)
   int os[3], oo[3];  // actual coord = o*os + oo (w h d)
@@ -381,22 +383,22 @@ __device__ __forceinline__ void finish_chunk(const FwdParams& p, float (&f)[16],
           if (cbase + i < p.cout) o[i] = f[i];
       }
     } else {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.out_ld + cbase;
+      unsigned short* o = reinterpret_cast<unsigned short*>(p.out) + vox * p.out_ld + cbase;
       if (cbase + 16 <= p.cout && (p.out_ld & 7) == 0) {
         uint4 lo, hi;
-        lo.x = pack_bf16x2(f[0], f[1]);
-        lo.y = pack_bf16x2(f[2], f[3]);
-        lo.z = pack_bf16x2(f[4], f[5]);
-        lo.w = pack_bf16x2(f[6], f[7]);
-        hi.x = pack_bf16x2(f[8], f[9]);
-        hi.y = pack_bf16x2(f[10], f[11]);
-        hi.z = pack_bf16x2(f[12], f[13]);
-        hi.w = pack_bf16x2(f[14], f[15]);
+        lo.x = pack16x2(f[0], f[1], p.out_f16);
+        lo.y = pack16x2(f[2], f[3], p.out_f16);
+        lo.z = pack16x2(f[4], f[5], p.out_f16);
+        lo.w = pack16x2(f[6], f[7], p.out_f16);
+        hi.x = pack16x2(f[8], f[9], p.out_f16);
+        hi.y = pack16x2(f[10], f[11], p.out_f16);
+        hi.z = pack16x2(f[12], f[13], p.out_f16);
+        hi.w = pack16x2(f[14], f[15], p.out_f16);
         reinterpret_cast<uint4*>(o)[0] = lo;
         reinterpret_cast<uint4*>(o)[1] = hi;
       } else {
         for (int i = 0; i < 16; ++i)
-          if (cbase + i < p.cout) o[i] = __float2bfloat16(f[i]);
+          if (cbase + i < p.cout) o[i] = pack16(f[i], p.out_f16);
       }
     }
   }
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    const uint32_t idesc = make_idesc_16(128, p.BN, 0, 0, p.in_f16);
     const uint32_t row_bytes = (uint32_t)p.BK * 2u;
     const uint32_t layout = swizzle_layout_for_bytes((int)row_bytes);
     const uint32_t sbo = 8u * row_bytes;
@@ -591,16 +593,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ov * p.out_ld + co0;
+            unsigned short* o = reinterpret_cast<unsigned short*>(p.out) + ov * p.out_ld + co0;
             uint4 lo, hi;
-            lo.x = pack_bf16x2(f[0], f[1]);
-            lo.y = pack_bf16x2(f[2], f[3]);
-            lo.z = pack_bf16x2(f[4], f[5]);
-            lo.w = pack_bf16x2(f[6], f[7]);
-            hi.x = pack_bf16x2(f[8], f[9]);
-            hi.y = pack_bf16x2(f[10], f[11]);
-            hi.z = pack_bf16x2(f[12], f[13]);
-            hi.w = pack_bf16x2(f[14], f[15]);
+            lo.x = pack16x2(f[0], f[1], p.out_f16);
+            lo.y = pack16x2(f[2], f[3], p.out_f16);
+            lo.z = pack16x2(f[4], f[5], p.out_f16);
+            lo.w = pack16x2(f[6], f[7], p.out_f16);
+            hi.x = pack16x2(f[8], f[9], p.out_f16);
+            hi.y = pack16x2(f[10], f[11], p.out_f16);
+            hi.z = pack16x2(f[12], f[13], p.out_f16);
+            hi.w = pack16x2(f[14], f[15], p.out_f16);
             reinterpret_cast<uint4*>(o)[0] = lo;
             reinterpret_cast<uint4*>(o)[1] = hi;
           }
@@ -758,6 +760,8 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
   p.AO[2] = out.d;
   p.out = out.ptr;
   p.out_f32 = out_f32;
+  p.out_f16 = out.dtype == REHR_F16;
+  p.in_f16 = in.dtype == REHR_F16;
   p.out_ld = out.ld;
   p.cout = cout;
   p.bias = bias;
@@ -1370,23 +1374,23 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
 // ------------------------------------------------------------------------------------------------
 // Weight packing: f32 src[r*sr + c*sc + t*st] -> bf16 dst[r][t][c]
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int T,
-                                   long long sr, long long sc, long long st) {
+__global__ void pack_weight_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int R, int C, int T,
+                                   long long sr, long long sc, long long st, int f16) {
   const long long total = (long long)R * T * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long rt = i / C;
     const int t = (int)(rt % T);
     const int r = (int)(rt / T);
-    dst[i] = __float2bfloat16(src[r * sr + c * sc + t * st]);
+    dst[i] = pack16(src[r * sr + c * sc + t * st], f16);
   }
 }
 
 // st == 1 (the T taps of one (r, c) pair are contiguous in src): block = (r, 64 consecutive c); the 64 runs of T floats are
 // read coalesced into shared memory and written back transposed as 64 consecutive bf16 per tap.
 static constexpr int kPackC = 64;
-__global__ void __launch_bounds__(256) pack_weight_runs_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R,
-                                                               int C, int T, long long sr, long long sc) {
+__global__ void __launch_bounds__(256) pack_weight_runs_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int R,
+                                                               int C, int T, long long sr, long long sc, int f16) {
   extern __shared__ float tile[];  // [kPackC][T + 1]
   const int r = blockIdx.y, c0 = blockIdx.x * kPackC;
   const int nc = min(kPackC, C - c0);
@@ -1397,12 +1401,12 @@ __global__ void __launch_bounds__(256) pack_weight_runs_kernel(const float* __re
   __syncthreads();
   for (int i = threadIdx.x; i < nc * T; i += 256) {
     const int t = i / nc, cl = i % nc;
-    dst[((long long)r * T + t) * C + c0 + cl] = __float2bfloat16(tile[cl * (T + 1) + t]);
+    dst[((long long)r * T + t) * C + c0 + cl] = pack16(tile[cl * (T + 1) + t], f16);
   }
 }
 
 int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long long sr, long long sc, long long st,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int f16) {
   const long long total = (long long)R * T * C;
   if (total == 0) return REHR_OK;
   if (st == 1 && T <= 343 && R <= 65535) {
@@ -1414,10 +1418,10 @@ int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long lo
         return REHR_CUDA_ERROR;
       attr = true;
     }
-    pack_weight_runs_kernel<<<grid, 256, smem, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, T, sr, sc);
+    pack_weight_runs_kernel<<<grid, 256, smem, stream>>>(src, reinterpret_cast<unsigned short*>(dst), R, C, T, sr, sc, f16);
   } else {
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, T, sr, sc, st);
+    pack_weight_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<unsigned short*>(dst), R, C, T, sr, sc, st, f16);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -68,6 +68,8 @@ struct alignas(64) MarchParams {
   uint32_t w_bytes, plane_bytes, chunk_stride, slot_stride, wtile_bytes;
   void* out;
   int out_f32;
+  int out_f16;  // 16-bit output format (rehr_dtype of y) when !out_f32
+  int in_f16;   // operand format of x AND of the packed weights (one tcgen05.mma takes one 16-bit format)
   long long out_ld;
   const float* bias;
   int act;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
         while (ra <= qb) {
           int rb = ra;
           while (rb < qb && ((rb + 1 - d0) & kSlotMask) != 0) ++rb;
-          const uint32_t idesc = make_idesc_bf16(128, (rb - ra + 1) * CT, 0, 0);
+          const uint32_t idesc = make_idesc_16(128, (rb - ra + 1) * CT, 0, 0, p.in_f16);
           const uint32_t b_lo = sw_lo + (((uint32_t)((ra - pl + R - p.kd_off) * CT) * kRowB) >> 4);
           const uint32_t d_tmem = tmem_base + (uint32_t)(((ra - d0) & kSlotMask) * CT);
           if (!(p.debug & 4) && elect_one_sync()) {
@@ -378,10 +380,10 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
                 for (int i = 0; i < kW; ++i)
                   if (i < nvalid) o[i] = f[i];
               } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
+                unsigned short* o = reinterpret_cast<unsigned short*>(p.out) + obase + cc;
 #pragma unroll
                 for (int i = 0; i < kW; ++i)
-                  if (i < nvalid) o[i] = __float2bfloat16(f[i]);
+                  if (i < nvalid) o[i] = pack16(f[i], p.out_f16);
               }
             } else if (p.out_f32) {
               float* o = reinterpret_cast<float*>(p.out) + obase + cc;
@@ -393,20 +395,20 @@ __global__ void __launch_bounds__(kMarchThreads, 1) conv_march_kernel(const __gr
                 for (int i = 0; i < kW; ++i) o[i] = f[i];
               }
             } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
+              unsigned short* o = reinterpret_cast<unsigned short*>(p.out) + obase + cc;
               if ((p.out_ld & 7) == 0) {
 #pragma unroll
                 for (int i = 0; i < kW; i += 8) {
                   uint4 u;
-                  u.x = pack_bf16x2(f[i], f[i + 1]);
-                  u.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                  u.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                  u.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                  u.x = pack16x2(f[i], f[i + 1], p.out_f16);
+                  u.y = pack16x2(f[i + 2], f[i + 3], p.out_f16);
+                  u.z = pack16x2(f[i + 4], f[i + 5], p.out_f16);
+                  u.w = pack16x2(f[i + 6], f[i + 7], p.out_f16);
                   *reinterpret_cast<uint4*>(o + i) = u;
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < kW; ++i) o[i] = __float2bfloat16(f[i]);
+                for (int i = 0; i < kW; ++i) o[i] = pack16(f[i], p.out_f16);
               }
             }
           }
@@ -578,6 +580,8 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
   if (x.ld % 8 != 0) return REHR_BAD_ALIGNMENT;
   p.out = y.ptr;
   p.out_f32 = y_is_f32;
+  p.out_f16 = y.dtype == REHR_F16;
+  p.in_f16 = x.dtype == REHR_F16;
   p.out_ld = y.ld;
   p.o_pw = y.ld;
   p.o_ph = (long long)y.w * y.ld;
@@ -676,8 +680,8 @@ static int dispatch_march(const MarchPlan& pl, cudaStream_t stream) {
 // forward of W[Cout][Cin][T]: s_co = Cin*T, s_ci = T, flip = 0;
 // input-gradient (dx[B] from dy[A]) of W[A][B][T]: cout := B, cin := A, s_co = T, s_ci = B*T, flip = 1.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int cout, int cout_pad, int cin,
-                                  int Ct, int BK, int ks, int kdn, long long s_co, long long s_ci, int flip) {
+__global__ void pack_march_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int cout, int cout_pad, int cin,
+                                  int Ct, int BK, int ks, int kdn, long long s_co, long long s_ci, int flip, int f16) {
   // kdn = stored depth taps: ks (cubic kernel) or 1 (planar k(1,ks,ks): source taps t = kh*ks + kw)
   const int chunks = cin / BK;
   const int T = kdn * ks * ks;
@@ -695,7 +699,7 @@ __global__ void pack_march_kernel(const float* __restrict__ src, __nv_bfloat16* 
     const int kd = kdn - 1 - j, kh = khw / ks, kw = khw % ks;
     const int t = (kd * ks + kh) * ks + kw;
     const int co = ct * Ct + col, ci = chunk * BK + k;
-    dst[i] = co < cout ? __float2bfloat16(src[co * s_co + ci * s_ci + (flip ? T - 1 - t : t)]) : __float2bfloat16(0.f);
+    dst[i] = co < cout ? pack16(src[co * s_co + ci * s_ci + (flip ? T - 1 - t : t)], f16) : (unsigned short)0;
   }
 }
 
@@ -768,9 +772,9 @@ size_t rehr_conv3d_march_weight_bytes(int cin, int cout, int ks) {
   return march_ct(cin, cout, ks, false) > 0 ? (size_t)ks * ks * ks * cin * pad16(cout) * 2 : 0;
 }
 
-int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
-                           rehr_stream stream) {
-  if (!src || !dst_bf16) return REHR_BAD_SHAPE;
+int rehr_pack_weight_march(const float* src, void* dst16, int cout, int cin, int ks, long long s_co, long long s_ci, int flip,
+                           int dtype, rehr_stream stream) {
+  if (!src || !dst16) return REHR_BAD_SHAPE;
   const bool planar = ks == 1;
   if (planar) ks = 3;
   const int kdn = planar ? 1 : ks;
@@ -778,8 +782,8 @@ int rehr_pack_weight_march(const float* src, void* dst_bf16, int cout, int cin, 
   if (ct == 0) return REHR_UNSUPPORTED;
   const long long total = (long long)pad16(cout) * cin * kdn * ks * ks;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  pack_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, pad16(cout), cin, ct,
-                                                             std::min(cin, 64), ks, kdn, s_co, s_ci, flip);
+  pack_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<unsigned short*>(dst16), cout, pad16(cout), cin, ct,
+                                                             std::min(cin, 64), ks, kdn, s_co, s_ci, flip, dtype == REHR_F16);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -4,6 +4,7 @@
 // sized as a multiple of the SM count; reductions are shuffle / shared-memory trees with deterministic
 // per-block partials (no float atomics on global memory).
 #include "engine.h"
+#include "ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -33,6 +34,20 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return u;
+}
+
+// 16-bit payloads of either storage format (rehr_tensor.dtype): fp16 != 0 selects fp16, else bf16
+__device__ __forceinline__ void x16x8_to_float(const uint4& u, float (&f)[8], int fp16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack16x2(w[i], fp16);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_x16x8(const float (&f)[8], int fp16) {
+  return make_uint4(pack16x2(f[0], f[1], fp16), pack16x2(f[2], f[3], fp16), pack16x2(f[4], f[5], fp16), pack16x2(f[6], f[7], fp16));
 }
 
 static bool bf16_tensor_ok(const rehr_tensor* t) {
@@ -72,6 +87,7 @@ struct StatArgs {
   float* partial;
   long long V;
   int C, tiles, vpb;
+  int y_f16;  // storage format of y (the gradients da1 / da2 are always bf16)
 };
 
 template <int MODE>
@@ -118,7 +134,7 @@ __global__ void __launch_bounds__(kStatThreads) in_reduce_kernel(const StatArgs 
         const long long v = vb + (long long)u * lanes;
         if (v >= v1) break;
         float y[8];
-        bf16x8_to_float(yv[u], y);
+        x16x8_to_float(yv[u], y, a.y_f16);
         if (MODE == 0) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -290,6 +306,10 @@ struct ApplyArgs {
   float slope;
   long long V;
   int C;
+  int y_f16, out_f16;    // storage formats of y and out (da1 / da2 are always bf16)
+  __nv_bfloat16* out2;   // MODE 0 only: optional second copy of the activation in the other 16-bit format (may be null)
+  long long ld_o2;
+  int out2_f16;
 };
 
 // MODE 0: a = lrelu(gamma*xhat + beta).  MODE 1: dy = gamma*rstd*(g - S1/V - xhat*S2/V).
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const ApplyArgs a) {
       const int g = (int)(it % groups);
       const long long vox = (long long)n * a.V + it / groups;
       float y[8], o[8];
-      bf16x8_to_float(yv[u], y);
+      x16x8_to_float(yv[u], y, a.y_f16);
       if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -365,7 +385,8 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const ApplyArgs a) {
           o[i] = sh[2 * C + c] * sh[C + c] * (gi - sh[4 * C + c] - xh * sh[5 * C + c]);
         }
       }
-      *reinterpret_cast<uint4*>(a.out + vox * a.ld_o + g * 8) = float_to_bf16x8(o);
+      *reinterpret_cast<uint4*>(a.out + vox * a.ld_o + g * 8) = float_to_x16x8(o, a.out_f16);
+      if (MODE == 0 && a.out2 != nullptr) *reinterpret_cast<uint4*>(a.out2 + vox * a.ld_o2 + g * 8) = float_to_x16x8(o, a.out2_f16);
     }
   }
 }
@@ -393,7 +414,8 @@ static constexpr int kPwMaxCin = 128;
 // the sample index comes from blockIdx.y, so the voxel loop carries no 64-bit division.
 template <int kPwMaxCout, int CIN>
 __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16* x, long long ld, const float* w,
-                                                            const float* bias, float* y, long long V, int cin_rt, int cout) {
+                                                            const float* bias, float* y, long long V, int cin_rt, int cout,
+                                                            int x_f16) {
   const int cin = CIN > 0 ? CIN : cin_rt;
   __shared__ float sw[kPwMaxCout * kPwMaxCin + kPwMaxCout];
   for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) sw[i] = w[i];
@@ -414,7 +436,7 @@ __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16*
 #pragma unroll
       for (int c = 0; c < CIN / 8; ++c) {
         float f[8];
-        bf16x8_to_float(raw[c], f);
+        x16x8_to_float(raw[c], f, x_f16);
 #pragma unroll
         for (int o = 0; o < kPwMaxCout; ++o)
           if (o < cout) {
@@ -425,7 +447,7 @@ __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16*
     } else {
       for (int c0 = 0; c0 < cin; c0 += 8) {
         float f[8];
-        bf16x8_to_float(*reinterpret_cast<const uint4*>(xp + c0), f);
+        x16x8_to_float(*reinterpret_cast<const uint4*>(xp + c0), f, x_f16);
 #pragma unroll
         for (int o = 0; o < kPwMaxCout; ++o)
           if (o < cout) {
@@ -444,7 +466,7 @@ __global__ void __launch_bounds__(256) pointwise_fwd_kernel(const __nv_bfloat16*
 template <int kPwMaxCout>
 __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16* x, long long ldx, const float* dy,
                                                             const float* w, __nv_bfloat16* dx, long long lddx, float* ws,
-                                                            long long V, int cin, int cout) {
+                                                            long long V, int cin, int cout, int x_f16) {
   __shared__ float sw[kPwMaxCout * kPwMaxCin];
   __shared__ float sacc[kPwMaxCout * (kPwMaxCin + 1)];
   for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) sw[i] = w[i];
@@ -483,8 +505,8 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
       gy1[o] = (o < cout && has1) ? dy[(long long)o * V + v1] : 0.f;
     }
     float f0[8], f1[8], d0[8], d1[8];
-    bf16x8_to_float(r0, f0);
-    bf16x8_to_float(r1, f1);
+    x16x8_to_float(r0, f0, x_f16);
+    x16x8_to_float(r1, f1, x_f16);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d0[i] = d1[i] = 0.f;
 #pragma unroll
@@ -603,7 +625,8 @@ static int channel_sum_blocks(const rehr_tensor* x) {
 // Depth-only linear upsampling, align_corners=True (ATen area_pixel_compute_source_index semantics)
 // =================================================================================================
 __global__ void __launch_bounds__(256) upsample_d_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* y,
-                                                         long long ldy, int N, int D, int OD, long long HW, int C) {
+                                                         long long ldy, int N, int D, int OD, long long HW, int C, int x_f16,
+                                                         int y_f16) {
   const int groups = C / 8;
   const long long items = (long long)N * OD * HW * groups;
   const float scale = OD > 1 ? (float)(D - 1) / (float)(OD - 1) : 0.f;
@@ -619,11 +642,11 @@ __global__ void __launch_bounds__(256) upsample_d_kernel(const __nv_bfloat16* x,
     const int i1 = i0 + (i0 < D - 1 ? 1 : 0);
     const float l1 = src - (float)i0, l0 = 1.f - l1;
     float a[8], b[8], o[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + i0) * HW + hw) * ldx + g * 8), a);
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + i1) * HW + hw) * ldx + g * 8), b);
+    x16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + i0) * HW + hw) * ldx + g * 8), a, x_f16);
+    x16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + i1) * HW + hw) * ldx + g * 8), b, x_f16);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = l0 * a[i] + l1 * b[i];
-    *reinterpret_cast<uint4*>(y + ((n * OD + od) * HW + hw) * ldy + g * 8) = float_to_bf16x8(o);
+    *reinterpret_cast<uint4*>(y + ((n * OD + od) * HW + hw) * ldy + g * 8) = float_to_x16x8(o, y_f16);
   }
 }
 __global__ void __launch_bounds__(256) upsample_d_bwd_kernel(const __nv_bfloat16* dy, long long lddy, __nv_bfloat16* dx,
@@ -688,8 +711,8 @@ __global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* src, _
     if (c < C && v < V) dst[((long long)n * V + v) * ld + c] = __float2bfloat16(tile[tx][k]);
   }
 }
-__global__ void __launch_bounds__(256) ndhwc_to_ncdhw_kernel(const __nv_bfloat16* src, long long ld, float* dst, long long V,
-                                                             int C) {
+__global__ void __launch_bounds__(256) ndhwc_to_ncdhw_kernel(const unsigned short* src, long long ld, float* dst, long long V,
+                                                             int C, int src_f16) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long v0 = (long long)blockIdx.x * 32;
@@ -698,13 +721,28 @@ __global__ void __launch_bounds__(256) ndhwc_to_ncdhw_kernel(const __nv_bfloat16
   for (int k = ty; k < 32; k += 8) {
     const long long v = v0 + k;
     const int c = c0 + tx;
-    tile[k][tx] = (c < C && v < V) ? __bfloat162float(src[((long long)n * V + v) * ld + c]) : 0.f;
+    tile[k][tx] = (c < C && v < V) ? unpack16(src[((long long)n * V + v) * ld + c], src_f16) : 0.f;
   }
   __syncthreads();
   for (int k = ty; k < 32; k += 8) {
     const int c = c0 + k;
     const long long v = v0 + tx;
     if (c < C && v < V) dst[((long long)n * C + c) * V + v] = tile[tx][k];
+  }
+}
+
+// 16-bit -> 16-bit format conversion of a (pitched) channels-last tensor: the bf16 twin of an fp16 forward activation that a
+// weight-gradient GEMM needs as its operand (its other operand, the gradient, is bf16 and one MMA takes one format)
+__global__ void __launch_bounds__(256) convert16_kernel(const __nv_bfloat16* x, long long ldx, int x_f16, __nv_bfloat16* y,
+                                                        long long ldy, int y_f16, long long vox_total, int C) {
+  const int groups = C / 8;
+  const long long items = vox_total * groups;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    const long long vox = it / groups;
+    float f[8];
+    x16x8_to_float(__ldcs(reinterpret_cast<const uint4*>(x + vox * ldx + g * 8)), f, x_f16);
+    *reinterpret_cast<uint4*>(y + vox * ldy + g * 8) = float_to_x16x8(f, y_f16);
   }
 }
 
@@ -1000,6 +1038,7 @@ int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream
   if (!bf16_tensor_ok(x) || !partial) return REHR_BAD_SHAPE;
   StatArgs a{};
   a.y = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
+  a.y_f16 = x->dtype == REHR_F16;
   a.ld_y = x->ld;
   a.partial = partial;
   a.V = voxels_per_sample(x);
@@ -1019,12 +1058,20 @@ int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long l
 }
 
 int rehr_instnorm_lrelu_apply(const rehr_tensor* y, const float* mean, const float* rstd, const float* gamma,
-                              const float* beta, float slope, const rehr_tensor* a, rehr_stream stream) {
+                              const float* beta, float slope, const rehr_tensor* a, const rehr_tensor* a2, rehr_stream stream) {
   if (!bf16_tensor_ok(y) || !bf16_tensor_ok(a) || y->c != a->c || y->n != a->n || voxels_per_sample(y) != voxels_per_sample(a))
     return REHR_BAD_SHAPE;
+  if (a2 && (!bf16_tensor_ok(a2) || a2->c != y->c || a2->n != y->n || voxels_per_sample(a2) != voxels_per_sample(y))) return REHR_BAD_SHAPE;
   ApplyArgs p{};
   p.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
   p.out = reinterpret_cast<__nv_bfloat16*>(a->ptr);
+  p.y_f16 = y->dtype == REHR_F16;
+  p.out_f16 = a->dtype == REHR_F16;
+  if (a2) {
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(a2->ptr);
+    p.ld_o2 = a2->ld;
+    p.out2_f16 = a2->dtype == REHR_F16;
+  }
   p.ld_y = y->ld;
   p.ld_o = a->ld;
   p.mean = mean;
@@ -1043,6 +1090,7 @@ int rehr_instnorm_lrelu_bwd_reduce(const rehr_tensor* y, const rehr_tensor* da1,
   if (!bf16_tensor_ok(y) || !bf16_tensor_ok(da1) || (da2 && !bf16_tensor_ok(da2)) || !partial) return REHR_BAD_SHAPE;
   StatArgs a{};
   a.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
+  a.y_f16 = y->dtype == REHR_F16;
   a.da1 = reinterpret_cast<const __nv_bfloat16*>(da1->ptr);
   a.da2 = da2 ? reinterpret_cast<const __nv_bfloat16*>(da2->ptr) : nullptr;
   a.ld_y = y->ld;
@@ -1077,6 +1125,8 @@ int rehr_instnorm_lrelu_bwd_apply(const rehr_tensor* y, const rehr_tensor* da1, 
     return REHR_BAD_SHAPE;
   ApplyArgs p{};
   p.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
+  p.y_f16 = y->dtype == REHR_F16;
+  p.out_f16 = dy->dtype == REHR_F16;
   p.da1 = reinterpret_cast<const __nv_bfloat16*>(da1->ptr);
   p.da2 = da2 ? reinterpret_cast<const __nv_bfloat16*>(da2->ptr) : nullptr;
   p.out = reinterpret_cast<__nv_bfloat16*>(dy->ptr);
@@ -1101,14 +1151,15 @@ int rehr_pointwise_fwd(const rehr_tensor* x, const float* w, const float* bias, 
   const long long V = voxels_per_sample(x);
   const dim3 grid((unsigned)std::max(1, grid_for(V, 256, 8)), (unsigned)x->n);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x->ptr);
+  const int xf = x->dtype == REHR_F16;
   if (cout <= 2 && x->c == 32)  // the nnU-Net segmentation head (decoder.seg_layers[-1], models/seg_model.py:44)
-    pointwise_fwd_kernel<2, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
+    pointwise_fwd_kernel<2, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout, xf);
   else if (cout <= 2)
-    pointwise_fwd_kernel<2, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
+    pointwise_fwd_kernel<2, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout, xf);
   else if (cout <= 4)
-    pointwise_fwd_kernel<4, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
+    pointwise_fwd_kernel<4, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout, xf);
   else
-    pointwise_fwd_kernel<8, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout);
+    pointwise_fwd_kernel<8, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, w, bias, y_ncdhw, V, x->c, cout, xf);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -1131,12 +1182,14 @@ int rehr_pointwise_bwd(const rehr_tensor* x, const float* dy_ncdhw, const float*
   __nv_bfloat16* dxp = dx ? reinterpret_cast<__nv_bfloat16*>(dx->ptr) : nullptr;
   const long long lddx = dx ? dx->ld : 0;
   float* wsp = reinterpret_cast<float*>(ws);
+  const int xf = x->dtype == REHR_F16;
+  if (dx && dx->dtype != REHR_BF16) return REHR_UNSUPPORTED;  // gradients are bf16
   if (cout <= 2)
-    pointwise_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout);
+    pointwise_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout, xf);
   else if (cout <= 4)
-    pointwise_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout);
+    pointwise_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout, xf);
   else
-    pointwise_bwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout);
+    pointwise_bwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, x->ld, dy_ncdhw, w, dxp, lddx, wsp, V, x->c, cout, xf);
   REHR_CHECK_LAUNCH();
   const int outs = cout * (x->c + 1);
   pointwise_bwd_reduce_kernel<<<outs, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, x->c, cout, dw,
@@ -1168,7 +1221,7 @@ int rehr_upsample_linear_d(const rehr_tensor* x, const rehr_tensor* y, rehr_stre
   const long long items = (long long)y->n * y->d * HW * (y->c / 8);
   upsample_d_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld,
                                                                            reinterpret_cast<__nv_bfloat16*>(y->ptr), y->ld, x->n, x->d,
-                                                                           y->d, HW, x->c);
+                                                                           y->d, HW, x->c, x->dtype == REHR_F16, y->dtype == REHR_F16);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -1196,7 +1249,19 @@ int rehr_ndhwc_bf16_to_ncdhw_f32(const rehr_tensor* src, float* dst, rehr_stream
   if (!src || !dst || !src->ptr) return REHR_BAD_SHAPE;
   const long long V = voxels_per_sample(src);
   dim3 grid((unsigned)((V + 31) / 32), (unsigned)((src->c + 31) / 32), (unsigned)src->n);
-  ndhwc_to_ncdhw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src->ptr), src->ld, dst, V, src->c);
+  ndhwc_to_ncdhw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned short*>(src->ptr), src->ld, dst, V, src->c,
+                                                                src->dtype == REHR_F16);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_convert16(const rehr_tensor* src, const rehr_tensor* dst, rehr_stream stream) {
+  if (!bf16_tensor_ok(src) || !bf16_tensor_ok(dst) || src->c != dst->c || src->n != dst->n || voxels_per_sample(src) != voxels_per_sample(dst))
+    return REHR_BAD_SHAPE;
+  const long long vox = (long long)src->n * voxels_per_sample(src);
+  convert16_kernel<<<grid_for(vox * (src->c / 8), 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src->ptr), src->ld, src->dtype == REHR_F16, reinterpret_cast<__nv_bfloat16*>(dst->ptr), dst->ld,
+      dst->dtype == REHR_F16, vox, src->c);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -42,7 +42,7 @@ size_t tapped_wgrad_workspace(const TapPlan& plan, const rehr_tensor& X, const r
 int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_tensor& Y, float* dw, long long s_n,
                         long long s_m, long long s_t, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
 int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long long sr, long long sc, long long st,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int f16 = 0);
 
 #define REHR_CHECK_LAUNCH()                                   \
   do {                                                        \

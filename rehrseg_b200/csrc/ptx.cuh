@@ -145,6 +145,14 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major
   return d;
 }
 
+// Instruction descriptor for kind::f16 with 16-bit A/B of ONE format (fp16: format code 0, bf16: 1; the two operands must share
+// the format -- mixed fp16 x bf16 raises "illegal instruction" on B200, tools/umma_mixed_probe.cu), fp32 D.
+__device__ __forceinline__ uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int fp16) {
+  uint32_t d = make_idesc_bf16(M, N, a_mn_major, b_mn_major);
+  if (fp16) d &= ~((1u << 7) | (1u << 10));
+  return d;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -153,6 +161,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// 16-bit activation storage formats (rehr_tensor.dtype): 0 = bf16, 1 = fp16.  fp16 stores saturate to +-65504 instead of
+// overflowing to inf (cvt.rn.satfinite), loads are exact in fp32 for both.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fp16) {
+  return fp16 ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ unsigned short pack16(float v, int fp16) {
+  return (unsigned short)(pack16x2(v, 0.f, fp16) & 0xffffu);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int fp16) {
+  if (fp16) {
+    float2 r;
+    asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(u));
+    return r;
+  }
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ float unpack16(unsigned short u, int fp16) { return unpack16x2((uint32_t)u, fp16).x; }
 
 }  // namespace rehr
 

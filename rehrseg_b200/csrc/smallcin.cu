@@ -6,6 +6,7 @@
 // train_all.py:524), weights live in shared memory, each thread produces one output voxel x 16 channels and
 // writes NDHWC bf16 so the next layer's TMA tiles are ready-made.
 #include "engine.h"
+#include "ptx.cuh"
 
 #include <cuda_bf16.h>
 
@@ -16,7 +17,7 @@ namespace rehr {
 // tensor-core stem (stem_mma.cu): Cin = 1, Cout = 32, k3 s1 p1
 bool stem_mma_supported(int cin, int cout, int wd);
 size_t stem_mma_wgrad_workspace();
-int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_bfloat16* y, long long ldy, int n, int d, int h, int wd,
+int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_bfloat16* y, long long ldy, int y_f16, int n, int d, int h, int wd,
                         int act, float slope, int planar, cudaStream_t stream);
 int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long lddy, int n, int d, int h, int wd, float* dw, int accumulate,
                           float* ws, int planar, cudaStream_t stream);
@@ -35,6 +36,7 @@ struct SmallCinArgs {
   int kd, kh, kw, sd, sh, sw, pd, ph, pw;
   int act;
   float slope;
+  int y_f16;           // storage format of y (rehr_dtype)
 };
 
 // weights in smem as [cin*T][cout] (cout fastest) so that a thread's 16 channels are 4 float4 broadcasts.
@@ -106,12 +108,12 @@ __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const SmallCinArgs a)
         if (a.act == REHR_ACT_LRELU) z = z > 0.f ? z : z * a.slope;
         f[i] = z;
       }
-      __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
-      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+      uint32_t* l2 = reinterpret_cast<uint32_t*>(&lo);
+      uint32_t* h2 = reinterpret_cast<uint32_t*>(&hi);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        l2[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        h2[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+        l2[i] = pack16x2(f[2 * i], f[2 * i + 1], a.y_f16);
+        h2[i] = pack16x2(f[8 + 2 * i], f[8 + 2 * i + 1], a.y_f16);
       }
       reinterpret_cast<uint4*>(o)[0] = lo;
       reinterpret_cast<uint4*>(o)[1] = hi;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const SmallCinArgs a)
           float z = acc[i];
           if (a.act == REHR_ACT_RELU) z = z > 0.f ? z : 0.f;
           if (a.act == REHR_ACT_LRELU) z = z > 0.f ? z : z * a.slope;
-          o[i] = __float2bfloat16(z);
+          reinterpret_cast<unsigned short*>(o)[i] = pack16(z, a.y_f16);
         }
     }
   }
@@ -203,13 +205,13 @@ __global__ void __launch_bounds__(256) smallcin_fwd_k3c32_kernel(const SmallCinA
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 u;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+        uint32_t* h2 = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float z0 = acc[8 * j + 2 * i], z1 = acc[8 * j + 2 * i + 1];
           if (a.act == REHR_ACT_RELU) { z0 = z0 > 0.f ? z0 : 0.f; z1 = z1 > 0.f ? z1 : 0.f; }
           if (a.act == REHR_ACT_LRELU) { z0 = z0 > 0.f ? z0 : z0 * a.slope; z1 = z1 > 0.f ? z1 : z1 * a.slope; }
-          h2[i] = __floats2bfloat162_rn(z0, z1);
+          h2[i] = pack16x2(z0, z1, a.y_f16);
         }
         o[j] = u;
       }
@@ -597,6 +599,7 @@ int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, i
   a.pd = desc->pd; a.ph = desc->ph; a.pw = desc->pw;
   a.act = act;
   a.slope = slope;
+  a.y_f16 = y->dtype == REHR_F16;
   const bool k3 = desc->kd == 3 && desc->kh == 3 && desc->kw == 3 && desc->sd == 1 && desc->sh == 1 && desc->sw == 1 &&
                   desc->pd == 1 && desc->ph == 1 && desc->pw == 1;
   // planar stem of anisotropic plans: k = (1,3,3), stride 1, pad (0,1,1)
@@ -604,7 +607,7 @@ int rehr_conv3d_smallcin_fwd(const rehr_conv_desc* desc, const float* x_ncdhw, i
                     desc->pd == 0 && desc->ph == 1 && desc->pw == 1;
   int rc = REHR_UNSUPPORTED;
   if ((k3 || k133) && stem_mma_supported(cin, y->c, w) && y->ld % 8 == 0) {
-    rc = launch_stem_fwd_mma(x_ncdhw, weight, bias, a.y, a.ldy, n, d, h, w, act, slope, k133 ? 1 : 0, (cudaStream_t)stream);
+    rc = launch_stem_fwd_mma(x_ncdhw, weight, bias, a.y, a.ldy, a.y_f16, n, d, h, w, act, slope, k133 ? 1 : 0, (cudaStream_t)stream);
     if (rc != REHR_OK && rc != REHR_UNSUPPORTED) return rc;
   }
   if (rc == REHR_UNSUPPORTED && k3 && y->c == 32 && cin <= 2) {

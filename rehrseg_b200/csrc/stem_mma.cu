@@ -32,6 +32,7 @@ struct StemArgs {
   int act;
   float slope;
   int planar;           // 1: k = (1,3,3), pad (0,1,1) (the stem of anisotropic plans): 9 taps, one staged plane
+  int y_f16;            // forward: storage format of y (rehr_dtype); the weight gradient's dY is always bf16
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -166,8 +167,8 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
           if (a.act == REHR_ACT_LRELU) z = z > 0.f ? z : z * a.slope;
           acc[nt][i] = z;
         }
-        *reinterpret_cast<uint32_t*>(mine + g * kStemRowPad + (nt * 8 + 2 * t) * 2) = pack_bf16x2(acc[nt][0], acc[nt][1]);
-        *reinterpret_cast<uint32_t*>(mine + (g + 8) * kStemRowPad + (nt * 8 + 2 * t) * 2) = pack_bf16x2(acc[nt][2], acc[nt][3]);
+        *reinterpret_cast<uint32_t*>(mine + g * kStemRowPad + (nt * 8 + 2 * t) * 2) = pack16x2(acc[nt][0], acc[nt][1], a.y_f16);
+        *reinterpret_cast<uint32_t*>(mine + (g + 8) * kStemRowPad + (nt * 8 + 2 * t) * 2) = pack16x2(acc[nt][2], acc[nt][3], a.y_f16);
       }
       __syncwarp();
 #pragma unroll
@@ -348,10 +349,11 @@ static constexpr int kStemWgradBlocks = 296;  // 2 x 148
 bool stem_mma_supported(int cin, int cout, int wd) { return cin == 1 && cout == 32 && stem_smem_bytes(wd, true) <= 160 * 1024; }
 size_t stem_mma_wgrad_workspace() { return (size_t)kStemWgradBlocks * 27 * 32 * sizeof(float); }
 
-int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_bfloat16* y, long long ldy, int n, int d, int h, int wd,
-                        int act, float slope, int planar, cudaStream_t stream) {
+int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_bfloat16* y, long long ldy, int y_f16, int n, int d, int h,
+                        int wd, int act, float slope, int planar, cudaStream_t stream) {
   StemArgs a;
   a.planar = planar;
+  a.y_f16 = y_f16;
   a.x = x; a.w = w; a.bias = bias; a.y = y; a.ldy = ldy; a.ws = nullptr;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = act; a.slope = slope;
   const size_t smem = stem_smem_bytes(wd, false);
@@ -369,6 +371,7 @@ int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long ldd
                           float* ws, int planar, cudaStream_t stream) {
   StemArgs a;
   a.planar = planar;
+  a.y_f16 = 0;
   a.x = x; a.w = nullptr; a.bias = nullptr; a.y = const_cast<__nv_bfloat16*>(dy); a.ldy = lddy; a.ws = ws;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = 0; a.slope = 0.f;
   const size_t smem = stem_smem_bytes(wd, true);

@@ -11,6 +11,7 @@ library and raises `RehrError` on a non-zero status.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Optional, Sequence, Tuple
 
@@ -90,6 +91,66 @@ class _timed:
 
 
 # --------------------------------------------------------------------------------------------------
+# 16-bit storage formats
+# --------------------------------------------------------------------------------------------------
+# Gradients (and every FLAVR activation) are bf16.  The forward activations of the InstanceNorm'ed SegModel path are stored in
+# fp16: InstanceNorm bounds them, fp16 keeps 3 more mantissa bits than bf16 at the same tensor-core rate and the same bytes, and
+# the logits land at ~1e-3 of the fp32 reference instead of ~9e-3 (tools/bf16_emulate.py).  fp16 stores
+# saturate (+-65504).  REHR_FWD_DTYPE=bf16 keeps bf16 MMA operands in the forward pass as well.
+#
+# PyTorch only sees bf16 tensors: an fp16 activation travels as a tensor of NOMINAL dtype bfloat16 whose Python object carries
+# `_rehr_h = True` (its 16-bit payload is fp16).  That keeps autograd's dtype bookkeeping on bf16, which is what the gradient of
+# such an activation really is.  Only engine functions may consume these tensors; `from_channels_last` converts at the boundary.
+# One tcgen05.mma takes ONE 16-bit format (mixed fp16 x bf16 operands are an illegal instruction, tools/umma_mixed_probe.cu), so
+# a weight-gradient GEMM (activation x bf16 gradient) needs a bf16 copy of the activation: `_rehr_bf` holds that twin, written
+# by the same pass that writes the fp16 activation.
+FWD_FP16 = os.environ.get("REHR_FWD_DTYPE", "fp16").lower() != "bf16"
+Y_FP16 = True   # storage of the pre-normalisation conv output y (never an MMA operand; consumed by the InstanceNorm kernels)
+
+
+def is_h(t) -> bool:
+    """True if `t`'s 16-bit payload is fp16 (see above)."""
+    return bool(getattr(t, "_rehr_h", False))
+
+
+def mark_h(t: torch.Tensor, twin: Optional[torch.Tensor] = None) -> torch.Tensor:
+    t._rehr_h = True
+    if twin is not None:
+        t._rehr_bf = twin
+    return t
+
+
+def to_float(t: torch.Tensor) -> torch.Tensor:
+    """fp32 values of an engine activation (channels-last, either storage format) -- for tests and debugging."""
+    h = is_h(t)
+    t = t.detach()
+    return t.view(torch.float16).float() if h else t.float()
+
+
+def convert16_raw(x: torch.Tensor, x_h: bool, out_h: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Copy of a channels-last 16-bit tensor in the other storage format (pitched channel slices allowed)."""
+    x = as_cl(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    xt, ot = rt(x, x_h), rt(out, out_h)
+    check(lib().rehr_convert16(C.byref(xt), C.byref(ot), stream_ptr()), "convert16")
+    _count()
+    return out
+
+
+def bf_twin(t: torch.Tensor) -> torch.Tensor:
+    """The bf16 operand of `t` for a weight-gradient GEMM: `t` itself unless its payload is fp16, then its twin (converted on
+    the spot if the producer did not write one, e.g. a frozen producer feeding a trainable consumer)."""
+    if not is_h(t):
+        return as_cl(t)
+    tw = getattr(t, "_rehr_bf", None)
+    if tw is None:
+        tw = convert16_raw(t, True, False)
+        t._rehr_bf = tw
+    return tw
+
+
+# --------------------------------------------------------------------------------------------------
 # packed-weight cache
 # --------------------------------------------------------------------------------------------------
 _wcache: dict = {}
@@ -97,10 +158,12 @@ USE_MARCH = True  # route eligible k3/s1/p1 layers through the halo-resident mar
 S2_WGRAD_MARCH_MIN_VOXELS = 262144  # dy voxels from which the per-parity-class marching wgrad of a stride-2 conv wins
 
 
-def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor:
-    """bf16 K-major operand of `weight` ([A][B][T...] fp32) -- kind 'fwd': [A][T][B], 'dgrad': [B][T][A].
+def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False) -> torch.Tensor:
+    """16-bit K-major operand of `weight` ([A][B][T...] fp32) -- kind 'fwd': [A][T][B], 'dgrad': [B][T][A]; `h`: packed as fp16
+    (must match the activation tensor the GEMM contracts it with), else bf16.
     Cached per parameter object and version counter (an optimiser step bumps the version -> repack)."""
-    key = (id(weight), kind)
+    key = (id(weight), kind, h)
+    dt = L.F16 if h else L.BF16
     ver = weight._version
     if cache:
         hit = _wcache.get(key)
@@ -116,20 +179,20 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True) -> torch.Tensor
     if kind == "march_fwd":      # conv A<-B, marching-kernel layout
         ks = int(weight.shape[2])
         out = torch.empty((lib().rehr_conv3d_march_weight_bytes(B, A, ks) // 2,), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), A, B, ks, B * T, T, 0, stream_ptr()), "pack_weight_march")
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), A, B, ks, B * T, T, 0, dt, stream_ptr()), "pack_weight_march")
     elif kind == "march_dgrad":  # its input-gradient B<-A (transposed, taps flipped)
         ks = int(weight.shape[2])
         out = torch.empty((lib().rehr_conv3d_march_weight_bytes(A, B, ks) // 2,), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, ks, T, B * T, 1, stream_ptr()), "pack_weight_march")
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, ks, T, B * T, 1, dt, stream_ptr()), "pack_weight_march")
     elif kind == "tconv_fused":  # ConvTranspose weight [Cin=A][Cout=B][T] -> [T][Cout][Cin]
         out = torch.empty((T, B, A), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight(ptr(w), ptr(out), T, A, B, 1, B * T, T, stream_ptr()), "pack_weight")
+        check(lib().rehr_pack_weight(ptr(w), ptr(out), T, A, B, 1, B * T, T, dt, stream_ptr()), "pack_weight")
     elif kind == "fwd":
         out = torch.empty((A, T, B), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight(ptr(w), ptr(out), A, B, T, B * T, T, 1, stream_ptr()), "pack_weight")
+        check(lib().rehr_pack_weight(ptr(w), ptr(out), A, B, T, B * T, T, 1, dt, stream_ptr()), "pack_weight")
     else:
         out = torch.empty((B, T, A), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight(ptr(w), ptr(out), B, A, T, T, B * T, 1, stream_ptr()), "pack_weight")
+        check(lib().rehr_pack_weight(ptr(w), ptr(out), B, A, T, T, B * T, 1, dt, stream_ptr()), "pack_weight")
     _count()
     if cache:
         _cache_put(key, weight, out)
@@ -244,27 +307,27 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], kernel: Triple, stride: Triple,
                padding: Triple, act: int = ACT_NONE, slope: float = 0.0, want_stats: bool = False,
-               out_f32: bool = False, out: Optional[torch.Tensor] = None):
-    """y = act(conv3d(x) + bias) on NDHWC bf16 `x`; optionally per-tile InstanceNorm partial sums.
-    Returns (y, stats_partial or None, tiles)."""
+               out_f32: bool = False, out: Optional[torch.Tensor] = None, x_h: bool = False, y_h: bool = False):
+    """y = act(conv3d(x) + bias) on NDHWC 16-bit `x`; optionally per-tile InstanceNorm partial sums.  `x_h` / `y_h`: the payload
+    of x / y is fp16 (the weights are packed in x's format).  Returns (y, stats_partial or None, tiles)."""
     x = as_cl(x)
     n, d, h, w, cin = x.shape
     cout = weight.shape[0]
     od, oh, ow = (_out_size(i, k, s, p) for i, k, s, p in zip((d, h, w), kernel, stride, padding))
     if out is None:
         out = torch.empty((n, od, oh, ow, cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
-    yt = rt(out)
+    yt = rt(out, y_h)
     desc = conv_desc(kernel, stride, padding)
     stats = None
     tiles = 0
     flops = 2.0 * n * od * oh * ow * cout * cin * kernel[0] * kernel[1] * kernel[2]
     tag = f"fwd {cin}->{cout} in{d}x{h}x{w} k{kernel} s{stride}" if _ktimer is not None else ""
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), cin, cout):
-        xt = rt(x)
+        xt = rt(x, x_h)
         if want_stats:
             tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt), int(kernel[0]))
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
-        wp = _packed(weight, "march_fwd")
+        wp = _packed(weight, "march_fwd", h=x_h)
         with _timed("conv_march_kernel", flops, tag):
             check(lib().rehr_conv3d_march_fwd(C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), int(kernel[0]), int(out_f32), act,
                                               float(slope), ptr(stats), stream_ptr()), "conv3d_march_fwd")
@@ -274,8 +337,8 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
         tiles = lib().rehr_conv3d_stats_tiles(C.byref(yt))
         if tiles > 0:
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=x.device)
-    wp = _packed(weight, "fwd")
-    xt = rt(x)
+    wp = _packed(weight, "fwd", h=x_h)
+    xt = rt(x, x_h)
     need = lib().rehr_conv3d_splitk_workspace(C.byref(desc), C.byref(xt), ptr(wp), C.byref(yt), 0)
     ws = _ws(need, x.device) if need else None
     with _timed("conv_tapped_gemm_kernel", flops, tag):
@@ -283,12 +346,12 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
                                        float(slope), ptr(stats), ptr(ws), need, stream_ptr()), "conv3d_fwd")
     _count(2 if need else 1)
     if want_stats and stats is None:
-        stats, tiles = instnorm_stats_raw(out)
+        stats, tiles = instnorm_stats_raw(out, y_h)
     return out, stats, tiles
 
 
-def instnorm_stats_raw(y: torch.Tensor):
-    yt = rt(y)
+def instnorm_stats_raw(y: torch.Tensor, y_h: bool = False):
+    yt = rt(y, y_h)
     tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
     stats = torch.empty((y.shape[0], tiles, y.shape[4], 2), dtype=torch.float32, device=y.device)
     check(lib().rehr_instnorm_stats(C.byref(yt), ptr(stats), stream_ptr()), "instnorm_stats")
@@ -396,13 +459,13 @@ def channel_sum_raw(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
-def act_bwd_raw(a: torch.Tensor, da: torch.Tensor, act: int, slope: float) -> torch.Tensor:
+def act_bwd_raw(a: torch.Tensor, da: torch.Tensor, act: int, slope: float, a_h: bool = False) -> torch.Tensor:
     """dy = da * act'(.) evaluated from the activation OUTPUT `a` (valid for ReLU and LeakyReLU with slope > 0)."""
     a, da = as_cl(a), as_cl(da)
     if act == ACT_NONE:
         return da
     dy = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
-    at, dat, dyt = rt(a), rt(da), rt(dy)
+    at, dat, dyt = rt(a, a_h), rt(da), rt(dy)
     check(lib().rehr_act_bwd(C.byref(at), C.byref(dat), act, float(slope), C.byref(dyt), stream_ptr()), "act_bwd")
     _count()
     return dy
@@ -413,18 +476,24 @@ def act_bwd_raw(a: torch.Tensor, da: torch.Tensor, act: int, slope: float) -> to
 # constructed at models/seg_model.py:174-191 with the ops chosen at train_all.py:474-493)
 # --------------------------------------------------------------------------------------------------
 class ConvNormAct(torch.autograd.Function):
+    """Returns the activation `a` (format FWD_FP16) and, when a gradient will be needed, its bf16 twin `a2` as a second,
+    non-differentiable output (the weight-gradient operand of the consumer; written by the same normalise pass)."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, kernel, stride, padding, eps, slope, small_cin, cat_room):
         dev = x.device
         cout = weight.shape[0]
         desc = conv_desc(kernel, stride, padding)
+        a_h = FWD_FP16
+        y_h = Y_FP16
+        train = any(ctx.needs_input_grad)
         if small_cin:
             # x is the caller's NCDHW fp32 tensor (train_all.py:524)
             xs = _f32(x)
             n, cin, d, h, w = xs.shape
             od, oh, ow = (_out_size(i, k, s, p) for i, k, s, p in zip((d, h, w), kernel, stride, padding))
             y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=dev)
-            yt = rt(y)
+            yt = rt(y, y_h)
             tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
             stats = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
             # NB the conv bias is NOT added: a per-channel constant is removed exactly by the InstanceNorm that follows
@@ -434,40 +503,50 @@ class ConvNormAct(torch.autograd.Function):
             _count(2)
             x_saved = xs
         else:
-            x_saved = as_cl(x)
-            y, stats, tiles = conv3d_raw(x_saved, weight, None, kernel, stride, padding, want_stats=True)
+            x_h = is_h(x)
+            x_saved = bf_twin(x) if train else None   # bf16 operand of this layer's weight gradient
+            y, stats, tiles = conv3d_raw(x, weight, None, kernel, stride, padding, want_stats=True, x_h=x_h, y_h=y_h)
         n = y.shape[0]
         vox = y.shape[1] * y.shape[2] * y.shape[3]
         mean = torch.empty((n, cout), dtype=torch.float32, device=dev)
         rstd = torch.empty((n, cout), dtype=torch.float32, device=dev)
         check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, cout, vox, float(eps), ptr(mean), ptr(rstd), stream_ptr()),
               "instnorm_finalize")
-        if cat_room:
-            # the activation doubles as the skip half of the decoder's concat buffer [up | skip] (models/seg_model.py:37):
-            # allocate 2C channels and write this layer's output into the upper half, so torch.cat never runs
-            buf = torch.empty((*y.shape[:4], 2 * cout), dtype=torch.bfloat16, device=dev)
-            a = _alias(buf, cout, y.shape, buf.stride())
-        else:
-            a = torch.empty_like(y)
-        yt, at = rt(y), rt(a)
+        want_twin = a_h and train
+
+        def alloc():
+            if cat_room:
+                # the activation doubles as the skip half of the decoder's concat buffer [up | skip] (models/seg_model.py:37):
+                # allocate 2C channels and write this layer's output into the upper half, so torch.cat never runs
+                buf = torch.empty((*y.shape[:4], 2 * cout), dtype=torch.bfloat16, device=dev)
+                return _alias(buf, cout, y.shape, buf.stride())
+            return torch.empty_like(y)
+
+        a = alloc()
+        a2 = alloc() if want_twin else None
+        yt, at = rt(y, y_h), rt(a, a_h)
+        a2t = rt(a2, False) if a2 is not None else None
         g32, b32 = _f32(gamma), _f32(beta)
         check(lib().rehr_instnorm_lrelu_apply(C.byref(yt), ptr(mean), ptr(rstd), ptr(g32), ptr(b32), float(slope), C.byref(at),
-                                              stream_ptr()), "instnorm_lrelu_apply")
+                                              C.byref(a2t) if a2t is not None else None, stream_ptr()), "instnorm_lrelu_apply")
         _count(2)
         ctx.save_for_backward(x_saved, weight, gamma, beta, y, mean, rstd)
-        ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None)
+        ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None, y_h)
         ctx.skip_key = (a.untyped_storage().data_ptr(), a.storage_offset()) if cat_room else None
-        return a
+        if a2 is not None:
+            ctx.mark_non_differentiable(a2)
+            return a, a2
+        return a, None
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, _da2_unused=None):
         x, weight, gamma, beta, y, mean, rstd = ctx.saved_tensors
-        kernel, stride, padding, slope, small_cin, has_bias = ctx.cfg
+        kernel, stride, padding, slope, small_cin, has_bias, y_h = ctx.cfg
         dev = y.device
         da = as_cl(da)
         n, cout = y.shape[0], y.shape[4]
         vox = y.shape[1] * y.shape[2] * y.shape[3]
-        yt, dat = rt(y), rt(da)
+        yt, dat = rt(y, y_h), rt(da)
         da2 = _skip_grads.pop(ctx.skip_key, None) if ctx.skip_key is not None else None
         da2t = rt(da2) if da2 is not None else None
         da2p = C.byref(da2t) if da2t is not None else None
@@ -513,10 +592,14 @@ class ConvNormAct(torch.autograd.Function):
 
 def conv_norm_act(x, weight, bias, gamma, beta, kernel, stride, padding, eps=1e-5, slope=0.01, small_cin=False,
                   cat_room=False):
-    a = ConvNormAct.apply(x, weight, bias, gamma, beta, tuple(kernel), tuple(stride), tuple(padding), float(eps),
-                          float(slope), bool(small_cin), bool(cat_room))
+    a, a2 = ConvNormAct.apply(x, weight, bias, gamma, beta, tuple(kernel), tuple(stride), tuple(padding), float(eps),
+                              float(slope), bool(small_cin), bool(cat_room))
+    if FWD_FP16:
+        mark_h(a, a2)
     if cat_room:
         a._rehr_cat = (2 * weight.shape[0], weight.shape[0])
+        if a2 is not None:
+            a2._rehr_cat = a._rehr_cat
     return a
 
 
@@ -531,7 +614,7 @@ class ConvAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, kernel, stride, padding, act, slope, out_f32, want_pool):
-        x = as_cl(x)
+        x = bf_twin(x)   # layers without InstanceNorm (sr_head, FLAVR) run on bf16 operands
         y, stats, tiles = conv3d_raw(x, weight, bias, kernel, stride, padding, act=act, slope=slope, out_f32=out_f32,
                                      want_stats=want_pool)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
@@ -710,6 +793,9 @@ class ConvTranspose(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, skip, kernel, stride, padding, act, slope):
+        x_h = is_h(x)
+        train = any(ctx.needs_input_grad)
+        x_bf = bf_twin(x) if train else None      # bf16 operand of the weight gradient
         x = as_cl(x)
         n, d, h, w, cin = x.shape
         cout = weight.shape[1]
@@ -717,36 +803,58 @@ class ConvTranspose(torch.autograd.Function):
         desc = conv_desc(kernel, stride, padding)
         ctx.cat = skip is not None
         ctx.skip_key = None
+        full2 = None
+
+        def whole(t):   # the [up | skip] buffer a cat_room activation lives in
+            tot, off = t._rehr_cat
+            return _alias(t, t.storage_offset() - off, (n, od, oh, ow, tot), (od * oh * ow * tot, oh * ow * tot, ow * tot, tot, 1))
+
         if skip is not None:
             tot, off = skip._rehr_cat
             ctx.skip_key = (skip.untyped_storage().data_ptr(), skip.storage_offset())
             if tot != 2 * cout or off != cout or tuple(skip.shape) != (n, od, oh, ow, cout):
                 raise L.RehrError("conv_transpose: skip does not sit in a matching [up | skip] concat buffer")
-            full = _alias(skip, skip.storage_offset() - off, (n, od, oh, ow, tot),
-                          (od * oh * ow * tot, oh * ow * tot, ow * tot, tot, 1))
+            if is_h(skip) != x_h:
+                raise L.RehrError("conv_transpose: input and skip use different 16-bit storage formats")
+            full = whole(skip)
             y = full[..., :cout]
         else:
             full = None
             y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
-        xt, yt = rt(x), rt(y)
+        xt, yt = rt(x, x_h), rt(y, x_h)
         if lib().rehr_convtranspose3d_fused_supported(C.byref(desc), cin, cout):
-            wp = _packed(weight, "tconv_fused")  # [T][Cout][Cin]
+            wp = _packed(weight, "tconv_fused", h=x_h)  # [T][Cout][Cin]
             check(lib().rehr_convtranspose3d_fused_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
                                                        float(slope), stream_ptr()), "convtranspose3d_fused_fwd")
             _count()
         else:
-            wp = _packed(weight, "dgrad")  # [Cout][T][Cin]
+            wp = _packed(weight, "dgrad", h=x_h)  # [Cout][T][Cin]
             check(lib().rehr_convtranspose3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
                                                  float(slope), stream_ptr()), "convtranspose3d_fwd")
             _count(stride[0] * stride[1] * stride[2])
-        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
-        ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
-        return full if skip is not None else y
+        if x_h and train:
+            # bf16 twin of the result for the weight-gradient GEMM of the consumer: the skip half already has one (written by
+            # the skip's normalise pass), the up-sampled half is converted here
+            if skip is not None:
+                tw = getattr(skip, "_rehr_bf", None)
+                if tw is not None and getattr(tw, "_rehr_cat", None) == skip._rehr_cat:
+                    full2 = whole(tw)
+                    convert16_raw(y, True, False, out=full2[..., :cout])
+                else:
+                    full2 = convert16_raw(full, True, False)
+            else:
+                full2 = convert16_raw(y, True, False)
+        ctx.save_for_backward(x_bf, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (kernel, stride, padding, act, slope, bias is not None, x_h)
+        out = full if skip is not None else y
+        if full2 is not None:
+            ctx.mark_non_differentiable(full2)
+        return out, full2
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, _twin_unused=None):
         x, weight, y = ctx.saved_tensors
-        kernel, stride, padding, act, slope, has_bias = ctx.cfg
+        kernel, stride, padding, act, slope, has_bias, y_h = ctx.cfg
         dskip = None
         if ctx.cat:  # da is the gradient of the whole [up | skip] buffer
             cout = weight.shape[1]
@@ -756,7 +864,7 @@ class ConvTranspose(torch.autograd.Function):
             if ctx.skip_key is not None and ctx.needs_input_grad[3]:
                 _skip_grads[ctx.skip_key] = dskip   # picked up by the skip producer's backward as its second gradient operand
                 dskip = None
-        dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
+        dy = act_bwd_raw(y, da, act, slope, a_h=y_h) if act != ACT_NONE else as_cl(da)
         desc = conv_desc(kernel, stride, padding)
         dyt, xt = rt(dy), rt(x)
         need = lib().rehr_convtranspose3d_wgrad_workspace(C.byref(desc), C.byref(xt), C.byref(dyt))
@@ -798,7 +906,10 @@ def conv_transpose(x, weight, bias, kernel, stride, padding=(0, 0, 0), act=ACT_N
     """ConvTranspose3d; with `skip` (an activation produced with cat_room) returns the [up | skip] concat buffer."""
     if skip is not None and concat_room_of(skip) is None:
         raise L.RehrError("conv_transpose(skip=...): the skip tensor was not produced with cat_room=True")
-    return ConvTranspose.apply(x, weight, bias, skip, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
+    out, twin = ConvTranspose.apply(x, weight, bias, skip, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
+    if is_h(x):
+        mark_h(out, twin)
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -807,12 +918,14 @@ def conv_transpose(x, weight, bias, kernel, stride, padding=(0, 0, 0), act=ACT_N
 class SegHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
+        x_h = is_h(x)
         x = as_cl(x)
         n, d, h, w, cin = x.shape
         cout = weight.shape[0]
         y = torch.empty((n, cout, d, h, w), dtype=torch.float32, device=x.device)
         w2 = _f32(weight).reshape(cout, cin)
-        xt = rt(x)
+        xt = rt(x, x_h)
+        ctx.x_h = x_h
         check(lib().rehr_pointwise_fwd(C.byref(xt), ptr(w2), ptr(_f32(bias)), ptr(y), cout, stream_ptr()), "pointwise_fwd")
         _count()
         ctx.save_for_backward(x, weight)
@@ -824,7 +937,7 @@ class SegHead(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         cout, cin = weight.shape[0], weight.shape[1]
         dy = _f32(dy)
-        xt = rt(x)
+        xt = rt(x, ctx.x_h)
         dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         dxt = rt(dx)
         dw = torch.empty((cout, cin), dtype=torch.float32, device=x.device)
@@ -847,10 +960,11 @@ def seg_head(x, weight, bias):
 class UpsampleD(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, out_d):
+        x_h = is_h(x)
         x = as_cl(x)
         n, d, h, w, c = x.shape
-        y = torch.empty((n, out_d, h, w, c), dtype=torch.bfloat16, device=x.device)
-        xt, yt = rt(x), rt(y)
+        y = torch.empty((n, out_d, h, w, c), dtype=torch.bfloat16, device=x.device)   # bf16: the sr_head has no InstanceNorm
+        xt, yt = rt(x, x_h), rt(y)
         check(lib().rehr_upsample_linear_d(C.byref(xt), C.byref(yt), stream_ptr()), "upsample_linear_d")
         _count()
         ctx.in_shape = tuple(x.shape)
@@ -896,10 +1010,11 @@ class FromChannelsLast(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
+        x_h = is_h(x)
         x = as_cl(x)
         n, d, h, w, c = x.shape
         y = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
-        xt = rt(x)
+        xt = rt(x, x_h)
         check(lib().rehr_ndhwc_bf16_to_ncdhw_f32(C.byref(xt), ptr(y), stream_ptr()), "ndhwc_to_ncdhw")
         _count()
         return y

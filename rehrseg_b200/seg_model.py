@@ -118,7 +118,15 @@ def run_transpconv(tc: nn.ConvTranspose3d, x: torch.Tensor, skip: torch.Tensor =
     room = F_.concat_room_of(skip)
     if room is not None and room == (2 * tc.out_channels, tc.out_channels):
         return F_.conv_transpose(x, tc.weight, tc.bias, k, s, p, skip=skip)
-    return torch.cat((F_.conv_transpose(x, tc.weight, tc.bias, k, s, p), skip), dim=4)
+    # no concat room (a caller-built skip): plain copy; fp16 payloads concatenate bit-wise, their bf16 twins likewise
+    up = F_.conv_transpose(x, tc.weight, tc.bias, k, s, p)
+    if F_.is_h(up) != F_.is_h(skip):
+        raise RehrError("run_transpconv: up-sampled tensor and skip use different 16-bit storage formats")
+    cat = torch.cat((up, skip), dim=4)
+    if F_.is_h(up):
+        tu, ts = getattr(up, "_rehr_bf", None), getattr(skip, "_rehr_bf", None)
+        F_.mark_h(cat, torch.cat((tu, ts), dim=4) if tu is not None and ts is not None else None)
+    return cat
 
 
 def decoder_forward(decoder: nn.Module, skips: Sequence[torch.Tensor]):

@@ -258,7 +258,7 @@ def test_conv_norm_act_block(shape, stride, engine):
     wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     gap, bep = ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
     a = Fn.conv_norm_act(xcl, wp, bp, gap, bep, (3, 3, 3), stride, (1, 1, 1), eps=1e-5, slope=0.01)
-    assert rel_l2(a.float().permute(0, 4, 1, 2, 3), ref) < TOL
+    assert rel_l2(Fn.to_float(a).permute(0, 4, 1, 2, 3), ref) < TOL
     gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
     dx, dw, dbias, dg, dbeta = torch.autograd.grad(a, (xcl, wp, bp, gap, bep), gcl)
     torch.cuda.synchronize()
@@ -289,7 +289,7 @@ def test_smallcin_stem_block():
     rdw, rdg, rdb = torch.autograd.grad(ref, (wr, gar, ber), bf16r(go))
     wp, bp, gap, bep = (t.clone().requires_grad_(True) for t in (w, b, ga, be))
     a = Fn.conv_norm_act(x, wp, bp, gap, bep, (3, 3, 3), (1, 1, 1), (1, 1, 1), small_cin=True)
-    assert rel_l2(a.float().permute(0, 4, 1, 2, 3), ref) < TOL
+    assert rel_l2(Fn.to_float(a).permute(0, 4, 1, 2, 3), ref) < TOL
     gcl = go.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
     dw, dg, dbeta = torch.autograd.grad(a, (wp, gap, bep), gcl)
     torch.cuda.synchronize()

@@ -1,53 +1,121 @@
-"""Whole-network parity: B200 engine (bf16, through the C-ABI) vs the oracle SegModel on CPU (fp32), same weights
-and inputs.  Bounds from north_star: relative L2 <= 1e-2 on logits (bf16), argmax agreement >= 99.9 % of voxels.
+"""Whole-network parity: B200 engine (through the C-ABI) vs the oracle SegModel on CPU (fp32), same weights and inputs.
 
-Argmax: with RANDOM-INIT weights (the protocol north_star prescribes) the two class logits are tied to within the bf16
-noise floor on ~0.3 % of voxels, so raw agreement is ~99.7 % for ANY bf16 implementation -- torch's own autocast/cuDNN
-path scores 99.60-99.65 % on these inputs (tests/diag_bf16_noise.py, profiles/r01_bf16_noise.log).  The tests therefore
-assert (a) >= 99.9 % on every voxel whose fp32 decision margin is above 4x the RMS logit error, and (b) raw agreement
-no worse than the reference's own bf16 GPU path on the same inputs.  Gradients: bf16 back-propagation through 22
-InstanceNorm layers is noisy for both (12-16 % here vs 14-18 % for autocast); bounded against autocast the same way."""
+Bounds are north_star's 16-bit ones, asserted as written: relative L2 <= 1e-2 on the logits AND on the HR logits, RAW argmax
+agreement >= 99.9 % of voxels -- on the random-init weights the protocol prescribes, for every synthetic plan, and at the
+benchmarked C1 shape (2 x 1 x 128^3).  They hold with room to spare since the forward pass keeps its activations in fp16
+(~1.2e-3 / 4.4e-3 / 99.96 % measured, tools/parity_report.py); the all-bf16 operand mode (REHR_FWD_DTYPE=bf16) is held to the
+logit bound only (6.9e-3 .. 8.4e-3: its argmax agreement on random-init weights is 99.7-99.8 %).
+
+Gradients (bf16 back-propagation vs fp32): a global bound, a bound on EVERY parameter, no parameter may lack a gradient the
+reference has, and the ill-conditioned transposed-conv bias gradients (a nearly cancelling sum, see oracle/parity.py) are held
+to a few units of the rounding noise of a bf16 sum."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
+LOGITS, ARGMAX = 1e-2, 0.999          # north_star
+GRAD_GLOBAL, GRAD_PARAM, TBIAS_NOISE = 0.10, 0.25, 8.0
+
+
+def _check(res, backward=True):
+    print({k: v for k, v in res.items() if k != "per_param_grad_rel_l2"})
+    assert res["rel_l2_logits"] <= LOGITS
+    assert res["rel_l2_hr_logits"] <= LOGITS
+    assert res["argmax_agreement"] >= ARGMAX
+    if backward:
+        assert res["missing_grads"] == []
+        assert res["rel_l2_grads_global"] <= GRAD_GLOBAL
+        bad = {k: v for k, v in res["per_param_grad_rel_l2"].items() if v > GRAD_PARAM}
+        assert not bad, bad
+        assert res["tconv_bias_err_over_bf16_sum_noise"] <= TBIAS_NOISE
+
 
 def test_segmodel_tiny_fwd_bwd():
     from oracle import parity
-    res = parity.segmodel_parity(patch=(16, 32, 32), batch=2, plan="tiny", backward=True, autocast_baseline=True)
-    print(res)
-    assert res["rel_l2_logits"] <= 1e-2
-    assert res["rel_l2_hr_logits"] <= 1e-2
-    assert res["argmax_agreement_clear_margin"] >= 0.999
-    assert res["argmax_agreement"] >= res["autocast_argmax_agreement"] - 5e-4
-    assert res["rel_l2_logits"] <= res["autocast_rel_l2_logits"]
-    assert res["rel_l2_grads_global"] <= 0.15
+    _check(parity.segmodel_parity(patch=(16, 32, 32), batch=2, plan="tiny", backward=True))
 
 
 def test_segmodel_3d_fullres_fwd_bwd_64():
     from oracle import parity
-    res = parity.segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", backward=True, autocast_baseline=True)
-    print(res)
-    assert res["rel_l2_logits"] <= 1e-2
-    assert res["rel_l2_hr_logits"] <= 1.25e-2  # HR head: two more bf16 conv layers on top of the U-Net features
-    assert res["argmax_agreement_clear_margin"] >= 0.999
-    assert res["argmax_agreement"] >= res["autocast_argmax_agreement"] - 5e-4
-    assert res["rel_l2_logits"] <= res["autocast_rel_l2_logits"]
-    assert res["rel_l2_grads_global"] <= 0.18
+    _check(parity.segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", backward=True))
 
 
-def test_segmodel_anisotropic_fwd():
+def test_segmodel_anisotropic_fwd_bwd():
     from oracle import parity
-    res = parity.segmodel_parity(patch=(8, 64, 64), batch=1, plan="anisotropic", backward=False, autocast_baseline=True)
-    print(res)
-    # 1.07e-2 here vs 1.41e-2 for torch autocast on the same inputs: the 1e-2 bf16 bound of north_star is the noise
-    # floor of two bf16 roundings per layer over 22 layers, so it is asserted on the C1 plan (3d_fullres, above) and this
-    # plan is held to "no worse than the reference's own bf16 GPU path" plus a 1.25e-2 cap.
-    assert res["rel_l2_logits"] <= 1.25e-2
-    assert res["rel_l2_logits"] <= res["autocast_rel_l2_logits"]
-    assert res["argmax_agreement_clear_margin"] >= 0.999
-    assert res["argmax_agreement"] >= res["autocast_argmax_agreement"] - 5e-4
+    _check(parity.segmodel_parity(patch=(8, 64, 64), batch=1, plan="anisotropic", backward=True))
+
+
+def test_segmodel_ragged_patch_fwd_bwd():
+    """Patch extents that are not multiples of the 16 x 8 marching tile / the 2^5 total stride of the plan."""
+    from oracle import parity
+    _check(parity.segmodel_parity(patch=(32, 96, 160), batch=1, plan="3d_fullres", backward=True, seed=5))
+
+
+def test_segmodel_bf16_operand_mode_meets_the_logit_bound(monkeypatch):
+    """REHR_FWD_DTYPE=bf16: bf16 MMA operands in the forward pass too (the pre-normalisation conv output stays fp16)."""
+    from oracle import parity
+    from rehrseg_b200 import functional as Fn
+    monkeypatch.setattr(Fn, "FWD_FP16", False)
+    Fn.clear_weight_cache()
+    res = parity.segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", backward=True)
+    print({k: v for k, v in res.items() if k != "per_param_grad_rel_l2"})
+    assert res["rel_l2_logits"] <= LOGITS
+    assert res["rel_l2_hr_logits"] <= LOGITS
+    assert res["argmax_agreement_clear_margin"] >= ARGMAX
+    assert res["missing_grads"] == [] and res["rel_l2_grads_global"] <= 0.18
+    Fn.clear_weight_cache()
+
+
+def test_c1_benchmarked_shape_graph_replayed_step_vs_oracle():
+    """BASELINE config 1 exactly as bench.py runs it: PlainConvUNet 3d_fullres, 2 x 1 x 128^3, loss = <logits, g> / numel, the
+    step replayed from ONE CUDA graph (graphs.GraphedTrainStep) -- logits, loss and every parameter gradient vs the fp32 oracle."""
+    import os
+    from oracle import seg_model as ref_seg
+    from oracle.parity import rel_l2
+    from rehrseg_b200 import seg_model as sm
+    from rehrseg_b200.graphs import GraphedTrainStep
+    torch.set_num_threads(os.cpu_count() or 8)
+    ref = ref_seg.build("3d_fullres")
+    mine = sm.plainconv_unet_3d_fullres()
+    mine.load_state_dict({k: v for k, v in ref.state_dict().items() if not k.startswith("sr_head")}, strict=True)
+    mine = mine.cuda()
+    x = torch.randn((2, 1, 128, 128, 128), generator=torch.Generator().manual_seed(0))
+    g = torch.randn((2, 2, 128, 128, 128), generator=torch.Generator().manual_seed(1))
+
+    def loss_fn(out, tgt):
+        return (out.float() * tgt).sum() / out.numel()
+
+    skips = ref.encoder(x)
+    out_r, _ = ref.decoder(skips)
+    loss_r = loss_fn(out_r, g)
+    loss_r.backward()
+    with torch.no_grad():
+        out_m = mine(x.cuda())
+    assert rel_l2(out_m, out_r) <= LOGITS
+    assert float((out_m.argmax(1).cpu() == out_r.argmax(1)).double().mean()) >= ARGMAX
+    step = GraphedTrainStep(mine, loss_fn, (x.cuda(), g.cuda()))
+    loss_m = float(step(x.cuda(), g.cuda()))
+    torch.cuda.synchronize()
+    assert abs(loss_m - float(loss_r)) <= 2e-2 * abs(float(loss_r)) + 1e-7
+    pr = dict(ref.named_parameters())
+    num = den = 0.0
+    bad = {}
+    for name, p in mine.named_parameters():
+        if name.endswith("conv.bias") and ".convs." in name:
+            continue      # exact zero under InstanceNorm
+        if name.startswith("decoder.transpconvs.") and name.endswith(".bias"):
+            continue      # ill-conditioned cancelling sum, bounded in the 64^3 tests against its bf16 noise yardstick
+        assert p.grad is not None, name
+        a, b = p.grad.double().cpu(), pr[name].grad.double()
+        num += float((a - b).pow(2).sum())
+        den += float(b.pow(2).sum())
+        r = float((a - b).norm() / (b.norm() + 1e-30))
+        if r > GRAD_PARAM:
+            bad[name] = r
+    print("C1 step: logits", rel_l2(out_m, out_r), "loss", loss_m, float(loss_r), "grads global", (num / den) ** 0.5)
+    assert (num / den) ** 0.5 <= GRAD_GLOBAL
+    assert not bad, bad
 
 
 def test_convert_reference_shaped_model_shares_parameters():
