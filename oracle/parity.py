@@ -76,7 +76,7 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
         pr = dict(ref.named_parameters())
         missing = []
         per_param = {}
-        tbias_ratio = 0.0
+        tbias = []
         for name, p in mine.named_parameters():
             if pr[name].grad is None:
                 continue
@@ -89,11 +89,11 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
             if name.startswith("decoder.transpconvs.") and name.endswith(".bias"):
                 # The up-sampled tensor feeds conv -> InstanceNorm, which removes a per-channel constant up to the zero-padding
                 # border effect, so this gradient is the (nearly cancelling) sum of V gradients: ill-conditioned.  It is judged
-                # against the rounding noise a sum of V bf16-rounded summands carries, sqrt(V) * rms_c * 2^-9, not against its
-                # own tiny norm (a dropped or truncated sum would miss by ~2^9 / sqrt(2) such units).
+                # against what V summands carrying the step's measured element-wise gradient error e (the global relative
+                # error below) add up to when their errors are independent, e * sqrt(sum_v g_c[v]^2), not against its own
+                # tiny norm; a dropped or truncated sum would miss by ~1 / (e * sqrt(2)) such units.
                 gup = up_outs[int(name.split(".")[2])].grad.detach().double()
-                noise = gup.pow(2).sum((0, 2, 3, 4)).sqrt() * 2.0 ** -9
-                tbias_ratio = max(tbias_ratio, float(((a - b).abs() / (noise + 1e-300)).max()))
+                tbias.append(((a - b).abs(), gup.pow(2).sum((0, 2, 3, 4)).sqrt()))
                 continue
             per_param[name] = float((a - b).norm() / (b.norm() + 1e-30))
             num += float((a - b).pow(2).sum())
@@ -105,6 +105,8 @@ def segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", device="cuda
         res["rel_l2_grads_worst"] = worst
         res["worst_grad"] = worst_name
         res["missing_grads"] = missing
-        res["tconv_bias_err_over_bf16_sum_noise"] = tbias_ratio
+        e_glob = res["rel_l2_grads_global"]
+        res["tconv_bias_err_over_incoherent_sum"] = max([float((err / (e_glob * scale + 1e-300)).max()) for err, scale in tbias],
+                                                        default=0.0)
         res["per_param_grad_rel_l2"] = per_param
     return res

@@ -172,10 +172,26 @@ def cl_strides_ok(t: torch.Tensor) -> bool:
     return all(t.shape[k] == 1 or t.stride(k) == exp[k] for k in range(5))
 
 
+def check_device(t: torch.Tensor) -> None:
+    """The library launches on the CURRENT device and stream (tensor maps, streams, kernel attributes are per device): a tensor
+    that lives on another GPU must not reach it.  Model-level entry points switch to their input's device (device_of)."""
+    if t.device.index != torch.cuda.current_device():
+        raise RehrError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: wrap the call in "
+                        "`with torch.cuda.device(tensor.device):` (the module-level forwards of rehrseg_b200 do)")
+
+
+def device_of(t: torch.Tensor):
+    """Context manager making `t`'s GPU the current device for the engine calls inside."""
+    if not t.is_cuda:
+        raise RehrError("rehrseg_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    return torch.cuda.device(t.device)
+
+
 def as_cl(t: torch.Tensor) -> torch.Tensor:
     """Return a channels-last ([N,D,H,W,C], pitch-strided) bf16 CUDA view/copy of `t` that the ABI accepts."""
     if not t.is_cuda:
         raise RehrError("rehrseg_b200 ops need CUDA tensors (no CPU fallback)")
+    check_device(t)
     if t.dtype != torch.bfloat16:
         t = t.to(torch.bfloat16)
     if not cl_strides_ok(t) or (t.data_ptr() % 16) != 0 or (_pitch(t) % 8) != 0:

@@ -46,16 +46,21 @@ static EncodeTiledFn get_encode() {
   return g_encode;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-    n = p.multiProcessorCount;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 static CUtensorMapSwizzle swizzle_for_chunk(int chunk) {
@@ -822,15 +827,7 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
   p.stages = stages;
   const size_t smem = 1024 + stages * stage_bytes + fwd_smem_tail_bytes();
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tapped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      g_last_cuda_error = (int)e;
-      return REHR_CUDA_ERROR;
-    }
-    attr_set = true;
-  }
+  REHR_SET_MAX_SMEM_ONCE(conv_tapped_gemm_kernel, 227 * 1024);
   const int total_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3] * p.n_tiles;
   // split-K when the output tiles cannot fill the machine and there is a long K loop to share
   const int kblocks = p.num_taps * p.cin_chunks;
@@ -1319,15 +1316,7 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
   if (ws_bytes < wp.ws_bytes || ws == nullptr) return REHR_WORKSPACE;
   wp.p.ws = reinterpret_cast<float*>(ws);
   wp.p.err = nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      g_last_cuda_error = (int)e;
-      return REHR_CUDA_ERROR;
-    }
-    attr_set = true;
-  }
+  REHR_SET_MAX_SMEM_ONCE(conv_wgrad_kernel, 227 * 1024);
   conv_wgrad_kernel<<<wp.grid, kWgradThreads, wp.smem, stream>>>(wp.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1412,12 +1401,7 @@ int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long lo
   if (st == 1 && T <= 343 && R <= 65535) {
     dim3 grid((C + kPackC - 1) / kPackC, R);
     const size_t smem = (size_t)kPackC * (T + 1) * sizeof(float);
-    static bool attr = false;
-    if (smem > 48 * 1024 && !attr) {
-      if (cudaFuncSetAttribute(pack_weight_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
-        return REHR_CUDA_ERROR;
-      attr = true;
-    }
+    if (smem > 48 * 1024) REHR_SET_MAX_SMEM_ONCE(pack_weight_runs_kernel, 96 * 1024);
     pack_weight_runs_kernel<<<grid, 256, smem, stream>>>(src, reinterpret_cast<unsigned short*>(dst), R, C, T, sr, sc, f16);
   } else {
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);

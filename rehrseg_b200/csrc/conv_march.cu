@@ -639,12 +639,7 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
 
 template <int BKT, int CHUNKS, int CT, int KS>
 static int launch_variant(const MarchPlan& pl, cudaStream_t stream) {
-  static cudaError_t attr_err = cudaFuncSetAttribute(conv_march_kernel<BKT, CHUNKS, CT, KS>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (attr_err != cudaSuccess) {
-    g_last_cuda_error = (int)attr_err;
-    return REHR_CUDA_ERROR;
-  }
+  REHR_SET_MAX_SMEM_ONCE((conv_march_kernel<BKT, CHUNKS, CT, KS>), 227 * 1024);
   conv_march_kernel<BKT, CHUNKS, CT, KS><<<pl.grid, kMarchThreads, pl.smem, stream>>>(pl.p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;

@@ -1346,16 +1346,7 @@ int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z,
   if (!x || !taps || !y || L <= 0) return REHR_BAD_SHAPE;
   if (L > kBlurMaxTaps) return REHR_UNSUPPORTED;
   const size_t smem = (size_t)(kBlurRows + L - 1) * 128 * sizeof(float);
-  static bool attr = false;
-  if (smem > 48 * 1024 && !attr) {
-    cudaError_t e = cudaFuncSetAttribute(blur1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((kBlurRows + kBlurMaxTaps) * 128 * sizeof(float)));
-    if (e != cudaSuccess) {
-      g_last_cuda_error = (int)e;
-      return REHR_CUDA_ERROR;
-    }
-    attr = true;
-  }
+  if (smem > 48 * 1024) REHR_SET_MAX_SMEM_ONCE(blur1d_kernel, (kBlurRows + kBlurMaxTaps) * 128 * sizeof(float));
   const long long tiles = Z * (long long)((X + kBlurRows - 1) / kBlurRows) * ((Y + 127) / 128);
   const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 6));
   blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);

@@ -44,6 +44,24 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
 int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long long sr, long long sc, long long st,
                        cudaStream_t stream, int f16 = 0);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process that drives several GPUs must apply it on
+// each of them, so the "already done" flag lives per device (index = cudaGetDevice()).
+static constexpr int kMaxDevices = 64;
+int current_device();
+#define REHR_SET_MAX_SMEM_ONCE(kernel, bytes)                                                                        \
+  do {                                                                                                               \
+    static bool done__[::rehr::kMaxDevices] = {};                                                                   \
+    const int dev__ = ::rehr::current_device();                                                                      \
+    if (!done__[dev__]) {                                                                                            \
+      cudaError_t ea__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));    \
+      if (ea__ != cudaSuccess) {                                                                                     \
+        ::rehr::g_last_cuda_error = (int)ea__;                                                                       \
+        return REHR_CUDA_ERROR;                                                                                      \
+      }                                                                                                              \
+      done__[dev__] = true;                                                                                          \
+    }                                                                                                                \
+  } while (0)
+
 #define REHR_CHECK_LAUNCH()                                   \
   do {                                                        \
     cudaError_t e__ = cudaGetLastError();                     \

@@ -332,7 +332,8 @@ static size_t stem_smem_bytes(int wd, bool wgrad) {
 }
 
 template <typename K>
-static int stem_set_smem(K kernel, size_t smem, size_t* cached) {
+static int stem_set_smem(K kernel, size_t smem, size_t* cached_per_device) {
+  size_t* cached = cached_per_device + current_device();
   if (smem > 48 * 1024 && smem > *cached) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -357,8 +358,8 @@ int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_
   a.x = x; a.w = w; a.bias = bias; a.y = y; a.ldy = ldy; a.ws = nullptr;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = act; a.slope = slope;
   const size_t smem = stem_smem_bytes(wd, false);
-  static size_t cached = 0;
-  int rc = stem_set_smem(stem_fwd_mma_kernel, smem, &cached);
+  static size_t cached[kMaxDevices] = {};
+  int rc = stem_set_smem(stem_fwd_mma_kernel, smem, cached);
   if (rc != REHR_OK) return rc;
   const long long tiles = (long long)n * d * ((h + 7) / 8);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 4));
@@ -375,8 +376,8 @@ int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long ldd
   a.x = x; a.w = nullptr; a.bias = nullptr; a.y = const_cast<__nv_bfloat16*>(dy); a.ldy = lddy; a.ws = ws;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = 0; a.slope = 0.f;
   const size_t smem = stem_smem_bytes(wd, true);
-  static size_t cached = 0;
-  int rc = stem_set_smem(stem_wgrad_mma_kernel, smem, &cached);
+  static size_t cached[kMaxDevices] = {};
+  int rc = stem_set_smem(stem_wgrad_mma_kernel, smem, cached);
   if (rc != REHR_OK) return rc;
   const long long tiles = (long long)n * d * ((h + 7) / 8);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)kStemWgradBlocks));

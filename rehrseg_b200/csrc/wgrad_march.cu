@@ -517,12 +517,7 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, Wg
 
 template <int CH, int PC, int KS>
 static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(wgrad_march_kernel<CH, PC, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (attr_err != cudaSuccess) {
-    g_last_cuda_error = (int)attr_err;
-    return REHR_CUDA_ERROR;
-  }
+  REHR_SET_MAX_SMEM_ONCE((wgrad_march_kernel<CH, PC, KS>), 227 * 1024);
   wgrad_march_kernel<CH, PC, KS><<<pl.grid, kWgmThreads, pl.smem, stream>>>(pl.p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;

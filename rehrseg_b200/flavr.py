@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, RehrError
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, RehrError, device_of
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -256,6 +256,12 @@ def flavr_forward(model: nn.Module, images: torch.Tensor, return_inetermediate_u
     """UNet_3D_3D.forward (FLAVR_arch.py:169-248)."""
     if not images.is_cuda:
         raise RehrError("rehrseg_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    with device_of(images):    # the library launches on the current device: follow the input's GPU
+        return _flavr_forward(model, images, return_inetermediate_uncertainty, return_inetermediate_feature)
+
+
+def _flavr_forward(model: nn.Module, images: torch.Tensor, return_inetermediate_uncertainty=False,
+                   return_inetermediate_feature=False):
     # in-place on the caller's tensor, exactly like the reference (callers clone first: train_all.py:98, sr_utils.py:125)
     mean_ = images[:, 0:1, ...].mean(2, keepdim=True).mean(3, keepdim=True).mean(4, keepdim=True)
     images[:, 0:1, ...] = images[:, 0:1, ...] - mean_

@@ -487,6 +487,7 @@ class ConvNormAct(torch.autograd.Function):
         a_h = FWD_FP16
         y_h = Y_FP16
         train = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)   # the bf16 twin is a non-differentiable output: no zero-filled gradient tensor for it
         if small_cin:
             # x is the caller's NCDHW fp32 tensor (train_all.py:524)
             xs = _f32(x)
@@ -540,6 +541,8 @@ class ConvNormAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _da2_unused=None):
+        if da is None:
+            return (None,) * 12
         x, weight, gamma, beta, y, mean, rstd = ctx.saved_tensors
         kernel, stride, padding, slope, small_cin, has_bias, y_h = ctx.cfg
         dev = y.device
@@ -795,6 +798,7 @@ class ConvTranspose(torch.autograd.Function):
     def forward(ctx, x, weight, bias, skip, kernel, stride, padding, act, slope):
         x_h = is_h(x)
         train = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)          # no zero-filled gradient for the non-differentiable twin output
         x_bf = bf_twin(x) if train else None      # bf16 operand of the weight gradient
         x = as_cl(x)
         n, d, h, w, cin = x.shape
@@ -853,6 +857,8 @@ class ConvTranspose(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _twin_unused=None):
+        if da is None:
+            return (None,) * 9
         x, weight, y = ctx.saved_tensors
         kernel, stride, padding, act, slope, has_bias, y_h = ctx.cfg
         dskip = None

@@ -21,7 +21,7 @@ class GraphedForward:
     def __init__(self, module, example: torch.Tensor, warmup: int = 2):
         if not example.is_cuda:
             raise ValueError("GraphedForward needs a CUDA example input")
-        self.module = module
+        from . import functional as Fn
         self.static_in = example.detach().clone()
         side = torch.cuda.Stream(device=example.device)
         side.wait_stream(torch.cuda.current_stream(example.device))
@@ -33,6 +33,10 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out = module(self.static_in)
+        # The captured kernels bake in the addresses of the packed 16-bit weight copies made during the warm-up.  Their only
+        # other owner is functional's weight cache, which anyone may clear (GraphedTrainStep, bench.py): hold them here so a
+        # replay can never read freed memory.  (The module itself is NOT kept: graphed() keys its cache on it weakly.)
+        self._packed_weights = [v[2] for v in Fn._wcache.values()]
 
     def __call__(self, x: torch.Tensor):
         if x.shape != self.static_in.shape:

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, RehrError
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, RehrError, device_of
 
 # ----------------------------------------------------------------------------------------------------------------
 # generic "run this module tree on the engine" helpers (work on the reference's modules and on ours)
@@ -209,9 +209,10 @@ def segmodel_forward(model: nn.Module, x: torch.Tensor, return_inetermediate_fea
     not depend on it, and the sliding-window evaluation only reads output 0 (utils/seg_utils.py:753)."""
     if not x.is_cuda:
         raise RehrError("rehrseg_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-    skips = encoder_forward(model.encoder, x)
-    out, features = decoder_forward(model.decoder, skips)
-    out_up = sr_head_forward(model.sr_head, features, model.upscale) if want_hr else None
+    with device_of(x):
+        skips = encoder_forward(model.encoder, x)
+        out, features = decoder_forward(model.decoder, skips)
+        out_up = sr_head_forward(model.sr_head, features, model.upscale) if want_hr else None
     if return_inetermediate_feature:
         return out, out_up, LazyNCDHW(skips)
     return out, out_up
@@ -378,7 +379,8 @@ class PlainConvUNet(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RehrError("rehrseg_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-        return decoder_forward(self.decoder, encoder_forward(self.encoder, x))
+        with device_of(x):
+            return decoder_forward(self.decoder, encoder_forward(self.encoder, x))
 
 
 class SegModel(nn.Module):

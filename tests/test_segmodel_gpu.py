@@ -8,14 +8,14 @@ logit bound only (6.9e-3 .. 8.4e-3: its argmax agreement on random-init weights 
 
 Gradients (bf16 back-propagation vs fp32): a global bound, a bound on EVERY parameter, no parameter may lack a gradient the
 reference has, and the ill-conditioned transposed-conv bias gradients (a nearly cancelling sum, see oracle/parity.py) are held
-to a few units of the rounding noise of a bf16 sum."""
+to a few units of what the step's element-wise gradient error adds up to over the summed voxels."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
 LOGITS, ARGMAX = 1e-2, 0.999          # north_star
-GRAD_GLOBAL, GRAD_PARAM, TBIAS_NOISE = 0.10, 0.25, 8.0
+GRAD_GLOBAL, GRAD_PARAM, TBIAS_NOISE = 0.10, 0.25, 6.0
 
 
 def _check(res, backward=True):
@@ -28,7 +28,7 @@ def _check(res, backward=True):
         assert res["rel_l2_grads_global"] <= GRAD_GLOBAL
         bad = {k: v for k, v in res["per_param_grad_rel_l2"].items() if v > GRAD_PARAM}
         assert not bad, bad
-        assert res["tconv_bias_err_over_bf16_sum_noise"] <= TBIAS_NOISE
+        assert res["tconv_bias_err_over_incoherent_sum"] <= TBIAS_NOISE
 
 
 def test_segmodel_tiny_fwd_bwd():
@@ -97,7 +97,7 @@ def test_c1_benchmarked_shape_graph_replayed_step_vs_oracle():
     step = GraphedTrainStep(mine, loss_fn, (x.cuda(), g.cuda()))
     loss_m = float(step(x.cuda(), g.cuda()))
     torch.cuda.synchronize()
-    assert abs(loss_m - float(loss_r)) <= 2e-2 * abs(float(loss_r)) + 1e-7
+    assert abs(loss_m - float(loss_r.detach())) <= 2e-2 * abs(float(loss_r.detach())) + 1e-7
     pr = dict(ref.named_parameters())
     num = den = 0.0
     bad = {}
@@ -106,6 +106,8 @@ def test_c1_benchmarked_shape_graph_replayed_step_vs_oracle():
             continue      # exact zero under InstanceNorm
         if name.startswith("decoder.transpconvs.") and name.endswith(".bias"):
             continue      # ill-conditioned cancelling sum, bounded in the 64^3 tests against its bf16 noise yardstick
+        if pr[name].grad is None:
+            continue      # not on the loss path in the reference either (seg layers of the deep-supervision outputs)
         assert p.grad is not None, name
         a, b = p.grad.double().cpu(), pr[name].grad.double()
         num += float((a - b).pow(2).sum())
@@ -113,7 +115,7 @@ def test_c1_benchmarked_shape_graph_replayed_step_vs_oracle():
         r = float((a - b).norm() / (b.norm() + 1e-30))
         if r > GRAD_PARAM:
             bad[name] = r
-    print("C1 step: logits", rel_l2(out_m, out_r), "loss", loss_m, float(loss_r), "grads global", (num / den) ** 0.5)
+    print("C1 step: logits", rel_l2(out_m, out_r), "loss", loss_m, float(loss_r.detach()), "grads global", (num / den) ** 0.5)
     assert (num / den) ** 0.5 <= GRAD_GLOBAL
     assert not bad, bad
 
