@@ -212,8 +212,13 @@ static int launch_in_reduce(const StatArgs& a, int N, cudaStream_t st) {
 // so a 1024-tile list costs ~32 dependent-free loads per thread instead of 1024 serial ones.
 static constexpr int kFinLanes = 32;
 
+// norm (optional): the affine + activation of this InstanceNorm as per-(n, channel) triples for "normalise on load" consumers,
+//   norm[(n*3 + 0) * c_total + c_off + c] = gamma*rstd,  [.. + 1 ..] = beta - mean*gamma*rstd,  [.. + 2 ..] = slope;
+// channels [0, c_off) of the same rows are set to the identity (1, 0, 1): the up-sampled half of a decoder concat buffer.
 __global__ void __launch_bounds__(32 * kFinLanes) in_finalize_kernel(const float* partial, int N, int tiles, int C,
-                                                                      double inv_count, float eps, float* mean, float* rstd) {
+                                                                      double inv_count, float eps, float* mean, float* rstd,
+                                                                      const float* gamma, const float* beta, float slope,
+                                                                      float* norm, int c_total, int c_off, float* norm_own) {
   __shared__ double sh1[kFinLanes][33], sh2[kFinLanes][33];
   const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
   const int n = blockIdx.y, c = blockIdx.x * 32 + cl;
@@ -240,8 +245,61 @@ __global__ void __launch_bounds__(32 * kFinLanes) in_finalize_kernel(const float
     const double m = a * inv_count;
     double var = b * inv_count - m * m;
     if (var < 0.0) var = 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
     mean[n * C + c] = (float)m;
-    rstd[n * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    rstd[n * C + c] = rs;
+    if (norm != nullptr) {
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      float* row = norm + (size_t)n * 3 * c_total + c_off + c;
+      row[0] = ga * rs;
+      row[c_total] = be - (float)m * ga * rs;
+      row[2 * c_total] = slope;
+      if (norm_own != nullptr) {  // the same triples as a dense [n][3][C] table (consumers of this tensor alone)
+        float* own = norm_own + (size_t)n * 3 * C + c;
+        own[0] = row[0];
+        own[C] = row[c_total];
+        own[2 * C] = slope;
+      }
+    }
+  }
+  if (norm != nullptr && blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < c_off; i += blockDim.x) {
+      float* row = norm + (size_t)n * 3 * c_total + i;
+      row[0] = 1.f;
+      row[c_total] = 0.f;
+      row[2 * c_total] = 1.f;
+    }
+  }
+}
+
+// a = lrelu_c(y * scale[n,c] + shift[n,c]) from norm triples (see in_finalize_kernel); optional second copy a2 in another format
+struct NormApplyArgs {
+  const __nv_bfloat16* y;
+  __nv_bfloat16 *out, *out2;
+  long long ld_y, ld_o, ld_o2, V;
+  const float* norm;
+  int C, y_f16, out_f16, out2_f16;
+};
+__global__ void __launch_bounds__(256) norm_apply_kernel(const NormApplyArgs a) {
+  extern __shared__ float sh[];  // [3][C]
+  const int n = blockIdx.y, C = a.C;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh[i] = a.norm[(size_t)n * 3 * C + i];
+  __syncthreads();
+  const int groups = C / 8;
+  const long long items = a.V * groups;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    const long long vox = (long long)n * a.V + it / groups;
+    float y[8], o[8];
+    x16x8_to_float(__ldcs(reinterpret_cast<const uint4*>(a.y + vox * a.ld_y + g * 8)), y, a.y_f16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = g * 8 + i;
+      const float z = fmaf(y[i], sh[c], sh[C + c]);
+      o[i] = z > 0.f ? z : z * sh[2 * C + c];
+    }
+    *reinterpret_cast<uint4*>(a.out + vox * a.ld_o + g * 8) = float_to_x16x8(o, a.out_f16);
+    if (a.out2 != nullptr) *reinterpret_cast<uint4*>(a.out2 + vox * a.ld_o2 + g * 8) = float_to_x16x8(o, a.out2_f16);
   }
 }
 
@@ -1052,7 +1110,37 @@ int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long l
                            float* rstd, rehr_stream stream) {
   if (!partial || !mean || !rstd || count <= 0) return REHR_BAD_SHAPE;
   in_finalize_kernel<<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
-                                                                       rstd);
+                                                                       rstd, nullptr, nullptr, 1.f, nullptr, 0, 0, nullptr);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_instnorm_finalize_norm(const float* partial, int n, int tiles, int c, long long count, float eps, const float* gamma,
+                                const float* beta, float slope, float* mean, float* rstd, float* norm, int c_total, int c_off,
+                                float* norm_own, rehr_stream stream) {
+  if (!partial || !mean || !rstd || !norm || count <= 0 || c_off < 0 || c_off + c > c_total) return REHR_BAD_SHAPE;
+  in_finalize_kernel<<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+                                                                       rstd, gamma, beta, slope, norm, c_total, c_off, norm_own);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_norm_apply(const rehr_tensor* y, const float* norm, const rehr_tensor* a, const rehr_tensor* a2, rehr_stream stream) {
+  if (!bf16_tensor_ok(y) || !bf16_tensor_ok(a) || !norm || y->c != a->c || y->n != a->n || voxels_per_sample(y) != voxels_per_sample(a))
+    return REHR_BAD_SHAPE;
+  if (a2 && (!bf16_tensor_ok(a2) || a2->c != y->c || a2->n != y->n || voxels_per_sample(a2) != voxels_per_sample(y))) return REHR_BAD_SHAPE;
+  NormApplyArgs p{};
+  p.y = reinterpret_cast<const __nv_bfloat16*>(y->ptr);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->ptr);
+  p.out2 = a2 ? reinterpret_cast<__nv_bfloat16*>(a2->ptr) : nullptr;
+  p.ld_y = y->ld; p.ld_o = a->ld; p.ld_o2 = a2 ? a2->ld : 0;
+  p.V = voxels_per_sample(y);
+  p.norm = norm;
+  p.C = y->c;
+  p.y_f16 = y->dtype == REHR_F16; p.out_f16 = a->dtype == REHR_F16; p.out2_f16 = a2 ? a2->dtype == REHR_F16 : 0;
+  const long long items = p.V * (p.C / 8);
+  int gx = std::max(1, grid_for(items, 256, 8) / std::max(1, y->n));
+  norm_apply_kernel<<<dim3(gx, y->n), 256, (size_t)3 * p.C * sizeof(float), (cudaStream_t)stream>>>(p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

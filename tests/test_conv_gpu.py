@@ -390,3 +390,109 @@ def test_wgrad_march_stride2(case):
     finally:
         Fn.S2_WGRAD_MARCH_MIN_VOXELS = old
     assert rel_l2(dw, ref) < 1e-3, (case, rel_l2(dw, ref))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# normalise-on-load: the marching kernels apply lrelu(x*scale + shift) to the landed tile instead of reading a materialised
+# activation.  Both paths round the same fp32 value to the same 16-bit format, so they must agree to the last bit of the
+# operand; the only difference left is the (identical) MMA accumulation -> results are compared at 1e-6.
+# ------------------------------------------------------------------------------------------------------------------
+def _raw_and_norm(n, dhw, c, seed, identity_lo=0):
+    g = torch.Generator().manual_seed(seed)
+    y = (2.0 * torch.randn((n, *dhw, c), generator=g) + 0.3).cuda().to(torch.float16)
+    norm = torch.empty((n, 3, c))
+    norm[:, 0] = 0.5 + torch.rand((n, c), generator=g)
+    norm[:, 1] = 0.3 * torch.randn((n, c), generator=g)
+    norm[:, 2] = 0.01
+    if identity_lo:
+        norm[:, 0, :identity_lo], norm[:, 1, :identity_lo], norm[:, 2, :identity_lo] = 1.0, 0.0, 1.0
+    return y.view(torch.bfloat16), norm.cuda().contiguous()
+
+
+NORM_CASES = [
+    # n, cin, cout, (d,h,w), kernel, padding, identity_lo
+    (2, 32, 32, (6, 16, 8), (3, 3, 3), (1, 1, 1), 0),
+    (1, 64, 32, (5, 20, 12), (3, 3, 3), (1, 1, 1), 32),      # [up | skip] concat table, ragged tiles
+    (2, 64, 64, (12, 32, 16), (3, 3, 3), (1, 1, 1), 0),      # Cout tiled 2 x 32
+    (1, 128, 64, (6, 16, 16), (3, 3, 3), (1, 1, 1), 64),     # 2 channel chunks, tile 16
+    (1, 32, 32, (4, 16, 16), (1, 3, 3), (0, 1, 1), 0),       # planar
+    (1, 32, 16, (9, 7, 5), (3, 3, 3), (1, 1, 1), 0),         # everything ragged
+]
+
+
+@pytest.mark.parametrize("case", NORM_CASES)
+def test_march_forward_normalise_on_load(case):
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, k, p, ident = case
+    y, norm = _raw_and_norm(n, dhw, cin, 31, ident)
+    Fn.mark_h(y)
+    y._rehr_norm = norm
+    a = Fn.plain_h(y)                                          # materialised fp16 activation (rehr_norm_apply)
+    yf = y.view(torch.float16).float()
+    z = yf * norm[:, 0].view(n, 1, 1, 1, cin) + norm[:, 1].view(n, 1, 1, 1, cin)
+    want_a = torch.where(z > 0, z, z * norm[:, 2].view(n, 1, 1, 1, cin))
+    assert rel_l2(a.view(torch.float16).float(), want_a) < 1e-3
+    w = (torch.randn((cout, cin, *k), generator=torch.Generator().manual_seed(32)) / (cin * k[0] * 9) ** 0.5).cuda()
+    assert Fn.norm_onload_fwd_ok(k, (1, 1, 1), p, cin, cout)
+    out1, st1, _ = Fn.conv3d_raw(y, w, None, k, (1, 1, 1), p, want_stats=True, x_h=True, y_h=True, norm=norm, op_h=True)
+    out2, st2, _ = Fn.conv3d_raw(a, w, None, k, (1, 1, 1), p, want_stats=True, x_h=True, y_h=True)
+    torch.cuda.synchronize()
+    assert rel_l2(out1.view(torch.float16).float(), out2.view(torch.float16).float()) < 1e-6
+    assert rel_l2(st1, st2) < 1e-6
+    ref = F.conv3d(want_a.permute(0, 4, 1, 2, 3), w.to(torch.float16).float(), None, padding=p)
+    assert rel_l2(out1.view(torch.float16).float().permute(0, 4, 1, 2, 3), ref) < 2e-3
+
+
+WG_NORM_CASES = [
+    (2, 32, 32, (16, 32, 32), (3, 3, 3), (1, 1, 1), 0),       # role / piece choice: CH 32
+    (1, 64, 32, (24, 44, 36), (3, 3, 3), (1, 1, 1), 32),      # [up | skip] table, ragged tiles, CH 64
+    (2, 64, 64, (12, 32, 32), (3, 3, 3), (1, 1, 1), 0),
+    (1, 128, 64, (16, 32, 32), (3, 3, 3), (1, 1, 1), 64),
+    (2, 32, 32, (8, 48, 40), (1, 3, 3), (0, 1, 1), 0),        # planar
+    (2, 32, 16, (17, 23, 29), (3, 3, 3), (1, 1, 1), 0),       # everything ragged
+]
+
+
+@pytest.mark.parametrize("case", WG_NORM_CASES)
+def test_march_wgrad_normalise_on_load(case):
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout, dhw, k, p, ident = case
+    assert Fn.wgrad_route((n, *dhw, cin), (n, *dhw, cout), k, (1, 1, 1), p) == "march"
+    y, norm = _raw_and_norm(n, dhw, cin, 33, ident)
+    Fn.mark_h(y)
+    y._rehr_norm = norm
+    abf = Fn.bf_twin(y)                                        # materialised bf16 activation
+    dy = torch.randn((n, *dhw, cout), generator=torch.Generator().manual_seed(34)).cuda().to(torch.bfloat16)
+    wshape = (cout, cin, *k)
+    dw1 = Fn.conv3d_wgrad_raw(y, dy, wshape, k, (1, 1, 1), p, norm=norm, x_h=True)
+    dw2 = Fn.conv3d_wgrad_raw(abf, dy, wshape, k, (1, 1, 1), p)
+    torch.cuda.synchronize()
+    assert rel_l2(dw1, dw2) < 1e-6
+    xr = abf.float().permute(0, 4, 1, 2, 3).requires_grad_(False)
+    wz = torch.zeros(wshape, device="cuda", requires_grad=True)
+    ref, = torch.autograd.grad(F.conv3d(xr, wz, None, padding=p), wz, dy.float().permute(0, 4, 1, 2, 3))
+    assert rel_l2(dw1, ref) < 2e-3
+
+
+@pytest.mark.parametrize("dhw", [(32, 64, 64), (31, 66, 61)])
+def test_march_s2_wgrad_normalise_on_load(dhw):
+    """Stride-2 stage entry: the parity-class views of the RAW producer output are normalised on load."""
+    from rehrseg_b200 import functional as Fn
+    n, cin, cout = 2, 32, 64
+    k, s, p = (3, 3, 3), (2, 2, 2), (1, 1, 1)
+    y, norm = _raw_and_norm(n, dhw, cin, 35)
+    Fn.mark_h(y)
+    y._rehr_norm = norm
+    abf = Fn.bf_twin(y)
+    odhw = tuple((v + 2 - 3) // 2 + 1 for v in dhw)
+    dy = torch.randn((n, *odhw, cout), generator=torch.Generator().manual_seed(36)).cuda().to(torch.bfloat16)
+    old = Fn.S2_WGRAD_MARCH_MIN_VOXELS
+    Fn.S2_WGRAD_MARCH_MIN_VOXELS = 0
+    try:
+        assert Fn.wgrad_route((n, *dhw, cin), (n, *odhw, cout), k, s, p) == "march_s2"
+        dw1 = Fn.conv3d_wgrad_raw(y, dy, (cout, cin, *k), k, s, p, norm=norm, x_h=True)
+        dw2 = Fn.conv3d_wgrad_raw(abf, dy, (cout, cin, *k), k, s, p)
+    finally:
+        Fn.S2_WGRAD_MARCH_MIN_VOXELS = old
+    torch.cuda.synchronize()
+    assert rel_l2(dw1, dw2) < 1e-6
