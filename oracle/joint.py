@@ -150,3 +150,51 @@ def ref_joint_step(model_seg, batch, model_sr=None, distiller=None, enable_uncer
     loss.backward()
     out["loss"] = loss.detach()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SR stage: BCEDiceLoss (utils/seg_utils.py:786-886) and the loop body of train_sr (train_all.py:118-139)
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_flatten(t):
+    c = t.size(1)
+    return t.permute((1, 0) + tuple(range(2, t.dim()))).contiguous().view(c, -1)
+
+
+def ref_per_channel_dice(inp, target, epsilon=1e-6):
+    """compute_per_channel_dice, utils/seg_utils.py:835-861 (weight=None)."""
+    assert inp.size() == target.size()
+    inp, target = _ref_flatten(inp), _ref_flatten(target).float()
+    intersect = (inp * target).sum(-1)
+    denominator = (inp * inp).sum(-1) + (target * target).sum(-1)
+    return 2 * (intersect / denominator.clamp(min=epsilon))
+
+
+class RefBCEDiceLoss(nn.Module):
+    def __init__(self, alpha, beta):
+        super().__init__()
+        self.alpha, self.beta = alpha, beta
+        self.bce = nn.BCEWithLogitsLoss()
+
+    def forward(self, inp, target):
+        dice = 1. - torch.mean(ref_per_channel_dice(torch.sigmoid(inp), target))
+        return self.alpha * self.bce(inp, target) + self.beta * dice
+
+
+def ref_sr_step(model, patches_lr, patches_hr, loss_obj, loss_seg, slice_separation, num_slices, enable_uncertainty):
+    """train_all.py:118-139 up to and including loss.backward(); returns the loss."""
+    if num_slices > 1:
+        patches_hr = patches_hr[:, :, int(slice_separation) * (num_slices // 2 - 1):int(slice_separation) * (num_slices // 2), ...]
+    if enable_uncertainty:
+        hat, uncertainty = model(patches_lr)
+        loss = loss_obj(hat[:, 0:1, ...], patches_hr[:, 0:1, ...])
+        loss += torch.mean(torch.div(torch.abs(hat[:, 0:1, ...] - patches_hr[:, 0:1, ...]), uncertainty) + torch.log(uncertainty))
+        error_map = torch.abs(hat[:, 0:1, ...].detach() - patches_hr[:, 0:1, ...])
+        loss += loss_obj(uncertainty, error_map)
+    else:
+        hat = model(patches_lr)
+        loss = loss_obj(hat[:, 0:1, ...], patches_hr[:, 0:1, ...])
+    loss += loss_seg(hat[:, 1:, ...], patches_hr[:, 1:, ...]) * 1.0
+    for p in model.parameters():
+        p.grad = None
+    loss.backward()
+    return loss.detach()

@@ -141,15 +141,89 @@ def sr_sweep_fixture() -> None:
     np.savez_compressed(os.path.join(OUT, "sr_sweep.npz"), vol=vol.numpy(), out=out.numpy())
 
 
+def sr_step_fixture() -> None:
+    """ONE iteration of the reference's own `train_all.train_sr` (train_all.py:114-152) on its own UNet_3D_3D, L1Loss and
+    BCEDiceLoss(1, 1), for the plain and the UASR head: a one-batch list stands in for the DataLoader, SGD(lr=0) keeps the weights
+    so the gradients left in `.grad` belong to the stored loss, and `LossProgBar` is replaced by a recorder (it only displays)."""
+    import tempfile
+    fa = refimport.load("models.FLAVR.FLAVR_arch")
+    ta = refimport.load("train_all")
+    seg_utils = refimport.load("utils.seg_utils")
+    seen = {}
+
+    class Recorder:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def update(self, d):
+            seen["loss"] = float(d["loss"].detach())
+
+    orig = ta.LossProgBar
+    ta.LossProgBar = Recorder
+    arrs = {}
+    try:
+        g = torch.Generator().manual_seed(8)
+        lr = torch.rand((2, 2, 4, 32, 32), generator=g)
+        lr[:, 1] = (lr[:, 1] > 0.8).float()
+        hr = torch.rand((2, 2, 16, 32, 32), generator=g)
+        hr[:, 1] = (hr[:, 1] > 0.8).float()
+        arrs.update(patches_lr=lr.numpy().copy(), patches_hr=hr.numpy().copy())
+        for tag, unc in (("plain", False), ("uasr", True)):
+            torch.manual_seed(1234)
+            net = fa.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=unc)
+            opt = torch.optim.SGD(net.parameters(), lr=0.0)
+            sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda i: 1.0)
+            with tempfile.TemporaryDirectory() as wd:
+                ta.train_sr(1, 2, net, opt, sched, [(lr.clone(), hr.clone())], torch.device("cpu"), torch.nn.L1Loss(),
+                            seg_utils.BCEDiceLoss(alpha=1, beta=1), 1, 4, 4, unc, wd, 1000)
+            named = dict(net.named_parameters())
+            arrs[f"{tag}_loss"] = np.array(seen["loss"])
+            arrs[f"{tag}_grad_stem"] = named["encoder.stem.0.weight"].grad.numpy().copy()
+            arrs[f"{tag}_grad_outconv"] = (named["outconv.1.weight"] if not unc else named["uncertainty_out.weight"]).grad.numpy().copy()
+            arrs[f"{tag}_grad_abs_sum"] = np.array(float(sum(p.grad.double().abs().sum() for p in net.parameters() if p.grad is not None)))
+    finally:
+        ta.LossProgBar = orig
+    np.savez_compressed(os.path.join(OUT, "sr_step.npz"), **arrs)
+
+
+def random_centers_fixture() -> None:
+    """The reference's own `get_random_centers` (utils/patch_ops.py:67-113) under a fixed `np.random.seed`: images from the legacy
+    RandomState(3) stream (stable across numpy versions), so the test can rebuild the inputs and compare centre by centre."""
+    patch_ops = refimport.load("utils.patch_ops")
+    rng = np.random.RandomState(3)
+    imgs = [rng.rand(20, 24, 9).astype(np.float32), rng.rand(20, 24, 9).astype(np.float32), rng.rand(18, 22, 9).astype(np.float32)]
+    cases = []
+    for weighted in (True, False):
+        for ps in ((8, 8, 1), (6, 10, 3)):
+            np.random.seed(11)
+            c = patch_ops.get_random_centers([im.copy() for im in imgs], ps, 25, weighted)
+            cases.append({"weighted": weighted, "patch_size": list(ps), "n": 25, "seed": 11,
+                          "centers": [[int(i), [int(v) for v in xyz]] for i, xyz in c]})
+    with open(os.path.join(OUT, "random_centers.json"), "w") as f:
+        json.dump(cases, f)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     import sys
+    if "--only-centers" in sys.argv:
+        random_centers_fixture()
+        return
     if "--only-joint" in sys.argv:
         joint_fixture()
         joint_step_fixture()
         return
     if "--only-sweep" in sys.argv:
         sr_sweep_fixture()
+        return
+    if "--only-sr-step" in sys.argv:
+        sr_step_fixture()
         return
     seg_utils = refimport.load("utils.seg_utils")
     patch_ops = refimport.load("utils.patch_ops")
@@ -261,6 +335,8 @@ def main() -> None:
     joint_fixture()
     joint_step_fixture()
     sr_sweep_fixture()
+    sr_step_fixture()
+    random_centers_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

@@ -9,6 +9,7 @@
   projected_size / ideal_size / find_integer_p / calc_slices_to_crop / get_patch   <- utils/patch_ops.py:6-64
   blur_same                                           <- F.conv2d(x, k, padding="same") at utils/train_set.py:325,332
   apply_to_vol_flavr                                  <- utils/sr_utils.py:102-135 (device-agnostic restatement)
+  calculate_dice / evaluate_case_tensors              <- utils/seg_utils.py:730-734, 736-784 (everything after preprocess_image)
 Pinned against the live reference functions (tests/test_oracle_vs_reference.py, run whenever /root/reference exists) and
 the committed fixtures tests/golden/*.npz|json generated FROM the reference by oracle/make_golden.py.
 """
@@ -188,3 +189,33 @@ def sr_volume_orientations(model, image, angles=(0,), pred_out_idx=0):
         res = apply_to_vol_flavr(model, rot, pred_out_idx).permute(0, 3, 1, 2)
         preds.append(rotate_vol_2d(res, -angle))
     return torch.mean(torch.stack(preds), dim=0)
+
+
+def calculate_dice(prediction, ground_truth, smooth=1e-5):
+    """utils/seg_utils.py:730-734."""
+    prediction = np.asarray(prediction).flatten()
+    ground_truth = np.asarray(ground_truth).flatten()
+    intersection = np.sum(prediction * ground_truth)
+    return (2. * intersection + smooth) / (np.sum(prediction) + np.sum(ground_truth) + smooth)
+
+
+def evaluate_case_tensors(model, lr_data, lr_label, slice_separation, patch_size, get_HR_results=False):
+    """utils/seg_utils.py:736-784 from the padding on (preprocess_image is NIfTI IO): pad, sliding window over output 0 with the
+    Gaussian, crop, softmax, argmax, Dice; optional HR branch over output 1 without the Gaussian (the reference's defaults)."""
+    model.eval()
+    lr_data, revert = tp.pad_nd_image(lr_data, patch_size, 'constant', {'value': 0}, True, None)
+    with torch.no_grad():
+        slicers = sliding_window_slicers(lr_data.shape[1:], list(patch_size))
+        logits = sliding_window_logits(lr_data, slicers, model, 0, 1, patch_size, use_gaussian=True, deep_supervision=False)
+    prediction = logits[tuple([slice(None), *revert[1:]])].squeeze(0)
+    prob = torch.softmax(prediction.float(), dim=0).numpy()
+    prediction_lr = prob.argmax(0).astype('uint8')
+    dice_lr = calculate_dice(prediction_lr, lr_label.squeeze(0).numpy().astype('uint8'))
+    if get_HR_results:
+        with torch.no_grad():
+            hr = sliding_window_logits(lr_data, slicers, model, 1, slice_separation,
+                                       [patch_size[0] * slice_separation, patch_size[1], patch_size[2]])
+        prediction_hr = torch.argmax(hr, dim=0).squeeze(0).numpy().astype('uint8')
+    else:
+        prediction_hr = prediction_lr
+    return prediction_lr, prediction_hr, dice_lr

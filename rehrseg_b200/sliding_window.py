@@ -72,6 +72,24 @@ def compute_gaussian(tile_size: Tuple[int, ...], sigma_scale: float = 1. / 8, va
     return g
 
 
+# The reference clears nnU-Net's lru_cache after every volume (utils/seg_utils.py:285), which re-runs scipy's Gaussian filter on
+# the host for every case (~0.9 s for a 128^3 tile against ~0.5 s of GPU work for a whole 256^3 volume).  The importance map only
+# depends on (tile, sigma, scale, dtype, device), so the drivers below keep it in their own memo; `compute_gaussian` and its
+# `.cache_clear()` stay what the reference expects.
+_gaussian_memo: dict = {}
+
+
+def importance_map(tile_size, sigma_scale: float = 1. / 8, value_scaling_factor: float = 10, dtype=torch.float16, device=None):
+    key = (tuple(int(t) for t in tile_size), float(sigma_scale), float(value_scaling_factor), dtype, str(device))
+    g = _gaussian_memo.get(key)
+    if g is None:
+        g = compute_gaussian(key[0], sigma_scale=sigma_scale, value_scaling_factor=value_scaling_factor, dtype=dtype, device=device)
+        if len(_gaussian_memo) >= 8:
+            _gaussian_memo.clear()
+        _gaussian_memo[key] = g
+    return g
+
+
 def pad_nd_image(image, new_shape, mode="constant", kwargs=None, return_slicer=False):
     """acvl_utils 0.2 `pad_nd_image` as the reference calls it (utils/seg_utils.py:741): pad the trailing len(new_shape)
     dims up to new_shape, below = diff // 2, above = diff // 2 + diff % 2; returns (padded, slicer)."""
@@ -188,7 +206,7 @@ def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, 
     data = data.to(dev)
     predicted_logits = torch.zeros((2, data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
     n_predictions = torch.zeros((data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
-    gaussian = compute_gaussian(tuple(patch_size), sigma_scale=1. / 8, value_scaling_factor=10, device=dev) if use_gaussian else 1
+    gaussian = importance_map(patch_size, 1. / 8, 10, device=dev) if use_gaussian else 1
     if out_idx == 0 and isinstance(network, torch.nn.Module) and hasattr(network, "sr_head") and hasattr(network, "upscale"):
         from .seg_model import LRHeadOnly, _EngineForward, SegModel
         if isinstance(network, (SegModel, _EngineForward)):
@@ -221,27 +239,30 @@ def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, 
 
 def predict_sliding_window_sharded(data: torch.Tensor, slicers, network, group=None, out_idx=None, slice_seperation=1,
                                    patch_size=[14, 320, 384], use_gaussian=True, deep_supervision=True,
-                                   accumulate_fn=None, shard_mirrors: bool = True):
+                                   accumulate_fn=None, shard_mirrors: bool = True, tiles_per_allreduce: int = 32):
     """N-GPU sliding window (one process per GPU).  The independent units are the (tile, mirror variant) forwards
     (27 x 8 = 216 for config 3): unit u = 8 * tile + variant runs on rank u % world, so the load is balanced even when the
-    tile count is not a multiple of the rank count (`shard_mirrors=False` deals whole tiles instead).  The variants of a
-    tile are summed on the tile's owner rank (tile % world) with one small fp32 reduce, the owner blends the mean exactly
-    like the single-GPU path (fp16 prediction, fp16 accumulators, utils/seg_utils.py:256-276), and ONE all-reduce merges the
-    per-rank buffers (fp32 on the wire: the reference's fp16 running sums depend on tile order, so the N-rank result matches
-    at tolerance, not bit for bit) before every rank finalises locally.  `accumulate_fn` lets the CPU/gloo test substitute
-    the blend."""
+    tile count is not a multiple of the rank count.  Every rank sums the variants it ran per tile (fp32); ONE all-reduce per
+    chunk of `tiles_per_allreduce` tiles completes the per-tile sums on every rank; then every rank blends ALL tiles locally in
+    the reference's tile order with the reference's fp16 arithmetic (utils/seg_utils.py:256-283) and finalises.  The result is
+    the same on every rank and differs from the single-GPU path only by the fp32 summation order of the 8 variants of a tile.
+    `shard_mirrors=False` deals whole tiles instead (each rank blends its tiles, fp32 all-reduce of the volume buffers);
+    `accumulate_fn` lets the CPU/gloo test substitute the blend of that variant."""
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if accumulate_fn is None and (world == 1 or shard_mirrors):
+        if world == 1:
+            return _internal_predict_sliding_window_return_logits(data, slicers, network, True, out_idx, slice_seperation, patch_size,
+                                                                  use_gaussian, deep_supervision)
+        return _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch_size, use_gaussian, deep_supervision,
+                                   rank, world, group, tiles_per_allreduce)
     if accumulate_fn is not None:
         logits, npred = accumulate_fn(data, [(i, sl) for i, sl in enumerate(slicers) if i % world == rank])
-    elif world == 1 or not shard_mirrors:
+    else:
         logits, npred = _internal_predict_sliding_window_return_logits(
             data, slicers, network, True, out_idx, slice_seperation, patch_size, use_gaussian, deep_supervision,
             tile_filter=lambda i: i % world == rank, finalize=False)
-    else:
-        logits, npred = _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch_size, use_gaussian,
-                                            deep_supervision, rank, world, group)
     if world > 1:
         l32, n32 = logits.float(), npred.float()
         dist.all_reduce(l32, group=group)
@@ -255,8 +276,8 @@ def predict_sliding_window_sharded(data: torch.Tensor, slicers, network, group=N
 
 
 def _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch_size, use_gaussian, deep_supervision, rank, world,
-                        group):
-    """This rank's share of the (tile, mirror variant) units; tiles it owns are blended into its fp16 full-volume buffers."""
+                        group, tiles_per_allreduce: int = 32):
+    """(tile, mirror variant) units dealt round-robin; per-tile variant sums all-reduced in chunks; local blend of all tiles."""
     import torch.distributed as dist
     if not torch.is_grad_enabled() and isinstance(network, torch.nn.Module):
         if out_idx == 0 and hasattr(network, "sr_head") and hasattr(network, "upscale"):
@@ -273,26 +294,35 @@ def _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch
     dev = data.device
     logits = torch.zeros((2, data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
     npred = torch.zeros((data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
-    gaussian = compute_gaussian(tuple(patch_size), sigma_scale=1. / 8, value_scaling_factor=10, device=dev) if use_gaussian else 1
+    gaussian = importance_map(patch_size, 1. / 8, 10, device=dev) if use_gaussian else 1
     variants = [()] + mirror_axes_combinations()
-    for i, sl in enumerate(slicers):
-        mine = [v for v in range(len(variants)) if (i * len(variants) + v) % world == rank]
-        owner = i % world
-        workon = data[sl][None]
-        part = None
-        for v in mine:
-            axes = variants[v]
-            p = _select(network(torch.flip(workon, axes) if axes else workon), out_idx, deep_supervision)
-            p = (torch.flip(p, axes) if axes else p).float()
-            part = p.clone() if part is None else part + p
-        if part is None:  # no variant of this tile landed here: contribute zeros to the tile's reduce
-            part = torch.zeros((1, logits.shape[0], *[s.stop - s.start for s in sl[1:]]), dtype=torch.float32, device=dev)
-            part = part if slice_seperation == 1 else part.repeat_interleave(slice_seperation, dim=2)
-        dist.reduce(part, dst=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        if rank == owner:
-            pred = (part[0] / len(variants)).to(torch.float16)
+    nv = len(variants)
+    for c0 in range(0, len(slicers), tiles_per_allreduce):
+        chunk = list(range(c0, min(len(slicers), c0 + tiles_per_allreduce)))
+        sums = None
+        for k, i in enumerate(chunk):
+            sl = slicers[i]
+            workon = data[sl][None]
+            for v in range(nv):
+                if (i * nv + v) % world != rank:
+                    continue
+                axes = variants[v]
+                p = _select(network(torch.flip(workon, axes) if axes else workon), out_idx, deep_supervision)
+                p = (torch.flip(p, axes) if axes else p).float()
+                if sums is None:
+                    sums = torch.zeros((len(chunk), *p.shape[1:]), dtype=torch.float32, device=dev)
+                sums[k] += p[0]
+        if sums is None:   # fewer units than ranks in this chunk: this rank still takes part in the collective
+            t = [s.stop - s.start for s in slicers[chunk[0]][1:]]
+            sums = torch.zeros((len(chunk), logits.shape[0], t[0] * slice_seperation, t[1], t[2]), dtype=torch.float32, device=dev)
+        dist.all_reduce(sums, group=group)
+        for k, i in enumerate(chunk):
+            sl = slicers[i]
+            pred = (sums[k] / nv).to(torch.float16)
             sw_accumulate(logits, npred, pred, gaussian, (sl[1].start * slice_seperation, sl[2].start, sl[3].start))
-    return logits, npred
+    if sw_finalize(logits, npred):
+        raise RuntimeError(INF_MESSAGE)
+    return logits
 
 
 def sliding_window_segment(model, lr_data, patch_size, slice_separation=1, out_idx=0, use_gaussian=True):
@@ -308,3 +338,41 @@ def sliding_window_segment(model, lr_data, patch_size, slice_separation=1, out_i
     prediction = predicted_logits[tuple([slice(None), *slicer_revert[1:]])]
     prediction = torch.softmax(prediction.float(), 0).argmax(0)
     return prediction.to(torch.uint8)
+
+
+def calculate_dice(prediction, ground_truth, smooth: float = 1e-5) -> float:
+    """utils/seg_utils.py:730-734: (2 |P n G| + smooth) / (|P| + |G| + smooth) on flattened label arrays (tensors or numpy)."""
+    if isinstance(prediction, torch.Tensor) or isinstance(ground_truth, torch.Tensor):
+        p = torch.as_tensor(prediction).flatten().double()
+        g = torch.as_tensor(ground_truth).to(p.device).flatten().double()
+        return float((2.0 * (p * g).sum() + smooth) / (p.sum() + g.sum() + smooth))
+    p, g = np.asarray(prediction).flatten(), np.asarray(ground_truth).flatten()
+    return float((2.0 * np.sum(p * g) + smooth) / (np.sum(p) + np.sum(g) + smooth))
+
+
+def evaluate_case_tensors(model, lr_data: torch.Tensor, lr_label: Optional[torch.Tensor], slice_separation: int, patch_size,
+                          get_HR_results: bool = False):
+    """The tensor part of `evaluate_case` (utils/seg_utils.py:736-784) -- everything between `preprocess_image` (file IO, out of
+    scope) and the return: pad to at least one tile, sliding window over output 0 (Gaussian blend, mirror TTA), crop the padding,
+    softmax / argmax -> uint8 LR labels, Dice against `lr_label`; with `get_HR_results` a second sliding window over output 1
+    (the x`slice_separation` SR head; no Gaussian, as the reference's call leaves `use_gaussian` at its default).
+    `lr_data` [1, X, Y, Z] (already z-scored), `lr_label` [1, X, Y, Z] or None.  Returns (prediction_lr, prediction_hr, dice_lr)."""
+    model.eval()
+    patch_size = list(patch_size)
+    dev = lr_data.device if lr_data.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    lr_data = lr_data.to(dev)
+    lr_data, slicer_revert = pad_nd_image(lr_data, patch_size, 'constant', {'value': 0}, True)
+    with torch.no_grad():
+        slicers = _internal_get_sliding_window_slicers(lr_data.shape[1:], patch_size=patch_size)
+        logits = _internal_predict_sliding_window_return_logits(lr_data, slicers, model, True, 0, 1, patch_size, use_gaussian=True,
+                                                                deep_supervision=False)
+        prediction = logits[tuple([slice(None), *slicer_revert[1:]])]
+        prediction_lr = torch.softmax(prediction.float(), dim=0).argmax(0).to(torch.uint8)
+        dice_lr = calculate_dice(prediction_lr, lr_label.squeeze(0).to(torch.uint8)) if lr_label is not None else None
+        if get_HR_results:
+            hr_patch = [patch_size[0] * slice_separation, patch_size[1], patch_size[2]]
+            hr_logits = _internal_predict_sliding_window_return_logits(lr_data, slicers, model, True, 1, slice_separation, hr_patch)
+            prediction_hr = torch.argmax(hr_logits, dim=0).to(torch.uint8)
+        else:
+            prediction_hr = prediction_lr
+    return prediction_lr, prediction_hr, dice_lr

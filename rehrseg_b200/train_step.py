@@ -10,6 +10,8 @@
   * `joint_train_step`     <- the loop body train_all.py:519-558: teacher sweep under no_grad, student forward with
                               `return_inetermediate_feature=True`, LR loss (uncertainty-weighted CE), HR loss (CE + Dice),
                               distillation on `features_seg[1]` / `features_sr[1]`, zero_grad / backward / step.
+  * `BCEDiceLoss`, `sr_train_step` <- the SR-stage loss `BCEDiceLoss(alpha, beta)` (utils/seg_utils.py:786-886) and the loop body
+                              of `train_sr`, train_all.py:118-139, incl. the UASR terms :125-130 (L1 + |err|/u + log u + L1(u, |err|)).
   * `allreduce_gradients`  <- what DistributedDataParallel would do for the reference: one flat bucket, mean over ranks
                               (NCCL over NVLink; InstanceNorm is per sample, so no other cross-rank traffic exists).
 
@@ -202,3 +204,64 @@ def joint_train_step(model_seg: nn.Module, batch: Sequence[torch.Tensor], loss_o
         opt.step()
     out["loss"] = loss.detach()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SR stage (BASELINE config 2's training step): train_all.py:114-152
+# ---------------------------------------------------------------------------------------------------------------
+class BCEDiceLoss(nn.Module):
+    """`BCEDiceLoss(alpha, beta)` = alpha * BCEWithLogits + beta * (1 - mean per-channel Dice of sigmoid(input)), the Dice with the
+    V-Net denominator sum(p^2) + sum(t^2) clamped at 1e-6 (utils/seg_utils.py:821-886; channel axis first, batch flattened in)."""
+
+    def __init__(self, alpha: float, beta: float):
+        super().__init__()
+        self.alpha, self.beta = alpha, beta
+        self.bce = nn.BCEWithLogitsLoss()
+
+    def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        prob = torch.sigmoid(input)
+        c = prob.size(1)
+        p = prob.transpose(0, 1).reshape(c, -1)
+        t = target.transpose(0, 1).reshape(c, -1).float()
+        dice = 2 * ((p * t).sum(-1) / ((p * p).sum(-1) + (t * t).sum(-1)).clamp(min=1e-6))
+        return self.alpha * self.bce(input, target) + self.beta * (1.0 - dice.mean())
+
+
+def sr_train_step(model: nn.Module, batch: Sequence[torch.Tensor], loss_obj: nn.Module, loss_seg: nn.Module,
+                  opt: Optional[torch.optim.Optimizer] = None, scheduler=None, slice_separation: int = 4, num_slices: int = 4,
+                  enable_uncertainty: bool = False, group=None, device=None) -> dict:
+    """One iteration of `train_sr` (train_all.py:118-139).  `batch` = (patches_lr [B,2,num_slices,H,W], patches_hr [B,2,S,H,W]) as the
+    DataLoader yields them; with `num_slices > 1` the target is the `slice_separation` HR slices between the two central LR slices
+    (:122-123).  `enable_uncertainty` adds the UASR terms :125-130 on the model's (prediction, uncertainty) pair.  The reference
+    calls `model(patches_lr)`, whose forward subtracts the channel-0 mean IN PLACE from the batch (FLAVR_arch.py:180-181) --
+    preserved: `patches_lr` on the device is mutated.  Gradients are averaged over `group` before the optimiser step."""
+    patches_lr, patches_hr = batch
+    device = device if device is not None else next(model.parameters()).device
+    patches_hr = patches_hr.to(device, non_blocking=True)
+    patches_lr = patches_lr.to(device, non_blocking=True)
+    if num_slices > 1:
+        patches_hr = patches_hr[:, :, int(slice_separation) * (num_slices // 2 - 1):int(slice_separation) * (num_slices // 2), ...]
+    if enable_uncertainty:
+        patches_hr_hat, uncertainty = model(patches_lr)
+        loss = loss_obj(patches_hr_hat[:, 0:1, ...], patches_hr[:, 0:1, ...])
+        loss = loss + torch.mean(torch.div(torch.abs(patches_hr_hat[:, 0:1, ...] - patches_hr[:, 0:1, ...]), uncertainty)
+                                 + torch.log(uncertainty))
+        error_map = torch.abs(patches_hr_hat[:, 0:1, ...].detach() - patches_hr[:, 0:1, ...])
+        loss = loss + loss_obj(uncertainty, error_map)
+    else:
+        patches_hr_hat = model(patches_lr)
+        loss = loss_obj(patches_hr_hat[:, 0:1, ...], patches_hr[:, 0:1, ...])
+    loss = loss + loss_seg(patches_hr_hat[:, 1:, ...], patches_hr[:, 1:, ...]) * 1.0
+    params = list(model.parameters())
+    if opt is not None:
+        opt.zero_grad()
+    else:
+        for p in params:
+            p.grad = None
+    loss.backward()
+    allreduce_gradients(params, group)
+    if opt is not None:
+        opt.step()
+    if scheduler is not None:
+        scheduler.step()
+    return {"loss": loss.detach()}

@@ -207,3 +207,36 @@ def fba(imgs: List, p="infinity"):
     F_._count()
     res = torch.fft.irfftn(out).to(torch.float32)
     return res.cpu().numpy() if as_numpy else res
+
+
+def get_random_centers(imgs_rot, patch_size, n_patches, weighted=True):
+    """utils/patch_ops.py:67-113: `n_patches` (rotation index, centre) pairs.  Each patch first draws its rotation uniformly; per
+    rotation the centre coordinates are drawn axis by axis from the marginals of a gradient-magnitude map (sum over axes of
+    sqrt|d/dx_k| of the sigma-1 Gaussian-smoothed image, zeroed within p//2 + 1 voxels of the borders of every axis with p > 1) or
+    uniformly when `weighted` is False; the list is shuffled at the end.  Host-side numpy / scipy like the reference (index
+    sampling for the CPU dataset); it consumes numpy's GLOBAL random stream in the reference's order (randint, one choice per axis
+    and rotation, shuffle), so the same `np.random.seed` gives the same centres."""
+    import numpy as np
+    from scipy.ndimage import gaussian_filter
+    which = np.random.randint(0, len(imgs_rot), size=n_patches)
+    centers = []
+    for i, img in enumerate(imgs_rot):
+        count = int(np.sum(which == i))
+        if weighted:
+            mag = np.sum([np.sqrt(np.abs(d)) for d in np.gradient(gaussian_filter(img, 1.0))], axis=0)
+            for axis, p in enumerate(patch_size):
+                if axis < mag.ndim and p > 1:           # no patch centre may sit where the patch would leave the image
+                    view = np.swapaxes(mag, 0, axis)
+                    view[: p // 2 + 1] = 0.0
+                    view[-p // 2 - 1:] = 0.0
+            joint = mag / mag.sum()
+            probs = []
+            for axis in range(joint.ndim):
+                m = joint.sum(axis=tuple(k for k in range(joint.ndim) if k != axis))
+                probs.append(m / m.sum())
+        else:
+            probs = [None] * img.ndim
+        draws = [np.random.choice(np.arange(0, dim), size=count, p=probs[axis]) for axis, dim in enumerate(img.shape)]
+        centers.extend((i, tuple(c)) for c in zip(*draws))
+    np.random.shuffle(centers)
+    return centers

@@ -144,3 +144,35 @@ def test_sr_volume_orientations_vs_oracle():
         got = flavr.sr_volume_orientations(mine, img.clone().cuda(), angles=(0, 180), max_batch=3)
     assert got.shape == want.shape
     assert rel(got, want) <= 1e-2
+
+
+@pytest.mark.parametrize("unc", [False, True])
+def test_sr_train_step_on_the_engine_vs_oracle(unc):
+    """BASELINE config 2's training step, `train_sr` (train_all.py:118-139) with the UASR loss terms (:125-130): the engine FLAVR
+    driven by rehrseg_b200.train_step.sr_train_step vs the oracle step on the fp32 CPU model -- loss and gradients."""
+    from oracle import joint as oj
+    from rehrseg_b200 import train_step as ts
+    ref, mine = _pair(unc, seed=9)
+    ref.train()
+    mine.train()
+    g = torch.Generator().manual_seed(13)
+    lr = torch.rand((2, 2, 4, 64, 64), generator=g)
+    lr[:, 1] = (lr[:, 1] > 0.8).float()
+    hr = torch.rand((2, 2, 16, 64, 64), generator=g)
+    hr[:, 1] = (hr[:, 1] > 0.8).float()
+    want = float(oj.ref_sr_step(ref, lr.clone(), hr.clone(), torch.nn.L1Loss(), oj.RefBCEDiceLoss(1, 1), 4, 4, unc))
+    lr_dev = lr.clone().cuda()
+    got = float(ts.sr_train_step(mine, (lr_dev, hr.clone()), torch.nn.L1Loss(), ts.BCEDiceLoss(1, 1), None, None, 4, 4, unc)["loss"])
+    assert abs(got - want) <= 1e-2 * abs(want), (got, want)
+    # the reference's forward subtracts the channel-0 mean from the caller's batch in place (FLAVR_arch.py:180-181)
+    assert rel(lr_dev[:, 0], lr[:, 0] - lr[:, 0:1].mean((2, 3, 4), keepdim=True)[:, 0]) <= 1e-5
+    pr = dict(ref.named_parameters())
+    num = den = 0.0
+    for name, p in mine.named_parameters():
+        assert (p.grad is None) == (pr[name].grad is None), name
+        if p.grad is None:
+            continue
+        a, b = p.grad.double().cpu(), pr[name].grad.double()
+        num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum())
+    print("sr step", "uasr" if unc else "plain", "loss", got, want, "grads global", (num / den) ** 0.5)
+    assert (num / den) ** 0.5 <= 8e-2

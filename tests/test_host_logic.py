@@ -124,3 +124,25 @@ def test_weight_cache_drops_dead_entries():
     live = sum(1 for v in Fn._wcache.values() if v[0]() is not None)
     assert live == len(keep) and len(Fn._wcache) <= 256 + len(keep)
     Fn.clear_weight_cache()
+
+
+def test_get_random_centers_matches_reference_fixture():
+    """utils/patch_ops.py:67-113: same numpy global-stream consumption (randint, per-axis choice, shuffle) and the same gradient
+    magnitude marginals -> centre for centre equal to what the reference's own function drew under the same seed."""
+    import json
+    import numpy as np
+    with open(os.path.join(G, "random_centers.json")) as f:
+        cases = json.load(f)
+    rng = np.random.RandomState(3)
+    imgs = [rng.rand(20, 24, 9).astype(np.float32), rng.rand(20, 24, 9).astype(np.float32), rng.rand(18, 22, 9).astype(np.float32)]
+    assert len(cases) == 4
+    for c in cases:
+        np.random.seed(c["seed"])
+        got = vo.get_random_centers([im.copy() for im in imgs], tuple(c["patch_size"]), c["n"], c["weighted"])
+        assert [[int(i), [int(v) for v in xyz]] for i, xyz in got] == c["centers"]
+        ps = c["patch_size"]
+        if c["weighted"]:   # no centre within p//2 + 1 of a border of an axis with p > 1
+            for i, xyz in got:
+                for ax, p in enumerate(ps):
+                    if p > 1:
+                        assert p // 2 + 1 <= xyz[ax] < imgs[i].shape[ax] - p // 2 - 1

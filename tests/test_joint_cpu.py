@@ -179,3 +179,43 @@ def test_oracle_joint_step_reproduces_the_reference_loop_body():
                               device=torch.device("cpu"))
     for k in ("loss", "loss_lr_seg", "loss_hr_seg", "distill_loss"):
         assert abs(float(got[k]) - float(W[k])) <= 2e-6 * max(1.0, abs(float(W[k]))), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SR stage: the loop body of train_sr (train_all.py:118-139) incl. the UASR terms, pinned by tests/golden/sr_step.npz, which the
+# reference's OWN train_sr produced on its own UNet_3D_3D / BCEDiceLoss (oracle/make_golden.py::sr_step_fixture)
+# ---------------------------------------------------------------------------------------------------------------
+S = np.load(os.path.join(ROOT, "tests", "golden", "sr_step.npz"))
+
+
+@pytest.mark.parametrize("unc", [False, True])
+def test_oracle_sr_step_reproduces_the_reference_train_sr(unc):
+    from oracle import flavr as of
+    tag = "uasr" if unc else "plain"
+    net = of.build(unc, seed=1234)
+    lr, hr = torch.from_numpy(S["patches_lr"]).clone(), torch.from_numpy(S["patches_hr"]).clone()
+    loss = oj.ref_sr_step(net, lr, hr, torch.nn.L1Loss(), oj.RefBCEDiceLoss(1, 1), 4, 4, unc)
+    assert abs(float(loss) - float(S[f"{tag}_loss"])) <= 2e-6 * abs(float(S[f"{tag}_loss"]))
+    named = dict(net.named_parameters())
+    assert _rel(named["encoder.stem.0.weight"].grad, S[f"{tag}_grad_stem"]) < 1e-4
+    head = named["uncertainty_out.weight"] if unc else named["outconv.1.weight"]
+    assert _rel(head.grad, S[f"{tag}_grad_outconv"]) < 1e-4
+    tot = float(sum(p.grad.double().abs().sum() for p in net.parameters() if p.grad is not None))
+    assert abs(tot - float(S[f"{tag}_grad_abs_sum"])) <= 1e-4 * float(S[f"{tag}_grad_abs_sum"])
+
+
+@pytest.mark.parametrize("unc", [False, True])
+def test_sr_train_step_mirror_matches_the_reference_fixture(unc):
+    """rehrseg_b200.train_step.sr_train_step + BCEDiceLoss (host logic, plain PyTorch) around a CPU stand-in network (the oracle
+    FLAVR: the engine module needs a GPU, tests/test_flavr_gpu.py drives the same function through it)."""
+    from oracle import flavr as of
+    tag = "uasr" if unc else "plain"
+    net = of.build(unc, seed=1234)
+    lr, hr = torch.from_numpy(S["patches_lr"]).clone(), torch.from_numpy(S["patches_hr"]).clone()
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    out = ts.sr_train_step(net, (lr, hr), torch.nn.L1Loss(), ts.BCEDiceLoss(1, 1), opt, None, 4, 4, unc, device=torch.device("cpu"))
+    assert abs(float(out["loss"]) - float(S[f"{tag}_loss"])) <= 2e-6 * abs(float(S[f"{tag}_loss"]))
+    assert _rel(dict(net.named_parameters())["encoder.stem.0.weight"].grad, S[f"{tag}_grad_stem"]) < 1e-4
+    x = torch.randn(3, 2, 4, 8, 8)
+    t = (torch.rand(3, 2, 4, 8, 8) > 0.5).float()
+    assert abs(float(ts.BCEDiceLoss(0.3, 0.7)(x, t)) - float(oj.RefBCEDiceLoss(0.3, 0.7)(x, t))) < 1e-6

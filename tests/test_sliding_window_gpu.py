@@ -98,13 +98,38 @@ def test_sliding_window_segmodel_vs_oracle():
     err = float((got.float().cpu() - want).norm() / want.norm())
     # bf16 noise floor of the 3-stage random-init net is ~1.0e-2 (torch autocast: 1.3e-2, tests/test_segmodel_gpu.py);
     # the blend itself is bit-exact (tests above), so the whole-driver bound is the network's.
-    assert err <= 1.25e-2, err
-    margin = (want[0] - want[1]).abs()
-    clear = margin > 4 * float((got.float().cpu() - want).pow(2).mean().sqrt())
-    agree = (got.float().cpu().argmax(0) == want.argmax(0))[clear].double().mean()
-    assert float(agree) >= 0.999, float(agree)   # north_star: argmax agreement >= 99.9 % (on voxels with a clear fp32 margin)
+    assert err <= 1e-2, err                      # north_star's 16-bit bound; the blend itself is bit-exact (tests above)
+    agree = (got.float().cpu().argmax(0) == want.argmax(0)).double().mean()
+    assert float(agree) >= 0.999, float(agree)   # north_star: raw argmax agreement >= 99.9 % of voxels
     labels = sw.sliding_window_segment(mine, data.cuda(), patch)
     assert labels.dtype == torch.uint8 and labels.shape == data.shape[1:]
+
+
+@pytest.mark.parametrize("hr", [False, True])
+def test_evaluate_case_tensor_part_vs_oracle(hr):
+    """`evaluate_case` after preprocess_image (utils/seg_utils.py:741-784): padding of a volume smaller than one tile in one axis,
+    sliding window, crop, softmax / argmax labels and the Dice score -- engine vs the oracle's restatement on the fp32 CPU model;
+    with `get_HR_results` also the SR-head labels (output 1, no Gaussian, slice separation 4)."""
+    from rehrseg_b200 import seg_model as sm, sliding_window as sw
+    from oracle import seg_model as ref_seg, volume as ov
+    ref = ref_seg.build("tiny").eval()
+    mine = sm.SegModel(**ref_seg.plan_kwargs("tiny"))
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda().eval()
+    g = torch.Generator().manual_seed(11)
+    data = torch.randn((1, 12, 40, 36), generator=g)            # 12 < 16: padded up to one tile along the first axis
+    label = (torch.rand((1, 12, 40, 36), generator=g) > 0.7).float()
+    patch = [16, 32, 32]
+    want_lr, want_hr, want_dice = ov.evaluate_case_tensors(ref, data, label, 4, patch, get_HR_results=hr)
+    got_lr, got_hr, got_dice = sw.evaluate_case_tensors(mine, data.cuda(), label.cuda(), 4, patch, get_HR_results=hr)
+    assert got_lr.dtype == torch.uint8 and tuple(got_lr.shape) == want_lr.shape == (12, 40, 36)
+    agree = float((got_lr.cpu().numpy() == want_lr).mean())
+    assert agree >= 0.999, agree
+    assert abs(got_dice - want_dice) <= 2e-3, (got_dice, want_dice)
+    assert abs(sw.calculate_dice(want_lr, label.squeeze(0).numpy().astype("uint8")) - want_dice) < 1e-12   # numpy branch, bit-equal
+    if hr:
+        assert tuple(got_hr.shape) == want_hr.shape
+        assert float((got_hr.cpu().numpy() == want_hr).mean()) >= 0.998
 
 
 def test_cuda_graph_replay_is_bit_identical():
