@@ -231,6 +231,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2-C5 / cuDNN-eager entries (bench_extras.py)")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="b200 arm: replay the step from one CUDA graph (rehrseg_b200.graphs.GraphedTrainStep) or launch it from Python")
     args = ap.parse_args()
@@ -380,22 +381,42 @@ def main() -> None:
         peaks = measured_peaks()
         for name, (n, tms, fl) in summ.items():
             kernels[name] = {"launches": n, "ms": round(tms, 4), "tflops": round(fl / tms / 1e9, 1) if tms > 0 else None}
-        if summ:
-            top = max(summ.items(), key=lambda kv: kv[1][1])
-            name, (n, tms, fl) = top
+        # dominant kernel = the (family, layer) INSTANTIATION with the largest time in the step -- a family mixes 1100 TFLOP/s
+        # layers with 200 TFLOP/s parity-class launches, so a family average says little about either
+        inst = {}
+        for name, tag, tms, fl in kt.rows():
+            n, t, f = inst.get((name, tag), (0, 0.0, 0.0))
+            inst[(name, tag)] = (n + 1, t + tms, f + fl)
+        if inst:
+            (name, tag), (n, tms, fl) = max(inst.items(), key=lambda kv: kv[1][1])
             achieved = fl / tms / 1e9
-            peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-            # DRAM bytes (read + write) of the largest launch of each family from the committed `ncu --set full` capture
-            # (profiles/r01_march_kernels_ncu_full_summary.txt: conv_march_kernel on the 64->32 128^3 layer, 805 MB algorithmic)
-            traffic = {"conv_march_kernel": 784.0e6}.get(name)
-            roof = {"kernel": name, "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic,
-                    "traffic_note": "dram read+write of the 64->32 @128^3 launch (463.9 GFLOP, 805 MB algorithmic), ncu --set full"
-                    if traffic else None, "launches_per_step": n,
-                    "avg_launch_ms": round(tms / n, 4), "flops_per_launch": fl / n,
+            # the instrumented step is ONE eager step after an idle gap (clocks at their burst level): burst peak is the denominator
+            peak = float(peaks["bf16_tflops"])
+            fam_n, fam_ms, fam_fl = summ[name]
+            # DRAM bytes (read + write) per launch of this instantiation from a committed `ncu --set full` capture, if one exists
+            traffic, traffic_file = None, None
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    ent = json.load(f).get(f"{name}|{tag}")
+                if ent:
+                    traffic, traffic_file = ent.get("dram_bytes_per_launch"), ent.get("file")
+            roof = {"kernel": name, "layer": tag, "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_file,
+                    "launches_per_step": n, "avg_launch_ms": round(tms / n, 4), "flops_per_launch": fl / n,
                     "share_of_step": round(tms / (ms / args.steps), 4),
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']}); kernel timed inside a step",
-                    "frac_of_burst": round(achieved / float(peaks["bf16_tflops"]), 4)}
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops, burst ({peaks['_source']}): the kernel is timed in a single "
+                                   "python-launched step after an idle gap (side-stream forks off while the event pairs are recorded)",
+                    "frac_of_sustained": round(achieved / float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), 4),
+                    "family": {"launches_per_step": fam_n, "ms": round(fam_ms, 4), "tflops": round(fam_fl / fam_ms / 1e9, 1),
+                               "share_of_step": round(fam_ms / (ms / args.steps), 4)}}
+
+    # the other BASELINE configs, same run (C3 sharded over all ranks; the single-GPU ones only at N = 1)
+    extras = {}
+    if args.impl == "b200" and not args.no_extras:
+        torch.cuda.empty_cache()
+        import bench_extras
+        extras = bench_extras.run_all(dev, measured_peaks(), rank, world, _oracle_unet, BATCH, PATCH)
 
     if rank != 0:
         if world > 1:
@@ -418,6 +439,12 @@ def main() -> None:
             "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": world * (x_host.numel() + g_host.numel()) * 4,
                     "d2h_bytes_per_step": world * 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
+    if extras:
+        line["configs"] = extras
+        for key in ("sw_volumes_per_s",):    # BASELINE.json's metric names volumes/s explicitly: surface it at the top level
+            v = extras.get("c3_sliding_window", {}).get(key)
+            if v is not None:
+                line[key] = v
     if args.impl != "b200":
         line["impl"] = args.impl
         line["gpu_launches"] = None

@@ -1,0 +1,192 @@
+"""The other BASELINE.json configs, timed in the same run as bench.py's C1 line so that every config carries a driver-visible
+number (BASELINE.json `metric` also names "volumes/sec SW infer"):
+
+  C2  FLAVR UNet3D self-SR fwd+bwd on [8,2,4,256,256] (plain head)                      -> flavr_samples_per_s
+  C3  sliding-window Gaussian-blended inference over a 256^3 volume, 27 tiles x 8 mirror
+      passes, tiles x mirrors sharded over the ranks                                     -> sw_volumes_per_s
+  C4  joint SR+seg step (anisotropic SegModel student, UASR FLAVR teacher sweep,
+      Distiller, SGD), batch 2 per GPU, h2d copies inside                                -> joint_ms_per_step
+  C5  blur degradation + 4-orientation SR sweep + FBA / mean fusion on 512x512x160
+      (one orientation sweep is timed and multiplied by the exact orientation count)    -> c5_pipeline_s
+  cuDNN  torch eager + bf16 autocast, channels_last_3d, C1 shape on the same GPU        -> eager_gpu_ms_per_step
+
+Every entry: device time from CUDA events (wall clock where host work is part of the path, said so), algorithmic work from
+SURVEY.md section 8(d), fraction of the MEASURED bf16 / HBM peak.  Failures never break the main line: the entry carries "error".
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+
+def _events(fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def c2_flavr(dev, peaks, steps=8, warm=3) -> dict:
+    from rehrseg_b200 import flavr
+    torch.manual_seed(0)
+    m = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=False).to(dev)
+    B = 8
+    x = torch.rand((B, 2, 4, 256, 256), device=dev)
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        m(x.clone()).float().mean().backward()
+
+    ms = _events(step, steps, warm)
+    tf = B * 1.650 / ms * 1e3     # 1.650 TFLOP fwd+bwd per 256^2 sample (plain head)
+    return {"config": "C2 FLAVR UNet3D self-SR fwd+bwd, [8,2,4,256,256], plain head, bf16", "flavr_samples_per_s": round(B / ms * 1e3, 2),
+            "ms_per_step": round(ms, 3), "tflops": round(tf, 1), "frac_bf16_peak_burst": round(tf / float(peaks["bf16_tflops"]), 4)}
+
+
+def c3_sliding_window(dev, peaks, world, iters=2) -> dict:
+    import torch.distributed as dist
+    from rehrseg_b200 import seg_model as sm, sliding_window as sw
+    torch.manual_seed(0)
+    model = sm.plainconv_3d_fullres().to(dev).eval()
+    vol = torch.randn((1, 256, 256, 256), generator=torch.Generator().manual_seed(3)).to(dev)
+    patch = [128, 128, 128]
+    slicers = sw._internal_get_sliding_window_slicers(vol.shape[1:], patch_size=patch)
+
+    def run():
+        with torch.no_grad():
+            return sw.predict_sliding_window_sharded(vol, slicers, model, out_idx=0, patch_size=patch, use_gaussian=True,
+                                                     deep_supervision=False)
+
+    run()                       # graph capture of the tile forward, importance map
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters / 1e3], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t)
+    tf = 206.2 / s              # 216 U-Net forwards = 206.2 TFLOP (the SR head is not computed: only output 0 is read)
+    return {"config": f"C3 sliding window, 256^3 volume, {len(slicers)} tiles x 8 mirror passes, Gaussian fp16 blend, (tile, mirror) units "
+                      f"sharded over {world} GPU(s)", "sw_volumes_per_s": round(1.0 / s, 3), "s_per_volume": round(s, 4),
+            "tflops_all_gpus": round(tf, 1), "frac_bf16_peak_burst": round(tf / world / float(peaks["bf16_tflops"]), 4),
+            "finite": bool(torch.isfinite(out.float()).all())}
+
+
+def c4_joint(dev, peaks, steps=6, warm=3) -> dict:
+    import itertools
+    from rehrseg_b200 import flavr, loss_ops, seg_model as sm, train_step as ts
+    aniso = dict(input_channels=1, n_stages=6, features_per_stage=[32, 64, 128, 256, 320, 320], conv_op=torch.nn.Conv3d,
+                 kernel_sizes=[[1, 3, 3], [1, 3, 3]] + [[3, 3, 3]] * 4,
+                 strides=[[1, 1, 1], [1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2], [1, 2, 2]], n_conv_per_stage=[2] * 6, num_classes=2,
+                 upscale=4, n_conv_per_stage_decoder=[2] * 5, conv_bias=True, norm_op=torch.nn.InstanceNorm3d,
+                 norm_op_kwargs={"eps": 1e-5, "affine": True}, dropout_op=None, dropout_op_kwargs=None, nonlin=torch.nn.LeakyReLU,
+                 nonlin_kwargs={"inplace": True}, deep_supervision=False)
+    torch.manual_seed(1234)
+    student = sm.SegModel(**aniso).to(dev)
+    teacher = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).to(dev).eval()
+    distiller = loss_ops.FusedDistiller(64, 64, 0.0, 1.0, 1.0).to(dev)
+    opt = torch.optim.SGD(itertools.chain(student.parameters(), distiller.parameters()), lr=1e-3, momentum=0.99, nesterov=True,
+                          weight_decay=3e-5)
+    lr_obj, hr_obj = loss_ops.build_fused_loss(False, 0), loss_ops.build_fused_loss(False, 1)
+    g = torch.Generator().manual_seed(4)
+    B, D, HW = 2, 16, 256
+    host = (torch.randn((B, 1, D, HW, HW), generator=g).pin_memory(),
+            (torch.rand((B, 1, D, HW, HW), generator=g) > 0.8).float().pin_memory(),
+            (torch.rand((B, 1, 4 * D, HW, HW), generator=g) > 0.8).float().pin_memory(),
+            (torch.rand((B, 1, D, HW, HW), generator=g) * 0.99 + 0.01).pin_memory())
+
+    def step():
+        out = ts.joint_train_step(student, host, lr_obj, hr_obj, opt, teacher, distiller, device=dev)
+        float(out["loss"])      # the loop reads its loss back, like the training script printing it
+
+    ms = _events(step, steps, warm)
+    tf = 15.5 / ms * 1e3        # student fwd+bwd 4.50 + teacher sweep 10.99 TFLOP per GPU-step
+    return {"config": "C4 joint SR+seg step: anisotropic SegModel student [2,1,16,256,256] x4 SR head, UASR FLAVR teacher sweep (15 windows), "
+                      "uncertainty-weighted CE + CE/Dice + Distiller(64,64,0,1,1), SGD, batch from pinned host memory",
+            "joint_ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 2), "tflops": round(tf, 1),
+            "frac_bf16_peak_burst": round(tf / float(peaks["bf16_tflops"]), 4)}
+
+
+def c5_pipeline(dev, peaks) -> dict:
+    from rehrseg_b200 import flavr, volume_ops as vo
+    g = torch.Generator(device=dev).manual_seed(5)
+    hr = torch.rand((160, 1, 512, 512), device=dev, generator=g)
+    taps = torch.exp(-0.5 * ((torch.arange(9.) - 4) / (3.873 / 2.355)) ** 2)
+    k = (taps / taps.sum()).reshape(1, 1, 9, 1).to(dev)
+    t_blur = _events(lambda: vo.blur_along_x(hr, k), 5, 2)
+    vols = [torch.rand((512, 512, 160), device=dev, generator=g) for _ in range(4)]
+    t_fba = _events(lambda: vo.fba(vols, "infinity"), 3, 2)
+    t_mean = _events(lambda: vo.mean_fuse(vols), 5, 2)
+    t_rot = _events(lambda: vo.rotate_vol_2d(vols[0], 90), 5, 2)
+    torch.manual_seed(0)
+    m = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=False).to(dev).eval()
+    lr = torch.rand((41, 2, 512, 512), device=dev, generator=g)
+    flavr.apply_to_vol_flavr(m, lr[:6], max_batch=4)   # warm-up (weight packs, allocator)
+    t_sweep = _events(lambda: flavr.apply_to_vol_flavr(m, lr, max_batch=4), 1, 0)
+    orient = 4
+    total = (t_blur + orient * (t_sweep + 2 * t_rot) + t_fba + t_mean) / 1e3
+    nbytes = hr.numel() * 8
+    return {"config": "C5 self-SR pipeline on 512x512x160: blur (9 taps) + 4 orientations x (rot90, 40-window FLAVR sweep, rot-90) + "
+                      "fba(p=inf) and mean fusion; one sweep timed, multiplied by the orientation count", "c5_pipeline_s": round(total, 4),
+            "blur_ms": round(t_blur, 4), "blur_gbs": round(nbytes / t_blur / 1e6, 1),
+            "blur_frac_hbm_peak": round(nbytes / t_blur / 1e6 / float(peaks["hbm_gbs"]), 4),
+            "fba_ms": round(t_fba, 3), "mean_fuse_ms": round(t_mean, 4), "mean_fuse_gbs": round(5 * vols[0].numel() * 4 / t_mean / 1e6, 1),
+            "rot90_ms": round(t_rot, 4), "rot90_gbs": round(2 * vols[0].numel() * 4 / t_rot / 1e6, 1),
+            "sweep_s_per_orientation": round(t_sweep / 1e3, 4), "sweep_tflops": round(40 * 2.2 / t_sweep * 1e3, 1),
+            "frac_bf16_peak_burst": round(orient * 40 * 2.2 / total / float(peaks["bf16_tflops"]), 4)}
+
+
+def eager_gpu(dev, make_oracle_unet, batch, patch, steps=3, warm=2) -> dict:
+    """The reference's own GPU path on the same box: torch eager + cuDNN, bf16 autocast, channels_last_3d (informational)."""
+    model = make_oracle_unet().to(dev).to(memory_format=torch.channels_last_3d)
+    x = torch.randn((batch, 1, *patch), device=dev)
+    gt = torch.randn((batch, 2, *patch), device=dev)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(x)
+        (torch.dot(out.float().reshape(-1), gt.reshape(-1)) / out.numel()).backward()
+
+    ms = _events(step, steps, warm)
+    return {"config": "C1 shape through torch eager + cuDNN, bf16 autocast, channels_last_3d, same GPU", "eager_gpu_ms_per_step": round(ms, 3),
+            "patches_per_s": round(batch / ms * 1e3, 2)}
+
+
+def run_all(dev, peaks, rank, world, make_oracle_unet, batch, patch) -> dict:
+    """rank 0 returns {name: entry}; C3 runs on every rank (sharded), the single-GPU configs only when world == 1."""
+    out = {}
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001 -- an extra must never take the main bench line down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        out[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+        torch.cuda.empty_cache()
+
+    guarded("c3_sliding_window", lambda: c3_sliding_window(dev, peaks, world))
+    if world == 1:
+        guarded("c2_flavr", lambda: c2_flavr(dev, peaks))
+        guarded("c4_joint", lambda: c4_joint(dev, peaks))
+        guarded("c5_pipeline", lambda: c5_pipeline(dev, peaks))
+        if os.environ.get("REHR_BENCH_EAGER", "1") != "0":
+            guarded("eager_gpu", lambda: eager_gpu(dev, make_oracle_unet, batch, patch))
+    return out if rank == 0 else {}
