@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace rehr {
@@ -40,7 +41,12 @@ int encode_tiled_bf16(CUtensorMap* m, const void* base, int rank, const unsigned
 
 static constexpr int kWgmThreads = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 TMEM zero / final drain
 static constexpr int kWTileH = 16, kWTileW = 8;
-static constexpr int kHStages = 4;        // halo-plane ring
+// Plain-plane ring: KS planes are read by a step, the rest is prefetch distance.  Measured (profiles/r02_s2wgrad_ncu_summary.txt):
+// neither 9 spare slots nor a 12-deep halo ring changes the stride-2 32->64 @128^3 weight gradient (0.64 ms either way): that
+// launch is bound by the RATE at which TMA fetches the 64-byte granules of the parity-class views (13 B/clk/SM), not by latency.
+static constexpr int kPSpare = 3;
+static constexpr int kMaxHStages = 12;    // halo-plane ring: as deep as shared memory allows (WgmParams::h_stages, >= 4): the loop is
+                                          // bound by TMA latency when a step issues few MMAs (parity classes of a stride-2 conv)
 
 struct alignas(64) WgmParams {
   CUtensorMap h_map;  // 5-D NDHWC, box (CH, 8 + KS - 1, 16 + KS - 1, 1, 1)
@@ -49,6 +55,7 @@ struct alignas(64) WgmParams {
   int tiles_h, tiles_w, Ds, n_seg;
   int n_hs, n_ps, n_combo, ctas_per_combo, items_per_combo;
   uint32_t h_stride;  // bytes per halo stage (1024-aligned)
+  int h_stages;       // halo ring depth
   // sub-setting for the parity classes of a stride-2 conv (rehr_conv3d_wgrad_march_s2): which MMA groups (in-plane offset rows)
   // and which of the fused depth planes j are needed; everything else would multiply zeros
   int g_mask, j_min, j_max;
@@ -90,7 +97,7 @@ struct WgmCfg {
   static constexpr uint32_t kPRowB = PC * 2;
   static constexpr uint32_t kPLayout = kPRowB == 64 ? 4u : 6u;
   static constexpr uint32_t kPSlotBytes = kWTileH * kWTileW * PC * 2;
-  static constexpr int kPRing = KS + 3, kMirror = KS - 1;
+  static constexpr int kPRing = KS + kPSpare, kMirror = KS - 1;
   static_assert(kGroups * kN <= 512, "accumulators must fit TMEM");
   __host__ __device__ static constexpr int row0(int g) {
     return kPaired ? ((2 * g) / 3) * kHaloW + (2 * g) % 3 : (g / kParts) * kHaloW + (g % kParts) * kApm;
@@ -132,22 +139,23 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_p = smem;                                                    // (kPRing + kMirror) plain-plane slots
   uint8_t* s_h = smem + (((size_t)(kPRing + Cfg::kMirror) * kPSlotBytes + 1023) & ~size_t(1023));  // kHStages x h_stride
+  const uint32_t kHStages = (uint32_t)p.h_stages;
   uint8_t* tail = s_h + (size_t)kHStages * p.h_stride;
   uint64_t* full_h = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_h = full_h + kHStages;
-  uint64_t* full_p = empty_h + kHStages;
+  uint64_t* empty_h = full_h + kMaxHStages;
+  uint64_t* full_p = empty_h + kMaxHStages;
   uint64_t* empty_p = full_p + kPRing;
   uint64_t* zero_bar = empty_p + kPRing;
   uint64_t* done_bar = zero_bar + 1;
   uint64_t* ready_h = done_bar + 1;       // [kHStages]  halo tile transformed
-  uint64_t* ready_p = ready_h + kHStages;  // [kPRing]    plain tile transformed
+  uint64_t* ready_p = ready_h + kMaxHStages;  // [kPRing]    plain tile transformed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_p + kPRing);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     if (p.n_cls == 0) tma_prefetch_desc(&p.h_map);
     tma_prefetch_desc(&p.p_map);
-    for (int i = 0; i < kHStages; ++i) {
+    for (int i = 0; i < kMaxHStages; ++i) {
       mbar_init(&full_h[i], 1);
       mbar_init(&empty_h[i], 1);
       mbar_init(&ready_h[i], 3);
@@ -611,8 +619,15 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, Wg
   p.h_stride = ((uint32_t)(halo_rows + 16) * CH * 2 + 1023u) & ~1023u;  // + slack rows read by discarded atoms
   out->grid = p.n_combo * p.ctas_per_combo;
   const size_t pslot = (size_t)kWTileH * kWTileW * PC * 2;
-  const size_t tailb = (3 * kHStages + 3 * (ks + 3) + 2) * 8 + 16;
-  out->smem = 1024 + (((size_t)(ks + 3 + ks - 1) * pslot + 1023) & ~size_t(1023)) + (size_t)kHStages * p.h_stride + tailb;
+  const size_t tailb = (3 * kMaxHStages + 3 * (ks + kPSpare) + 2) * 8 + 16;
+  const size_t fixed = 1024 + (((size_t)(ks + kPSpare + ks - 1) * pslot + 1023) & ~size_t(1023)) + tailb;
+  {
+    const char* e = getenv("REHR_WGM_HSTAGES");  // development: force the halo ring depth
+    const int want = e ? atoi(e) : 4;
+    p.h_stages = (int)std::min<size_t>((size_t)std::max(4, std::min(want, kMaxHStages)), (227 * 1024 - fixed) / p.h_stride);
+    if (p.h_stages < 4) return REHR_UNSUPPORTED;
+  }
+  out->smem = fixed + (size_t)p.h_stages * p.h_stride;
   out->ws_bytes = (size_t)out->grid * out->groups * 128 * ks * PC * sizeof(float);
   return REHR_OK;
 }
