@@ -446,9 +446,9 @@ def test_march_forward_normalise_on_load(case):
 WG_NORM_CASES = [
     (2, 32, 32, (16, 32, 32), (3, 3, 3), (1, 1, 1), 0),       # role / piece choice: CH 32
     (1, 64, 32, (24, 44, 36), (3, 3, 3), (1, 1, 1), 32),      # [up | skip] table, ragged tiles, CH 64
-    (2, 64, 64, (12, 32, 32), (3, 3, 3), (1, 1, 1), 0),
-    (1, 128, 64, (16, 32, 32), (3, 3, 3), (1, 1, 1), 64),
-    (2, 32, 32, (8, 48, 40), (1, 3, 3), (0, 1, 1), 0),        # planar
+    (2, 64, 64, (16, 32, 32), (3, 3, 3), (1, 1, 1), 0),
+    (2, 128, 64, (16, 32, 32), (3, 3, 3), (1, 1, 1), 64),
+    (2, 32, 32, (10, 48, 40), (1, 3, 3), (0, 1, 1), 0),       # planar
     (2, 32, 16, (17, 23, 29), (3, 3, 3), (1, 1, 1), 0),       # everything ragged
 ]
 
