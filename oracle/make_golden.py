@@ -192,6 +192,27 @@ def sr_step_fixture() -> None:
     np.savez_compressed(os.path.join(OUT, "sr_step.npz"), **arrs)
 
 
+def wdsr_fixture() -> None:
+    """The reference's own WDSR (models/wdsr.py) with the unavailable third-party `resize` replaced by the identity, which is what
+    a resampling factor of 1 (integer scale) amounts to: forward on a seeded input + the gradient of the head for a seeded cotangent."""
+    import warnings
+    wd = refimport.load("models.wdsr")
+    wd.resize = lambda x, factors, order=3: x
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(1234)
+        net = wd.WDSR(out_channel=2, n_resblocks=2, num_channels=32, scale=4.0)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((2, 2, 16, 12), generator=g)
+    out = net(x)
+    cot = torch.randn(out.shape, generator=g)
+    (out * cot).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "wdsr_small.npz"), x=x.numpy(), out=out.detach().numpy(), cot=cot.numpy(),
+                        keys=np.array(list(net.state_dict().keys())), head_v=net.head.weight_v.detach().numpy(),
+                        grad_head_g=net.head.weight_g.grad.numpy(), grad_tail_v=net.tail.conv0.weight_v.grad.numpy(),
+                        patch=np.array(net.calc_out_patch_size([16, 12])))
+
+
 def random_centers_fixture() -> None:
     """The reference's own `get_random_centers` (utils/patch_ops.py:67-113) under a fixed `np.random.seed`: images from the legacy
     RandomState(3) stream (stable across numpy versions), so the test can rebuild the inputs and compare centre by centre."""
@@ -214,6 +235,9 @@ def main() -> None:
     import sys
     if "--only-centers" in sys.argv:
         random_centers_fixture()
+        return
+    if "--only-wdsr" in sys.argv:
+        wdsr_fixture()
         return
     if "--only-joint" in sys.argv:
         joint_fixture()
@@ -337,6 +361,7 @@ def main() -> None:
     sr_sweep_fixture()
     sr_step_fixture()
     random_centers_fixture()
+    wdsr_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

@@ -240,3 +240,38 @@ def get_random_centers(imgs_rot, patch_size, n_patches, weighted=True):
         centers.extend((i, tuple(c)) for c in zip(*draws))
     np.random.shuffle(centers)
     return centers
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# post-processing of the SR stage outputs (the tensor parts of utils/sr_utils.py:244-304, after parse_image's file IO)
+# ----------------------------------------------------------------------------------------------------------------
+def zeroonenorm(data: torch.Tensor) -> torch.Tensor:
+    """utils/sr_utils.py:279-282: min-max normalise to [0, 255] (fp32)."""
+    data = data.float()
+    lo, hi = data.amin(), data.amax()
+    return (data - lo) / (hi - lo) * 255.0
+
+
+def postprocess_flavr_volume(image: torch.Tensor, blur_kernel: torch.Tensor) -> torch.Tensor:
+    """`postprocess_flavr` (utils/sr_utils.py:284-304) between the two parse_image reads and the return: min-max normalise the SR
+    volume [X, Y, Z] to [0, 255], move z first ([Z, 1, X, Y]), blur along x with the slice-profile kernel [1, 1, L, 1]
+    (F.conv2d(..., padding="same") -> rehr_blur1d) and move z back.  Returns [X, Y, Z] fp32 on the GPU."""
+    if image.dim() != 3:
+        raise RehrError("postprocess_flavr_volume expects the [X, Y, Z] SR volume")
+    vol = zeroonenorm(image.cuda() if not image.is_cuda else image)
+    z_first = vol.permute(2, 0, 1).unsqueeze(1)                        # z, 1, x, y
+    return blur_along_x(z_first, blur_kernel).squeeze(1).permute(1, 2, 0)
+
+
+def postprocess_smore_volume(image: torch.Tensor, blur_kernel: torch.Tensor):
+    """`postprocess_smore` (utils/sr_utils.py:244-277) after the volume [X, Y, Z, 2] (image, label) has been assembled: returns
+    (img_hr [X,Y,Z,1], label_hr uint8 [X,Y,Z,1], image_x_rgb [Z,1,X,Y], image_y_rgb [Z,1,Y,X]) -- the two in-plane orientations of
+    the image channel blurred along their first in-plane axis."""
+    if image.dim() != 4 or image.shape[-1] < 2:
+        raise RehrError("postprocess_smore_volume expects [X, Y, Z, 2] (image, label)")
+    image = image.cuda() if not image.is_cuda else image
+    img_hr = image[..., :1]
+    label_hr = image[..., 1:].to(torch.uint8)
+    image_x = image.permute(2, 3, 0, 1)[:, 0:1]                        # z, channel, x, y
+    image_y = image.permute(2, 3, 1, 0)[:, 0:1]                        # z, channel, y, x
+    return img_hr, label_hr, blur_along_x(image_x, blur_kernel), blur_along_x(image_y, blur_kernel)

@@ -141,3 +141,21 @@ def test_oracle_sr_sweep_matches_reference_apply_to_vol_flavr():
     want = torch.from_numpy(z["out"])
     assert got.shape == want.shape == (16, 2, 24, 20)
     assert float((got - want).norm() / want.norm()) <= 1e-5
+
+
+def test_oracle_wdsr_reproduces_the_reference_module():
+    """oracle/wdsr.py vs tests/golden/wdsr_small.npz (the reference's own WDSR, `resize` by 1 = identity): same state_dict keys,
+    same default init, same output and gradients."""
+    import warnings
+    from oracle import wdsr as ow
+    z = np.load(os.path.join(G, "wdsr_small.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = ow.build()
+    assert list(net.state_dict().keys()) == list(z["keys"])
+    assert np.array_equal(net.head.weight_v.detach().numpy(), z["head_v"])
+    out = net(torch.from_numpy(z["x"]))
+    assert float((out.detach() - torch.from_numpy(z["out"])).norm() / torch.from_numpy(z["out"]).norm()) < 1e-6
+    (out * torch.from_numpy(z["cot"])).sum().backward()
+    assert np.allclose(net.head.weight_g.grad.numpy(), z["grad_head_g"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(net.tail.conv0.weight_v.grad.numpy(), z["grad_tail_v"], rtol=1e-4, atol=1e-6)

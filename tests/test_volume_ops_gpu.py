@@ -99,3 +99,27 @@ def test_target_pad_device_matches_numpy():
     padded, pads = vo.target_pad(torch.from_numpy(z["pad_in"]).cuda(), (10, 9, 7), mode="reflect")
     assert np.array_equal(padded.cpu().numpy(), z["pad_out"]) and np.array_equal(np.array(pads), z["pad_pads"])
     assert np.array_equal(vo.crop(padded, pads).cpu().numpy(), z["pad_crop"])
+
+
+def test_postprocess_volumes_match_the_reference_arithmetic():
+    """utils/sr_utils.py:244-304 after parse_image: zeroonenorm, z-first, F.conv2d(.., padding="same") blur along x, z back
+    (`postprocess_flavr`), and the two blurred in-plane orientations of `postprocess_smore` -- vs the same lines in torch on the CPU."""
+    import torch.nn.functional as F
+    from rehrseg_b200 import volume_ops as vo
+    g = torch.Generator().manual_seed(21)
+    image = torch.randn((24, 20, 9), generator=g) * 3 + 1
+    taps = torch.exp(-0.5 * ((torch.arange(9.) - 4) / 1.6) ** 2)
+    k = (taps / taps.sum()).reshape(1, 1, 9, 1)
+    x = image.numpy()
+    x = (x - x.min()) / (x.max() - x.min()) * 255.0                                        # zeroonenorm
+    want = F.conv2d(torch.from_numpy(x.transpose(2, 0, 1)).unsqueeze(1), k, padding="same").squeeze(1).numpy().transpose(1, 2, 0)
+    got = vo.postprocess_flavr_volume(image.cuda(), k.cuda())
+    assert tuple(got.shape) == want.shape
+    assert float((got.cpu() - torch.from_numpy(want)).norm() / torch.from_numpy(want).norm()) < 1e-5
+    vol = torch.stack([image, (image > 1).float()], dim=-1)                                # [X, Y, Z, 2]
+    img_hr, label_hr, xr, yr = vo.postprocess_smore_volume(vol.cuda(), k.cuda())
+    v = vol.numpy()
+    want_x = F.conv2d(torch.from_numpy(v.transpose(2, 3, 0, 1))[:, 0:1], k, padding="same")
+    want_y = F.conv2d(torch.from_numpy(v.transpose(2, 3, 1, 0).copy())[:, 0:1], k, padding="same")
+    assert label_hr.dtype == torch.uint8 and tuple(img_hr.shape) == (24, 20, 9, 1)
+    assert float((xr.cpu() - want_x).norm() / want_x.norm()) < 1e-5 and float((yr.cpu() - want_y).norm() / want_y.norm()) < 1e-5
