@@ -213,7 +213,10 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False
     Cached per parameter object and version counter (an optimiser step bumps the version -> repack)."""
     key = (id(weight), kind, h)
     dt = L.F16 if h else L.BF16
-    ver = weight._version
+    if weight.is_inference():      # tensors made under torch.inference_mode() carry no version counter: pack, never cache
+        ver, cache = -1, False
+    else:
+        ver = weight._version
     if cache:
         hit = _wcache.get(key)
         if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
@@ -256,6 +259,8 @@ def _cache_put(key, weight: torch.Tensor, out: torch.Tensor) -> None:
     """Insert an operand copy.  Backward passes look their weights up through autograd's saved tensors, which are fresh Python
     objects every step: their entries die with them (the weak reference clears) and would otherwise pile up in a training loop that
     never calls clear_weight_cache(), each holding a packed bf16 copy -- so dead entries are dropped once the table grows."""
+    if weight.is_inference():
+        return
     if len(_wcache) >= 256:
         for k in [k for k, v in _wcache.items() if v[0]() is None]:
             del _wcache[k]
