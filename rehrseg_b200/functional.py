@@ -207,20 +207,9 @@ USE_MARCH = True  # route eligible k3/s1/p1 layers through the halo-resident mar
 S2_WGRAD_MARCH_MIN_VOXELS = 262144  # dy voxels from which the per-parity-class marching wgrad of a stride-2 conv wins
 
 
-def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False) -> torch.Tensor:
-    """16-bit K-major operand of `weight` ([A][B][T...] fp32) -- kind 'fwd': [A][T][B], 'dgrad': [B][T][A]; `h`: packed as fp16
-    (must match the activation tensor the GEMM contracts it with), else bf16.
-    Cached per parameter object and version counter (an optimiser step bumps the version -> repack)."""
-    key = (id(weight), kind, h)
+def _pack_into(weight: torch.Tensor, kind: str, h: bool, out: Optional[torch.Tensor] = None, extra=None) -> torch.Tensor:
+    """Launch the pack kernel of `kind` for `weight` into `out` (allocated when None) on the current stream."""
     dt = L.F16 if h else L.BF16
-    if weight.is_inference():      # tensors made under torch.inference_mode() carry no version counter: pack, never cache
-        ver, cache = -1, False
-    else:
-        ver = weight._version
-    if cache:
-        hit = _wcache.get(key)
-        if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
-            return hit[2]
     A, B = weight.shape[0], weight.shape[1]
     T = weight[0, 0].numel()
     w = weight.detach()
@@ -228,43 +217,113 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False
         w = w.contiguous()
     if w.dtype != torch.float32:
         w = w.float()
+
+    def buf(n_or_shape):
+        if out is not None:
+            return out
+        shape = (n_or_shape,) if isinstance(n_or_shape, int) else n_or_shape
+        return torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+
     if kind == "march_fwd":      # conv A<-B, marching-kernel layout
         ks = int(weight.shape[2])
-        out = torch.empty((lib().rehr_conv3d_march_weight_bytes(B, A, ks) // 2,), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), A, B, ks, B * T, T, 0, dt, stream_ptr()), "pack_weight_march")
+        o = buf(lib().rehr_conv3d_march_weight_bytes(B, A, ks) // 2)
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(o), A, B, ks, B * T, T, 0, dt, stream_ptr()), "pack_weight_march")
     elif kind == "march_dgrad":  # its input-gradient B<-A (transposed, taps flipped)
         ks = int(weight.shape[2])
-        out = torch.empty((lib().rehr_conv3d_march_weight_bytes(A, B, ks) // 2,), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight_march(ptr(w), ptr(out), B, A, ks, T, B * T, 1, dt, stream_ptr()), "pack_weight_march")
+        o = buf(lib().rehr_conv3d_march_weight_bytes(A, B, ks) // 2)
+        check(lib().rehr_pack_weight_march(ptr(w), ptr(o), B, A, ks, T, B * T, 1, dt, stream_ptr()), "pack_weight_march")
+    elif kind == "s2dgrad":      # parity-class weights of a stride-2 input gradient; extra = (kernel, stride, padding)
+        desc = conv_desc(*extra)
+        o = buf(lib().rehr_conv3d_march_s2dgrad_weight_bytes(C.byref(desc), B, A) // 2)
+        check(lib().rehr_pack_weight_march_s2dgrad(C.byref(desc), ptr(w), ptr(o), B, A, stream_ptr()), "pack_weight_march_s2dgrad")
     elif kind == "tconv_fused":  # ConvTranspose weight [Cin=A][Cout=B][T] -> [T][Cout][Cin]
-        out = torch.empty((T, B, A), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight(ptr(w), ptr(out), T, A, B, 1, B * T, T, dt, stream_ptr()), "pack_weight")
+        o = buf((T, B, A))
+        check(lib().rehr_pack_weight(ptr(w), ptr(o), T, A, B, 1, B * T, T, dt, stream_ptr()), "pack_weight")
     elif kind == "fwd":
-        out = torch.empty((A, T, B), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight(ptr(w), ptr(out), A, B, T, B * T, T, 1, dt, stream_ptr()), "pack_weight")
+        o = buf((A, T, B))
+        check(lib().rehr_pack_weight(ptr(w), ptr(o), A, B, T, B * T, T, 1, dt, stream_ptr()), "pack_weight")
     else:
-        out = torch.empty((B, T, A), dtype=torch.bfloat16, device=w.device)
-        check(lib().rehr_pack_weight(ptr(w), ptr(out), B, A, T, T, B * T, 1, dt, stream_ptr()), "pack_weight")
+        o = buf((B, T, A))
+        check(lib().rehr_pack_weight(ptr(w), ptr(o), B, A, T, T, B * T, 1, dt, stream_ptr()), "pack_weight")
     _count()
+    return o
+
+
+_pending_prepack = None   # fork object of refresh_weight_cache(): joined by the first cache hit of the step
+
+
+def _join_prepack() -> None:
+    global _pending_prepack
+    if _pending_prepack is not None:
+        fk, _pending_prepack = _pending_prepack, None
+        fk.join()
+
+
+def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False, extra=None) -> torch.Tensor:
+    """16-bit K-major operand of `weight` ([A][B][T...] fp32) -- kind 'fwd': [A][T][B], 'dgrad': [B][T][A], the marching layouts,
+    ...; `h`: packed as fp16 (must match the activation tensor the GEMM contracts it with), else bf16.
+    Cached per parameter object and version counter (an optimiser step bumps the version -> repack, or refresh_weight_cache()
+    re-packs every cached copy in place at the start of a step)."""
+    key = (id(weight), kind, h, extra)
+    if weight.is_inference():      # tensors made under torch.inference_mode() carry no version counter: pack, never cache
+        ver, cache = -1, False
+    else:
+        ver = weight._version
+    if cache:
+        hit = _wcache.get(key)
+        if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
+            _join_prepack()
+            return hit[2]
+    out = _pack_into(weight, kind, h, None, extra)
     if cache:
         _cache_put(key, weight, out)
     return out
 
 
 def clear_weight_cache() -> None:
+    _join_prepack()
     _wcache.clear()
 
 
+def refresh_weight_cache() -> int:
+    """Re-pack every cached 16-bit operand copy IN PLACE from the current parameter values, on a side stream forked from the
+    current one (events only: CUDA-graph capturable), and mark them current.  Called at the start of a training step after the
+    optimiser update: the ~50 small pack kernels then run next to the first layers instead of in front of each conv, and the
+    addresses the kernels see stay fixed (what a captured graph needs).  The first cache hit of the step joins the side stream.
+    Returns the number of copies refreshed (0 on the very first step: nothing is cached yet and the packs happen lazily)."""
+    global _pending_prepack
+    _join_prepack()
+    live = [(k, v) for k, v in _wcache.items() if v[0]() is not None]
+    for k in [k for k, v in _wcache.items() if v[0]() is None]:
+        del _wcache[k]
+    if not live:
+        return 0
+    fk = _fork(live[0][1][2].device)
+    with fk:
+        for key, (wref, _ver, out) in live:
+            w = wref()
+            _pack_into(w, key[1], key[2], out, key[3])
+            _wcache[key] = (wref, w._version, out)
+    _pending_prepack = fk
+    return len(live)
+
+
 def _cache_put(key, weight: torch.Tensor, out: torch.Tensor) -> None:
-    """Insert an operand copy.  Backward passes look their weights up through autograd's saved tensors, which are fresh Python
-    objects every step: their entries die with them (the weak reference clears) and would otherwise pile up in a training loop that
-    never calls clear_weight_cache(), each holding a packed bf16 copy -- so dead entries are dropped once the table grows."""
+    """Insert an operand copy; dead entries (weights that were garbage collected) are dropped once the table grows."""
     if weight.is_inference():
         return
     if len(_wcache) >= 256:
         for k in [k for k, v in _wcache.items() if v[0]() is None]:
             del _wcache[k]
     _wcache[key] = (weakref.ref(weight), weight._version, out)
+
+
+def _orig_weight(ctx, saved: torch.Tensor) -> torch.Tensor:
+    """The Parameter object the forward saw (autograd's saved tensor is a fresh Python object every step, which would miss the
+    packed-weight cache and defeat refresh_weight_cache): kept as a weak reference on the ctx."""
+    ref = getattr(ctx, "wref", None)
+    w = ref() if ref is not None else None
+    return w if (w is not None and w.data_ptr() == saved.data_ptr()) else saved
 
 
 def _out_size(i: int, k: int, s: int, p: int) -> int:
@@ -446,19 +505,7 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
             and dy.shape[1] * dy.shape[2] * dy.shape[3] >= 4096 and dy.shape[4] <= 64:
         # stride-2 stage-entry conv: one marching launch per output parity class (small volumes stay on the split-K path;
         # with more than 64 dy channels the resident-weight tile shrinks to 16 columns and the tapped kernel is faster)
-        key = (id(weight), "s2dgrad", tuple(stride))
-        hit = _wcache.get(key) if cache else None
-        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
-            wp = hit[2]
-        else:
-            w32 = _f32(weight)
-            wp = torch.empty((lib().rehr_conv3d_march_s2dgrad_weight_bytes(C.byref(desc), cin, dy.shape[4]) // 2,),
-                             dtype=torch.bfloat16, device=dy.device)
-            check(lib().rehr_pack_weight_march_s2dgrad(C.byref(desc), ptr(w32), ptr(wp), cin, dy.shape[4], stream_ptr()),
-                  "pack_weight_march_s2dgrad")
-            _count()
-            if cache:
-                _cache_put(key, weight, wp)
+        wp = _packed(weight, "s2dgrad", cache, extra=(tuple(kernel), tuple(stride), tuple(padding)))
         dyt, dxt = rt(dy), rt(dx)
         with _timed("conv_march_kernel", flops, tag):
             check(lib().rehr_conv3d_march_s2dgrad(C.byref(desc), C.byref(dyt), ptr(wp), C.byref(dxt), stream_ptr()),
@@ -646,6 +693,7 @@ class ConvNormAct(torch.autograd.Function):
         rstd = torch.empty((n, cout), dtype=torch.float32, device=dev)
         g32, b32 = _f32(gamma), _f32(beta)
         ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None, y_h, x_raw_h)
+        ctx.wref = weakref.ref(weight)
         if defer:
             ctot, coff = (2 * cout, cout) if cat_room else (cout, 0)
             norm = torch.empty((n, 3, ctot), dtype=torch.float32, device=dev)
@@ -681,6 +729,7 @@ class ConvNormAct(torch.autograd.Function):
         if da is None:
             return (None,) * 12
         x, x_norm, weight, gamma, beta, y, mean, rstd = ctx.saved_tensors
+        weight = _orig_weight(ctx, weight)
         kernel, stride, padding, slope, small_cin, has_bias, y_h, x_raw_h = ctx.cfg
         dev = y.device
         da = as_cl(da)
@@ -769,6 +818,7 @@ class ConvAct(torch.autograd.Function):
                                      want_stats=want_pool)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (kernel, stride, padding, act, slope, bias is not None)
+        ctx.wref = weakref.ref(weight)
         if want_pool:
             if act != ACT_NONE:
                 raise L.RehrError("want_pool needs the pre-activation output (act=ACT_NONE)")
@@ -785,6 +835,7 @@ class ConvAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, da, *_unused):
         x, weight, y = ctx.saved_tensors
+        weight = _orig_weight(ctx, weight)
         kernel, stride, padding, act, slope, has_bias = ctx.cfg
         dy = act_bwd_raw(y, da, act, slope) if act != ACT_NONE else as_cl(da)
         cout = weight.shape[0]
@@ -1003,6 +1054,7 @@ class ConvTranspose(torch.autograd.Function):
                 full2 = convert16_raw(y, True, False)
         ctx.save_for_backward(x_bf, weight, y if act != ACT_NONE else None)
         ctx.cfg = (kernel, stride, padding, act, slope, bias is not None, x_h)
+        ctx.wref = weakref.ref(weight)
         out = full if skip is not None else y
         if full2 is not None:
             ctx.mark_non_differentiable(full2)
@@ -1013,6 +1065,7 @@ class ConvTranspose(torch.autograd.Function):
         if da is None:
             return (None,) * 9
         x, weight, y = ctx.saved_tensors
+        weight = _orig_weight(ctx, weight)
         kernel, stride, padding, act, slope, has_bias, y_h = ctx.cfg
         dskip = None
         if ctx.cat:  # da is the gradient of the whole [up | skip] buffer

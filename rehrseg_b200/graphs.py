@@ -97,12 +97,16 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._eager()
         self.grads = [p.grad for p in self.params]     # static gradient tensors (None for parameters the loss does not reach)
+        # the captured pack kernels write the cached 16-bit weight copies in place: keep them alive with the graph
+        from . import functional as Fn
+        self._packed_weights = [v[2] for v in Fn._wcache.values()]
 
     def _eager(self):
         from . import functional as Fn
-        # the bf16 operand copies must be re-derived INSIDE the captured step (a cache hit at capture time would bake stale
-        # weights into the graph): drop the cache so every pack kernel is part of the graph and re-reads the live parameters
-        Fn.clear_weight_cache()
+        # the 16-bit operand copies must be re-derived INSIDE the captured step from the live parameters (a plain cache hit at
+        # capture time would bake stale weights into the graph): every cached copy is re-packed in place on a side stream
+        # (a parallel branch of the graph) while the first layers run; the first warm-up step packs lazily instead
+        Fn.refresh_weight_cache()
         if self.before_step is not None:
             self.before_step()
         for p in self.params:
@@ -110,6 +114,7 @@ class GraphedTrainStep:
         out = self.model(self.static_inputs[0])
         loss = self.loss_fn(out, *self.static_inputs[1:])
         loss.backward()
+        Fn._join_prepack()   # (a model without a cached operand copy never joined the pack branch)
         return loss.detach()
 
     def load(self, *inputs, non_blocking: bool = True):
