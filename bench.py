@@ -278,7 +278,8 @@ def main() -> None:
     if use_graph:
         from rehrseg_b200.graphs import GraphedTrainStep
         # the whole step (weight re-pack, forward, loss, backward) captured once; replays re-read the live parameters
-        gstep = GraphedTrainStep(model, loss_fn, (x_dev, g_dev))
+        # N > 1: the data-parallel gradient mean is captured too, in buckets that overlap the backward pass
+        gstep = GraphedTrainStep(model, loss_fn, (x_dev, g_dev), dp_group=True if world > 1 else None)
         x_dev, g_dev = gstep.static_inputs       # "resident" steps run on the static inputs without any copy
 
     def fwd_bwd(x, g, eager=False):
@@ -295,7 +296,7 @@ def main() -> None:
                     out = model(x)
             loss = loss_fn(out, g)
             loss.backward()
-        if world > 1:  # data-parallel gradient mean over NVLink (one flat bucket)
+        if world > 1 and not (use_graph and not eager):  # python-launched step: gradient mean over NVLink through one flat bucket
             if dp["active"] is None:
                 dp["active"] = [p for p in params if p.grad is not None]
             grads = [p.grad for p in dp["active"]]

@@ -76,10 +76,23 @@ class GraphedTrainStep:
                                             # every replay and re-attached to the parameters after it
 
     The first input is the network input; all inputs must keep their shapes.  `loss` is a static tensor, valid until the next call.
+
+    Data parallel (`dp_group` = a torch.distributed group, or True for the default group): the gradient mean is part of the captured
+    step and OVERLAPS the backward pass -- the parameters are cut into `dp_buckets` buckets of equal bytes in the order their
+    gradients become final, and as soon as the last gradient of a bucket has been written the bucket is all-reduced (AVG, one
+    coalesced NCCL launch over the gradients themselves: no gather / scatter copies) on a communication stream that the compute
+    stream joins after the backward pass.  Every rank issues the same collectives in the same (autograd) order.
     """
 
-    def __init__(self, model, loss_fn, example_inputs, warmup: int = 2, before_step=None):
+    def __init__(self, model, loss_fn, example_inputs, warmup: int = 2, before_step=None, dp_group=None, dp_buckets: int = 6):
         self.model, self.loss_fn, self.before_step = model, loss_fn, before_step
+        self._dp = None
+        if dp_group is not None and dp_group is not False:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                group = None if dp_group is True else dp_group
+                if dist.get_world_size(group) > 1:
+                    self._dp = {"group": group, "buckets": int(dp_buckets), "plan": None, "hooks": []}
         self.static_inputs = tuple(t.detach().clone() if t.is_cuda else t.detach().to(next(model.parameters()).device)
                                    for t in example_inputs)
         dev = self.static_inputs[0].device
@@ -87,6 +100,8 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            if self._dp is not None:
+                self._plan_buckets(dev)
             for _ in range(warmup):
                 self._eager()
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -94,12 +109,68 @@ class GraphedTrainStep:
         for p in self.params:
             p.grad = None                    # gradients are (re)created inside the capture: static addresses, plain assignment
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread of torch.distributed polls events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self._dp is not None else "global"):
             self.loss = self._eager()
         self.grads = [p.grad for p in self.params]     # static gradient tensors (None for parameters the loss does not reach)
         # the captured pack kernels write the cached 16-bit weight copies in place: keep them alive with the graph
         from . import functional as Fn
         self._packed_weights = [v[2] for v in Fn._wcache.values()]
+
+    # ---- data-parallel gradient mean, overlapped with the backward pass --------------------------------------------------
+    def _plan_buckets(self, dev) -> None:
+        """One plain backward with hooks that record the order in which the gradients become final; buckets of equal bytes in
+        that order; permanent hooks that fire a bucket's all-reduce when its last gradient has been accumulated."""
+        order = []
+        hs = [p.register_post_accumulate_grad_hook(lambda q, order=order: order.append(q)) for p in self.params]
+        self._plain_step()
+        for h in hs:
+            h.remove()
+        total = sum(p.numel() for p in order)
+        nb = max(1, min(self._dp["buckets"], len(order)))
+        buckets, cur, acc = [], [], 0
+        for p in order:
+            cur.append(p)
+            acc += p.numel()
+            if acc >= total * (len(buckets) + 1) / nb and len(buckets) < nb - 1:
+                buckets.append(cur)
+                cur = []
+        if cur:
+            buckets.append(cur)
+        self._dp["plan"] = buckets
+        self._dp["of"] = {id(p): b for b, ps in enumerate(buckets) for p in ps}
+        self._dp["comm"] = torch.cuda.Stream(device=dev)
+        self._dp["left"] = [0] * len(buckets)
+        self._dp["hooks"] = [p.register_post_accumulate_grad_hook(self._on_grad) for ps in buckets for p in ps]
+
+    def _on_grad(self, p) -> None:
+        dp = self._dp
+        if not dp.get("armed"):
+            return
+        b = dp["of"][id(p)]
+        dp["left"][b] -= 1
+        if dp["left"][b] == 0:
+            self._allreduce_bucket(b)
+
+    def _allreduce_bucket(self, b: int) -> None:
+        import torch.distributed as dist
+        dp = self._dp
+        dev = self.static_inputs[0].device
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        dp["comm"].wait_event(ev)
+        with torch.cuda.stream(dp["comm"]):
+            with dist._coalescing_manager(group=dp["group"], device=dev, async_ops=False):
+                for q in dp["plan"][b]:
+                    dist.all_reduce(q.grad, op=dist.ReduceOp.AVG, group=dp["group"])
+
+    def _plain_step(self):
+        for p in self.params:
+            p.grad = None
+        out = self.model(self.static_inputs[0])
+        loss = self.loss_fn(out, *self.static_inputs[1:])
+        loss.backward()
+        return loss
 
     def _eager(self):
         from . import functional as Fn
@@ -113,7 +184,19 @@ class GraphedTrainStep:
             p.grad = None
         out = self.model(self.static_inputs[0])
         loss = self.loss_fn(out, *self.static_inputs[1:])
-        loss.backward()
+        if self._dp is not None:
+            self._dp["left"] = [len(ps) for ps in self._dp["plan"]]
+            self._dp["armed"] = True
+        try:
+            loss.backward()
+        finally:
+            if self._dp is not None:
+                self._dp["armed"] = False
+        if self._dp is not None:                 # the compute stream continues after every bucket's all-reduce
+            dev = self.static_inputs[0].device
+            ev = torch.cuda.Event()
+            ev.record(self._dp["comm"])
+            torch.cuda.current_stream(dev).wait_event(ev)
         Fn._join_prepack()   # (a model without a cached operand copy never joined the pack branch)
         return loss.detach()
 

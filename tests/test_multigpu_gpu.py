@@ -56,6 +56,26 @@ for i, p in enumerate(params):
     assert all(torch.equal(gathered[0], q) for q in gathered), "ranks disagree after the all-reduce"
 assert worst < 1e-5, worst
 
+# the same mean from the CUDA-graph step with the bucketed all-reduce captured inside and overlapped with the backward pass
+from rehrseg_b200.graphs import GraphedTrainStep
+def loss_fn(out, t):
+    return (out.float() * t).sum() / t.numel()
+xb, tb = batch(rank)
+step = GraphedTrainStep(model, loss_fn, (xb, tb), dp_group=True, dp_buckets=4)
+for _ in range(2):
+    step(xb, tb)
+torch.cuda.synchronize()
+worst_g = 0.0
+for i, p in enumerate(params):
+    if p.grad is None:
+        continue
+    want = sum(o[i] for o in own) / world
+    worst_g = max(worst_g, float((p.grad - want).abs().max() / (want.abs().max() + 1e-20)))
+    gathered = [torch.empty_like(p.grad) for _ in range(world)]
+    dist.all_gather(gathered, p.grad)
+    assert all(torch.equal(gathered[0], q) for q in gathered), "ranks disagree after the captured all-reduce"
+assert worst_g < 1e-4, worst_g
+
 # sharded sliding window vs the single-GPU driver
 torch.manual_seed(3)
 seg = sm.SegModel(**ref_seg.plan_kwargs("tiny")).to(dev).eval()
@@ -71,7 +91,7 @@ both = [torch.empty_like(shard) for _ in range(world)]
 dist.all_gather(both, shard)
 assert torch.equal(both[0], both[1])
 if rank == 0:
-    print(f"MULTIGPU_OK grads_max_rel {worst:.2e} sw_rel_l2 {err:.2e} tiles {len(sl)}", flush=True)
+    print(f"MULTIGPU_OK grads_max_rel {worst:.2e} graph_dp_max_rel {worst_g:.2e} sw_rel_l2 {err:.2e} tiles {len(sl)}", flush=True)
 dist.destroy_process_group()
 '''
 
