@@ -419,9 +419,26 @@ def main() -> None:
         import bench_extras
         extras = bench_extras.run_all(dev, measured_peaks(), rank, world, _oracle_unet, BATCH, PATCH)
 
+    def teardown():
+        """Captured NCCL kernels must be gone before the communicator is destroyed (GraphedTrainStep.close); a watchdog makes sure a
+        stuck teardown can never hold the job: the JSON line is already out by then."""
+        if world <= 1:
+            return
+        if gstep is not None:
+            gstep.close()
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(20):
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        dist.barrier()
+        dist.destroy_process_group()
+        done.set()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown()
         return
     per_step = ms / args.steps
     value = world * BATCH * args.steps / (ms / 1e3)
@@ -452,8 +469,7 @@ def main() -> None:
     if world == 1 and args.impl == "b200" and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == "__main__":

@@ -200,6 +200,19 @@ class GraphedTrainStep:
         Fn._join_prepack()   # (a model without a cached operand copy never joined the pack branch)
         return loss.detach()
 
+    def close(self) -> None:
+        """Drop the captured graph (and the gradient hooks).  REQUIRED before `torch.distributed.destroy_process_group()` when the
+        data-parallel all-reduces were captured: tearing the NCCL communicator down while a live graph still holds its kernels
+        blocks forever (observed on B200 / torch 2.11 / NCCL 2.28)."""
+        if self._dp is not None:
+            for h in self._dp.get("hooks", []):
+                h.remove()
+            self._dp["hooks"] = []
+        self.graph = None
+        self.grads = None
+        dev = self.static_inputs[0].device
+        torch.cuda.synchronize(dev)
+
     def load(self, *inputs, non_blocking: bool = True):
         """Copy a batch (pinned host or device tensors) into the static input buffers on the current stream."""
         for dst, src in zip(self.static_inputs, inputs):

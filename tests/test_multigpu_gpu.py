@@ -90,6 +90,7 @@ assert err < 2e-3, err
 both = [torch.empty_like(shard) for _ in range(world)]
 dist.all_gather(both, shard)
 assert torch.equal(both[0], both[1])
+step.close()     # captured NCCL kernels must be released before the communicator is destroyed
 if rank == 0:
     print(f"MULTIGPU_OK grads_max_rel {worst:.2e} graph_dp_max_rel {worst_g:.2e} sw_rel_l2 {err:.2e} tiles {len(sl)}", flush=True)
 dist.destroy_process_group()
