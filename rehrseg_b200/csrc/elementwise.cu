@@ -372,7 +372,7 @@ struct ApplyArgs {
 
 // MODE 0: a = lrelu(gamma*xhat + beta).  MODE 1: dy = gamma*rstd*(g - S1/V - xhat*S2/V).
 template <int MODE>
-__global__ void __launch_bounds__(256) in_apply_kernel(const ApplyArgs a) {
+__global__ void __launch_bounds__(256, MODE == 1 ? 4 : 1) in_apply_kernel(const ApplyArgs a) {
   extern __shared__ float sh[];  // MODE0: scale, shift ; MODE1: mean, rstd, gamma, beta, m1, m2
   const int n = blockIdx.y;
   const int C = a.C;

@@ -83,7 +83,10 @@ struct alignas(64) WgmParams {
 //   * halo tile: the KS in-plane offsets of one kernel row (kh) are consecutive tile rows, so they are stacked along M through
 //     LBO = one row; 128 / CH of them fit one MMA ("part"); for CH = 64, KS = 3 the 9 offsets are paired freely instead
 //     (any two rows form an arithmetic progression), which needs 5 MMAs instead of 6.
-template <int CH, int PC, int KS>
+// JP = number of fused depth planes that own accumulator columns (default KS).  The parity classes of a stride-2 conv never use
+// the plane q - 1 (j = 0), so JP = 2 there: N <= 2 * PC, which lets ONE piece cover all 64 dY channels (PC = 64, 3 x 128 TMEM
+// columns) -- X is then streamed once instead of once per 32-channel dY piece, in 128-byte instead of 64-byte dY rows.
+template <int CH, int PC, int KS, int JP = KS>
 struct WgmCfg {
   static constexpr int R = (KS - 1) / 2;
   static constexpr int kHaloH = kWTileH + KS - 1, kHaloW = kWTileW + KS - 1, kHaloRows = kHaloH * kHaloW;
@@ -91,11 +94,12 @@ struct WgmCfg {
   static constexpr int kParts = (KS + kApm - 1) / kApm;   // MMAs per kernel row
   static constexpr bool kPaired = (CH == 64 && KS == 3);
   static constexpr int kGroups = kPaired ? 5 : KS * kParts;
-  static constexpr int kN = KS * PC;                      // accumulator columns per group
+  static constexpr int kN = JP * PC;                      // accumulator columns per group
+  static constexpr int kJ0 = KS - JP;                     // first fused plane index that owns accumulator columns
   static constexpr uint32_t kRowB = CH * 2;
   static constexpr uint32_t kLayout = kRowB == 128 ? 2u : (kRowB == 64 ? 4u : 6u);
   static constexpr uint32_t kPRowB = PC * 2;
-  static constexpr uint32_t kPLayout = kPRowB == 64 ? 4u : 6u;
+  static constexpr uint32_t kPLayout = kPRowB == 128 ? 2u : (kPRowB == 64 ? 4u : 6u);
   static constexpr uint32_t kPSlotBytes = kWTileH * kWTileW * PC * 2;
   static constexpr int kPRing = KS + kPSpare, kMirror = KS - 1;
   static_assert(kGroups * kN <= 512, "accumulators must fit TMEM");
@@ -129,9 +133,9 @@ __device__ __forceinline__ WgmItem wgm_decode(const WgmParams& p, int item) {
   return c;
 }
 
-template <int CH, int PC, int KS>
+template <int CH, int PC, int KS, int JP = KS>
 __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __grid_constant__ WgmParams p) {
-  using Cfg = WgmCfg<CH, PC, KS>;
+  using Cfg = WgmCfg<CH, PC, KS, JP>;
   constexpr int R = Cfg::R;
   constexpr int kPRing = Cfg::kPRing;
   constexpr uint32_t kPSlotBytes = Cfg::kPSlotBytes;
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
         const uint32_t idesc = make_idesc_bf16(128, max(jhi - jlo + 1, 1) * PC, 1, 1);
         const uint32_t a_lo = sh_lo + st * hstride_lo;
         const uint32_t b_lo = (sp_lo + s0 * (kPSlotBytes >> 4)) | kBLoLbo;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(jlo * PC);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((jlo - Cfg::kJ0) * PC);   // host guarantees j_min >= kJ0
         if (wgm_elect()) {
           if (jlo <= jhi) {
 #pragma unroll
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kWgmThreads, 1) wgrad_march_kernel(const __gri
 struct WgmReduceParams {
   const float* ws;
   float* dw;
-  int CH, PC, KS, groups, apm, parts, paired;
+  int CH, PC, KS, JP, groups, apm, parts, paired;
   int n_hs, n_ps, n_combo, ctas_per_combo;
   int role;  // 0: Hh = X (ch = ci, cp = co), 1: Hh = dY (ch = co, cp = ci)
   int Ci, Co;        // channels of the dW tensor (Co may be smaller than the padded dY the kernel saw)
@@ -445,7 +449,7 @@ struct WgmReduceParams {
 //   SLICED = false: block = PC (cpl) x 256/PC consecutive ch, every thread walks its SHORT partial list alone.
 template <bool SLICED>
 __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduceParams p) {
-  __shared__ float red[16][33];
+  __shared__ float red[16][65];   // [256 / PC slices][PC plain channels]: PC <= 64
   const int cpl = threadIdx.x % p.PC, sub = threadIdx.x / p.PC;
   const int nsub = 256 / p.PC;
   int idx = blockIdx.x;
@@ -475,10 +479,12 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
   }
   const bool chok = ch < p.CH;
   const int m = at * p.CH + (chok ? ch : 0);
-  const int kn = p.KS * p.PC;
+  const int kn = p.JP * p.PC;
+  const int jc = j - (p.KS - p.JP);      // accumulator column block of fused plane j (planes below KS - JP own none)
+  if (jc < 0) return;
   const int combo = hs * p.n_ps + ps;
   const size_t per_cta = (size_t)p.groups * 128 * kn;
-  const size_t off = ((size_t)g * 128 + m) * kn + j * p.PC + cpl;
+  const size_t off = ((size_t)g * 128 + m) * kn + jc * p.PC + cpl;
   float t = 0.f;
   if (SLICED) {
     float acc = 0.f;
@@ -527,7 +533,7 @@ __global__ void __launch_bounds__(256) wgrad_march_reduce_kernel(const WgmReduce
 // ------------------------------------------------------------------------------------------------
 struct WgmPlan {
   WgmParams p;
-  int CH, PC, KS, role, grid, groups, planar;
+  int CH, PC, KS, JP, role, grid, groups, planar;
   size_t smem, ws_bytes;
 };
 
@@ -538,7 +544,8 @@ static int wgm_groups(int ch, int ks) {
 }
 
 // instantiated (CH, PC, KS) variants
-static bool wgm_variant_ok(int ch, int pc, int ks) {
+static bool wgm_variant_ok(int ch, int pc, int ks, int jp = 0) {
+  if (ks == 3 && jp == 2) return ch == 32 && pc == 64;   // stride-2 parity classes, all dY channels in one piece
   if (ks == 3) return (ch == 32 || ch == 64) && (pc == 32 || pc == 16);
   if (ks == 5) return ch == 16 && pc == 16;
   return false;
@@ -568,7 +575,7 @@ static int wgm_choose(int ci, int co, int ks, int* role, int* CH, int* PC) {
 }
 
 // ks_code: 3 / 5 = cubic kernel; 1 = planar k(1,3,3), pad (0,1,1): the k3 machinery restricted to the centre depth offset
-static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, WgmPlan* out, int force_role = -1) {
+static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, WgmPlan* out, int force_role = -1, int jp2 = 0) {
   WgmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   const int ks = ks_code == 1 ? 3 : ks_code;
@@ -582,6 +589,12 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, Wg
     PC = chp % 32 == 0 ? 32 : (chp % 16 == 0 ? 16 : 0);
     if (CH == 0 || PC == 0 || !wgm_variant_ok(CH, PC, ks)) return REHR_UNSUPPORTED;
     role = force_role;
+  }
+  out->JP = ks;
+  if (jp2 && force_role == 0 && x.c % 32 == 0 && x.c % 64 != 0 && dy.c % 64 == 0 && wgm_variant_ok(32, 64, ks, 2) &&
+      !getenv("REHR_WGM_NO_PC64")) {
+    CH = 32; PC = 64; role = 0;      // only the planes q, q + 1 own accumulators (see WgmCfg): one piece covers 64 dY channels
+    out->JP = 2;
   }
   p.g_mask = 0xffff;
   p.j_min = 0;
@@ -628,14 +641,14 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, Wg
     if (p.h_stages < 4) return REHR_UNSUPPORTED;
   }
   out->smem = fixed + (size_t)p.h_stages * p.h_stride;
-  out->ws_bytes = (size_t)out->grid * out->groups * 128 * ks * PC * sizeof(float);
+  out->ws_bytes = (size_t)out->grid * out->groups * 128 * out->JP * PC * sizeof(float);
   return REHR_OK;
 }
 
-template <int CH, int PC, int KS>
+template <int CH, int PC, int KS, int JP = KS>
 static int launch_wgm(const WgmPlan& pl, cudaStream_t stream) {
-  REHR_SET_MAX_SMEM_ONCE((wgrad_march_kernel<CH, PC, KS>), 227 * 1024);
-  wgrad_march_kernel<CH, PC, KS><<<pl.grid, kWgmThreads, pl.smem, stream>>>(pl.p);
+  REHR_SET_MAX_SMEM_ONCE((wgrad_march_kernel<CH, PC, KS, JP>), 227 * 1024);
+  wgrad_march_kernel<CH, PC, KS, JP><<<pl.grid, kWgmThreads, pl.smem, stream>>>(pl.p);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -648,7 +661,8 @@ using namespace rehr;
 static int wgm_launch_kernel(const WgmPlan& pl, cudaStream_t stream) {
   const int ks = pl.KS;
   int rc = REHR_UNSUPPORTED;
-  if (ks == 3 && pl.CH == 32 && pl.PC == 32) rc = launch_wgm<32, 32, 3>(pl, stream);
+  if (ks == 3 && pl.JP == 2 && pl.CH == 32 && pl.PC == 64) rc = launch_wgm<32, 64, 3, 2>(pl, stream);
+  else if (ks == 3 && pl.CH == 32 && pl.PC == 32) rc = launch_wgm<32, 32, 3>(pl, stream);
   else if (ks == 3 && pl.CH == 64 && pl.PC == 32) rc = launch_wgm<64, 32, 3>(pl, stream);
   else if (ks == 3 && pl.CH == 32 && pl.PC == 16) rc = launch_wgm<32, 16, 3>(pl, stream);
   else if (ks == 3 && pl.CH == 64 && pl.PC == 16) rc = launch_wgm<64, 16, 3>(pl, stream);
@@ -668,6 +682,7 @@ static int wgm_reduce(const WgmPlan& pl, const float* ws, int ctas_per_combo, in
   r.CH = pl.CH;
   r.PC = pl.PC;
   r.KS = ks;
+  r.JP = pl.JP;
   r.groups = pl.groups;
   r.apm = 128 / pl.CH;
   r.parts = (ks + r.apm - 1) / r.apm;
@@ -805,7 +820,7 @@ static int wgm_s2_plan(const rehr_conv_desc* d, const rehr_tensor* x, const rehr
   rehr_tensor xv = *dy;  // the iteration space is the dy grid; the halo operand is a parity class of X with X's channels
   xv.c = x->c;
   xv.ld = x->ld;
-  return plan_wgm(xv, *dy, 3, pl, 0);
+  return plan_wgm(xv, *dy, 3, pl, 0, d->sd == 2 ? 1 : 0);   // depth stride 2: no class uses the plane q - 1
 }
 
 int rehr_conv3d_wgrad_march_s2_supported(const rehr_conv_desc* d, const rehr_tensor* x, const rehr_tensor* dy) {
@@ -908,7 +923,7 @@ static int wgrad_march_s2_impl(const rehr_conv_desc* d, const rehr_tensor* x, co
   pl.grid = p.cls_begin[n_cls];
   rc = wgm_launch_kernel(pl, stream);
   if (rc != REHR_OK) return rc;
-  const size_t per_cta = (size_t)pl.groups * 128 * pl.KS * pl.PC;
+  const size_t per_cta = (size_t)pl.groups * 128 * pl.JP * pl.PC;
   const int cs[3] = {s[0], s[1], s[2]};
   for (int c = 0; c < n_cls; ++c) {
     rc = wgm_reduce(pl, p.ws + (size_t)p.cls_begin[c] * per_cta, share[c], x->c, dy->c, dw, accumulate, cs, cls_r[c], stream);

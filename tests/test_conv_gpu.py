@@ -368,7 +368,8 @@ def test_flavr_stem_smallcin_raw():
 
 
 @pytest.mark.parametrize("case", [(1, 32, 64, (16, 128, 128), (2, 2, 2)), (1, 64, 32, (15, 130, 126), (2, 2, 2)),
-                                  (1, 32, 32, (8, 128, 128), (1, 2, 2))])
+                                  (1, 32, 32, (8, 128, 128), (1, 2, 2)), (2, 32, 64, (33, 66, 70), (2, 2, 2)),
+                                  (1, 32, 128, (32, 128, 128), (2, 2, 2))])
 def test_wgrad_march_stride2(case):
     """Per-parity-class marching weight gradient of the stride-2 stage-entry convs (strided TMA views of x, offset masks),
     forced on for these mid-size shapes, against torch autograd."""
