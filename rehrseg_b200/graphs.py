@@ -154,8 +154,10 @@ class GraphedTrainStep:
 
     def _allreduce_bucket(self, b: int) -> None:
         import torch.distributed as dist
+        from . import functional as Fn
         dp = self._dp
         dev = self.static_inputs[0].device
+        Fn.join_pending_wgrad()          # weight gradients of this bucket may still be running on the side stream
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         dp["comm"].wait_event(ev)
@@ -198,6 +200,7 @@ class GraphedTrainStep:
             ev.record(self._dp["comm"])
             torch.cuda.current_stream(dev).wait_event(ev)
         Fn._join_prepack()   # (a model without a cached operand copy never joined the pack branch)
+        Fn.join_pending_wgrad()
         return loss.detach()
 
     def close(self) -> None:
