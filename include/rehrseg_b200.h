@@ -126,6 +126,10 @@ int rehr_convtranspose3d_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, c
 int rehr_convtranspose3d_fused_supported(const rehr_conv_desc* desc, int cin, int cout);
 int rehr_convtranspose3d_fused_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
                                    const rehr_tensor* y, int act, float slope, rehr_stream stream);
+/* Same, and a second copy y2 of the result (same shape; its own buffer, pitch and 16-bit format) written by the same epilogue: the
+ * bf16 twin of the fp16 up-sampled half of [up | skip] that the weight gradient of the decoder conv contracts with bf16 gradients. */
+int rehr_convtranspose3d_fused_fwd2(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                                    const rehr_tensor* y, const rehr_tensor* y2, int act, float slope, rehr_stream stream);
 int rehr_convtranspose3d_dgrad(const rehr_conv_desc* desc, const rehr_tensor* dy, const void* w_packed /*[Cin][T][Cout]*/,
                                const rehr_tensor* dx, rehr_stream stream);
 size_t rehr_convtranspose3d_wgrad_workspace(const rehr_conv_desc* desc, const rehr_tensor* x, const rehr_tensor* dy);

@@ -80,6 +80,7 @@ def _declare(L: C.CDLL) -> None:
         "rehr_convtranspose3d_fwd": (i, [D, T, vp, vp, T, i, f, vp]),
         "rehr_convtranspose3d_fused_supported": (i, [D, i, i]),
         "rehr_convtranspose3d_fused_fwd": (i, [D, T, vp, vp, T, i, f, vp]),
+        "rehr_convtranspose3d_fused_fwd2": (i, [D, T, vp, vp, T, T, i, f, vp]),
         "rehr_convtranspose3d_dgrad": (i, [D, T, vp, T, vp]),
         "rehr_convtranspose3d_wgrad_workspace": (sz, [D, T, T]),
         "rehr_convtranspose3d_wgrad": (i, [D, T, T, vp, i, vp, sz, vp]),

@@ -277,8 +277,19 @@ int rehr_convtranspose3d_fused_supported(const rehr_conv_desc* d, int cin, int c
   if (d->sd * d->sh * d->sw > 8) return 0;  // class offset table of the scatter epilogue
   return 1;
 }
+static int tconv_fused_impl(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias, const rehr_tensor* y,
+                            const rehr_tensor* y2, int act, float slope, rehr_stream stream);
 int rehr_convtranspose3d_fused_fwd(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
                                    const rehr_tensor* y, int act, float slope, rehr_stream stream) {
+  return tconv_fused_impl(desc, x, w_packed, bias, y, nullptr, act, slope, stream);
+}
+int rehr_convtranspose3d_fused_fwd2(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias,
+                                    const rehr_tensor* y, const rehr_tensor* y2, int act, float slope, rehr_stream stream) {
+  if (!y2 || !y2->ptr || !y || y2->n != y->n || y2->d != y->d || y2->h != y->h || y2->w != y->w || y2->c != y->c) return REHR_BAD_SHAPE;
+  return tconv_fused_impl(desc, x, w_packed, bias, y, y2, act, slope, stream);
+}
+static int tconv_fused_impl(const rehr_conv_desc* desc, const rehr_tensor* x, const void* w_packed, const float* bias, const rehr_tensor* y,
+                            const rehr_tensor* y2, int act, float slope, rehr_stream stream) {
   if (!desc || !x || !y || !x->ptr || !y->ptr || !w_packed) return REHR_BAD_SHAPE;
   if (!rehr_convtranspose3d_fused_supported(desc, x->c, y->c)) return REHR_UNSUPPORTED;
   if (x->n != y->n || y->d != x->d * desc->sd || y->h != x->h * desc->sh || y->w != x->w * desc->sw) return REHR_BAD_SHAPE;
@@ -297,7 +308,8 @@ int rehr_convtranspose3d_fused_fwd(const rehr_conv_desc* desc, const rehr_tensor
   const int O[4] = {x->w, x->h, x->d, x->n};
   const int os[3] = {1, 1, 1}, oo[3] = {0, 0, 0};
   const int sc[3] = {desc->sw, desc->sh, desc->sd};
-  return launch_tapped_gemm(plan, *x, w_packed, 0, bias, *y, 0, O, os, oo, act, slope, nullptr, (cudaStream_t)stream, sc);
+  return launch_tapped_gemm(plan, *x, w_packed, 0, bias, *y, 0, O, os, oo, act, slope, nullptr, (cudaStream_t)stream, sc, nullptr, 0, nullptr,
+                            y2);
 }
 
 // ---- ConvTranspose3d = the same conv read backwards (weight [Cin][Cout][T], underlying conv Cin <- Cout) ----

@@ -289,6 +289,11 @@ struct alignas(64) FwdParams {
   int out_f32;
   int out_f16;     // 16-bit output format (rehr_dtype of the output tensor) when !out_f32
   int in_f16;      // operand format of the input tensor AND of the packed weights
+  // scatter epilogue only: optional second copy of the result in another buffer / 16-bit format (the bf16 twin of an fp16
+  // up-sampled tensor inside the [up | skip] buffer that the consumer's weight gradient reads), written from the same registers
+  void* out2;
+  long long out2_ld;
+  int out2_f16;
   long long out_ld;
   int O[4];        // class-local output extents (w h d n)
   int os[3], oo[3];  // actual coord = o*os + oo (w h d)
@@ -610,6 +615,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tapped_gemm_kernel(const 
             hi.w = pack16x2(f[14], f[15], p.out_f16);
             reinterpret_cast<uint4*>(o)[0] = lo;
             reinterpret_cast<uint4*>(o)[1] = hi;
+            if (p.out2 != nullptr) {
+              unsigned short* o2 = reinterpret_cast<unsigned short*>(p.out2) + ov * p.out2_ld + co0;
+              lo.x = pack16x2(f[0], f[1], p.out2_f16);
+              lo.y = pack16x2(f[2], f[3], p.out2_f16);
+              lo.z = pack16x2(f[4], f[5], p.out2_f16);
+              lo.w = pack16x2(f[6], f[7], p.out2_f16);
+              hi.x = pack16x2(f[8], f[9], p.out2_f16);
+              hi.y = pack16x2(f[10], f[11], p.out2_f16);
+              hi.z = pack16x2(f[12], f[13], p.out2_f16);
+              hi.w = pack16x2(f[14], f[15], p.out2_f16);
+              reinterpret_cast<uint4*>(o2)[0] = lo;
+              reinterpret_cast<uint4*>(o2)[1] = hi;
+            }
           }
           continue;
         }
@@ -727,7 +745,7 @@ static size_t fwd_smem_tail_bytes() { return (2 * kMaxStages + 4) * 8 + 16 + 2 *
 int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w_packed, int w_rows,
                        const float* bias, const rehr_tensor& out, int out_f32, const int O[4], const int os[3],
                        const int oo[3], int act, float slope, float* stats, cudaStream_t stream, const int* scatter_s, void* ws,
-                       size_t ws_bytes, size_t* ws_need) {
+                       size_t ws_bytes, size_t* ws_need, const rehr_tensor* out2) {
   const int cin = in.c;
   const int ncls = scatter_s ? scatter_s[0] * scatter_s[1] * scatter_s[2] : 1;
   const int cout = out.c * ncls;  // GEMM N: all parity classes side by side in scatter mode
@@ -767,6 +785,12 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
   p.out_f32 = out_f32;
   p.out_f16 = out.dtype == REHR_F16;
   p.in_f16 = in.dtype == REHR_F16;
+  if (out2 != nullptr) {
+    if (!scatter_s || out2->c != out.c || out2->ld % 8 != 0 || (reinterpret_cast<uintptr_t>(out2->ptr) & 15) != 0) return REHR_UNSUPPORTED;
+    p.out2 = out2->ptr;
+    p.out2_ld = out2->ld;
+    p.out2_f16 = out2->dtype == REHR_F16;
+  }
   p.out_ld = out.ld;
   p.cout = cout;
   p.bias = bias;

@@ -37,7 +37,8 @@ void choose_box(int W, int H, int D, int N, int vox, int box[4]);
 int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w_packed, int w_rows,
                        const float* bias, const rehr_tensor& out, int out_f32, const int O[4], const int os[3],
                        const int oo[3], int act, float slope, float* stats, cudaStream_t stream,
-                       const int* scatter_s = nullptr, void* ws = nullptr, size_t ws_bytes = 0, size_t* ws_need = nullptr);
+                       const int* scatter_s = nullptr, void* ws = nullptr, size_t ws_bytes = 0, size_t* ws_need = nullptr,
+                       const rehr_tensor* out2 = nullptr);
 size_t tapped_wgrad_workspace(const TapPlan& plan, const rehr_tensor& X, const rehr_tensor& Y);
 int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_tensor& Y, float* dw, long long s_n,
                         long long s_m, long long s_t, int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);

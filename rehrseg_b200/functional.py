@@ -26,6 +26,7 @@ Triple = Tuple[int, int, int]
 # launch accounting (bench.py reports `gpu_launches`)
 # --------------------------------------------------------------------------------------------------
 _launches = 0
+path_hits = {"tconv_bias_from_epilogue_sums": 0, "tconv_twin_from_epilogue": 0}   # which fused shortcuts really ran (tests read this)
 
 
 def launches() -> int:
@@ -420,7 +421,8 @@ def join_pending_wgrad() -> None:
     _wgrad_pending.clear()
 
 
-def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bool, cache: bool = True, norm=None, x_h=False):
+def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bool, cache: bool = True, norm=None, x_h=False,
+                     want_chsum: bool = False):
     """(dx or None, dw) of a conv.  The weight-gradient chain runs on a side stream (events only: graph-capturable): joined right
     after the input gradient for small layers (two latency-bound chains side by side), or -- WGRAD_DEFER_JOIN, inside an autograd
     backward pass -- at the end of the pass.  `norm` / `x_h`: x is a raw conv output normalised on load (conv3d_wgrad_raw)."""
@@ -431,7 +433,7 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
         fk = _fork(dy.device)
         with fk:
             conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
-        dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache)
+        dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
         deferred = False
         if WGRAD_DEFER_JOIN:
             try:
@@ -444,7 +446,7 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
         if not deferred:
             fk.join()
         return dx, dw
-    dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache) if need_dx else None
+    dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum) if need_dx else None
     return dx, conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, norm=norm, x_h=x_h)
 
 
@@ -522,7 +524,10 @@ def instnorm_stats_raw(y: torch.Tensor, y_h: bool = False):
 
 
 def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[int], kernel: Triple, stride: Triple,
-                     padding: Triple, cache: bool = True) -> torch.Tensor:
+                     padding: Triple, cache: bool = True, want_chsum: bool = False) -> torch.Tensor:
+    """dx = conv^T(dy).  `want_chsum`: where the marching kernel runs, its epilogue also leaves the per-(sample, tile, channel) sums
+    of the fp32 accumulators on the result (`dx._rehr_chsum`, f32 [n][tiles][cin][2]): the bias gradient of a transposed conv
+    that produced (part of) the conv's input then needs no pass over dx."""
     dy = as_cl(dy)
     n, d, h, w, cin = in_shape
     dx = torch.empty((n, d, h, w, cin), dtype=torch.bfloat16, device=dy.device)
@@ -532,10 +537,16 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
     if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), dy.shape[4], cin):
         wp = _packed(weight, "march_dgrad", cache)
         dyt, dxt = rt(dy), rt(dx)
+        stats = None
+        if want_chsum:
+            tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(dyt), C.byref(dxt), int(kernel[0]))
+            stats = torch.empty((n, tiles, cin, 2), dtype=torch.float32, device=dy.device)
         with _timed("conv_march_kernel", flops, tag):
-            check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), int(kernel[0]), 0, ACT_NONE, 0.0, None,
+            check(lib().rehr_conv3d_march_fwd(C.byref(dyt), ptr(wp), None, C.byref(dxt), int(kernel[0]), 0, ACT_NONE, 0.0, ptr(stats),
                                               stream_ptr()), "conv3d_march_dgrad")
         _count()
+        if stats is not None:
+            dx._rehr_chsum = stats
         return dx
     if USE_MARCH and lib().rehr_conv3d_march_s2dgrad_supported(C.byref(desc), cin, dy.shape[4]) \
             and dy.shape[1] * dy.shape[2] * dy.shape[3] >= 4096 and dy.shape[4] <= 64:
@@ -730,6 +741,7 @@ class ConvNormAct(torch.autograd.Function):
         g32, b32 = _f32(gamma), _f32(beta)
         ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None, y_h, x_raw_h)
         ctx.wref = weakref.ref(weight)
+        ctx.x_upcat = bool(getattr(x, "_rehr_upcat", False))   # x = [up | skip]: the transposed conv wants channel sums of dx
         if defer:
             ctot, coff = (2 * cout, cout) if cat_room else (cout, 0)
             norm = torch.empty((n, 3, ctot), dtype=torch.float32, device=dev)
@@ -808,7 +820,7 @@ class ConvNormAct(torch.autograd.Function):
                 _count()
         else:
             dx, dw = _dgrad_and_wgrad(x, dy, weight, weight.shape, kernel, stride, padding, ctx.needs_input_grad[0],
-                                      norm=x_norm, x_h=x_raw_h)
+                                      norm=x_norm, x_h=x_raw_h, want_chsum=ctx.x_upcat)
         # A per-channel constant added before InstanceNorm is removed by the mean subtraction: d(loss)/d(bias) == 0
         # exactly (PyTorch's value is rounding noise of the same sum).
         dbias = torch.zeros((cout,), dtype=torch.float32, device=dev) if has_bias else None
@@ -1066,17 +1078,28 @@ class ConvTranspose(torch.autograd.Function):
             full = None
             y = torch.empty((n, od, oh, ow, cout), dtype=torch.bfloat16, device=x.device)
         xt, yt = rt(x, x_h), rt(y, x_h)
+        twin_done = False
         if lib().rehr_convtranspose3d_fused_supported(C.byref(desc), cin, cout):
             wp = _packed(weight, "tconv_fused", h=x_h)  # [T][Cout][Cin]
-            check(lib().rehr_convtranspose3d_fused_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
-                                                       float(slope), stream_ptr()), "convtranspose3d_fused_fwd")
+            tw = getattr(skip, "_rehr_bf", None) if (skip is not None and x_h and train and not skip_deferred) else None
+            if tw is not None and getattr(tw, "_rehr_cat", None) == skip._rehr_cat:
+                # the bf16 twin of the up-sampled half goes straight into the twin's [up | skip] buffer from the same epilogue
+                full2 = whole(tw)
+                y2t = rt(full2[..., :cout], False)
+                check(lib().rehr_convtranspose3d_fused_fwd2(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt),
+                                                            C.byref(y2t), act, float(slope), stream_ptr()), "convtranspose3d_fused_fwd2")
+                twin_done = True
+                path_hits["tconv_twin_from_epilogue"] += 1
+            else:
+                check(lib().rehr_convtranspose3d_fused_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
+                                                           float(slope), stream_ptr()), "convtranspose3d_fused_fwd")
             _count()
         else:
             wp = _packed(weight, "dgrad", h=x_h)  # [Cout][T][Cin]
             check(lib().rehr_convtranspose3d_fwd(C.byref(desc), C.byref(xt), ptr(wp), ptr(_f32(bias)), C.byref(yt), act,
                                                  float(slope), stream_ptr()), "convtranspose3d_fwd")
             _count(stride[0] * stride[1] * stride[2])
-        if x_h and train and not skip_deferred:
+        if x_h and train and not skip_deferred and not twin_done:
             # bf16 twin of the result for the weight-gradient GEMM of the consumer: the skip half already has one (written by
             # the skip's normalise pass), the up-sampled half is converted here
             if skip is not None:
@@ -1104,6 +1127,7 @@ class ConvTranspose(torch.autograd.Function):
         weight = _orig_weight(ctx, weight)
         kernel, stride, padding, act, slope, has_bias, y_h = ctx.cfg
         dskip = None
+        chsum = getattr(da, "_rehr_chsum", None) if ctx.cat else None   # left by the marching input gradient that produced da
         if ctx.cat:  # da is the gradient of the whole [up | skip] buffer
             cout = weight.shape[1]
             da = as_cl(da)
@@ -1127,7 +1151,12 @@ class ConvTranspose(torch.autograd.Function):
                   "convtranspose3d_wgrad")
             _count(2)
             if has_bias:
-                channel_sum_raw(dy, out=db)
+                if chsum is not None and act == ACT_NONE and chsum.shape[2] >= weight.shape[1]:
+                    # bias gradient = sum over voxels of d(up): the fp32 accumulator sums of the producing kernel's epilogue
+                    torch.sum(chsum[:, :, :weight.shape[1], 0], dim=(0, 1), out=db)
+                    path_hits["tconv_bias_from_epilogue_sums"] += 1
+                else:
+                    channel_sum_raw(dy, out=db)
 
         voxels = dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3]
         fk = None
@@ -1157,6 +1186,8 @@ def conv_transpose(x, weight, bias, kernel, stride, padding=(0, 0, 0), act=ACT_N
     out, twin = ConvTranspose.apply(x, weight, bias, skip, tuple(kernel), tuple(stride), tuple(padding), int(act), float(slope))
     if is_h(x):
         mark_h(out, twin)
+    if skip is not None:
+        out._rehr_upcat = True
     if skip is not None and norm_of(skip) is not None:
         # [up | skip] where the skip half still holds the raw conv output of its block: the buffer is a deferred activation whose
         # table is the identity on the up-sampled channels (written by the skip's finalize pass)

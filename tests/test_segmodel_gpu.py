@@ -36,6 +36,18 @@ def test_segmodel_tiny_fwd_bwd():
     _check(parity.segmodel_parity(patch=(16, 32, 32), batch=2, plan="tiny", backward=True))
 
 
+def test_fused_shortcuts_are_taken():
+    """The transposed-conv bias gradient comes from the channel sums the marching input-gradient epilogue leaves on its result, and
+    the bf16 twin of the up-sampled tensor from the transposed conv's own epilogue -- both must really run on this path (their
+    results are covered by the parity checks of this file)."""
+    from oracle import parity
+    from rehrseg_b200 import functional as Fn
+    before = dict(Fn.path_hits)
+    parity.segmodel_parity(patch=(16, 32, 32), batch=1, plan="tiny", backward=True)
+    assert Fn.path_hits["tconv_bias_from_epilogue_sums"] > before["tconv_bias_from_epilogue_sums"]
+    assert Fn.path_hits["tconv_twin_from_epilogue"] > before["tconv_twin_from_epilogue"]
+
+
 def test_segmodel_3d_fullres_fwd_bwd_64():
     from oracle import parity
     _check(parity.segmodel_parity(patch=(64, 64, 64), batch=1, plan="3d_fullres", backward=True))
