@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -61,6 +62,22 @@ int sm_count() {
     n[dev] = v;
   }
   return n[dev];
+}
+
+// Dynamic shared memory a tensor-core conv CTA may plan with.  The persistent conv kernels run one CTA per SM and would otherwise
+// take all 227 KB, which keeps every other kernel off the SM (each resident CTA needs its static shared memory + 1 KB): leaving
+// a few KB free lets the HBM-bound InstanceNorm passes of the other sample stream become resident NEXT to a conv CTA
+// (functional.py, sample streams).  REHR_SMEM_RESERVE_KB overrides the reserve (0 = the kernels take everything).
+size_t smem_budget() {
+  static size_t v = 0;
+  if (v == 0) {
+    const char* e = getenv("REHR_SMEM_RESERVE_KB");
+    int kb = e ? atoi(e) : kDefaultSmemReserveKB;
+    if (kb < 0) kb = 0;
+    if (kb > 64) kb = 64;
+    v = (size_t)(227 - kb) * 1024;
+  }
+  return v;
 }
 
 static CUtensorMapSwizzle swizzle_for_chunk(int chunk) {
@@ -845,7 +862,7 @@ int launch_tapped_gemm(const TapPlan& plan, const rehr_tensor& in, const void* w
     if (rc != REHR_OK) return rc;
   }
   const size_t stage_bytes = (size_t)128 * BK * 2 + (size_t)BN * BK * 2;
-  const size_t budget = 227 * 1024 - 1024 - fwd_smem_tail_bytes();
+  const size_t budget = smem_budget() - 1024 - fwd_smem_tail_bytes();
   int stages = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
   if (stages < 2) return REHR_UNSUPPORTED;
   p.stages = stages;
@@ -1258,7 +1275,7 @@ static int plan_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_tens
   p.gpc = std::min(std::min(512 / p.BN, kMaxGroupsPerCta), p.num_groups);
   // shared memory: choose the largest voxel block that still leaves >= 2 stages
   const size_t tailb = (2 * kMaxStages + 2) * 8 + 64;
-  const size_t budget = 227 * 1024 - 1024 - tailb;
+  const size_t budget = smem_budget() - 1024 - tailb;
   int BKV = 128;
   for (;;) {
     size_t sb = (size_t)BKV * 2 * (p.BN + (size_t)p.gpc * 128);

@@ -123,7 +123,10 @@ __device__ __forceinline__ bool elect_one_sync() {
 // descriptor increments: a single thread must issue one tcgen05.mma every ~50 clk (tools/umma_rate2.cu measures
 // 40 clk/MMA for this code shape vs 120-280 clk/MMA with run-time descriptor arithmetic).
 template <int BKT, int CHUNKS, int CT, int KS, bool XF>
-__global__ void __launch_bounds__(XF ? kMarchThreadsXf : kMarchThreads, 1) conv_march_kernel(const __grid_constant__ MarchParams p) {
+#ifndef REHR_MARCH_MAXNREG
+#define REHR_MARCH_MAXNREG 255
+#endif
+__global__ void __launch_bounds__(XF ? kMarchThreadsXf : kMarchThreads) __maxnreg__(XF ? 224 : REHR_MARCH_MAXNREG) conv_march_kernel(const __grid_constant__ MarchParams p) {
   constexpr int R = MarchGeo<KS>::R;
   constexpr int kHaloW = MarchGeo<KS>::kHaloW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -621,7 +624,7 @@ static int plan_march(const rehr_tensor& x, const rehr_tensor& y, int ks_code, M
   p.slot_stride = p.chunks * p.chunk_stride;
   p.plane_bytes = p.chunks * halo_rows * rowb;
   const size_t fixed = 1024 + ((p.w_bytes + 1023u) & ~1023u) + march_tail_bytes();
-  const size_t budget = 227 * 1024;
+  const size_t budget = smem_budget();
   if (fixed + 2 * (size_t)p.slot_stride > budget) return REHR_UNSUPPORTED;
   p.ring = (int)std::min<size_t>(kMaxRing, (budget - fixed) / p.slot_stride);
   out->smem = fixed + (size_t)p.ring * p.slot_stride;

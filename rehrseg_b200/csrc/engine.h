@@ -29,6 +29,8 @@ struct TapPlan {
 
 extern thread_local int g_last_cuda_error;
 int sm_count();
+static constexpr int kDefaultSmemReserveKB = 0;
+size_t smem_budget();
 
 int build_fwd_taps(const rehr_conv_desc& cd, const rehr_tensor& in, TapPlan* plan);
 int build_dgrad_taps(const rehr_conv_desc& cd, const int cls[3], TapPlan* plan);

@@ -637,7 +637,7 @@ static int plan_wgm(const rehr_tensor& x, const rehr_tensor& dy, int ks_code, Wg
   {
     const char* e = getenv("REHR_WGM_HSTAGES");  // development: force the halo ring depth
     const int want = e ? atoi(e) : 4;
-    p.h_stages = (int)std::min<size_t>((size_t)std::max(4, std::min(want, kMaxHStages)), (227 * 1024 - fixed) / p.h_stride);
+    p.h_stages = (int)std::min<size_t>((size_t)std::max(4, std::min(want, kMaxHStages)), (smem_budget() - fixed) / p.h_stride);
     if (p.h_stages < 4) return REHR_UNSUPPORTED;
   }
   out->smem = fixed + (size_t)p.h_stages * p.h_stride;

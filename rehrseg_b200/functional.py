@@ -250,14 +250,24 @@ def _pack_into(weight: torch.Tensor, kind: str, h: bool, out: Optional[torch.Ten
     return o
 
 
-_pending_prepack = None   # fork object of refresh_weight_cache(): joined by the first cache hit of the step
+_pending_prepack = None   # fork object of refresh_weight_cache(): joined at the end of the step (or by clear_weight_cache)
+_pack_events: dict = {}   # cache key -> event recorded on the pack stream right after that copy was re-packed
 
 
 def _join_prepack() -> None:
     global _pending_prepack
+    _pack_events.clear()
     if _pending_prepack is not None:
         fk, _pending_prepack = _pending_prepack, None
         fk.join()
+
+
+def _await_pack(key) -> None:
+    """Make the current stream wait for the refresh of ONE cached copy (not for the whole pack stream: the ~55 small pack kernels
+    of a step take ~0.6 ms back to back, and the first convs would otherwise sit idle until the last of them has run)."""
+    ev = _pack_events.pop(key, None)
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
 
 
 def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False, extra=None) -> torch.Tensor:
@@ -273,7 +283,7 @@ def _packed(weight: torch.Tensor, kind: str, cache: bool = True, h: bool = False
     if cache:
         hit = _wcache.get(key)
         if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
-            _join_prepack()
+            _await_pack(key)
             return hit[2]
     out = _pack_into(weight, kind, h, None, extra)
     if cache:
@@ -290,7 +300,8 @@ def refresh_weight_cache() -> int:
     """Re-pack every cached 16-bit operand copy IN PLACE from the current parameter values, on a side stream forked from the
     current one (events only: CUDA-graph capturable), and mark them current.  Called at the start of a training step after the
     optimiser update: the ~50 small pack kernels then run next to the first layers instead of in front of each conv, and the
-    addresses the kernels see stay fixed (what a captured graph needs).  The first cache hit of the step joins the side stream.
+    addresses the kernels see stay fixed (what a captured graph needs).  A cache hit waits for the event of its own copy only; the
+    caller joins the pack stream at the end of the step (_join_prepack).
     Returns the number of copies refreshed (0 on the very first step: nothing is cached yet and the packs happen lazily)."""
     global _pending_prepack
     _join_prepack()
@@ -305,6 +316,9 @@ def refresh_weight_cache() -> int:
             w = wref()
             _pack_into(w, key[1], key[2], out, key[3])
             _wcache[key] = (wref, w._version, out)
+            ev = torch.cuda.Event()
+            ev.record(fk.side)
+            _pack_events[key] = ev
     _pending_prepack = fk
     return len(live)
 
@@ -378,10 +392,20 @@ class _fork:
             side = _side_streams[key] = torch.cuda.Stream(device=device)
         self.side = side
         self.ctx = None
+        self.ev = None
+
+    def fork_point(self):
+        """Fix the point of the main stream the side stream will wait for NOW (work issued on the main stream between this call
+        and `with self:` is not waited for)."""
+        self.ev = torch.cuda.Event()
+        self.ev.record(self.main)
 
     def __enter__(self):
-        ev = torch.cuda.Event()
-        ev.record(self.main)
+        ev = self.ev
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+        self.ev = None
         self.side.wait_event(ev)
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
@@ -403,10 +427,38 @@ class _fork:
 # gradient CTA on every SM.  The side stream is joined once, by a final callback of the autograd engine (and before any bucket
 # all-reduce, graphs.GraphedTrainStep).  Operands are kept alive until then (their memory must not be recycled by the main stream
 # while the side stream still reads it).
-# Measured on the C1 step: 12.64 ms deferred vs 12.75 ms joined per layer -- the marching CTAs own their SM's shared memory, so
-# little else becomes resident next to them.  OFF by default: autograd's AccumulateGrad may CLONE the returned dW on the main
-# stream (whenever it cannot steal the tensor) before the side stream has written it; the per-layer join has no such window.
-WGRAD_DEFER_JOIN = os.environ.get("REHR_WGRAD_DEFER", "0") == "1"
+# Launch order matters: two machine-filling GEMMs cannot share an SM, so the one launched first runs first.  The input gradient
+# goes first (the next layer's InstanceNorm passes depend on it), the weight gradient second, and those passes then run NEXT to
+# the weight gradient (tools/overlap_probe.py: about half of their time disappears behind it).  Measured on the C1 step
+# (tools/ab_step.py): 12.76 ms joined per layer, 12.41 ms deferred with the old weight-gradient-first order only for the small
+# layers, 12.28 ms deferred with the input gradient first everywhere.
+# The window this opens: autograd's AccumulateGrad touches the returned dW on the MAIN stream whenever it cannot simply adopt the
+# tensor (an existing .grad to add to, a hook that reads it).  So the deferral is (a) only taken for parameters whose .grad is
+# None, and (b) only ON inside `deferred_wgrad()` -- entered by graphs.GraphedTrainStep, which owns the whole step, joins before
+# its bucket all-reduces and at the end of the step.  Plain eager use keeps the per-layer join.  REHR_WGRAD_DEFER=1 forces it on
+# everywhere, =0 off everywhere.
+_DEFER_ENV = os.environ.get("REHR_WGRAD_DEFER", "")
+WGRAD_DEFER_JOIN = _DEFER_ENV == "1"
+DGRAD_FIRST_MIN_VOXELS = int(os.environ.get("REHR_DFIRST_MIN_VOXELS", str(2 * 32 ** 3)))
+
+
+class deferred_wgrad:
+    """Context: weight-gradient chains started inside stay on the side stream until `join_pending_wgrad()` / the end of the
+    backward pass (see above).  The caller guarantees nothing reads a .grad on the main stream before that."""
+
+    def __enter__(self):
+        global WGRAD_DEFER_JOIN
+        self.prev = WGRAD_DEFER_JOIN
+        if _DEFER_ENV != "0":
+            WGRAD_DEFER_JOIN = True
+        return self
+
+    def __exit__(self, *exc):
+        global WGRAD_DEFER_JOIN
+        WGRAD_DEFER_JOIN = self.prev
+        return False
+
+
 _wgrad_pending: list = []
 
 
@@ -431,11 +483,20 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
     if side_ok and (WGRAD_DEFER_JOIN or voxels <= WGRAD_SIDE_MAX_VOXELS):
         dw = torch.empty(tuple(wshape), dtype=torch.float32, device=dy.device)   # owned by the main stream's pool
         fk = _fork(dy.device)
-        with fk:
-            conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
-        dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
+        if WGRAD_DEFER_JOIN and voxels >= DGRAD_FIRST_MIN_VOXELS:
+            # machine-filling layer: the two GEMMs cannot share an SM.  The input gradient goes first -- the NEXT layer's
+            # InstanceNorm passes depend on it -- and the weight gradient is made to WAIT for it (fork point after the launch):
+            # inside a replayed CUDA graph two independent branches start in no particular order, a dependency is the only
+            # way to fix it.  The InstanceNorm passes then run next to the weight gradient.
+            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
+            with fk:
+                conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
+        else:
+            with fk:
+                conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
+            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
         deferred = False
-        if WGRAD_DEFER_JOIN:
+        if WGRAD_DEFER_JOIN and getattr(weight, "grad", None) is None:   # AccumulateGrad then adopts dw without touching it
             try:
                 if not _wgrad_pending:
                     torch.autograd.Variable._execution_engine.queue_callback(join_pending_wgrad)

@@ -190,7 +190,8 @@ class GraphedTrainStep:
             self._dp["left"] = [len(ps) for ps in self._dp["plan"]]
             self._dp["armed"] = True
         try:
-            loss.backward()
+            with Fn.deferred_wgrad():    # this step owns every .grad until it returns: weight gradients join at the end
+                loss.backward()
         finally:
             if self._dp is not None:
                 self._dp["armed"] = False
