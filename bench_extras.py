@@ -41,14 +41,23 @@ def c2_flavr(dev, peaks, steps=8, warm=3) -> dict:
     B = 8
     x = torch.rand((B, 2, 4, 256, 256), device=dev)
 
-    def step():
-        for p in m.parameters():
-            p.grad = None
-        m(x.clone()).float().mean().backward()
+    # the step is ~700 launches of 5-300 us: issued from Python it is bound by the host (26.5 ms in a quiet process, 35 ms here next
+    # to bench.py's sampler / CPU-baseline threads), so it is replayed from one CUDA graph like the C1 step
+    from rehrseg_b200.graphs import GraphedTrainStep
 
-    ms = _events(step, steps, warm)
+    class _Fresh(torch.nn.Module):          # UNet_3D_3D.forward subtracts the mean from images[:, 0:1] IN PLACE (FLAVR_arch.py:172)
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+        def forward(self, images):
+            return self.net(images.clone())
+
+    gs = GraphedTrainStep(_Fresh(m), lambda out: out.float().mean(), (x,))
+    ms = _events(gs.replay, steps, warm)
+    gs.close()
     tf = B * 1.650 / ms * 1e3     # 1.650 TFLOP fwd+bwd per 256^2 sample (plain head)
-    return {"config": "C2 FLAVR UNet3D self-SR fwd+bwd, [8,2,4,256,256], plain head, bf16", "flavr_samples_per_s": round(B / ms * 1e3, 2),
+    return {"config": "C2 FLAVR UNet3D self-SR fwd+bwd, [8,2,4,256,256], plain head, bf16, one CUDA graph per step", "flavr_samples_per_s": round(B / ms * 1e3, 2),
             "ms_per_step": round(ms, 3), "tflops": round(tf, 1), "frac_bf16_peak_burst": round(tf / float(peaks["bf16_tflops"]), 4)}
 
 

@@ -243,12 +243,20 @@ def _dec_up(mod: nn.Module, x):
     return _gate(mod.upconv[1], y, None, act=ACT_LRELU, slope=0.2)
 
 
+_reflect_idx: dict = {}
+
+
 def _reflect_pad_hw(x: torch.Tensor, p: int) -> torch.Tensor:
     """nn.ReflectionPad2d(p) on a channels-last [B,1,H,W,C] tensor (index gathers; FLAVR_arch.py:153-156)."""
     h, w = x.shape[2], x.shape[3]
-    ih = torch.cat([torch.arange(p, 0, -1), torch.arange(h), torch.arange(h - 2, h - 2 - p, -1)]).to(x.device)
-    iw = torch.cat([torch.arange(p, 0, -1), torch.arange(w), torch.arange(w - 2, w - 2 - p, -1)]).to(x.device)
-    return x.index_select(2, ih).index_select(3, iw)
+    key = (p, h, w, x.device)
+    idx = _reflect_idx.get(key)
+    if idx is None:      # built ON the device (no host copy: the forward stays capturable in a CUDA graph), once per shape
+        def one(n):
+            return torch.cat([torch.arange(p, 0, -1, device=x.device), torch.arange(n, device=x.device),
+                              torch.arange(n - 2, n - 2 - p, -1, device=x.device)])
+        idx = _reflect_idx[key] = (one(h), one(w))
+    return x.index_select(2, idx[0]).index_select(3, idx[1])
 
 
 def flavr_forward(model: nn.Module, images: torch.Tensor, return_inetermediate_uncertainty=False,

@@ -496,7 +496,9 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
                 conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
             dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
         deferred = False
-        if WGRAD_DEFER_JOIN and getattr(weight, "grad", None) is None:   # AccumulateGrad then adopts dw without touching it
+        # a leaf parameter without a .grad: AccumulateGrad adopts dw without touching it (a view of a parameter, e.g. FLAVR's 2-D
+        # fuse convs seen as 5-D, sends dw through a ViewBackward first: joined per layer)
+        if WGRAD_DEFER_JOIN and weight.is_leaf and weight.grad is None:
             try:
                 if not _wgrad_pending:
                     torch.autograd.Variable._execution_engine.queue_callback(join_pending_wgrad)
