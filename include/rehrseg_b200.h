@@ -163,6 +163,16 @@ int rehr_conv3d_march_norm_supported(const rehr_conv_desc* desc, int cin, int co
 int rehr_conv3d_march_fwd_norm(const rehr_tensor* x, const float* norm, int op_dtype, const void* w_march, const float* bias,
                                const rehr_tensor* y, int ks, int y_is_f32, int act, float slope, float* stats, rehr_stream stream);
 
+/* Batched weight re-pack (csrc/pack_batch.cu).  Between rehr_pack_batch_begin() and rehr_pack_batch_launch() every
+ * rehr_pack_weight / rehr_pack_weight_march / rehr_pack_weight_march_s2dgrad call ON THIS THREAD is recorded instead of launched;
+ * rehr_pack_batch_launch issues all of them as ONE kernel (one per 128 recorded calls) whose job table travels in the kernel
+ * parameters -- no upload, capturable in a CUDA graph; results are bit-identical to the individual launches.  Replaces the ~57
+ * per-parameter repacks a training step does after optimizer.step() (the reference has no counterpart: cuDNN reads
+ * the fp32 NCDHW weights directly, train_all.py:553-555).  rehr_pack_batch_abort drops a recording without launching. */
+int rehr_pack_batch_begin(void);
+int rehr_pack_batch_launch(rehr_stream stream);
+int rehr_pack_batch_abort(void);
+
 /* Input gradient of a k3 / pad 1 conv with strides in {1, 2} (the nnU-Net stage-entry convs) through the marching kernel:
  * every output parity class of dx is a stride-1 correlation over dy with 1 or 2 taps per strided dimension, written in place
  * at (2i + r).  w = conv weight f32 [Cout][Cin][27]; cin / cout are the CONV's channel counts. */

@@ -98,6 +98,9 @@ def _declare(L: C.CDLL) -> None:
         "rehr_conv3d_march_s2dgrad_supported": (i, [D, i, i]),
         "rehr_conv3d_march_s2dgrad_weight_bytes": (sz, [D, i, i]),
         "rehr_pack_weight_march_s2dgrad": (i, [D, vp, vp, i, i, vp]),
+        "rehr_pack_batch_begin": (i, []),
+        "rehr_pack_batch_launch": (i, [vp]),
+        "rehr_pack_batch_abort": (i, []),
         "rehr_conv3d_march_s2dgrad": (i, [D, T, vp, T, vp]),
         "rehr_conv3d_wgrad_march_supported": (i, [D, T, T]),
         "rehr_conv3d_wgrad_march_workspace": (sz, [T, T, i]),

@@ -1439,6 +1439,12 @@ int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long lo
                        cudaStream_t stream, int f16) {
   const long long total = (long long)R * T * C;
   if (total == 0) return REHR_OK;
+  if (pack_recording()) {
+    PackJob j{};
+    j.src = src; j.dst = dst; j.kind = 0; j.f16 = f16;
+    j.R = R; j.C = C; j.T = T; j.sr = sr; j.sc = sc; j.st = st;
+    return pack_record(j);
+  }
   if (st == 1 && T <= 343 && R <= 65535) {
     dim3 grid((C + kPackC - 1) / kPackC, R);
     const size_t smem = (size_t)kPackC * (T + 1) * sizeof(float);

@@ -877,6 +877,13 @@ int rehr_pack_weight_march(const float* src, void* dst16, int cout, int cin, int
   const int ct = march_ct(cin, cout, ks, planar);
   if (ct == 0) return REHR_UNSUPPORTED;
   const long long total = (long long)pad16(cout) * cin * kdn * ks * ks;
+  if (pack_recording()) {
+    PackJob j{};
+    j.src = src; j.dst = dst16; j.kind = 1; j.f16 = dtype == REHR_F16; j.total = total;
+    j.cout = cout; j.cout_pad = pad16(cout); j.cin = cin; j.Ct = ct; j.BK = std::min(cin, 64); j.ks = ks; j.kdn = kdn;
+    j.s_co = s_co; j.s_ci = s_ci; j.flip = flip;
+    return pack_record(j);
+  }
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   pack_march_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<unsigned short*>(dst16), cout, pad16(cout), cin, ct,
                                                              std::min(cin, 64), ks, kdn, s_co, s_ci, flip, dtype == REHR_F16);
@@ -929,6 +936,13 @@ int rehr_pack_weight_march_s2dgrad(const rehr_conv_desc* d, const float* w, void
   if (!rehr_conv3d_march_s2dgrad_supported(d, cin, cout)) return REHR_UNSUPPORTED;
   const int ct = march_ct(cout, cin, 3, false);
   const long long total = (long long)d->sd * d->sh * d->sw * 27 * cout * pad16(cin);
+  if (pack_recording()) {
+    PackJob j{};
+    j.src = w; j.dst = dst_bf16; j.kind = 2; j.f16 = 0; j.total = total;
+    j.cin = cout; j.cout = cin; j.cout_pad = pad16(cin); j.Ct = ct; j.BK = std::min(cout, 64);   // A = conv Cout, B = conv Cin
+    j.sd = d->sd; j.sh = d->sh; j.sw = d->sw;
+    return pack_record(j);
+  }
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   pack_march_s2dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(dst_bf16), cout, cin, pad16(cin),
                                                                       ct, std::min(cout, 64), d->sd, d->sh, d->sw);

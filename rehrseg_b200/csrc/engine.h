@@ -47,6 +47,23 @@ int launch_tapped_wgrad(const TapPlan& plan, const rehr_tensor& X, const rehr_te
 int launch_pack_weight(const float* src, void* dst, int R, int C, int T, long long sr, long long sc, long long st,
                        cudaStream_t stream, int f16 = 0);
 
+// One recorded weight-pack call (pack_batch.cu).  kind 0: generic [R][T][C] gather; 1: marching layout; 2: marching layout of the
+// parity classes of a stride-2 input gradient.  Plain data: the table travels in the kernel parameters.
+static constexpr int kPackBatchMax = 128;
+struct PackJob {
+  const float* src;
+  void* dst;
+  long long total;          // destination elements
+  long long sr, sc, st;     // kind 0 source strides
+  long long s_co, s_ci;     // kind 1 source strides
+  int kind, f16, runs, nblocks, block0;
+  int R, C, T;                                        // kind 0
+  int cout, cout_pad, cin, Ct, BK, ks, kdn, flip;     // kind 1 (kind 2: cin = A, cout = B, cout_pad = Bpad)
+  int sd, sh, sw;                                     // kind 2
+};
+bool pack_recording();          // this thread is between rehr_pack_batch_begin and rehr_pack_batch_launch
+int pack_record(PackJob job);   // append (fills total / runs / nblocks)
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process that drives several GPUs must apply it on
 // each of them, so the "already done" flag lives per device (index = cudaGetDevice()).
 static constexpr int kMaxDevices = 64;

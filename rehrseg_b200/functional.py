@@ -250,6 +250,8 @@ def _pack_into(weight: torch.Tensor, kind: str, h: bool, out: Optional[torch.Ten
     return o
 
 
+PACK_BATCHED = os.environ.get("REHR_PACK_BATCHED", "1") != "0"
+PACK_BATCH_SPLITS = tuple(int(v) for v in os.environ.get("REHR_PACK_SPLITS", "200000,2000000,8000000").split(",") if v)   # cumulative elements
 _pending_prepack = None   # fork object of refresh_weight_cache(): joined at the end of the step (or by clear_weight_cache)
 _pack_events: dict = {}   # cache key -> event recorded on the pack stream right after that copy was re-packed
 
@@ -310,15 +312,47 @@ def refresh_weight_cache() -> int:
         del _wcache[k]
     if not live:
         return 0
-    fk = _fork(live[0][1][2].device)
+    fk = _fork(live[0][1][2].device, "pack")
     with fk:
-        for key, (wref, _ver, out) in live:
-            w = wref()
-            _pack_into(w, key[1], key[2], out, key[3])
-            _wcache[key] = (wref, w._version, out)
-            ev = torch.cuda.Event()
-            ev.record(fk.side)
-            _pack_events[key] = ev
+        if PACK_BATCHED:
+            # a few batched launches (csrc/pack_batch.cu: the calls below are recorded, not launched), one event per batch.  The
+            # cache is in order of first use, so the first batches hold the small full-resolution layers the step needs at once;
+            # the bulk (the 256-320 channel layers, the input-gradient layouts) follows in the last one and has ~2 ms to finish.
+            global _launches
+            bounds, acc = [], 0
+            limits = list(PACK_BATCH_SPLITS)
+            for i, (key, (wref, _ver, out)) in enumerate(live):
+                acc += out.numel()
+                if limits and acc > limits[0]:
+                    bounds.append(i + 1)
+                    limits.pop(0)
+            bounds = sorted(set(b for b in bounds if b < len(live))) + [len(live)]
+            first = 0
+            for last in bounds:
+                check(lib().rehr_pack_batch_begin(), "pack_batch_begin")
+                try:
+                    for key, (wref, _ver, out) in live[first:last]:
+                        w = wref()
+                        _pack_into(w, key[1], key[2], out, key[3])
+                        _wcache[key] = (wref, w._version, out)
+                except Exception:
+                    lib().rehr_pack_batch_abort()
+                    raise
+                check(lib().rehr_pack_batch_launch(stream_ptr()), "pack_batch_launch")
+                _launches -= (last - first) - (last - first + 127) // 128      # _pack_into counted one launch per copy
+                ev = torch.cuda.Event()
+                ev.record(fk.side)
+                for key, _ in live[first:last]:
+                    _pack_events[key] = ev
+                first = last
+        else:
+            for key, (wref, _ver, out) in live:
+                w = wref()
+                _pack_into(w, key[1], key[2], out, key[3])
+                _wcache[key] = (wref, w._version, out)
+                ev = torch.cuda.Event()
+                ev.record(fk.side)
+                _pack_events[key] = ev
     _pending_prepack = fk
     return len(live)
 
@@ -383,13 +417,20 @@ WGRAD_SIDE_MAX_VOXELS = 2 * 64 ** 3   # measured on the C1 step: 12.58 ms at 2 *
 _side_streams: dict = {}
 
 
+# Stream priorities.  The side stream of the weight-gradient chains has the HIGH priority graphs.GraphedTrainStep also gives its
+# capture stream (kernel nodes of a captured graph keep the priority of the stream they were captured from), the re-pack stream
+# ("pack") the default = lowest one: the one batched pack kernel of a step is ~36K small blocks, and at equal priority they queue
+# in front of the blocks of the first forward kernels and hold them up (measured: the stem's statistics pass started 165 us late).
+SIDE_PRIORITY = int(os.environ.get("REHR_SIDE_PRIORITY", "-1"))
+
+
 class _fork:
-    def __init__(self, device):
+    def __init__(self, device, kind: str = "wgrad"):
         self.main = torch.cuda.current_stream(device)
-        key = (device.index if device.index is not None else torch.cuda.current_device())
+        key = (device.index if device.index is not None else torch.cuda.current_device(), kind)
         side = _side_streams.get(key)
         if side is None:
-            side = _side_streams[key] = torch.cuda.Stream(device=device)
+            side = _side_streams[key] = torch.cuda.Stream(device=device, priority=SIDE_PRIORITY if kind == "wgrad" else 0)
         self.side = side
         self.ctx = None
         self.ev = None

@@ -109,8 +109,12 @@ class GraphedTrainStep:
         for p in self.params:
             p.grad = None                    # gradients are (re)created inside the capture: static addresses, plain assignment
         self.graph = torch.cuda.CUDAGraph()
+        # The capture stream has HIGH priority (kernel nodes keep it): the step's main chain and its weight-gradient branch run
+        # ahead of the low-priority re-pack branch (functional.SIDE_PRIORITY).
         # thread_local: the NCCL watchdog thread of torch.distributed polls events while this thread captures
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self._dp is not None else "global"):
+        from . import functional as Fn
+        cap = torch.cuda.Stream(device=dev, priority=Fn.SIDE_PRIORITY)
+        with torch.cuda.graph(self.graph, stream=cap, capture_error_mode="thread_local" if self._dp is not None else "global"):
             self.loss = self._eager()
         self.grads = [p.grad for p in self.params]     # static gradient tensors (None for parameters the loss does not reach)
         # the captured pack kernels write the cached 16-bit weight copies in place: keep them alive with the graph
