@@ -78,7 +78,10 @@ __device__ __forceinline__ int stem_tap_offset(int k, int Wa, int planar) {
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
+// PLANAR (k = (1,3,3)) is a template parameter: with a run-time tap count the K loop stays rolled and the B fragments / tap offsets
+// it indexes end up in local memory (one LDL per MMA operand -- what made the first version latency bound, IPC 0.17 per scheduler).
+template <bool PLANAR>
+__global__ void __launch_bounds__(256, 3) stem_fwd_mma_kernel(const StemArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int Wp = (a.wd + 15) / 16 * 16;  // row length rounded up to whole 16-voxel M tiles
   const int Wa = Wp + 2;
@@ -86,13 +89,13 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
   uint8_t* sout = smem_raw + (((size_t)30 * Wa * sizeof(float) + 15) & ~size_t(15));  // [8 warps][16 rows][kStemRowPad]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int ntaps = a.planar ? 9 : 27;
-  const int ksteps = a.planar ? 1 : 2;  // K = taps padded to 16 / 32
+  constexpr int ntaps = PLANAR ? 9 : 27;
+  constexpr int ksteps = PLANAR ? 1 : 2;  // K = taps padded to 16 / 32
 
   // B fragments: B[k = tap][n = co] = W[co][tap], hi / lo split; b0 = (k = 2t, 2t+1), b1 = (k = 2t+8, 2t+9), n = g
   uint32_t bhi[2][4][2], blo[2][4][2];
 #pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
+  for (int ks = 0; ks < ksteps; ++ks)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
   // this thread's 8 tap offsets: index (ks, h, j) -> k = ks*16 + h*8 + 2t + j
   int koff[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) koff[i] = stem_tap_offset((i >> 2) * 16 + ((i >> 1) & 1) * 8 + 2 * t + (i & 1), Wa, a.planar);
+  for (int i = 0; i < 8; ++i) koff[i] = stem_tap_offset((i >> 2) * 16 + ((i >> 1) & 1) * 8 + 2 * t + (i & 1), Wa, PLANAR);
   float bias[4][2];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
       // A fragments: a0 = (row g, k 2t..), a1 = (row g+8, k 2t..), a2 = (row g, k 2t+8..), a3 = (row g+8, k 2t+8..)
       uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
+      for (int ks = 0; ks < ksteps; ++ks)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -148,8 +151,7 @@ __global__ void __launch_bounds__(256) stem_fwd_mma_kernel(const StemArgs a) {
         acc[nt][1] = acc[nt][3] = bias[nt][1];
       }
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        if (ks >= ksteps) break;  // warp-uniform
+      for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           mma_bf16_16816(acc[nt], ahi[ks], bhi[ks][nt][0], bhi[ks][nt][1]);
@@ -191,7 +193,8 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "r"(smem_u32(smem_ptr)));
 }
 
-__global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
+template <bool PLANAR>
+__global__ void __launch_bounds__(256, 3) stem_wgrad_mma_kernel(const StemArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int Wp = (a.wd + 15) / 16 * 16;
   const int Wa = Wp + 2;
@@ -202,11 +205,11 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
   // A[m = tap][k = voxel]: a0 = (tap mt*16+g, v 2t..2t+1), a1 = (tap +8, same v), a2 = (tap, v 2t+8..), a3 = (tap +8, v 2t+8..)
   int toff[4];     // staged-row offsets of the taps g, g+8, g+16, g+24
   float tmask[4];  // 0 for the padding taps >= 27
+  constexpr int ntaps = PLANAR ? 9 : 27;
+  constexpr int mtiles = PLANAR ? 1 : 2;  // taps padded to 16 / 32
 #pragma unroll
-  const int ntaps = a.planar ? 9 : 27;
-  const int mtiles = a.planar ? 1 : 2;  // taps padded to 16 / 32
   for (int i = 0; i < 4; ++i) {
-    toff[i] = stem_tap_offset(g + 8 * i, Wa, a.planar);
+    toff[i] = stem_tap_offset(g + 8 * i, Wa, PLANAR);
     tmask[i] = (g + 8 * i) < ntaps ? 1.f : 0.f;
   }
   float acc[2][4][4];
@@ -263,8 +266,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_mma_kernel(const StemArgs a) {
       for (int p = 0; p < 2; ++p) ldmatrix_x4_trans(bfr[p], buf + lm_v * kStemRowPad + (p * 16 + lm_c) * 2);
       // A fragments (im2col of the fp32 rows, hi / lo)
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        if (mt >= mtiles) break;  // warp-uniform
+      for (int mt = 0; mt < mtiles; ++mt) {
         uint32_t ahi[4], alo[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -345,7 +347,7 @@ static int stem_set_smem(K kernel, size_t smem, size_t* cached_per_device) {
   return REHR_OK;
 }
 
-static constexpr int kStemWgradBlocks = 296;  // 2 x 148
+static constexpr int kStemWgradBlocks = 444;  // 3 x 148 (launch bound: 3 blocks per SM)
 
 bool stem_mma_supported(int cin, int cout, int wd) { return cin == 1 && cout == 32 && stem_smem_bytes(wd, true) <= 160 * 1024; }
 size_t stem_mma_wgrad_workspace() { return (size_t)kStemWgradBlocks * 27 * 32 * sizeof(float); }
@@ -358,12 +360,13 @@ int launch_stem_fwd_mma(const float* x, const float* w, const float* bias, __nv_
   a.x = x; a.w = w; a.bias = bias; a.y = y; a.ldy = ldy; a.ws = nullptr;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = act; a.slope = slope;
   const size_t smem = stem_smem_bytes(wd, false);
-  static size_t cached[kMaxDevices] = {};
-  int rc = stem_set_smem(stem_fwd_mma_kernel, smem, cached);
+  static size_t cached[2 * kMaxDevices] = {};
+  int rc = planar ? stem_set_smem(stem_fwd_mma_kernel<true>, smem, cached + kMaxDevices) : stem_set_smem(stem_fwd_mma_kernel<false>, smem, cached);
   if (rc != REHR_OK) return rc;
   const long long tiles = (long long)n * d * ((h + 7) / 8);
-  const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 4));
-  stem_fwd_mma_kernel<<<blocks, 256, smem, stream>>>(a);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 3));
+  if (planar) stem_fwd_mma_kernel<true><<<blocks, 256, smem, stream>>>(a);
+  else stem_fwd_mma_kernel<false><<<blocks, 256, smem, stream>>>(a);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -376,12 +379,13 @@ int launch_stem_wgrad_mma(const float* x, const __nv_bfloat16* dy, long long ldd
   a.x = x; a.w = nullptr; a.bias = nullptr; a.y = const_cast<__nv_bfloat16*>(dy); a.ldy = lddy; a.ws = ws;
   a.n = n; a.d = d; a.h = h; a.wd = wd; a.act = 0; a.slope = 0.f;
   const size_t smem = stem_smem_bytes(wd, true);
-  static size_t cached[kMaxDevices] = {};
-  int rc = stem_set_smem(stem_wgrad_mma_kernel, smem, cached);
+  static size_t cached[2 * kMaxDevices] = {};
+  int rc = planar ? stem_set_smem(stem_wgrad_mma_kernel<true>, smem, cached + kMaxDevices) : stem_set_smem(stem_wgrad_mma_kernel<false>, smem, cached);
   if (rc != REHR_OK) return rc;
   const long long tiles = (long long)n * d * ((h + 7) / 8);
   const int blocks = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)kStemWgradBlocks));
-  stem_wgrad_mma_kernel<<<blocks, 256, smem, stream>>>(a);
+  if (planar) stem_wgrad_mma_kernel<true><<<blocks, 256, smem, stream>>>(a);
+  else stem_wgrad_mma_kernel<false><<<blocks, 256, smem, stream>>>(a);
   REHR_CHECK_LAUNCH();
   stem_wgrad_reduce_kernel<<<planar ? 9 : 27, 256, 0, stream>>>(ws, blocks, dw, accumulate, planar ? 9 : 27);
   REHR_CHECK_LAUNCH();
