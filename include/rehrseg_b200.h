@@ -163,6 +163,19 @@ int rehr_conv3d_march_norm_supported(const rehr_conv_desc* desc, int cin, int co
 int rehr_conv3d_march_fwd_norm(const rehr_tensor* x, const float* norm, int op_dtype, const void* w_march, const float* bias,
                                const rehr_tensor* y, int ks, int y_is_f32, int act, float slope, float* stats, rehr_stream stream);
 
+/* Input gradient of a stride-1 k3 marching layer whose INPUT is the activation of a Conv -> InstanceNorm -> LeakyReLU block
+ * (ConvDropoutNormReLU, models/seg_model.py:174-191): besides dx = conv^T(dy) the epilogue accumulates that block's InstanceNorm
+ * backward sums from the fp32 accumulators -- S1 = sum g, S2raw = sum g*y with g = (scale*y + shift > 0 ? 1 : slope) * dx, y_prod =
+ * the block's pre-normalisation tensor (shape of dx), norm_prod = its f32 [n][3][c] (scale, shift, slope) table from
+ * rehr_instnorm_finalize_norm -- into stats [n][rehr_conv3d_march_stats_tiles(dy, dx, ks)][c][2].  The block's stand-alone reduce
+ * pass (rehr_instnorm_lrelu_bwd_reduce) is then not needed: rehr_instnorm_lrelu_bwd_finalize_raw converts the raw sums
+ * (sum g*xhat = rstd * (sum g*y - mean * sum g)).  cin_dy / cout_dx: channels of dy / dx. */
+int rehr_conv3d_march_dgrad_inred_supported(const rehr_conv_desc* desc, int cin_dy, int cout_dx);
+int rehr_conv3d_march_dgrad_inred(const rehr_tensor* dy, const void* w_march, const rehr_tensor* dx, int ks, const rehr_tensor* y_prod,
+                                  const float* norm_prod, float* stats, rehr_stream stream);
+int rehr_instnorm_lrelu_bwd_finalize_raw(const float* partial, int n, int tiles, int c, const float* mean, const float* rstd,
+                                         float* sums, float* dgamma, float* dbeta, int accumulate, rehr_stream stream);
+
 /* Batched weight re-pack (csrc/pack_batch.cu).  Between rehr_pack_batch_begin() and rehr_pack_batch_launch() every
  * rehr_pack_weight / rehr_pack_weight_march / rehr_pack_weight_march_s2dgrad call ON THIS THREAD is recorded instead of launched;
  * rehr_pack_batch_launch issues all of them as ONE kernel (one per 128 recorded calls) whose job table travels in the kernel

@@ -98,6 +98,9 @@ def _declare(L: C.CDLL) -> None:
         "rehr_conv3d_march_s2dgrad_supported": (i, [D, i, i]),
         "rehr_conv3d_march_s2dgrad_weight_bytes": (sz, [D, i, i]),
         "rehr_pack_weight_march_s2dgrad": (i, [D, vp, vp, i, i, vp]),
+        "rehr_conv3d_march_dgrad_inred_supported": (i, [D, i, i]),
+        "rehr_conv3d_march_dgrad_inred": (i, [T, vp, T, i, T, vp, vp, vp]),
+        "rehr_instnorm_lrelu_bwd_finalize_raw": (i, [vp, i, i, i, vp, vp, vp, vp, vp, i, vp]),
         "rehr_pack_batch_begin": (i, []),
         "rehr_pack_batch_launch": (i, [vp]),
         "rehr_pack_batch_abort": (i, []),

@@ -83,6 +83,13 @@ struct alignas(64) MarchParams {
   int act;
   float slope;
   float* stats;  // [N][tiles_per_sample][Cout][2] or null
+  // RED variants (input gradient whose result is the gradient of an InstanceNorm + LeakyReLU activation): y = the pre-normalisation
+  // tensor of THAT block (same voxels / channels as the output), red_norm = its f32 [N][3][Cout] table (scale, shift, slope).  The
+  // statistics slots then receive  S1 = sum g,  S2raw = sum g*y  with  g = (scale*y + shift > 0 ? 1 : slope) * output
+  const unsigned short* red_y;
+  const float* red_norm;
+  long long red_ld;
+  int red_f16;
   int* err;
   long long* prof;  // development only: per-role cycle counters of CTA 0 (env REHR_MARCH_PROF)
   int debug;  // development only (env REHR_MARCH_DEBUG): bit0 skip input TMA, bit1 skip epilogue body, bit2 skip MMAs,
@@ -122,7 +129,7 @@ __device__ __forceinline__ bool elect_one_sync() {
 // the MMA issue sequence of one input plane (9 * CHUNKS * BKT/16 instructions) is fully unrolled with constant
 // descriptor increments: a single thread must issue one tcgen05.mma every ~50 clk (tools/umma_rate2.cu measures
 // 40 clk/MMA for this code shape vs 120-280 clk/MMA with run-time descriptor arithmetic).
-template <int BKT, int CHUNKS, int CT, int KS, bool XF>
+template <int BKT, int CHUNKS, int CT, int KS, bool XF, bool RED = false>
 #ifndef REHR_MARCH_MAXNREG
 #define REHR_MARCH_MAXNREG 255
 #endif
@@ -420,6 +427,16 @@ __global__ void __launch_bounds__(XF ? kMarchThreadsXf : kMarchThreads) __maxnre
       for (int q = d0; q < d1; ++q) {
         const int s = (q - d0) & kSlotMask;
         const long long te0 = clock64();
+        // RED: this voxel's y row is requested BEFORE the wait for the plane's accumulators, so its global-memory latency
+        // overlaps the MMAs still running (issued after the wait it sat on the critical path of every plane: +65 % kernel time)
+        uint4 ypre[RED ? CT / 8 : 1];
+        if constexpr (RED) {
+          if (valid_hw && q < p.OD) {
+            const long long yoff = ((((long long)c.n * p.D + q) * p.H + oh) * p.W + ow) * p.red_ld + cbase;
+#pragma unroll
+            for (int i = 0; i < CT / 8; ++i) ypre[i] = __ldg(reinterpret_cast<const uint4*>(p.red_y + yoff + 8 * i));
+          }
+        }
         mbar_wait(&tfull_bar[s], (tfull_par >> s) & 1u, p.err, 41);
         tfull_par ^= 1u << s;
         tc_fence_after();
@@ -450,7 +467,40 @@ __global__ void __launch_bounds__(XF ? kMarchThreadsXf : kMarchThreads) __maxnre
                 if (i < nvalid) f[i] += __ldg(p.bias + cbase + c0 + i);
             }
           }
-          if (p.stats != nullptr && valid) {
+          if constexpr (RED) {
+            // InstanceNorm + LeakyReLU backward sums of the block that produced this conv's input, taken from the fp32
+            // accumulators on their way out (saves that block's stand-alone reduce pass over dA and y)
+            if (valid) {
+              const float* nt = p.red_norm + (long long)c.n * 3 * p.Cout + cbase + c0;
+#pragma unroll
+              for (int i = 0; i < kW; i += 8) {
+                const uint4 yu = ypre[(c0 + i) / 8];
+                const uint32_t yw[4] = {yu.x, yu.y, yu.z, yu.w};
+                float yv[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 t2 = unpack16x2(yw[k], p.red_f16);
+                  yv[2 * k] = t2.x;
+                  yv[2 * k + 1] = t2.y;
+                }
+#pragma unroll
+                for (int h4 = 0; h4 < 8; h4 += 4) {
+                  const float4 A4 = __ldg(reinterpret_cast<const float4*>(nt + i + h4));
+                  const float4 B4 = __ldg(reinterpret_cast<const float4*>(nt + p.Cout + i + h4));
+                  const float4 S4 = __ldg(reinterpret_cast<const float4*>(nt + 2 * p.Cout + i + h4));
+                  const float Ai[4] = {A4.x, A4.y, A4.z, A4.w}, Bi[4] = {B4.x, B4.y, B4.z, B4.w}, Si[4] = {S4.x, S4.y, S4.z, S4.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float yy = yv[h4 + k];
+                    const float z = fmaf(Ai[k], yy, Bi[k]);
+                    const float gi = z > 0.f ? f[i + h4 + k] : f[i + h4 + k] * Si[k];
+                    s1[c0 + i + h4 + k] += gi;
+                    s2[c0 + i + h4 + k] = fmaf(gi, yy, s2[c0 + i + h4 + k]);
+                  }
+                }
+              }
+            }
+          } else if (p.stats != nullptr && valid) {
 #pragma unroll
             for (int i = 0; i < kW; ++i) {
               s1[c0 + i] += f[i];
@@ -659,7 +709,7 @@ struct MarchExt {
 
 int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, const rehr_tensor& y, int ks_code, int y_is_f32, int act,
                  float slope, float* stats, cudaStream_t stream, const MarchExt* ext = nullptr, const float* norm = nullptr,
-                 int op_dtype = REHR_BF16) {
+                 int op_dtype = REHR_BF16, const rehr_tensor* red_y = nullptr, const float* red_norm = nullptr) {
   MarchPlan pl;
   int rc = plan_march(x, y, ks_code, &pl, 0);
   if (rc != REHR_OK) return rc;
@@ -693,6 +743,18 @@ int launch_march(const rehr_tensor& x, const void* w_march, const float* bias, c
   p.act = act;
   p.slope = slope;
   p.stats = stats;
+  p.red_y = nullptr;
+  p.red_norm = nullptr;
+  if (red_y != nullptr) {
+    // same voxels and channels as the output, whole channel tiles, plain stride-1 layer
+    if (ext || norm || !stats || !red_norm || y_is_f32 || red_y->n != y.n || red_y->d != y.d || red_y->h != y.h || red_y->w != y.w ||
+        red_y->c != y.c || y.c % p.Ct != 0 || red_y->ld % 8 != 0 || (reinterpret_cast<uintptr_t>(red_y->ptr) & 15) != 0)
+      return REHR_UNSUPPORTED;
+    p.red_y = reinterpret_cast<const unsigned short*>(red_y->ptr);
+    p.red_norm = red_norm;
+    p.red_ld = red_y->ld;
+    p.red_f16 = red_y->dtype == REHR_F16;
+  }
   p.err = nullptr;
   {
     const char* dbg = getenv("REHR_MARCH_DEBUG");
@@ -734,6 +796,16 @@ static int launch_variant(const MarchPlan& pl, cudaStream_t stream) {
     if constexpr (CT <= 32 && KS == 3) {   // the transform warps cost registers: 64-column epilogues keep the 192-thread shape
       REHR_SET_MAX_SMEM_ONCE((conv_march_kernel<BKT, CHUNKS, CT, KS, true>), 227 * 1024);
       conv_march_kernel<BKT, CHUNKS, CT, KS, true><<<pl.grid, kMarchThreadsXf, pl.smem, stream>>>(pl.p);
+      REHR_CHECK_LAUNCH();
+      return REHR_OK;
+    } else {
+      return REHR_UNSUPPORTED;
+    }
+  }
+  if (pl.p.red_y != nullptr) {
+    if constexpr (KS == 3 && CT <= 32) {   // the layers whose input is a Conv -> InstanceNorm -> LeakyReLU block at 16 .. 128 channels
+      REHR_SET_MAX_SMEM_ONCE((conv_march_kernel<BKT, CHUNKS, CT, KS, false, true>), 227 * 1024);
+      conv_march_kernel<BKT, CHUNKS, CT, KS, false, true><<<pl.grid, kMarchThreads, pl.smem, stream>>>(pl.p);
       REHR_CHECK_LAUNCH();
       return REHR_OK;
     } else {
@@ -900,6 +972,23 @@ int rehr_conv3d_march_fwd(const rehr_tensor* x, const void* w_march, const float
                           int act, float slope, float* stats, rehr_stream stream) {
   if (!x || !y || !x->ptr || !y->ptr || !w_march) return REHR_BAD_SHAPE;
   return launch_march(*x, w_march, bias, *y, ks, y_is_f32, act, slope, stats, (cudaStream_t)stream);
+}
+
+// Input gradient dx = conv^T(dy) of a stride-1 marching layer whose INPUT was the activation of a Conv -> InstanceNorm -> LeakyReLU
+// block: y_prod = that block's pre-normalisation tensor (same shape as dx), norm_prod = its f32 [n][3][c] table (scale, shift,
+// slope) from rehr_instnorm_finalize_norm.  Besides dx the epilogue leaves the block's backward sums (S1 = sum g, S2raw = sum g*y)
+// in stats [n][rehr_conv3d_march_stats_tiles][c][2]; rehr_instnorm_lrelu_bwd_finalize_raw turns them into (sum g, sum g*xhat).
+int rehr_conv3d_march_dgrad_inred_supported(const rehr_conv_desc* d, int cin_dy, int cout_dx) {
+  const int ks = march_ks_of(d);
+  if (ks != 3) return 0;
+  const int ct = march_ct(cin_dy, cout_dx, 3, false);
+  return ct > 0 && ct <= 32 && cout_dx % ct == 0 ? 1 : 0;
+}
+int rehr_conv3d_march_dgrad_inred(const rehr_tensor* dy, const void* w_march, const rehr_tensor* dx, int ks, const rehr_tensor* y_prod,
+                                  const float* norm_prod, float* stats, rehr_stream stream) {
+  if (!dy || !dx || !dy->ptr || !dx->ptr || !w_march || !y_prod || !y_prod->ptr || !norm_prod || !stats) return REHR_BAD_SHAPE;
+  return launch_march(*dy, w_march, nullptr, *dx, ks, 0, REHR_ACT_NONE, 0.f, stats, (cudaStream_t)stream, nullptr, nullptr, REHR_BF16,
+                      y_prod, norm_prod);
 }
 
 // Same, with the producer's InstanceNorm + LeakyReLU applied on the operand path: x is the RAW conv output of the producing

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const NormApplyArgs a) 
 // partial [n][tiles][c][2] -> sums [n][c][2]; dgamma[c] = sum_n S2, dbeta[c] = sum_n S1.  Same thread layout; grid = C/32.
 __global__ void __launch_bounds__(32 * kFinLanes) in_bwd_finalize_kernel(const float* partial, int N, int tiles, int C,
                                                                           float* sums, float* dgamma, float* dbeta,
-                                                                          int accumulate) {
+                                                                          int accumulate, const float* raw_mean, const float* raw_rstd) {
   __shared__ double sh1[kFinLanes][33], sh2[kFinLanes][33];
   const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(32 * kFinLanes) in_bwd_finalize_kernel(const f
           a2 += sh2[l][cl];
         }
         const int n = n0 + k;
+        // raw partials (sum g, sum g*y) from a conv epilogue: sum g*xhat = rstd * (sum g*y - mean * sum g)
+        if (raw_mean != nullptr) a2 = (double)raw_rstd[n * C + c] * (a2 - (double)raw_mean[n * C + c] * a1);
         sums[((long long)n * C + c) * 2] = (float)a1;
         sums[((long long)n * C + c) * 2 + 1] = (float)a2;
         b += a1;
@@ -1201,7 +1203,17 @@ int rehr_instnorm_lrelu_bwd_finalize(const float* partial, int n, int tiles, int
                                      float* dgamma, float* dbeta, int accumulate, rehr_stream stream) {
   (void)rstd;
   if (!partial || !sums) return REHR_BAD_SHAPE;
-  in_bwd_finalize_kernel<<<(c + 31) / 32, 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, sums, dgamma, dbeta, accumulate);
+  in_bwd_finalize_kernel<<<(c + 31) / 32, 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, sums, dgamma, dbeta, accumulate,
+                                                                                     nullptr, nullptr);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_instnorm_lrelu_bwd_finalize_raw(const float* partial, int n, int tiles, int c, const float* mean, const float* rstd, float* sums,
+                                         float* dgamma, float* dbeta, int accumulate, rehr_stream stream) {
+  if (!partial || !sums || !mean || !rstd) return REHR_BAD_SHAPE;
+  in_bwd_finalize_kernel<<<(c + 31) / 32, 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, sums, dgamma, dbeta, accumulate,
+                                                                                     mean, rstd);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -26,7 +26,7 @@ Triple = Tuple[int, int, int]
 # launch accounting (bench.py reports `gpu_launches`)
 # --------------------------------------------------------------------------------------------------
 _launches = 0
-path_hits = {"tconv_bias_from_epilogue_sums": 0, "tconv_twin_from_epilogue": 0}   # which fused shortcuts really ran (tests read this)
+path_hits = {"tconv_bias_from_epilogue_sums": 0, "tconv_twin_from_epilogue": 0, "in_bwd_sums_from_dgrad_epilogue": 0}   # which fused shortcuts really ran (tests read this)
 
 
 def launches() -> int:
@@ -515,7 +515,7 @@ def join_pending_wgrad() -> None:
 
 
 def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bool, cache: bool = True, norm=None, x_h=False,
-                     want_chsum: bool = False):
+                     want_chsum: bool = False, inred=None):
     """(dx or None, dw) of a conv.  The weight-gradient chain runs on a side stream (events only: graph-capturable): joined right
     after the input gradient for small layers (two latency-bound chains side by side), or -- WGRAD_DEFER_JOIN, inside an autograd
     backward pass -- at the end of the pass.  `norm` / `x_h`: x is a raw conv output normalised on load (conv3d_wgrad_raw)."""
@@ -529,13 +529,13 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
             # InstanceNorm passes depend on it -- and the weight gradient is made to WAIT for it (fork point after the launch):
             # inside a replayed CUDA graph two independent branches start in no particular order, a dependency is the only
             # way to fix it.  The InstanceNorm passes then run next to the weight gradient.
-            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
+            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum, inred=inred)
             with fk:
                 conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
         else:
             with fk:
                 conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, out=dw, norm=norm, x_h=x_h)
-            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum)
+            dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum, inred=inred)
         deferred = False
         # a leaf parameter without a .grad: AccumulateGrad adopts dw without touching it (a view of a parameter, e.g. FLAVR's 2-D
         # fuse convs seen as 5-D, sends dw through a ViewBackward first: joined per layer)
@@ -550,7 +550,7 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
         if not deferred:
             fk.join()
         return dx, dw
-    dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum) if need_dx else None
+    dx = conv3d_dgrad_raw(dy, weight, x.shape, kernel, stride, padding, cache=cache, want_chsum=want_chsum, inred=inred) if need_dx else None
     return dx, conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, norm=norm, x_h=x_h)
 
 
@@ -627,8 +627,29 @@ def instnorm_stats_raw(y: torch.Tensor, y_h: bool = False):
     return stats, tiles
 
 
+# Fused InstanceNorm-backward sums.  When the input of a stride-1 marching conv is the activation of a Conv -> InstanceNorm ->
+# LeakyReLU block, the conv's input-gradient epilogue also accumulates that block's backward sums (sum g, sum g*y) from its fp32
+# accumulators (rehr_conv3d_march_dgrad_inred), so the block's stand-alone reduce pass over dA and y does not run.  The producer
+# advertises what the epilogue needs on its output tensor (`_rehr_prod`), the result carries the partial sums (`_rehr_insums`).
+# Measured on the C1 step (tools/ab_step.py, tools/timeline.py) and left OFF: the extra epilogue work (y row + 24 table loads + 5
+# operations per accumulator) makes the drain of a plane longer than its MMAs on the 32-channel layers -- the 32<-32 @128^3 input
+# gradient goes from 256 to 430 us to save a 113 us reduce pass that mostly hides behind the weight gradient anyway; 64<-64 @64^3
+# 124 -> 150 us for a 31 us pass; step 12.17 ms off vs 12.25-12.35 ms on.  Kept as a tested path (REHR_INRED=1) for layers with
+# long K loops, where the four drain warps have the slack.
+INRED = os.environ.get("REHR_INRED", "0") == "1"
+
+
+class _Prod:
+    """What a ConvNormAct block leaves on its activation for a fusing consumer: y (pre-normalisation), its format, the f32
+    [n][3][c] (scale, shift, slope) table."""
+    __slots__ = ("y", "y_h", "norm")
+
+    def __init__(self, y, y_h, norm):
+        self.y, self.y_h, self.norm = y, y_h, norm
+
+
 def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[int], kernel: Triple, stride: Triple,
-                     padding: Triple, cache: bool = True, want_chsum: bool = False) -> torch.Tensor:
+                     padding: Triple, cache: bool = True, want_chsum: bool = False, inred: Optional[_Prod] = None) -> torch.Tensor:
     """dx = conv^T(dy).  `want_chsum`: where the marching kernel runs, its epilogue also leaves the per-(sample, tile, channel) sums
     of the fp32 accumulators on the result (`dx._rehr_chsum`, f32 [n][tiles][cin][2]): the bias gradient of a transposed conv
     that produced (part of) the conv's input then needs no pass over dx."""
@@ -642,6 +663,18 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
         wp = _packed(weight, "march_dgrad", cache)
         dyt, dxt = rt(dy), rt(dx)
         stats = None
+        if inred is not None and not want_chsum and tuple(inred.y.shape) == tuple(dx.shape) \
+                and lib().rehr_conv3d_march_dgrad_inred_supported(C.byref(desc), dy.shape[4], cin):
+            tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(dyt), C.byref(dxt), int(kernel[0]))
+            stats = torch.empty((n, tiles, cin, 2), dtype=torch.float32, device=dy.device)
+            ypt = rt(inred.y, inred.y_h)
+            with _timed("conv_march_kernel", flops, tag):
+                check(lib().rehr_conv3d_march_dgrad_inred(C.byref(dyt), ptr(wp), C.byref(dxt), int(kernel[0]), C.byref(ypt),
+                                                          ptr(inred.norm), ptr(stats), stream_ptr()), "conv3d_march_dgrad_inred")
+            _count()
+            dx._rehr_insums = (stats, tiles, inred.y.data_ptr())
+            path_hits["in_bwd_sums_from_dgrad_epilogue"] = path_hits.get("in_bwd_sums_from_dgrad_epilogue", 0) + 1
+            return dx
         if want_chsum:
             tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(dyt), C.byref(dxt), int(kernel[0]))
             stats = torch.empty((n, tiles, cin, 2), dtype=torch.float32, device=dy.device)
@@ -779,6 +812,8 @@ class ConvNormAct(torch.autograd.Function):
       weight-gradient operand of the consumer; written by the same normalise pass).
     The second / third outputs are non-differentiable side tensors; the gradient of output 0 is always d(loss)/d(activation)."""
 
+    last_prod = None   # set by forward for the wrapper (conv_norm_act) to hang on the returned activation
+
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, kernel, stride, padding, eps, slope, small_cin, cat_room):
         dev = x.device
@@ -846,6 +881,8 @@ class ConvNormAct(torch.autograd.Function):
         ctx.cfg = (kernel, stride, padding, slope, small_cin, bias is not None, y_h, x_raw_h)
         ctx.wref = weakref.ref(weight)
         ctx.x_upcat = bool(getattr(x, "_rehr_upcat", False))   # x = [up | skip]: the transposed conv wants channel sums of dx
+        # x is the activation of another block of this kind: its backward sums come out of this conv's input-gradient epilogue
+        ctx.prod = getattr(x, "_rehr_prod", None) if (INRED and train and not small_cin and ctx.needs_input_grad[0]) else None
         if defer:
             ctot, coff = (2 * cout, cout) if cat_room else (cout, 0)
             norm = torch.empty((n, 3, ctot), dtype=torch.float32, device=dev)
@@ -860,8 +897,16 @@ class ConvNormAct(torch.autograd.Function):
             if norm_own is not None:
                 ctx.mark_non_differentiable(norm_own)
             return y, norm, norm_own
-        check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, cout, vox, float(eps), ptr(mean), ptr(rstd), stream_ptr()),
-              "instnorm_finalize")
+        ConvNormAct.last_prod = None
+        if INRED and train and not cat_room:
+            # same finalize, which also leaves the (scale, shift, slope) table a fusing consumer's input-gradient epilogue reads
+            ntab = torch.empty((n, 3, cout), dtype=torch.float32, device=dev)
+            check(lib().rehr_instnorm_finalize_norm(ptr(stats), n, tiles, cout, vox, float(eps), ptr(g32), ptr(b32), float(slope),
+                                                    ptr(mean), ptr(rstd), ptr(ntab), cout, 0, None, stream_ptr()), "instnorm_finalize_norm")
+            ConvNormAct.last_prod = _Prod(y, y_h, ntab)
+        else:
+            check(lib().rehr_instnorm_finalize(ptr(stats), n, tiles, cout, vox, float(eps), ptr(mean), ptr(rstd), stream_ptr()),
+                  "instnorm_finalize")
         want_twin = a_h and train
         a = alloc(y.shape)
         a2 = alloc(y.shape) if want_twin else None
@@ -884,7 +929,9 @@ class ConvNormAct(torch.autograd.Function):
         weight = _orig_weight(ctx, weight)
         kernel, stride, padding, slope, small_cin, has_bias, y_h, x_raw_h = ctx.cfg
         dev = y.device
+        da_in = da
         da = as_cl(da)
+        global _launches
         n, cout = y.shape[0], y.shape[4]
         vox = y.shape[1] * y.shape[2] * y.shape[3]
         yt, dat = rt(y, y_h), rt(da)
@@ -893,15 +940,22 @@ class ConvNormAct(torch.autograd.Function):
         da2p = C.byref(da2t) if da2t is not None else None
         g32 = _f32(gamma) if gamma is not None else None
         b32 = _f32(beta) if beta is not None else None
-        tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
-        partial = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
-        check(lib().rehr_instnorm_lrelu_bwd_reduce(C.byref(yt), C.byref(dat), da2p, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
-                                                   float(slope), ptr(partial), stream_ptr()), "instnorm_bwd_reduce")
         sums = torch.empty((n, cout, 2), dtype=torch.float32, device=dev)
         dgamma = torch.empty((cout,), dtype=torch.float32, device=dev)
         dbeta = torch.empty((cout,), dtype=torch.float32, device=dev)
-        check(lib().rehr_instnorm_lrelu_bwd_finalize(ptr(partial), n, tiles, cout, ptr(rstd), ptr(sums), ptr(dgamma), ptr(dbeta),
-                                                     0, stream_ptr()), "instnorm_bwd_finalize")
+        ins = getattr(da_in, "_rehr_insums", None)
+        if ins is not None and da2 is None and ins[2] == y.data_ptr() and tuple(ins[0].shape) == (n, ins[1], cout, 2):
+            # the consumer's input-gradient epilogue already summed g and g*y over this block's voxels (conv3d_dgrad_raw)
+            check(lib().rehr_instnorm_lrelu_bwd_finalize_raw(ptr(ins[0]), n, ins[1], cout, ptr(mean), ptr(rstd), ptr(sums), ptr(dgamma),
+                                                             ptr(dbeta), 0, stream_ptr()), "instnorm_bwd_finalize_raw")
+            _launches -= 1
+        else:
+            tiles = lib().rehr_instnorm_stats_tiles(C.byref(yt))
+            partial = torch.empty((n, tiles, cout, 2), dtype=torch.float32, device=dev)
+            check(lib().rehr_instnorm_lrelu_bwd_reduce(C.byref(yt), C.byref(dat), da2p, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
+                                                       float(slope), ptr(partial), stream_ptr()), "instnorm_bwd_reduce")
+            check(lib().rehr_instnorm_lrelu_bwd_finalize(ptr(partial), n, tiles, cout, ptr(rstd), ptr(sums), ptr(dgamma), ptr(dbeta),
+                                                         0, stream_ptr()), "instnorm_bwd_finalize")
         dy = torch.empty_like(y)
         dyt = rt(dy)
         check(lib().rehr_instnorm_lrelu_bwd_apply(C.byref(yt), C.byref(dat), da2p, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
@@ -924,7 +978,7 @@ class ConvNormAct(torch.autograd.Function):
                 _count()
         else:
             dx, dw = _dgrad_and_wgrad(x, dy, weight, weight.shape, kernel, stride, padding, ctx.needs_input_grad[0],
-                                      norm=x_norm, x_h=x_raw_h, want_chsum=ctx.x_upcat)
+                                      norm=x_norm, x_h=x_raw_h, want_chsum=ctx.x_upcat, inred=ctx.prod)
         # A per-channel constant added before InstanceNorm is removed by the mean subtraction: d(loss)/d(bias) == 0
         # exactly (PyTorch's value is rounding noise of the same sum).
         dbias = torch.zeros((cout,), dtype=torch.float32, device=dev) if has_bias else None
@@ -947,6 +1001,8 @@ def conv_norm_act(x, weight, bias, gamma, beta, kernel, stride, padding, eps=1e-
         return a
     if FWD_FP16:
         mark_h(a, s1)
+    if ConvNormAct.last_prod is not None:
+        a._rehr_prod, ConvNormAct.last_prod = ConvNormAct.last_prod, None
     if cat_room:
         a._rehr_cat = (2 * weight.shape[0], weight.shape[0])
         if s1 is not None:
