@@ -145,7 +145,7 @@ def c5_pipeline(dev, peaks) -> dict:
     torch.manual_seed(0)
     m = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=False).to(dev).eval()
     lr = torch.rand((41, 2, 512, 512), device=dev, generator=g)
-    flavr.apply_to_vol_flavr(m, lr[:6], max_batch=4)   # warm-up (weight packs, allocator)
+    flavr.apply_to_vol_flavr(m, lr[:9], max_batch=4)   # warm-up (weight packs, allocator, capture of the 4-window forward)
     t_sweep = _events(lambda: flavr.apply_to_vol_flavr(m, lr, max_batch=4), 1, 0)
     orient = 4
     total = (t_blur + orient * (t_sweep + 2 * t_rot) + t_fba + t_mean) / 1e3

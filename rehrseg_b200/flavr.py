@@ -355,9 +355,11 @@ def _windows(vol: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.stack([padded.narrow(dim, st, 4) for st in range(z - 1)], dim=0)
 
 
-def apply_to_vol_flavr(model, image: torch.Tensor, pred_out_idx=None, max_batch: int = 8) -> torch.Tensor:
+def apply_to_vol_flavr(model, image: torch.Tensor, pred_out_idx=None, max_batch: int = 8, use_graph: bool = True) -> torch.Tensor:
     """utils/sr_utils.py:102-135.  `image` [Z, C, X, Y] -> [4(Z-1), C', Y, X] (the reference's axis order), computed with
-    `max_batch` windows per forward instead of one, on the device (the reference moves every window result to the CPU)."""
+    `max_batch` windows per forward instead of one, on the device (the reference moves every window result to the CPU).
+    `use_graph`: the full-size window batches all have one shape, so their forward (~200 launches of 5-300 us, bound by the host
+    when issued from Python) is captured once and replayed (graphs.graphed; re-captured when the weights change)."""
     if image.shape[0] < 3:
         raise RehrError("apply_to_vol_flavr needs at least 3 slices (the reference indexes image[0:3])")
     dev = image.device if image.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -369,12 +371,20 @@ def apply_to_vol_flavr(model, image: torch.Tensor, pred_out_idx=None, max_batch:
     win = _windows(image, 0)                                       # [Z-1, 4, C, X, Y]
     win = win.permute(0, 2, 1, 4, 3)                               # -> [Z-1, C, 4, Y, X]   (batch.permute(1,0,3,2) per window)
     outs = []
-    with torch.inference_mode():
+    with torch.no_grad():
         for s in range(0, win.shape[0], max_batch):
-            sr = model(win[s:s + max_batch].contiguous().clone())
+            batch = win[s:s + max_batch].contiguous()
+            if use_graph and batch.shape[0] == max_batch and win.shape[0] >= 2 * max_batch:
+                from .graphs import graphed
+                sr = graphed(model, batch)(batch)        # static outputs: copied out below before the next replay
+                replayed = True
+            else:
+                sr = model(batch.clone())                 # (the forward subtracts the mean from its input in place)
+                replayed = False
             if pred_out_idx is not None and isinstance(sr, tuple):
                 sr = sr[pred_out_idx]
-            outs.append(sr[:, :, :, :oy, :ox])
+            sr = sr[:, :, :, :oy, :ox]
+            outs.append(sr.clone() if replayed else sr)
     res = torch.cat(outs, dim=0)                                   # [Z-1, C', 4, Y, X]
     return res.permute(0, 2, 1, 3, 4).reshape(-1, res.shape[1], res.shape[3], res.shape[4])
 
