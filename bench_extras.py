@@ -119,14 +119,20 @@ def c4_joint(dev, peaks, steps=6, warm=3) -> dict:
             (torch.rand((B, 1, 4 * D, HW, HW), generator=g) > 0.8).float().pin_memory(),
             (torch.rand((B, 1, D, HW, HW), generator=g) * 0.99 + 0.01).pin_memory())
 
+    # the whole iteration (teacher sweep, student forward, losses, backward) replayed from one CUDA graph; per step: batch copied
+    # from pinned host memory into the static inputs, replay, SGD step, loss read back like the training script printing it
+    gs = ts.GraphedJointStep(student, tuple(t.to(dev) for t in host), lr_obj, hr_obj, teacher, distiller)
+
     def step():
-        out = ts.joint_train_step(student, host, lr_obj, hr_obj, opt, teacher, distiller, device=dev)
-        float(out["loss"])      # the loop reads its loss back, like the training script printing it
+        out = gs(host)
+        opt.step()
+        float(out["loss"])
 
     ms = _events(step, steps, warm)
+    gs.close()
     tf = 15.5 / ms * 1e3        # student fwd+bwd 4.50 + teacher sweep 10.99 TFLOP per GPU-step
     return {"config": "C4 joint SR+seg step: anisotropic SegModel student [2,1,16,256,256] x4 SR head, UASR FLAVR teacher sweep (15 windows), "
-                      "uncertainty-weighted CE + CE/Dice + Distiller(64,64,0,1,1), SGD, batch from pinned host memory",
+                      "uncertainty-weighted CE + CE/Dice + Distiller(64,64,0,1,1), SGD, batch from pinned host memory, one CUDA graph per step",
             "joint_ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 2), "tflops": round(tf, 1),
             "frac_bf16_peak_burst": round(tf / float(peaks["bf16_tflops"]), 4)}
 

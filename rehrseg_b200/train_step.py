@@ -206,6 +206,82 @@ def joint_train_step(model_seg: nn.Module, batch: Sequence[torch.Tensor], loss_o
     return out
 
 
+class _JointGraphModule(nn.Module):
+    """What graphs.GraphedTrainStep needs of a "model" for the stage-2 step: the trainable parameters (student + distiller) and a
+    forward on the first static input.  The frozen teacher is deliberately NOT a sub-module (its parameters get no gradients)."""
+
+    def __init__(self, model_seg: nn.Module, distiller: Optional[nn.Module], model_sr: Optional[nn.Module]):
+        super().__init__()
+        self.model_seg = model_seg
+        self.distiller = distiller
+        self._teacher = [model_sr]
+
+    def forward(self, img: torch.Tensor):
+        model_sr = self._teacher[0]
+        if model_sr is not None and self.distiller is not None:
+            return ("distill", img)
+        return ("plain", img)
+
+
+class GraphedJointStep:
+    """The stage-2 iteration (train_all.py:519-558: teacher window sweep, student forward, uncertainty-weighted CE + CE/Dice,
+    structural distillation, backward) captured into ONE CUDA graph and replayed; the optimiser step stays outside.
+
+        step = GraphedJointStep(model_seg, batch0, loss_lr, loss_hr, model_sr, distiller)
+        for batch in loader:                      # host (pinned) or device tensors of the captured shapes
+            out = step(batch)                     # copies the batch into the static inputs, replays; out = static loss terms
+            opt.step()                            # .grad tensors are static, re-attached after every replay
+
+    Same arithmetic as `joint_train_step` (tests/test_joint_gpu.py compares the two); inside the graph the weight gradients stay
+    on their side stream until the end of the step and the 16-bit weight copies are re-packed in a few batched launches."""
+
+    def __init__(self, model_seg: nn.Module, example_batch: Sequence[torch.Tensor], loss_obj_lr_seg: nn.Module,
+                 loss_obj_hr_seg: nn.Module, model_sr: Optional[nn.Module] = None, distiller: Optional[nn.Module] = None,
+                 enable_uncertainty: bool = True, dp_group=None):
+        from .graphs import GraphedTrainStep
+        device = next(model_seg.parameters()).device
+        model_seg.train()
+        self.terms: dict = {}
+        distill = model_sr is not None and distiller is not None
+        terms = self.terms
+
+        def loss_fn(tagged, pseudo_label_lr, label_sr, uncertainty_lr):
+            _, pseudo_img_lr = tagged
+            if distill:
+                with torch.no_grad():
+                    features_sr = _flavr.get_intermediate_features(model_sr, pseudo_img_lr, pseudo_label_lr, device,
+                                                                   normalize=_flavr.zscore_normalization)
+                pseudo_seg_lr, seg_sr, features_seg = model_seg(pseudo_img_lr, return_inetermediate_feature=True)
+            else:
+                pseudo_seg_lr, seg_sr = model_seg(pseudo_img_lr)
+            if enable_uncertainty:
+                loss_lr_seg = loss_obj_lr_seg(pseudo_seg_lr, pseudo_label_lr, uncertainty_lr)
+                loss_hr_seg = loss_obj_hr_seg(seg_sr, label_sr, None)
+            else:
+                loss_lr_seg = loss_obj_lr_seg(pseudo_seg_lr, pseudo_label_lr)
+                loss_hr_seg = loss_obj_hr_seg(seg_sr, label_sr)
+            loss = loss_lr_seg + loss_hr_seg
+            terms["loss_lr_seg"], terms["loss_hr_seg"] = loss_lr_seg.detach(), loss_hr_seg.detach()
+            if distill:
+                distill_loss = distiller(features_seg[1], features_sr[1])
+                loss = loss + distill_loss
+                terms["distill_loss"] = distill_loss.detach()
+            return loss
+
+        self.module = _JointGraphModule(model_seg, distiller if distill else None, model_sr if distill else None)
+        self.step = GraphedTrainStep(self.module, loss_fn, tuple(example_batch), dp_group=dp_group)
+
+    def __call__(self, batch: Sequence[torch.Tensor]) -> dict:
+        self.step.load(*batch)
+        loss = self.step.replay()
+        out = dict(self.terms)
+        out["loss"] = loss
+        return out
+
+    def close(self) -> None:
+        self.step.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # SR stage (BASELINE config 2's training step): train_all.py:114-152
 # ---------------------------------------------------------------------------------------------------------------

@@ -90,3 +90,36 @@ def test_joint_step_sgd_updates_parameters_and_caches():
     fresh = ts.joint_train_step(clone, batch, lr_obj, hr_obj, None)
     assert abs(float(second["loss"]) - float(first["loss"])) > 1e-5
     assert abs(float(second["loss"]) - float(fresh["loss"])) <= 1e-5 * max(1.0, abs(float(fresh["loss"])))
+
+
+def test_graphed_joint_step_matches_the_python_launched_one():
+    """train_step.GraphedJointStep (the whole stage-2 iteration replayed from one CUDA graph) against joint_train_step on the same
+    weights and batch: same kernels, so losses and gradients agree to summation-order accuracy; a second replay with another batch
+    must follow the new data (static inputs are re-loaded, the teacher's in-place z-score included)."""
+    from rehrseg_b200 import flavr, loss_ops, seg_model as sm, train_step as ts
+    from oracle import seg_model as ref_seg
+    torch.manual_seed(7)
+    student = sm.SegModel(**ref_seg.plan_kwargs("anisotropic")).cuda()
+    teacher = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).cuda().eval()
+    dist_mod = loss_ops.FusedDistiller(64, 64, 0.0, 1.0, 1.0).cuda()
+    lr_obj, hr_obj = loss_ops.build_fused_loss(False, 0), loss_ops.build_fused_loss(False, 1)
+    params = list(student.parameters()) + list(dist_mod.parameters())
+    batches = [tuple(t.cuda() for t in _batch(s, b=2, d=8, hw=64)) for s in (4, 5)]
+
+    want = []
+    for b in batches:
+        out = ts.joint_train_step(student, tuple(t.clone() for t in b), lr_obj, hr_obj, None, teacher, dist_mod)
+        torch.cuda.synchronize()
+        want.append(({k: float(v) for k, v in out.items()}, [None if p.grad is None else p.grad.clone() for p in params]))
+
+    step = ts.GraphedJointStep(student, tuple(t.clone() for t in batches[0]), lr_obj, hr_obj, teacher, dist_mod)
+    for b, (terms, grads) in zip(batches, want):
+        got = step(tuple(t.clone() for t in b))
+        torch.cuda.synchronize()
+        for k, v in terms.items():
+            assert abs(float(got[k]) - v) <= 1e-4 * max(1.0, abs(v)), (k, float(got[k]), v)
+        for p, g in zip(params, grads):
+            assert (p.grad is None) == (g is None)
+            if g is not None:
+                assert rel(p.grad, g) <= 2e-3, rel(p.grad, g)
+    step.close()
