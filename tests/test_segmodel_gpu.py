@@ -191,3 +191,42 @@ def test_graphed_train_step_matches_eager_and_tracks_weight_updates():
     got = float(step(x, t))
     want, _ = eager(x, t)
     assert abs(got - want) <= 1e-6 * max(1.0, abs(want)) and abs(want - l0) > 1e-6
+
+
+def test_deep_supervision_outputs_and_gradients():
+    """`decoder.deep_supervision = True` (toggled by the caller, train_all.py:562,574): the decoder returns one segmentation per
+    stage, largest first (models/seg_model.py:41-52).  Every scale within the 16-bit logit bound, and the lower-resolution heads --
+    which only exist on this path -- get gradients that match the fp32 oracle."""
+    from oracle import seg_model as ref_seg
+    from rehrseg_b200 import seg_model as sm
+    ref = ref_seg.build("tiny")
+    mine = sm.SegModel(**ref_seg.plan_kwargs("tiny"))
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    ref.decoder.deep_supervision = True
+    mine.decoder.deep_supervision = True
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 1, 16, 32, 32), generator=g)
+    out_r, up_r = ref(x)
+    out_m, up_m = mine(x.cuda())
+    assert isinstance(out_m, (list, tuple)) and len(out_m) == len(out_r) == len(ref.decoder.stages)
+    cots = [torch.randn(o.shape, generator=g) for o in out_r]
+    for a, b in zip(out_m, out_r):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert float((a.detach().float().cpu() - b.detach()).norm() / b.detach().norm()) <= LOGITS
+    assert float((up_m.detach().float().cpu() - up_r.detach()).norm() / up_r.detach().norm()) <= LOGITS
+    sum((o * c).mean() for o, c in zip(out_r, cots)).backward()
+    sum((o.float() * c.cuda()).mean() for o, c in zip(out_m, cots)).backward()
+    torch.cuda.synchronize()
+    pr = dict(ref.named_parameters())
+    checked = 0
+    for name, p in mine.named_parameters():
+        gr = pr[name].grad
+        if gr is None or (name.endswith("conv.bias") and ".convs." in name):   # biases in front of InstanceNorm: exactly zero here
+            continue
+        assert p.grad is not None, name
+        if "seg_layers" in name:
+            err = float((p.grad.float().cpu() - gr).norm() / (gr.norm() + 1e-30))
+            assert err <= 5e-2, (name, err)
+            checked += 1
+    assert checked == 2 * len(ref.decoder.seg_layers)

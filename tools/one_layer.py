@@ -13,6 +13,9 @@ w = torch.randn((cout, cin, 3, 3, 3), device="cuda") / (27 * cin) ** 0.5
 k, s, p = (3, 3, 3), (st,) * 3, (1, 1, 1)
 y, _, _ = Fn.conv3d_raw(x, w, None, k, s, p, want_stats=True)
 dy = torch.randn_like(y)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 for _ in range(iters):
     if what == "fwd":
         Fn.conv3d_raw(x, w, None, k, s, p, want_stats=True)
@@ -20,5 +23,6 @@ for _ in range(iters):
         Fn.conv3d_dgrad_raw(dy, w, x.shape, k, s, p)
     else:
         Fn.conv3d_wgrad_raw(x, dy, w.shape, k, s, p)
+e1.record()
 torch.cuda.synchronize()
-print("done", what, cin, cout, sp, st)
+print("done", what, cin, cout, sp, st, f"{e0.elapsed_time(e1) / iters * 1e3:.1f} us per launch")
