@@ -1,17 +1,26 @@
 """GPU parity of the conv engine (through the C-ABI) against torch fp32 convolutions on the same bf16-rounded
-operands.  Tolerance: relative L2 <= 1e-2 (north_star's bf16 bound); in practice ~2e-3 (one bf16 rounding)."""
+operands.  Tolerance: relative L2 <= 4e-3 -- about twice what the one 16-bit rounding of the result costs (2^-9 / sqrt(3) ~ 1.1e-3
+relative per element), far below north_star's 1e-2 whole-network bound: a wrong halo row / tap of a 3x3x3 kernel moves > 1e-2 --
+plus a max-abs bound of a few output ulps, which a single wrong voxel breaks."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-2
+TOL = 4e-3
 
 
 def rel_l2(a, b):
     a, b = a.double(), b.double()
     return float((a.detach() - b.detach()).norm() / (b.detach().norm() + 1e-30))
+
+
+def max_abs_ok(got, ref, ulps=3.0):
+    """Every element within `ulps` bf16 ulps of the LARGEST reference magnitude (one ulp = 2^-8 relative): what one rounding of the
+    result plus fp32 summation-order noise can cost; a voxel that misses a tap or reads a wrong halo row is off by far more."""
+    err = float((got.double() - ref.double()).abs().max())
+    return err <= ulps * 2.0 ** -8 * float(ref.abs().max())
 
 
 def bf16r(t):
@@ -98,6 +107,7 @@ def test_conv3d_fwd(case, engine):
     got = y.float().permute(0, 4, 1, 2, 3)
     assert got.shape == ref.shape
     assert rel_l2(got, ref) < TOL, (case, rel_l2(got, ref))
+    assert max_abs_ok(got, ref), case
 
 
 @pytest.mark.parametrize("case", FWD_CASES[:4] + FWD_CASES[6:9])
@@ -127,6 +137,7 @@ def test_conv3d_dgrad(case, engine):
     dx = Fn.conv3d_dgrad_raw(gcl, w, (n, *dhw, cin), k, s, p, cache=False)
     torch.cuda.synchronize()
     assert rel_l2(dx.float().permute(0, 4, 1, 2, 3), ref) < TOL, case
+    assert max_abs_ok(dx.float().permute(0, 4, 1, 2, 3), ref), case
 
 
 WGRAD_MARCH_CASES = [
