@@ -64,7 +64,7 @@ typedef enum { REHR_ACT_NONE = 0, REHR_ACT_RELU = 1, REHR_ACT_LRELU = 2 } rehr_a
 
 const char* rehr_strerror(int status);
 int rehr_last_cuda_error(void);     /* cudaError_t of the last failing CUDA call on this thread */
-int rehr_version(void);             /* ABI version, currently 4 (rehr_tensor.dtype, dtype arguments of the weight packers) */
+int rehr_version(void);             /* ABI version, currently 5 (4: rehr_tensor.dtype, dtype arguments of the weight packers; 5: batched re-pack, *_dgrad_inred, *_bwd_finalize_raw added -- additive) */
 int rehr_device_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------

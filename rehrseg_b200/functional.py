@@ -503,6 +503,18 @@ class deferred_wgrad:
 _wgrad_pending: list = []
 
 
+def pending_wgrad_event():
+    """An event that completes when every weight-gradient chain issued so far on the side stream has run (None if there is none
+    pending).  For a consumer on ANOTHER stream (the communication stream of a bucketed all-reduce): it waits for this event
+    instead of making the main stream join the side stream.  The chains stay pending: their operands are released by the join."""
+    if not _wgrad_pending:
+        return None
+    fk = _wgrad_pending[-1][0]
+    ev = torch.cuda.Event()
+    ev.record(fk.side)
+    return ev
+
+
 def join_pending_wgrad() -> None:
     """Make the current stream wait for every weight-gradient chain still running on the side stream; release their operands."""
     if not _wgrad_pending:

@@ -161,10 +161,14 @@ class GraphedTrainStep:
         from . import functional as Fn
         dp = self._dp
         dev = self.static_inputs[0].device
-        Fn.join_pending_wgrad()          # weight gradients of this bucket may still be running on the side stream
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         dp["comm"].wait_event(ev)
+        # weight gradients of this bucket may still be running on the side stream: the COMMUNICATION stream waits for them, the
+        # compute stream goes on with the backward pass (it joins the side stream at the end of the step)
+        ev_side = Fn.pending_wgrad_event()
+        if ev_side is not None:
+            dp["comm"].wait_event(ev_side)
         with torch.cuda.stream(dp["comm"]):
             with dist._coalescing_manager(group=dp["group"], device=dev, async_ops=False):
                 for q in dp["plan"][b]:
