@@ -566,6 +566,20 @@ def _dgrad_and_wgrad(x, dy, weight, wshape, kernel, stride, padding, need_dx: bo
     return dx, conv3d_wgrad_raw(x, dy, wshape, kernel, stride, padding, norm=norm, x_h=x_h)
 
 
+MARCH_MAX_WIDE = int(os.environ.get("REHR_MARCH_MAX_WIDE", "128"))
+
+
+def _march_route(desc, c_operand: int, c_result: int) -> bool:
+    """Marching kernel or tapped GEMM for a stride-1 k3 / k5 conv (forward: operand = x, result = y; input gradient: operand = dy,
+    result = dx).  With 128 operand channels the marching kernel keeps only a 16-channel result tile resident (N = 48 per A-read:
+    operand-feed bound at ~500 TFLOP/s), so once the result has >= 128 channels the tapped GEMM (N = 128) wins -- measured,
+    tools/route_probe.py: 128->128 @32^3 fwd 119 -> 88 us, dgrad 103 -> 83 us; dgrad 256<-128 @32^3 168 -> 92 us; while 128->64
+    @64^3 stays on the marching kernel (319 vs 526 us)."""
+    if not (USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), int(c_operand), int(c_result))):
+        return False
+    return not (c_operand >= 128 and c_result >= MARCH_MAX_WIDE)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
 
@@ -592,7 +606,7 @@ def conv3d_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     tiles = 0
     flops = 2.0 * n * od * oh * ow * cout * cin * kernel[0] * kernel[1] * kernel[2]
     tag = f"fwd {cin}->{cout} in{d}x{h}x{w} k{kernel} s{stride}" if _ktimer is not None else ""
-    if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), cin, cout):
+    if _march_route(desc, cin, cout):
         xt = rt(x, x_h)
         if want_stats:
             tiles = lib().rehr_conv3d_march_stats_tiles(C.byref(xt), C.byref(yt), int(kernel[0]))
@@ -671,7 +685,7 @@ def conv3d_dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, in_shape: Sequence[
     desc = conv_desc(kernel, stride, padding)
     flops = 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * dy.shape[4] * cin * kernel[0] * kernel[1] * kernel[2]
     tag = f"dgrad {cin}<-{dy.shape[4]} in{d}x{h}x{w} k{kernel} s{stride}" if _ktimer is not None else ""
-    if USE_MARCH and lib().rehr_conv3d_march_supported(C.byref(desc), dy.shape[4], cin):
+    if _march_route(desc, dy.shape[4], cin):
         wp = _packed(weight, "march_dgrad", cache)
         dyt, dxt = rt(dy), rt(dx)
         stats = None
