@@ -580,6 +580,30 @@ def _march_route(desc, c_operand: int, c_result: int) -> bool:
     return not (c_operand >= 128 and c_result >= MARCH_MAX_WIDE)
 
 
+# The exactly-zero bias gradients of the Conv -> InstanceNorm blocks (one per layer) are slices of ONE zero-filled buffer per
+# backward pass instead of one fill kernel each (22 launches on the C1 step).  A fresh buffer per pass: whatever the caller does to
+# a .grad in place can never leak into the next step.
+_zero_pool: dict = {}
+
+
+def _zero_pool_reset() -> None:
+    _zero_pool.clear()
+
+
+def _zero_grad_slice(n: int, device) -> torch.Tensor:
+    st = _zero_pool.get(device)
+    if st is None or st[1] + n > st[0].numel():
+        try:
+            if not _zero_pool:
+                torch.autograd.Variable._execution_engine.queue_callback(_zero_pool_reset)
+        except RuntimeError:      # not inside a backward pass: no pooling
+            return torch.zeros((n,), dtype=torch.float32, device=device)
+        st = _zero_pool[device] = [torch.zeros((max(8192, n),), dtype=torch.float32, device=device), 0]
+    out = st[0][st[1]:st[1] + n]
+    st[1] += (n + 3) // 4 * 4        # 16-byte aligned slices
+    return out
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
 
@@ -1007,7 +1031,7 @@ class ConvNormAct(torch.autograd.Function):
                                       norm=x_norm, x_h=x_raw_h, want_chsum=ctx.x_upcat, inred=ctx.prod)
         # A per-channel constant added before InstanceNorm is removed by the mean subtraction: d(loss)/d(bias) == 0
         # exactly (PyTorch's value is rounding noise of the same sum).
-        dbias = torch.zeros((cout,), dtype=torch.float32, device=dev) if has_bias else None
+        dbias = _zero_grad_slice(cout, dev) if has_bias else None
         return dx, dw.to(weight.dtype), dbias, dgamma if gamma is not None else None, dbeta if beta is not None else None, \
             None, None, None, None, None, None, None
 
