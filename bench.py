@@ -377,7 +377,7 @@ def main() -> None:
             torch.cuda._sleep(200_000_000)  # let the host run ahead so launch latency stays out of the event pairs
             fwd_bwd(x_dev, g_dev, eager=True)   # launched from Python so that every conv-engine launch gets its event pair
         if use_graph:
-            launches = (Fn.launches() - l0) * args.steps   # a replay issues the same kernels as the eager step it captured
+            launches = gstep.engine_launches * args.steps   # engine kernels counted while the replayed step was captured
         summ = kt.summary()
         peaks = measured_peaks()
         for name, (n, tms, fl) in summ.items():

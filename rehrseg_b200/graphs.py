@@ -114,8 +114,10 @@ class GraphedTrainStep:
         # thread_local: the NCCL watchdog thread of torch.distributed polls events while this thread captures
         from . import functional as Fn
         cap = torch.cuda.Stream(device=dev, priority=Fn.SIDE_PRIORITY)
+        l0 = Fn.launches()
         with torch.cuda.graph(self.graph, stream=cap, capture_error_mode="thread_local" if self._dp is not None else "global"):
             self.loss = self._eager()
+        self.engine_launches = Fn.launches() - l0      # engine kernels one replay issues (ATen / NCCL nodes not counted)
         self.grads = [p.grad for p in self.params]     # static gradient tensors (None for parameters the loss does not reach)
         # the captured pack kernels write the cached 16-bit weight copies in place: keep them alive with the graph
         from . import functional as Fn
