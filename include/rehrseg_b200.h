@@ -328,6 +328,13 @@ int rehr_sw_finalize(void* logits_f16, const void* npred_f16, int C, long long v
  * utils/sr_utils.py:272,276,302): L-tap cross-correlation along X, zero padded, f32. */
 int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z, int X, int Y, rehr_stream stream);
 
+/* Low-resolution simulation of the SR stage: `resize(img, (slice_separation, 1), order=3 | 0)` (utils/train_set.py:395-396,
+ * third-party resize.pytorch, source unavailable) as resampling along ONE axis of x[outer][n_in][inner] with step `step`, same
+ * field of view (sample i at (i + 0.5) * step - 0.5), n_out = round(n_in / step) chosen by the caller; order 3 = cubic
+ * convolution (A = -0.75) with clamped indices, order 0 = nearest.  f32.  The definition is the stand-in of oracle/degrade.py. */
+int rehr_resample_axis(const float* x, float* y, long long outer, int n_in, int n_out, long long inner, float step, int order,
+                       rehr_stream stream);
+
 /* rotate_vol_2d (utils/rotate.py:5-31): rot90 by k quarter turns over dims (0,1) of vol[X][Y][inner]. */
 int rehr_rot90(const void* src, void* dst, int X, int Y, long long inner_bytes, int k, rehr_stream stream);
 

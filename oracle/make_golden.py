@@ -230,9 +230,55 @@ def random_centers_fixture() -> None:
         json.dump(cases, f)
 
 
+def sr_degrade_fixture() -> None:
+    """The reference's OWN `TrainSetMultiple.__getitem__` (utils/train_set.py:337-434) and `load_img` pre-filter (:321-333) on a
+    seeded synthetic volume, with the third-party `resize` replaced by the stand-in oracle/degrade.py defines (its source is not
+    available; everything around it is the reference's code).  The dataset object is built without `__init__` (which reads NIfTI /
+    HDF5 files through packages the image does not have): `__getitem__` only reads the attributes set below.  Python's `random`
+    is seeded per case; the case list covers both transposition branches, both zero-slice branches, all flips and the final
+    permutation, a patch larger than the volume (padding) and a non-integer slice separation."""
+    import random
+    from . import degrade as od
+    refimport.install()
+    import importlib
+    importlib.import_module("resize.pytorch").resize = od.resize_standin
+    train_set = refimport.load("utils.train_set")
+    train_set.resize = od.resize_standin            # (the module did `from resize.pytorch import resize` at import time)
+    rng = np.random.RandomState(21)
+    X, Y, Z = 40, 36, 24
+    img = rng.rand(X, Y, Z, 1).astype(np.float32)
+    lab = (rng.rand(X, Y, Z, 1) > 0.7).astype(np.uint8)
+    taps = np.exp(-0.5 * ((np.arange(9.0) - 4) / (3.873 / 2.355)) ** 2)
+    kernel = torch.tensor(taps / taps.sum(), dtype=torch.float32).reshape(1, 1, 9, 1)
+    image = np.concatenate([img, lab.astype(np.float32)], axis=-1)
+    fx, fy = od.blur_prefilter(image, kernel)
+    out = {"img": img, "lab": lab, "kernel": kernel.numpy(), "filtered_x": fx, "filtered_y": fy}
+    cases = []
+    configs = [((32, 32, 1), 4.0, True, True), ((16, 20, 3), 4.0, True, True), ((48, 32, 1), 4.0, True, False),
+               ((32, 32, 1), 3.2, True, True), ((24, 24, 1), 4.0, False, True)]
+    for ci, (ps, sep, blur, flip) in enumerate(configs):
+        ds = object.__new__(train_set.TrainSetMultiple)
+        ds.imgs_hr, ds.labels_hr = [img], [lab]
+        ds.imgs_filtered_x, ds.imgs_filtered_y = [fx], [fy]
+        ds.blur, ds.slice_separation, ds.patch_size = blur, sep, list(ps)
+        ds.train_transform, ds.random_flip = None, flip
+        for seed in range(8):
+            random.seed(1000 * ci + seed)
+            lr, hr = ds.__getitem__(0)
+            key = f"c{ci}_s{seed}"
+            out[key + "_lr"], out[key + "_hr"] = lr.numpy(), hr.numpy()
+            cases.append({"key": key, "patch_size": list(ps), "slice_separation": sep, "blur": blur, "random_flip": flip,
+                          "seed": 1000 * ci + seed})
+    out["cases"] = np.frombuffer(json.dumps(cases).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "sr_degrade.npz"), **out)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     import sys
+    if "--only-degrade" in sys.argv:
+        sr_degrade_fixture()
+        return
     if "--only-centers" in sys.argv:
         random_centers_fixture()
         return
@@ -362,6 +408,7 @@ def main() -> None:
     sr_step_fixture()
     random_centers_fixture()
     wdsr_fixture()
+    sr_degrade_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

@@ -139,6 +139,7 @@ def _declare(L: C.CDLL) -> None:
         "rehr_sw_accumulate": (i, [vp, vp, vp, i, vp] + [i] * 10 + [vp]),
         "rehr_sw_finalize": (i, [vp, vp, i, ll, vp, vp]),
         "rehr_blur1d": (i, [vp, vp, i, vp, ll, i, i, vp]),
+        "rehr_resample_axis": (i, [vp, vp, ll, i, i, ll, f, i, vp]),
         "rehr_rot90": (i, [vp, vp, i, i, ll, i, vp]),
         "rehr_fba_combine": (i, [vp, i, f, vp, ll, vp]),
         "rehr_mean_stack": (i, [vp, i, vp, ll, vp]),

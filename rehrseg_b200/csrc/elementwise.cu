@@ -993,6 +993,44 @@ __global__ void __launch_bounds__(128) blur1d_kernel(const float* x, float* y, c
 // =================================================================================================
 // rot90 over dims (0,1) of vol[X][Y][inner], torch.rot90 semantics
 // =================================================================================================
+// Resampling along ONE axis of x[outer][n_in][inner] -> y[outer][n_out][inner] with step `d` and the same field of view: output
+// sample i sits at p = (i + 0.5) * d - 0.5 input samples.  order 3: cubic convolution (A = -0.75, the kernel of torch's bicubic
+// grid_sample) over the 4 neighbours floor(p) - 1 .. floor(p) + 2 with indices clamped to the volume; order 0: nearest
+// (floor(p + 0.5), clamped).  The low-resolution simulation of the SR stage, `resize(img, (slice_separation, 1), order)` at
+// utils/train_set.py:395-396 -- the third-party `resize` package is not available, this is the stand-in oracle/degrade.py defines.
+__global__ void __launch_bounds__(256) resample_axis_kernel(const float* __restrict__ x, float* __restrict__ y, long long outer, int n_in,
+                                                            int n_out, long long inner, float d, int order) {
+  const long long total = outer * n_out * inner;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e % inner;
+    const long long t = e / inner;
+    const int i = (int)(t % n_out);
+    const long long o = t / n_out;
+    const float p = ((float)i + 0.5f) * d - 0.5f;
+    const float* src = x + o * n_in * inner + r;
+    float v;
+    if (order == 0) {
+      int j = (int)floorf(p + 0.5f);
+      j = min(max(j, 0), n_in - 1);
+      v = src[(long long)j * inner];
+    } else {
+      const float fl = floorf(p);
+      const float f = p - fl;
+      const int j0 = (int)fl;
+      const float A = -0.75f;
+      const float w0 = ((A * (f + 1.f) - 5.f * A) * (f + 1.f) + 8.f * A) * (f + 1.f) - 4.f * A;
+      const float w1 = ((A + 2.f) * f - (A + 3.f)) * f * f + 1.f;
+      const float g = 1.f - f;
+      const float w2 = ((A + 2.f) * g - (A + 3.f)) * g * g + 1.f;
+      const float w3 = ((A * (g + 1.f) - 5.f * A) * (g + 1.f) + 8.f * A) * (g + 1.f) - 4.f * A;
+      const int a0 = min(max(j0 - 1, 0), n_in - 1), a1 = min(max(j0, 0), n_in - 1);
+      const int a2 = min(max(j0 + 1, 0), n_in - 1), a3 = min(max(j0 + 2, 0), n_in - 1);
+      v = w0 * src[(long long)a0 * inner] + w1 * src[(long long)a1 * inner] + w2 * src[(long long)a2 * inner] + w3 * src[(long long)a3 * inner];
+    }
+    y[e] = v;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) rot90_kernel(const T* src, T* dst, int X, int Y, long long inner, int k) {
   const int OX = (k & 1) ? Y : X, OY = (k & 1) ? X : Y;
@@ -1450,6 +1488,17 @@ int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z,
   const long long tiles = Z * (long long)((X + kBlurRows - 1) / kBlurRows) * ((Y + 127) / 128);
   const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 6));
   blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_resample_axis(const float* x, float* y, long long outer, int n_in, int n_out, long long inner, float step, int order,
+                       rehr_stream stream) {
+  if (!x || !y || outer <= 0 || n_in <= 0 || n_out <= 0 || inner <= 0 || !(step > 0.f)) return REHR_BAD_SHAPE;
+  if (order != 0 && order != 3) return REHR_UNSUPPORTED;
+  const long long total = outer * n_out * inner;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm_count() * 16));
+  resample_axis_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, outer, n_in, n_out, inner, step, order);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -218,6 +218,8 @@ def _pack_into(weight: torch.Tensor, kind: str, h: bool, out: Optional[torch.Ten
         w = w.contiguous()
     if w.dtype != torch.float32:
         w = w.float()
+    if _pack_keepalive is not None and w.data_ptr() != weight.data_ptr():
+        _pack_keepalive.append(w)     # a recorded (batched) pack reads this temporary only when the batch is launched
 
     def buf(n_or_shape):
         if out is not None:
@@ -251,6 +253,7 @@ def _pack_into(weight: torch.Tensor, kind: str, h: bool, out: Optional[torch.Ten
 
 
 PACK_BATCHED = os.environ.get("REHR_PACK_BATCHED", "1") != "0"
+_pack_keepalive: Optional[list] = None   # while pack calls are being recorded: fp32 / contiguous temporaries of the weights
 PACK_BATCH_SPLITS = tuple(int(v) for v in os.environ.get("REHR_PACK_SPLITS", "200000,2000000,8000000").split(",") if v)   # cumulative elements
 _pending_prepack = None   # fork object of refresh_weight_cache(): joined at the end of the step (or by clear_weight_cache)
 _pack_events: dict = {}   # cache key -> event recorded on the pack stream right after that copy was re-packed
@@ -328,17 +331,21 @@ def refresh_weight_cache() -> int:
                     limits.pop(0)
             bounds = sorted(set(b for b in bounds if b < len(live))) + [len(live)]
             first = 0
+            global _pack_keepalive
             for last in bounds:
                 check(lib().rehr_pack_batch_begin(), "pack_batch_begin")
+                _pack_keepalive = []
                 try:
                     for key, (wref, _ver, out) in live[first:last]:
                         w = wref()
                         _pack_into(w, key[1], key[2], out, key[3])
                         _wcache[key] = (wref, w._version, out)
+                    check(lib().rehr_pack_batch_launch(stream_ptr()), "pack_batch_launch")
                 except Exception:
                     lib().rehr_pack_batch_abort()
                     raise
-                check(lib().rehr_pack_batch_launch(stream_ptr()), "pack_batch_launch")
+                finally:
+                    _pack_keepalive = None    # (the launch is stream-ordered before any later reuse of the temporaries' memory)
                 _launches -= (last - first) - (last - first + 127) // 128      # _pack_into counted one launch per copy
                 ev = torch.cuda.Event()
                 ev.record(fk.side)
@@ -497,6 +504,7 @@ class deferred_wgrad:
     def __exit__(self, *exc):
         global WGRAD_DEFER_JOIN
         WGRAD_DEFER_JOIN = self.prev
+        join_pending_wgrad()      # also after an exception inside the pass: nothing may stay pending (and keep operands alive)
         return False
 
 

@@ -159,3 +159,51 @@ def test_oracle_wdsr_reproduces_the_reference_module():
     (out * torch.from_numpy(z["cot"])).sum().backward()
     assert np.allclose(net.head.weight_g.grad.numpy(), z["grad_head_g"], rtol=1e-4, atol=1e-6)
     assert np.allclose(net.tail.conv0.weight_v.grad.numpy(), z["grad_tail_v"], rtol=1e-4, atol=1e-6)
+
+
+def test_oracle_sr_sample_synthesis_matches_reference_getitem():
+    """tests/golden/sr_degrade.npz: the reference's OWN `TrainSetMultiple.__getitem__` (utils/train_set.py:337-434) and `load_img`
+    pre-filter (:321-333) with the resize stand-in injected, 40 seeded cases -> oracle.degrade.train_sample / blur_prefilter must
+    reproduce them bit for bit (same statements, same `random` stream)."""
+    import json
+    import random
+    from oracle import degrade as od
+    z = np.load(os.path.join(G, "sr_degrade.npz"))
+    cases = json.loads(bytes(z["cases"]).decode())
+    assert len(cases) == 40
+    image = np.concatenate([z["img"], z["lab"].astype(np.float32)], axis=-1)
+    fx, fy = od.blur_prefilter(image, torch.from_numpy(z["kernel"]))
+    assert np.array_equal(fx, z["filtered_x"]) and np.array_equal(fy, z["filtered_y"])
+    branches = set()
+    for c in cases:
+        random.seed(c["seed"])
+        lr, hr = od.train_sample(z["img"], z["lab"], fx, fy, c["patch_size"], c["slice_separation"], c["blur"], c["random_flip"])
+        assert np.array_equal(lr.numpy(), z[c["key"] + "_lr"]), c
+        assert np.array_equal(hr.numpy(), z[c["key"] + "_hr"]), c
+        branches.add((lr.shape[1] < lr.shape[2], bool((lr[:, 0] == 0).all() or (lr[:, -1] == 0).all())))
+    assert len(branches) >= 3      # both final permutations and the slice-dropout branch occur in the fixture
+
+
+def test_resize_standin_properties():
+    """The stand-in for the unavailable third-party `resize` (oracle/degrade.py): identity at step 1, exact on constants (the cubic
+    weights sum to 1), nearest picks floor(p + 0.5), output length round(n / d), and it agrees with torch's own bicubic grid_sample
+    (A = -0.75, align_corners=True on the same sample positions, border padding) away from the borders."""
+    from oracle import degrade as od
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 1, 40, 7), generator=g)
+    assert torch.equal(od.resize_standin(x, (1, 1), 3), x)
+    assert od.resize_standin(x, (4.0, 1), 3).shape == (2, 1, 10, 7) and od.resize_standin(x, (3.2, 1), 3).shape == (2, 1, 12, 7)
+    c = torch.full((1, 1, 33, 3), 2.5)
+    assert float((od.resize_standin(c, (2.5, 1), 3) - 2.5).abs().max()) < 1e-6
+    r = torch.arange(40.0).reshape(1, 1, 40, 1)
+    assert od.resize_standin(r, (4.0, 1), 0).flatten().tolist() == [2.0 + 4 * i for i in range(10)]     # p = 1.5, 5.5, ... -> floor(p + 0.5)
+    # cubic vs torch.grid_sample on the same positions
+    d = 4.0
+    n_in, n_out = 40, 10
+    pos = (torch.arange(n_out) + 0.5) * d - 0.5
+    gy = 2 * pos / (n_in - 1) - 1
+    gx = torch.linspace(-1, 1, 7)
+    grid = torch.stack(torch.meshgrid(gy, gx, indexing="ij"), dim=-1).flip(-1).unsqueeze(0).repeat(2, 1, 1, 1)
+    want = torch.nn.functional.grid_sample(x, grid, mode="bicubic", padding_mode="border", align_corners=True)
+    got = od.resize_standin(x, (d, 1), 3)
+    assert float((got[:, :, 1:-1] - want[:, :, 1:-1]).abs().max()) < 1e-5
