@@ -335,6 +335,20 @@ int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z,
 int rehr_resample_axis(const float* x, float* y, long long outer, int n_in, int n_out, long long inner, float step, int order,
                        rehr_stream stream);
 
+/* Stage-2 spatial augmentation: `augment_spatial` (utils/seg_utils.py:378-458) in the dummy-2D
+ * configuration of get_training_transforms (:652-676) resamples every slice of a patch under one affine map per sample through
+ * batchgenerators' interpolate_img = scipy.ndimage.map_coordinates(order 3 for the image / uncertainty, order 1 per label for the
+ * segmentations, mode "constant").
+ *   rehr_bspline_prefilter_axis: scipy's cubic B-spline prefilter (mirror boundary) in place along the middle axis of
+ *     c[outer][n][inner] -- call once per image axis before order-3 sampling.
+ *   rehr_affine_sample2d: dst[s][i][j] = value of slice s at A_k (i - (px-1)/2, j - (py-1)/2) + c_k, k = s / slices_per_sample,
+ *     affine = f32 device [samples][6] (a00 a01 a10 a11 cx cy).  order 3: src holds the prefiltered coefficients, positions outside
+ *     [0, n-1] give cval.  order 1: interpolate_img(is_seg=True): for each of the n_labels (<= 8, ascending, HOST array) label
+ *     values the bilinear interpolation of its indicator; the result is the last label reaching 0.5, 0 outside the image. */
+int rehr_bspline_prefilter_axis(float* c, long long outer, int n, long long inner, rehr_stream stream);
+int rehr_affine_sample2d(const float* src, float* dst, const float* affine, int slices, int x, int y, int px, int py, int slices_per_sample,
+                         int order, float cval, const float* labels_host, int n_labels, rehr_stream stream);
+
 /* rotate_vol_2d (utils/rotate.py:5-31): rot90 by k quarter turns over dims (0,1) of vol[X][Y][inner]. */
 int rehr_rot90(const void* src, void* dst, int X, int Y, long long inner_bytes, int k, rehr_stream stream);
 

@@ -273,9 +273,52 @@ def sr_degrade_fixture() -> None:
     np.savez_compressed(os.path.join(OUT, "sr_degrade.npz"), **out)
 
 
+def spatial_aug_fixture() -> None:
+    """The reference's OWN `augment_spatial` (utils/seg_utils.py:378-480) in the dummy-2D stage-2 configuration, with the
+    batchgenerators helpers it imports replaced by the restatements of oracle/augment.py (the package is not installed) and
+    scipy's real map_coordinates; `np.random` seeded per case.  Cases: the configured probabilities (0.2 / 0.2), forced rotation,
+    forced scaling, both; a patch equal to and smaller than the image."""
+    from . import augment as oa
+    seg_utils = refimport.load("utils.seg_utils")
+    for name in ("create_zero_centered_coordinate_mesh", "rotate_coords_2d", "rotate_coords_3d", "scale_coords", "interpolate_img",
+                 "elastic_deform_coordinates"):
+        setattr(seg_utils, name, getattr(oa, name))
+    rng = np.random.RandomState(5)
+    b, cz, X, Y = 2, 3, 28, 24
+    data = rng.randn(b, cz, X, Y).astype(np.float32)
+    blobs = rng.rand(b, 4 * cz, X, Y) > 0.6
+    seg_sr = blobs.astype(np.float32)
+    seg = seg_sr[:, ::4].copy()
+    unc = (1 - rng.rand(b, cz, X, Y) * 0.99).astype(np.float32)
+    out = {"data": data, "seg": seg, "seg_sr": seg_sr, "uncertainty": unc}
+    cases = []
+    configs = [((28, 24), 0.2, 0.2), ((28, 24), 1.0, 0.0), ((28, 24), 0.0, 1.0), ((20, 16), 1.0, 1.0), ((25, 24), 0.2, 0.2)]
+    for ci, (ps, p_rot, p_scale) in enumerate(configs):
+        for seed in range(3):
+            np.random.seed(100 * ci + seed)
+            d, segs = seg_utils.augment_spatial(data.copy(), [seg.copy(), seg_sr.copy(), unc.copy()], patch_size=ps,
+                                                patch_center_dist_from_border=None, do_elastic_deform=False, alpha=(0, 0), sigma=(0, 0),
+                                                do_rotation=True, angle_x=(-np.pi, np.pi), angle_y=(0, 0), angle_z=(0, 0),
+                                                do_scale=True, scale=(0.7, 1.4), border_mode_data="constant", border_cval_data=0,
+                                                order_data=3, border_mode_seg="constant", border_cval_seg=-1, order_seg=1,
+                                                random_crop=False, p_el_per_sample=0, p_scale_per_sample=p_scale,
+                                                p_rot_per_sample=p_rot, independent_scale_for_each_axis=False, p_rot_per_axis=1,
+                                                enable_uncertainty=True)
+            key = f"c{ci}_s{seed}"
+            out[key + "_data"] = d
+            for name, v in zip(("seg", "seg_sr", "uncertainty"), segs):
+                out[key + "_" + name] = v
+            cases.append({"key": key, "patch_size": list(ps), "p_rot": p_rot, "p_scale": p_scale, "seed": 100 * ci + seed})
+    out["cases"] = np.frombuffer(json.dumps(cases).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "spatial_aug.npz"), **out)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     import sys
+    if "--only-spatial" in sys.argv:
+        spatial_aug_fixture()
+        return
     if "--only-degrade" in sys.argv:
         sr_degrade_fixture()
         return
@@ -409,6 +452,7 @@ def main() -> None:
     random_centers_fixture()
     wdsr_fixture()
     sr_degrade_fixture()
+    spatial_aug_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

@@ -140,6 +140,8 @@ def _declare(L: C.CDLL) -> None:
         "rehr_sw_finalize": (i, [vp, vp, i, ll, vp, vp]),
         "rehr_blur1d": (i, [vp, vp, i, vp, ll, i, i, vp]),
         "rehr_resample_axis": (i, [vp, vp, ll, i, i, ll, f, i, vp]),
+        "rehr_bspline_prefilter_axis": (i, [vp, ll, i, ll, vp]),
+        "rehr_affine_sample2d": (i, [vp, vp, vp, i, i, i, i, i, i, i, f, vp, i, vp]),
         "rehr_rot90": (i, [vp, vp, i, i, ll, i, vp]),
         "rehr_fba_combine": (i, [vp, i, f, vp, ll, vp]),
         "rehr_mean_stack": (i, [vp, i, vp, ll, vp]),

@@ -993,6 +993,125 @@ __global__ void __launch_bounds__(128) blur1d_kernel(const float* x, float* y, c
 // =================================================================================================
 // rot90 over dims (0,1) of vol[X][Y][inner], torch.rot90 semantics
 // =================================================================================================
+// -------------------------------------------------------------------------------------------------
+// Order-3 spline resampling of 2-D slices under an affine map: the stage-2 spatial augmentation (rotation / scaling of every slice of
+// a patch, `augment_spatial` -> batchgenerators `interpolate_img` -> scipy.ndimage.map_coordinates, utils/seg_utils.py:378-458).
+// scipy's order-3 interpolation = (1) cubic B-spline prefilter of the image along each axis (one causal + one anti-causal
+// recursion with the pole z = sqrt(3) - 2 and MIRROR boundary initialisation, gain 6), (2) evaluation of the 4 x 4 B-spline taps
+// around the sample position with mirrored tap indices; mode "constant": positions outside [0, n - 1] give cval.
+// -------------------------------------------------------------------------------------------------
+// in place along the middle axis of c[outer][n][inner]; one thread per line
+__global__ void __launch_bounds__(128) bspline_prefilter_kernel(float* __restrict__ c, long long outer, int n, long long inner) {
+  const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (line >= outer * inner || n < 2) return;
+  float* p = c + (line / inner) * (long long)n * inner + (line % inner);
+  const double z = -0.26794919243112270647;  // sqrt(3) - 2
+  const double gain = 6.0;                   // (1 - z)(1 - 1/z)
+  // causal initialisation, mirror boundary: c0 = sum_k z^k s[k] over the mirrored, periodised line (scipy _init_causal_mirror)
+  const double zn1 = pow(z, (double)(n - 1));
+  double c0 = gain * ((double)p[0] + zn1 * (double)p[(long long)(n - 1) * inner]);
+  double zi = z;
+  // the terms decay as z^i: beyond ~40 samples they are below fp64 resolution of the sum
+  const int horizon = min(n - 1, 48);
+  for (int i = 1; i < horizon; ++i) {
+    c0 += gain * zi * ((double)p[(long long)i * inner] + zn1 * (double)p[(long long)(n - 1 - i) * inner]);
+    zi *= z;
+  }
+  c0 /= 1.0 - zn1 * zn1;
+  double prev = c0;
+  p[0] = (float)c0;
+  // the recursion runs in double and keeps the running value in a register; the stored coefficients are fp32
+  double last2 = 0.0;
+  for (int i = 1; i < n; ++i) {
+    const double v = gain * (double)p[(long long)i * inner] + z * prev;
+    if (i == n - 2) last2 = v;
+    p[(long long)i * inner] = (float)v;
+    prev = v;
+  }
+  if (n == 2) last2 = c0;
+  double nxt = (z * last2 + prev) * z / (z * z - 1.0);   // anti-causal initialisation (mirror)
+  p[(long long)(n - 1) * inner] = (float)nxt;
+  for (int i = n - 2; i >= 0; --i) {
+    const double v = z * (nxt - (double)p[(long long)i * inner]);
+    p[(long long)i * inner] = (float)v;
+    nxt = v;
+  }
+}
+
+struct AffineSampleArgs {
+  const float* src;     // [S][X][Y]: B-spline coefficients (order 3) or the image itself (order 1 / labels)
+  float* dst;           // [S][PX][PY]
+  const float* affine;  // [samples][6]: a00 a01 a10 a11 cx cy   (source position = A * (i - (PX-1)/2, j - (PY-1)/2) + c)
+  int S, X, Y, PX, PY, per_sample;  // slices per sample (slice s uses affine[s / per_sample])
+  int order;            // 3: cubic B-spline of coefficients; 1: per-label linear interpolation (is_seg)
+  float cval;
+  int n_labels;
+  float labels[8];      // order 1: ascending label values; the result is the LAST label whose interpolated indicator is >= 0.5
+};
+
+__device__ __forceinline__ int mirror_idx(int i, int n) {
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  i = abs(i) % period;
+  return i < n ? i : period - i;
+}
+
+__global__ void __launch_bounds__(256) affine_sample2d_kernel(const AffineSampleArgs a) {
+  const long long total = (long long)a.S * a.PX * a.PY;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % a.PY);
+    const long long t = e / a.PY;
+    const int i = (int)(t % a.PX);
+    const int s = (int)(t / a.PX);
+    const float* A = a.affine + (long long)(s / a.per_sample) * 6;
+    // double precision for the position (the reference computes it in fp64; an fp32 position moves a sample by up to 3e-5 pixels)
+    const double mi = (double)i - 0.5 * (double)(a.PX - 1), mj = (double)j - 0.5 * (double)(a.PY - 1);
+    const double x = (double)A[0] * mi + (double)A[1] * mj + (double)A[4];
+    const double y = (double)A[2] * mi + (double)A[3] * mj + (double)A[5];
+    const float* img = a.src + (long long)s * a.X * a.Y;
+    float out;
+    if (x < 0.0 || x > (double)(a.X - 1) || y < 0.0 || y > (double)(a.Y - 1)) {
+      out = a.order == 3 ? a.cval : 0.f;        // labels: an all-cval (-1) sample never reaches 0.5 -> the zero initialisation stays
+    } else if (a.order == 3) {
+      const int fx = (int)floor(x), fy = (int)floor(y);
+      const float tx = (float)(x - (double)fx), ty = (float)(y - (double)fy);
+      float wx[4], wy[4];
+      wx[0] = (1.f - tx) * (1.f - tx) * (1.f - tx) * (1.f / 6.f);
+      wx[1] = (3.f * tx * tx * tx - 6.f * tx * tx + 4.f) * (1.f / 6.f);
+      wx[2] = (-3.f * tx * tx * tx + 3.f * tx * tx + 3.f * tx + 1.f) * (1.f / 6.f);
+      wx[3] = tx * tx * tx * (1.f / 6.f);
+      wy[0] = (1.f - ty) * (1.f - ty) * (1.f - ty) * (1.f / 6.f);
+      wy[1] = (3.f * ty * ty * ty - 6.f * ty * ty + 4.f) * (1.f / 6.f);
+      wy[2] = (-3.f * ty * ty * ty + 3.f * ty * ty + 3.f * ty + 1.f) * (1.f / 6.f);
+      wy[3] = ty * ty * ty * (1.f / 6.f);
+      float v = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float* row = img + (long long)mirror_idx(fx - 1 + p, a.X) * a.Y;
+        float r = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r += wy[q] * row[mirror_idx(fy - 1 + q, a.Y)];
+        v += wx[p] * r;
+      }
+      out = v;
+    } else {
+      const int fx = (int)floor(x), fy = (int)floor(y);
+      const float tx = (float)(x - (double)fx), ty = (float)(y - (double)fy);
+      const int x1 = mirror_idx(fx + 1, a.X), y1 = mirror_idx(fy + 1, a.Y);
+      const float v00 = img[(long long)fx * a.Y + fy], v01 = img[(long long)fx * a.Y + y1];
+      const float v10 = img[(long long)x1 * a.Y + fy], v11 = img[(long long)x1 * a.Y + y1];
+      out = 0.f;
+      for (int l = 0; l < a.n_labels; ++l) {
+        const float c = a.labels[l];
+        const float ind = (1.f - tx) * ((1.f - ty) * (v00 == c ? 1.f : 0.f) + ty * (v01 == c ? 1.f : 0.f)) +
+                          tx * ((1.f - ty) * (v10 == c ? 1.f : 0.f) + ty * (v11 == c ? 1.f : 0.f));
+        if (ind >= 0.5f) out = c;
+      }
+    }
+    a.dst[e] = out;
+  }
+}
+
 // Resampling along ONE axis of x[outer][n_in][inner] -> y[outer][n_out][inner] with step `d` and the same field of view: output
 // sample i sits at p = (i + 0.5) * d - 0.5 input samples.  order 3: cubic convolution (A = -0.75, the kernel of torch's bicubic
 // grid_sample) over the 4 neighbours floor(p) - 1 .. floor(p) + 2 with indices clamped to the volume; order 0: nearest
@@ -1488,6 +1607,32 @@ int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z,
   const long long tiles = Z * (long long)((X + kBlurRows - 1) / kBlurRows) * ((Y + 127) / 128);
   const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 6));
   blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_bspline_prefilter_axis(float* c, long long outer, int n, long long inner, rehr_stream stream) {
+  if (!c || outer <= 0 || n <= 0 || inner <= 0) return REHR_BAD_SHAPE;
+  if (n < 2) return REHR_OK;
+  const long long lines = outer * inner;
+  bspline_prefilter_kernel<<<(unsigned)((lines + 127) / 128), 128, 0, (cudaStream_t)stream>>>(c, outer, n, inner);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_affine_sample2d(const float* src, float* dst, const float* affine, int slices, int x, int y, int px, int py, int slices_per_sample,
+                         int order, float cval, const float* labels_host, int n_labels, rehr_stream stream) {
+  if (!src || !dst || !affine || slices <= 0 || x <= 0 || y <= 0 || px <= 0 || py <= 0 || slices_per_sample <= 0) return REHR_BAD_SHAPE;
+  if (order != 3 && order != 1) return REHR_UNSUPPORTED;
+  if (order == 1 && (n_labels <= 0 || n_labels > 8 || !labels_host)) return REHR_UNSUPPORTED;
+  AffineSampleArgs a{};
+  a.src = src; a.dst = dst; a.affine = affine;
+  a.S = slices; a.X = x; a.Y = y; a.PX = px; a.PY = py; a.per_sample = slices_per_sample;
+  a.order = order; a.cval = cval; a.n_labels = order == 1 ? n_labels : 0;
+  for (int i = 0; i < a.n_labels; ++i) a.labels[i] = labels_host[i];
+  const long long total = (long long)slices * px * py;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm_count() * 16));
+  affine_sample2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -207,3 +207,21 @@ def test_resize_standin_properties():
     want = torch.nn.functional.grid_sample(x, grid, mode="bicubic", padding_mode="border", align_corners=True)
     got = od.resize_standin(x, (d, 1), 3)
     assert float((got[:, :, 1:-1] - want[:, :, 1:-1]).abs().max()) < 1e-5
+
+
+def test_oracle_spatial_augmentation_matches_reference_augment_spatial():
+    """tests/golden/spatial_aug.npz: the reference's OWN `augment_spatial` (utils/seg_utils.py:378-480; batchgenerators helpers
+    restated, scipy's real map_coordinates), 15 seeded cases -> oracle.augment.augment_spatial_2d must reproduce them bit for bit."""
+    import json
+    from oracle import augment as oa
+    z = np.load(os.path.join(G, "spatial_aug.npz"))
+    cases = json.loads(bytes(z["cases"]).decode())
+    assert len(cases) == 15
+    for c in cases:
+        np.random.seed(c["seed"])
+        d, segs = oa.augment_spatial_2d(z["data"].copy(), [z["seg"].copy(), z["seg_sr"].copy(), z["uncertainty"].copy()],
+                                        tuple(c["patch_size"]), p_scale_per_sample=c["p_scale"], p_rot_per_sample=c["p_rot"],
+                                        enable_uncertainty=True)
+        assert np.array_equal(d, z[c["key"] + "_data"]), c
+        for s_, name in zip(segs, ("seg", "seg_sr", "uncertainty")):
+            assert np.array_equal(s_, z[c["key"] + "_" + name]), (c, name)
