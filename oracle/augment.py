@@ -129,7 +129,7 @@ def augment_spatial_2d(data, seg_list, patch_size, do_rotation=True, angle_x=(-n
 
 
 def spatial_transform_dummy_2d(data_dict: dict, patch_size_zxy, keys=("seg", "seg_sr", "uncertainty"), enable_uncertainty=True,
-                               rng=np.random) -> dict:
+                               rng=np.random, **aug_kw) -> dict:
     """Convert3DTo2DTransform -> MySpatialTransform(patch_size[1:]) -> Convert2DTo3DTransform on {'data', *keys} (numpy
     [b, c, z, x, y]), utils/seg_utils.py:652-676."""
     shapes = {}
@@ -137,8 +137,82 @@ def spatial_transform_dummy_2d(data_dict: dict, patch_size_zxy, keys=("seg", "se
     for k in ("data", *keys):
         flat[k], shapes[k] = convert_3d_to_2d(data_dict[k])
     d, segs = augment_spatial_2d(flat["data"], [flat[k] for k in keys], tuple(patch_size_zxy[1:]), enable_uncertainty=enable_uncertainty,
-                                 rng=rng)
+                                 rng=rng, **aug_kw)
     out = {"data": convert_2d_to_3d(d, shapes["data"])}
     for k, s in zip(keys, segs):
         out[k] = convert_2d_to_3d(s, shapes[k])
     return out
+
+
+# ---- TrainSetMultipleSegSREfficient.__getitem__ (utils/train_set.py:102-159) -----------------------------------------------------
+def zscore_normalization_np(image: np.ndarray) -> np.ndarray:
+    """utils/seg_utils.py:149-155 (numpy branch)."""
+    image = image.astype(np.float32, copy=False)
+    mean = image.mean()
+    std = image.std()
+    image -= mean
+    image /= (max(std, 1e-8))
+    return image
+
+
+def _target_pad_const(img, target_dims):
+    from .volume import get_pads
+    pads = tuple(get_pads(t, d) for t, d in zip(target_dims, img.shape))
+    return np.pad(img, pads, mode="constant")
+
+
+def stage2_sample(img, label, uncertainty, patch_size, separation: int, norm=True, random_flip=True, use_uncertainty=True,
+                  transform=None, rng_py=None):
+    """The reference's `__getitem__` statement by statement; `transform(**dict)` stands for `self.train_transform` (the spatial part
+    of it is `spatial_transform_dummy_2d` + a tensor conversion; the intensity transforms are third-party batchgenerators classes).
+    img / label / uncertainty: [X, Y, Z] arrays; patch_size = (x, y, z_lr)."""
+    import random as _random
+    import torch
+    rng = rng_py or _random
+    img = img.copy()
+    if norm:
+        img = zscore_normalization_np(img)
+    ps = patch_size
+    x_0 = rng.randint(0, max(img.shape[0] - ps[0], 0))
+    y_0 = rng.randint(0, max(img.shape[1] - ps[1], 0))
+    z_0 = rng.randint(0, max(img.shape[2] - ps[2] * separation, 0))
+    sl = (slice(x_0, x_0 + ps[0]), slice(y_0, y_0 + ps[1]), slice(z_0, z_0 + ps[2] * separation))
+    img = img[sl]
+    target_shape = [max(s, p) for s, p in zip(img.shape, (ps[0], ps[1], ps[2] * separation))]
+    img = _target_pad_const(img, target_shape)
+    label = _target_pad_const(label[sl], target_shape)
+    if use_uncertainty:
+        uncertainty = _target_pad_const(uncertainty[sl], target_shape)
+    if random_flip:
+        for axis in (0, 1, 2):
+            if rng.random() < 0.5:
+                img = np.flip(img, axis=axis)
+                label = np.flip(label, axis=axis)
+                uncertainty = np.flip(uncertainty, axis=axis) if use_uncertainty else None
+    img = img[:, :, ::separation]
+    label_lr = label[:, :, ::separation]
+    img = img.copy().transpose(2, 1, 0)[None, None, ...]
+    label = label.copy().transpose(2, 1, 0)[None, None, ...]
+    label_lr = label_lr.copy().transpose(2, 1, 0)[None, None, ...]
+    if use_uncertainty:
+        uncertainty_lr = uncertainty[:, :, ::separation]
+        uncertainty_lr = uncertainty_lr.copy().transpose(2, 1, 0)[None, None, ...]
+        uncertainty_lr = 1 - uncertainty_lr / 255. * 0.99
+        out_data = transform(**{"data": img.astype("float32"), "seg": label_lr, "seg_sr": label, "uncertainty": uncertainty_lr})
+        uncertainty_lr = out_data["uncertainty"].squeeze(0)
+    else:
+        out_data = transform(**{"data": img.astype("float32"), "seg": label_lr, "seg_sr": label})
+        uncertainty_lr = 0
+    return out_data["data"].squeeze(0), out_data["seg"].squeeze(0), out_data["seg_sr"].squeeze(0), uncertainty_lr
+
+
+def spatial_only_transform(patch_size_zyx, enable_uncertainty=True, rng=np.random, **aug_kw):
+    """`get_training_transforms` (utils/seg_utils.py:632-727) reduced to its in-tree spatial part + NumpyToTensor('float')."""
+    import torch
+    keys = ("seg", "seg_sr", "uncertainty") if enable_uncertainty else ("seg", "seg_sr")
+
+    def run(**dd):
+        out = spatial_transform_dummy_2d(dd, patch_size_zyx, keys=keys, enable_uncertainty=enable_uncertainty, rng=rng, **aug_kw)
+        return {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in out.items()}
+
+    return run

@@ -313,9 +313,71 @@ def spatial_aug_fixture() -> None:
     np.savez_compressed(os.path.join(OUT, "spatial_aug.npz"), **out)
 
 
+def stage2_sample_fixture() -> None:
+    """The reference's OWN `TrainSetMultipleSegSREfficient.__getitem__` (utils/train_set.py:102-159) on a seeded synthetic subject.
+    The dataset object is built without `__init__` (it reads HDF5 files); `train_transform` is the spatial part of what
+    `get_training_transforms` composes (:652-676): the dummy-2D reshapes (nnunetv2, restated), the reference's OWN
+    `MySpatialTransform` instance with the arguments of :660-673, and the float-tensor conversion -- the intensity transforms
+    that follow are batchgenerators classes the image does not have."""
+    import random
+    from . import augment as oa
+    seg_utils = refimport.load("utils.seg_utils")
+    for name in ("create_zero_centered_coordinate_mesh", "rotate_coords_2d", "rotate_coords_3d", "scale_coords", "interpolate_img",
+                 "elastic_deform_coordinates"):
+        setattr(seg_utils, name, getattr(oa, name))
+    train_set = refimport.load("utils.train_set")
+    rng = np.random.RandomState(8)
+    X, Y, Z, sep = 36, 30, 20, 4
+    img = (rng.rand(X, Y, Z) * 300).astype(np.float32)
+    lab = (rng.rand(X, Y, Z) > 0.6).astype(np.uint8)
+    unc = (rng.rand(X, Y, Z) * 255).astype(np.uint8)
+    out = {"img": img, "lab": lab, "unc": unc}
+    cases = []
+    for ci, (ps, p_rot, p_scale) in enumerate([((32, 24, 3), 0.2, 0.2), ((32, 24, 3), 1.0, 1.0), ((40, 24, 2), 1.0, 0.0)]):
+        patch_zyx = (ps[2], ps[1], ps[0])        # target_patch_size[::-1] of utils/train_set.py:77
+        mst = seg_utils.MySpatialTransform(
+            patch_zyx[1:], patch_center_dist_from_border=None, do_elastic_deform=False, alpha=(0, 0), sigma=(0, 0), do_rotation=True,
+            angle_x=(-np.pi, np.pi), angle_y=(0, 0), angle_z=(0, 0), p_rot_per_axis=1, do_scale=True, scale=(0.7, 1.4),
+            border_mode_data="constant", border_cval_data=0, order_data=3, border_mode_seg="constant", border_cval_seg=-1, order_seg=1,
+            random_crop=False, label_key=["seg", "seg_sr", "uncertainty"], p_el_per_sample=0, p_scale_per_sample=p_scale,
+            p_rot_per_sample=p_rot, independent_scale_for_each_axis=False, enable_uncertainty=True)
+
+        def transform(**dd):
+            shapes = {}
+            for k in list(dd):
+                dd[k], shapes[k] = oa.convert_3d_to_2d(dd[k])
+            dd = mst(**dd)
+            return {k: torch.from_numpy(np.ascontiguousarray(oa.convert_2d_to_3d(v, shapes[k]))).float() for k, v in dd.items()}
+
+        class H5Like:          # an h5py dataset: `d[:]` reads a FRESH array (the reference normalises what it reads in place)
+            def __init__(self, a):
+                self.a = a
+
+            def __getitem__(self, k):
+                return self.a[k].copy()
+
+        ds = object.__new__(train_set.TrainSetMultipleSegSREfficient)
+        ds.imgs, ds.labels, ds.uncertainties = [H5Like(img)], [H5Like(lab)], [H5Like(unc)]
+        ds.norm, ds.patch_size, ds.separation, ds.uncertainty, ds.random_flip = True, list(ps), sep, True, True
+        ds.train_transform = transform
+        for seed in range(4):
+            random.seed(50 * ci + seed)
+            np.random.seed(50 * ci + seed)
+            res = ds.__getitem__(0)
+            key = f"c{ci}_s{seed}"
+            for name, v in zip(("img", "label_lr", "label", "uncertainty_lr"), res):
+                out[key + "_" + name] = v.numpy()
+            cases.append({"key": key, "patch_size": list(ps), "separation": sep, "p_rot": p_rot, "p_scale": p_scale, "seed": 50 * ci + seed})
+    out["cases"] = np.frombuffer(json.dumps(cases).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "stage2_sample.npz"), **out)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     import sys
+    if "--only-stage2" in sys.argv:
+        stage2_sample_fixture()
+        return
     if "--only-spatial" in sys.argv:
         spatial_aug_fixture()
         return
@@ -453,6 +515,7 @@ def main() -> None:
     wdsr_fixture()
     sr_degrade_fixture()
     spatial_aug_fixture()
+    stage2_sample_fixture()
     print("golden fixtures written to", OUT, {k: os.path.getsize(os.path.join(OUT, k)) for k in sorted(os.listdir(OUT))})
 
 

@@ -105,7 +105,7 @@ def augment_spatial(data: torch.Tensor, seg_list: Optional[List[torch.Tensor]], 
 
 
 def spatial_transform_dummy_2d(data_dict: dict, patch_size_zxy: Sequence[int], keys=("seg", "seg_sr", "uncertainty"),
-                               enable_uncertainty=True, rng=np.random, seg_labels: Optional[Sequence[float]] = None) -> dict:
+                               enable_uncertainty=True, rng=np.random, seg_labels: Optional[Sequence[float]] = None, **aug_kw) -> dict:
     """Convert3DTo2DTransform -> MySpatialTransform(patch_size[1:]) -> Convert2DTo3DTransform (utils/seg_utils.py:652-676) on CUDA
     tensors {'data', *keys} of shape [b, c, z, x, y]: the slices of a patch become channels and share the sample's affine map."""
     shapes, flat = {}, {}
@@ -114,8 +114,89 @@ def spatial_transform_dummy_2d(data_dict: dict, patch_size_zxy: Sequence[int], k
         shapes[k] = t.shape
         flat[k] = t.reshape(t.shape[0], t.shape[1] * t.shape[2], t.shape[3], t.shape[4])
     d, segs = augment_spatial(flat["data"], [flat[k] for k in keys], tuple(patch_size_zxy[1:]), enable_uncertainty=enable_uncertainty,
-                              rng=rng, seg_labels=seg_labels)
+                              rng=rng, seg_labels=seg_labels, **aug_kw)
     out = {"data": d.reshape(shapes["data"][0], shapes["data"][1], shapes["data"][2], d.shape[-2], d.shape[-1])}
     for k, s in zip(keys, segs):
         out[k] = s.reshape(shapes[k][0], shapes[k][1], shapes[k][2], s.shape[-2], s.shape[-1])
     return out
+
+
+class Stage2Sampler:
+    """`TrainSetMultipleSegSREfficient` (utils/train_set.py:21-159) with the subjects resident on the GPU: `sample(i)` is
+    `__getitem__` -- z-score of the volume, random crop (Python `random`, the reference's order), constant padding, flips, slice
+    decimation, the [1, 1, z, y, x] layout, the uncertainty rescaling -- followed by the SPATIAL part of `self.train_transform`
+    (`spatial_transform_dummy_2d`, `np.random`).  The intensity transforms `get_training_transforms` appends after it are
+    third-party batchgenerators classes and are not part of this port; `batch` stacks samples like the DataLoader's collate."""
+
+    def __init__(self, patch_size: Sequence[int], separation: int, norm: bool = True, random_flip: bool = True,
+                 uncertainty: bool = True, device=None, p_rot_per_sample: float = 0.2, p_scale_per_sample: float = 0.2):
+        self.patch_size = list(patch_size)            # (x, y, z_lr) as in the reference's patch_size_ori
+        self.separation = int(separation)
+        self.norm, self.random_flip, self.uncertainty = bool(norm), bool(random_flip), bool(uncertainty)
+        self.p_rot, self.p_scale = float(p_rot_per_sample), float(p_scale_per_sample)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.imgs: List[torch.Tensor] = []
+        self.labels: List[torch.Tensor] = []
+        self.uncertainties: List[Optional[torch.Tensor]] = []
+
+    def __len__(self) -> int:
+        return len(self.imgs)
+
+    def add_subject(self, img, label, uncertainty=None) -> None:
+        """[X, Y, Z] volumes.  The reference z-scores the volume it has just read on every `__getitem__` (utils/train_set.py:106-107,
+        utils/seg_utils.py:149-155); the volume is constant, so it is normalised once here."""
+        im = torch.as_tensor(img).to(self.device, torch.float32).clone()
+        if self.norm:
+            mean, std = im.mean(), im.std(unbiased=False)
+            im = (im - mean) / torch.clamp(std, min=1e-8)
+        self.imgs.append(im)
+        self.labels.append(torch.as_tensor(label).to(self.device))
+        self.uncertainties.append(None if uncertainty is None else torch.as_tensor(uncertainty).to(self.device))
+
+    @staticmethod
+    def _pad(t: torch.Tensor, target) -> torch.Tensor:
+        from .volume_ops import get_pads
+        flat = []
+        for b, a in reversed([get_pads(tt, d) for tt, d in zip(target, t.shape)]):
+            flat += [b, a]
+        return torch.nn.functional.pad(t, flat) if any(flat) else t
+
+    def sample(self, i: int, rng_py=None, rng_np=np.random, seg_labels: Optional[Sequence[float]] = None):
+        import random as _random
+        rng = rng_py or _random
+        img, label = self.imgs[i], self.labels[i]
+        ps, sep = self.patch_size, self.separation
+        x_0 = rng.randint(0, max(img.shape[0] - ps[0], 0))
+        y_0 = rng.randint(0, max(img.shape[1] - ps[1], 0))
+        z_0 = rng.randint(0, max(img.shape[2] - ps[2] * sep, 0))
+        sl = (slice(x_0, x_0 + ps[0]), slice(y_0, y_0 + ps[1]), slice(z_0, z_0 + ps[2] * sep))
+        img = img[sl]
+        target = [max(s, p) for s, p in zip(img.shape, (ps[0], ps[1], ps[2] * sep))]
+        img = self._pad(img, target)
+        label = self._pad(label[sl], target)
+        unc = self._pad(self.uncertainties[i][sl], target) if self.uncertainty else None
+        if self.random_flip:
+            for axis in (0, 1, 2):
+                if rng.random() < 0.5:
+                    img, label = img.flip(axis), label.flip(axis)
+                    unc = unc.flip(axis) if unc is not None else None
+        img = img[:, :, ::sep]
+        label_lr = label[:, :, ::sep]
+        dd = {"data": img.permute(2, 1, 0)[None, None].float(), "seg": label_lr.permute(2, 1, 0)[None, None].float(),
+              "seg_sr": label.permute(2, 1, 0)[None, None].float()}
+        keys = ["seg", "seg_sr"]
+        if self.uncertainty:
+            unc_lr = unc[:, :, ::sep].permute(2, 1, 0)[None, None]
+            dd["uncertainty"] = 1 - unc_lr.double() / 255. * 0.99        # numpy promotes the uint8 map to float64 here
+            dd["uncertainty"] = dd["uncertainty"].float()
+            keys.append("uncertainty")
+        patch_zyx = (ps[2], ps[1], ps[0])                                  # target_patch_size[::-1], utils/train_set.py:77
+        out = spatial_transform_dummy_2d({k: v.contiguous() for k, v in dd.items()}, patch_zyx, keys=tuple(keys),
+                                         enable_uncertainty=self.uncertainty, rng=rng_np, seg_labels=seg_labels,
+                                         p_rot_per_sample=self.p_rot, p_scale_per_sample=self.p_scale)
+        unc_out = out["uncertainty"].squeeze(0) if self.uncertainty else 0
+        return out["data"].squeeze(0), out["seg"].squeeze(0), out["seg_sr"].squeeze(0), unc_out
+
+    def batch(self, indices: Sequence[int], rng_py=None, rng_np=np.random, seg_labels: Optional[Sequence[float]] = None):
+        rows = [self.sample(i, rng_py, rng_np, seg_labels) for i in indices]
+        return tuple(torch.stack([r[k] for r in rows]) for k in range(4 if self.uncertainty else 3))

@@ -73,3 +73,27 @@ def test_dummy_2d_wrapper_matches_the_oracle():
             assert _close(got[k], want[k]), (seed, k)
         for k in ("seg", "seg_sr"):
             assert float((got[k].cpu().numpy() == want[k]).mean()) >= 0.999, (seed, k)
+
+
+def test_stage2_samples_match_the_reference_getitem():
+    """rehrseg_b200.augment.Stage2Sampler against tests/golden/stage2_sample.npz: outputs of the reference's OWN
+    `TrainSetMultipleSegSREfficient.__getitem__` (utils/train_set.py:102-159) with its own `MySpatialTransform` as the transform,
+    under the same `random` / `np.random` seeds."""
+    import random
+    from rehrseg_b200 import augment
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "stage2_sample.npz"))
+    cases = json.loads(bytes(z["cases"]).decode())
+    assert len(cases) == 12
+    for c in cases:
+        ds = augment.Stage2Sampler(c["patch_size"], c["separation"], p_rot_per_sample=c["p_rot"], p_scale_per_sample=c["p_scale"])
+        ds.add_subject(z["img"], z["lab"], z["unc"])
+        random.seed(c["seed"])
+        np.random.seed(c["seed"])
+        got = ds.sample(0)
+        for name, g in zip(("img", "label_lr", "label", "uncertainty_lr"), got):
+            want = z[c["key"] + "_" + name]
+            assert tuple(g.shape) == want.shape, (c, name)
+            if name in ("img", "uncertainty_lr"):
+                assert _close(g, want, 3e-4), (c, name)
+            else:
+                assert float((g.cpu().numpy() == want).mean()) >= 0.999, (c, name)

@@ -225,3 +225,23 @@ def test_oracle_spatial_augmentation_matches_reference_augment_spatial():
         assert np.array_equal(d, z[c["key"] + "_data"]), c
         for s_, name in zip(segs, ("seg", "seg_sr", "uncertainty")):
             assert np.array_equal(s_, z[c["key"] + "_" + name]), (c, name)
+
+
+def test_oracle_stage2_sample_matches_reference_getitem():
+    """tests/golden/stage2_sample.npz: the reference's OWN `TrainSetMultipleSegSREfficient.__getitem__` (utils/train_set.py:102-159)
+    with its own `MySpatialTransform` as `train_transform` (dummy-2D reshapes restated), 12 seeded cases -> oracle.augment.stage2_sample
+    + spatial_only_transform must reproduce all four outputs bit for bit."""
+    import json
+    import random
+    from oracle import augment as oa
+    z = np.load(os.path.join(G, "stage2_sample.npz"))
+    cases = json.loads(bytes(z["cases"]).decode())
+    assert len(cases) == 12
+    for c in cases:
+        random.seed(c["seed"])
+        np.random.seed(c["seed"])
+        ps = c["patch_size"]
+        tr = oa.spatial_only_transform((ps[2], ps[1], ps[0]), True, p_rot_per_sample=c["p_rot"], p_scale_per_sample=c["p_scale"])
+        res = oa.stage2_sample(z["img"], z["lab"], z["unc"], ps, c["separation"], transform=tr)
+        for name, v in zip(("img", "label_lr", "label", "uncertainty_lr"), res):
+            assert np.array_equal(v.numpy(), z[c["key"] + "_" + name]), (c, name)
