@@ -166,6 +166,79 @@ def c5_pipeline(dev, peaks) -> dict:
             "frac_bf16_peak_burst": round(orient * 40 * 2.2 / total / float(peaks["bf16_tflops"]), 4)}
 
 
+def loaders(dev) -> dict:
+    """The two data pipelines in front of the networks, on the GPU: SR-stage sample synthesis
+    (degrade.SRTrainSampler, 96x96 pairs from a resident 512x512x160 volume) and the stage-2 spatial augmentation
+    (augment.spatial_transform_dummy_2d, one batch of 2 patches = 112 slices of 256^2, rotation + scaling forced on).  Wall clock
+    (their cost is host launches), next to the oracle's CPU statements in one process on a bounded sample."""
+    import random
+    import numpy as np
+    from rehrseg_b200 import augment, degrade
+    from oracle import augment as oa, degrade as od
+    rng = np.random.RandomState(0)
+    img = rng.rand(512, 512, 160, 1).astype(np.float32)
+    lab = (rng.rand(512, 512, 160, 1) > 0.7).astype(np.uint8)
+    taps = np.exp(-0.5 * ((np.arange(9.0) - 4) / (3.873 / 2.355)) ** 2)
+    kernel = torch.tensor(taps / taps.sum(), dtype=torch.float32).reshape(1, 1, 9, 1)
+    ds = degrade.SRTrainSampler([96, 96, 1], 4.0, blur=True, random_flip=True, blur_kernel=kernel.to(dev))
+    t0 = time.perf_counter()
+    ds.add_subject(img, lab)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t0
+    random.seed(0)
+    B = 32
+    for _ in range(3):
+        ds.batch([0] * B)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ds.batch([0] * B)
+    torch.cuda.synchronize()
+    sr_rate = 10 * B / (time.perf_counter() - t0)
+    # CPU statements of the reference's __getitem__ (crop of an already filtered volume: a slab keeps the sample bounded)
+    fx = np.ascontiguousarray(img.transpose(2, 3, 0, 1))
+    fy = np.ascontiguousarray(img.transpose(2, 3, 1, 0))
+    random.seed(0)
+    t0 = time.perf_counter()
+    for _ in range(32):
+        od.train_sample(img, lab, fx, fy, [96, 96, 1], 4.0, True, True)
+    sr_cpu = 32 / (time.perf_counter() - t0)
+
+    class Forced:          # every sample rotates and scales (the reference: 20 % each)
+        def __init__(self, seed):
+            self.r = np.random.RandomState(seed)
+
+        def uniform(self, *a):
+            return self.r.uniform(*a) if a else 0.0
+
+        def random(self):
+            return self.r.random_sample()
+
+    b, z, X, Y = 2, 16, 256, 256
+    dd = {"data": rng.randn(b, 1, z, X, Y).astype(np.float32), "seg": (rng.rand(b, 1, z, X, Y) > 0.5).astype(np.float32),
+          "seg_sr": (rng.rand(b, 1, 4 * z, X, Y) > 0.5).astype(np.float32), "uncertainty": rng.rand(b, 1, z, X, Y).astype(np.float32)}
+    ddev = {k: torch.from_numpy(v).to(dev) for k, v in dd.items()}
+    for _ in range(3):
+        augment.spatial_transform_dummy_2d(ddev, (z, X, Y), rng=Forced(1), seg_labels=(0.0, 1.0))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        augment.spatial_transform_dummy_2d(ddev, (z, X, Y), rng=Forced(1), seg_labels=(0.0, 1.0))
+    torch.cuda.synchronize()
+    aug_ms = (time.perf_counter() - t0) / 10 * 1e3
+    small = {k: v[:1, :, :(4 if k != "seg_sr" else 16)] for k, v in dd.items()}      # bounded CPU sample: 1 patch, 4 LR slices
+    t0 = time.perf_counter()
+    oa.spatial_transform_dummy_2d({k: v.copy() for k, v in small.items()}, (4, X, Y), rng=Forced(1))
+    aug_cpu_s = (time.perf_counter() - t0) * (b * z / 4)                                # scaled to the full batch by the slice count
+    return {"config": "GPU data pipelines: SR-stage sample synthesis (96x96 pairs, resident 512x512x160 volume) and stage-2 spatial "
+                      "augmentation (2 patches [1,16,256,256] + LR/HR labels + uncertainty, rotation and scaling forced)",
+            "sr_sampler_samples_per_s": round(sr_rate, 0), "sr_sampler_cpu_port_samples_per_s": round(sr_cpu, 0),
+            "sr_volume_prefilter_s": round(t_pre, 3), "stage2_augment_ms_per_batch": round(aug_ms, 3),
+            "stage2_augment_patches_per_s": round(b / aug_ms * 1e3, 0),
+            "stage2_augment_cpu_port_s_per_batch": round(aug_cpu_s, 3), "cpu_port": "oracle statements, 1 process; augmentation: 1/8 of "
+            "the batch's slices timed and scaled"}
+
+
 def eager_gpu(dev, make_oracle_unet, batch, patch, steps=3, warm=2) -> dict:
     """The reference's own GPU path on the same box: torch eager + cuDNN, bf16 autocast, channels_last_3d (informational)."""
     model = make_oracle_unet().to(dev).to(memory_format=torch.channels_last_3d)
@@ -202,6 +275,7 @@ def run_all(dev, peaks, rank, world, make_oracle_unet, batch, patch) -> dict:
         guarded("c2_flavr", lambda: c2_flavr(dev, peaks))
         guarded("c4_joint", lambda: c4_joint(dev, peaks))
         guarded("c5_pipeline", lambda: c5_pipeline(dev, peaks))
+        guarded("loaders", lambda: loaders(dev))
         if os.environ.get("REHR_BENCH_EAGER", "1") != "0":
             guarded("eager_gpu", lambda: eager_gpu(dev, make_oracle_unet, batch, patch))
     return out if rank == 0 else {}
