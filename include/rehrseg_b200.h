@@ -328,6 +328,19 @@ int rehr_sw_finalize(void* logits_f16, const void* npred_f16, int C, long long v
  * utils/sr_utils.py:272,276,302): L-tap cross-correlation along X, zero padded, f32. */
 int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z, int X, int Y, rehr_stream stream);
 
+/* UASR head of UNet_3D_3D (models/FLAVR/FLAVR_arch.py:203-227,244-246): softmax over `experts` (= 16) mixing weights per pixel and
+ * output slice, img = sum p (tanh(o_img) + 1) / 2, seg = sum p o_seg, uncertainty = sigmoid(sum p w + b), forward and backward in
+ * one pass each.  out_cl / ue_cl: the two fp32 channels-last conv outputs [batch * hw][n_out * 2 * experts] / [..][n_out * experts]
+ * (feature_fuse1 / uncertainty_early); res f32 [batch][2][n_out][hw], unc f32 [batch][1][n_out][hw]; backward: d_res / d_unc (either
+ * may be NULL) -> d_out_cl, d_ue_cl and per-block partial sums [rehr_uasr_mixture_blocks][experts + 1] of the uncertainty layer's
+ * weight / bias gradients (the caller sums them). */
+int rehr_uasr_mixture_blocks(long long pixels, int n_out);
+int rehr_uasr_mixture_fwd(const float* out_cl, const float* ue_cl, const float* w, const float* b, float* res, float* unc, long long batch,
+                          long long hw, int n_out, int experts, rehr_stream stream);
+int rehr_uasr_mixture_bwd(const float* out_cl, const float* ue_cl, const float* w, const float* b, const float* d_res, const float* d_unc,
+                          float* d_out_cl, float* d_ue_cl, float* partial, long long batch, long long hw, int n_out, int experts,
+                          rehr_stream stream);
+
 /* Low-resolution simulation of the SR stage: `resize(img, (slice_separation, 1), order=3 | 0)` (utils/train_set.py:395-396,
  * third-party resize.pytorch, source unavailable) as resampling along ONE axis of x[outer][n_in][inner] with step `step`, same
  * field of view (sample i at (i + 0.5) * step - 0.5), n_out = round(n_in / step) chosen by the caller; order 3 = cubic

@@ -139,6 +139,9 @@ def _declare(L: C.CDLL) -> None:
         "rehr_sw_accumulate": (i, [vp, vp, vp, i, vp] + [i] * 10 + [vp]),
         "rehr_sw_finalize": (i, [vp, vp, i, ll, vp, vp]),
         "rehr_blur1d": (i, [vp, vp, i, vp, ll, i, i, vp]),
+        "rehr_uasr_mixture_blocks": (i, [ll, i]),
+        "rehr_uasr_mixture_fwd": (i, [vp, vp, vp, vp, vp, vp, ll, ll, i, i, vp]),
+        "rehr_uasr_mixture_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i, i, vp]),
         "rehr_resample_axis": (i, [vp, vp, ll, i, i, ll, f, i, vp]),
         "rehr_bspline_prefilter_axis": (i, [vp, ll, i, ll, vp]),
         "rehr_affine_sample2d": (i, [vp, vp, vp, i, i, i, i, i, i, i, f, vp, i, vp]),

@@ -1112,6 +1112,139 @@ __global__ void __launch_bounds__(256) affine_sample2d_kernel(const AffineSample
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// UASR head of the FLAVR network (models/FLAVR/FLAVR_arch.py:203-227,244-246): per pixel and output slice, a softmax over
+// E = 16 experts mixes the experts' image / segmentation predictions and gives the uncertainty:
+//   p = softmax(ue[0..E)),  img = sum_e p_e (tanh(o[2e]) + 1) / 2,  seg = sum_e p_e o[2e+1],  unc = sigmoid(sum_e p_e w_e + b).
+// The reference spells this as ~10 PyTorch passes over [B, 32, n_out, H, W] fp32 tensors; here one pass reads the two conv outputs
+// where they lie (channels-last fp32 [pixel][slice*2E + c] and [pixel][slice*E + e]) and writes NCDHW results.
+// -------------------------------------------------------------------------------------------------
+static constexpr int kUasrE = 16;
+
+struct UasrArgs {
+  const float* out;   // [pixels][n_out * 2E]
+  const float* ue;    // [pixels][n_out * E]
+  const float* w;     // [E]
+  const float* b;     // [1]
+  float* res;         // [B][2][n_out][HW]
+  float* unc;         // [B][1][n_out][HW]
+  const float* d_res; // backward
+  const float* d_unc;
+  float* d_out;       // [pixels][n_out * 2E]
+  float* d_ue;        // [pixels][n_out * E]
+  float* partial;     // [blocks][E + 1]: per-block sums of d_u * p_e and of d_u
+  long long pixels, HW;
+  int n_out;
+};
+
+__device__ __forceinline__ void uasr_load(const UasrArgs& a, long long px, int o, float (&x)[2 * kUasrE], float (&p)[kUasrE]) {
+  const float4* po = reinterpret_cast<const float4*>(a.out + (px * a.n_out + o) * (2 * kUasrE));
+  const float4* pu = reinterpret_cast<const float4*>(a.ue + (px * a.n_out + o) * kUasrE);
+#pragma unroll
+  for (int i = 0; i < 2 * kUasrE / 4; ++i) {
+    const float4 v = __ldg(po + i);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+  float m = -3.4e38f;
+#pragma unroll
+  for (int i = 0; i < kUasrE / 4; ++i) {
+    const float4 v = __ldg(pu + i);
+    p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w;
+  }
+#pragma unroll
+  for (int e = 0; e < kUasrE; ++e) m = fmaxf(m, p[e]);
+  float sum = 0.f;
+#pragma unroll
+  for (int e = 0; e < kUasrE; ++e) {
+    p[e] = expf(p[e] - m);
+    sum += p[e];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int e = 0; e < kUasrE; ++e) p[e] *= inv;
+}
+
+__global__ void __launch_bounds__(128) uasr_mixture_fwd_kernel(const UasrArgs a) {
+  __shared__ float sw[kUasrE + 1];
+  if (threadIdx.x <= kUasrE) sw[threadIdx.x] = threadIdx.x < kUasrE ? a.w[threadIdx.x] : a.b[0];
+  __syncthreads();
+  const long long total = a.pixels * a.n_out;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(t / a.pixels);          // slice-major: consecutive threads = consecutive pixels (coalesced NCDHW stores)
+    const long long px = t - (long long)o * a.pixels;
+    float x[2 * kUasrE], p[kUasrE];
+    uasr_load(a, px, o, x, p);
+    float img = 0.f, seg = 0.f, u = sw[kUasrE];
+#pragma unroll
+    for (int e = 0; e < kUasrE; ++e) {
+      img = fmaf(p[e], 0.5f * (tanhf(x[2 * e]) + 1.f), img);
+      seg = fmaf(p[e], x[2 * e + 1], seg);
+      u = fmaf(p[e], sw[e], u);
+    }
+    const long long bidx = px / a.HW, hw = px - bidx * a.HW;
+    a.res[((bidx * 2 + 0) * a.n_out + o) * a.HW + hw] = img;
+    a.res[((bidx * 2 + 1) * a.n_out + o) * a.HW + hw] = seg;
+    a.unc[(bidx * a.n_out + o) * a.HW + hw] = 1.f / (1.f + expf(-u));
+  }
+}
+
+__global__ void __launch_bounds__(128) uasr_mixture_bwd_kernel(const UasrArgs a) {
+  __shared__ float sw[kUasrE + 1];
+  __shared__ float sred[4][kUasrE + 1];
+  if (threadIdx.x <= kUasrE) sw[threadIdx.x] = threadIdx.x < kUasrE ? a.w[threadIdx.x] : a.b[0];
+  __syncthreads();
+  float aw[kUasrE + 1];
+#pragma unroll
+  for (int e = 0; e <= kUasrE; ++e) aw[e] = 0.f;
+  const long long total = a.pixels * a.n_out;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(t / a.pixels);
+    const long long px = t - (long long)o * a.pixels;
+    float x[2 * kUasrE], p[kUasrE];
+    uasr_load(a, px, o, x, p);
+    const long long bidx = px / a.HW, hw = px - bidx * a.HW;
+    const float d_img = a.d_res ? a.d_res[((bidx * 2 + 0) * a.n_out + o) * a.HW + hw] : 0.f;
+    const float d_seg = a.d_res ? a.d_res[((bidx * 2 + 1) * a.n_out + o) * a.HW + hw] : 0.f;
+    float u = sw[kUasrE];
+#pragma unroll
+    for (int e = 0; e < kUasrE; ++e) u = fmaf(p[e], sw[e], u);
+    const float s = 1.f / (1.f + expf(-u));
+    const float d_u = a.d_unc ? a.d_unc[(bidx * a.n_out + o) * a.HW + hw] * s * (1.f - s) : 0.f;
+    float q[kUasrE], dx[2 * kUasrE];
+    float pq = 0.f;
+#pragma unroll
+    for (int e = 0; e < kUasrE; ++e) {
+      const float th = tanhf(x[2 * e]);
+      q[e] = d_img * 0.5f * (th + 1.f) + d_seg * x[2 * e + 1] + d_u * sw[e];
+      pq = fmaf(p[e], q[e], pq);
+      dx[2 * e] = d_img * p[e] * 0.5f * (1.f - th * th);
+      dx[2 * e + 1] = d_seg * p[e];
+      aw[e] = fmaf(d_u, p[e], aw[e]);
+    }
+    aw[kUasrE] += d_u;
+    float4* po = reinterpret_cast<float4*>(a.d_out + (px * a.n_out + o) * (2 * kUasrE));
+#pragma unroll
+    for (int i = 0; i < 2 * kUasrE / 4; ++i) po[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
+    float4* pu = reinterpret_cast<float4*>(a.d_ue + (px * a.n_out + o) * kUasrE);
+#pragma unroll
+    for (int i = 0; i < kUasrE / 4; ++i)
+      pu[i] = make_float4(p[4 * i] * (q[4 * i] - pq), p[4 * i + 1] * (q[4 * i + 1] - pq), p[4 * i + 2] * (q[4 * i + 2] - pq),
+                          p[4 * i + 3] * (q[4 * i + 3] - pq));
+  }
+  // per-block sums of the uncertainty layer's gradients (fixed order: warp shuffle, then the 4 warps)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e <= kUasrE; ++e) {
+    float v = aw[e];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) sred[warp][e] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= kUasrE)
+    a.partial[(long long)blockIdx.x * (kUasrE + 1) + threadIdx.x] = sred[0][threadIdx.x] + sred[1][threadIdx.x] + sred[2][threadIdx.x] + sred[3][threadIdx.x];
+}
+
 // Resampling along ONE axis of x[outer][n_in][inner] -> y[outer][n_out][inner] with step `d` and the same field of view: output
 // sample i sits at p = (i + 0.5) * d - 0.5 input samples.  order 3: cubic convolution (A = -0.75, the kernel of torch's bicubic
 // grid_sample) over the 4 neighbours floor(p) - 1 .. floor(p) + 2 with indices clamped to the volume; order 0: nearest
@@ -1607,6 +1740,36 @@ int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z,
   const long long tiles = Z * (long long)((X + kBlurRows - 1) / kBlurRows) * ((Y + 127) / 128);
   const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 6));
   blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+static int uasr_blocks(long long total) { return (int)std::max<long long>(1, std::min<long long>((total + 127) / 128, (long long)sm_count() * 16)); }
+
+int rehr_uasr_mixture_blocks(long long pixels, int n_out) { return uasr_blocks(pixels * n_out); }
+
+int rehr_uasr_mixture_fwd(const float* out_cl, const float* ue_cl, const float* w, const float* b, float* res, float* unc, long long batch,
+                          long long hw, int n_out, int experts, rehr_stream stream) {
+  if (!out_cl || !ue_cl || !w || !b || !res || !unc || batch <= 0 || hw <= 0 || n_out <= 0) return REHR_BAD_SHAPE;
+  if (experts != kUasrE) return REHR_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(out_cl) | reinterpret_cast<uintptr_t>(ue_cl)) & 15) != 0) return REHR_BAD_ALIGNMENT;
+  UasrArgs a{};
+  a.out = out_cl; a.ue = ue_cl; a.w = w; a.b = b; a.res = res; a.unc = unc;
+  a.pixels = batch * hw; a.HW = hw; a.n_out = n_out;
+  uasr_mixture_fwd_kernel<<<uasr_blocks(a.pixels * n_out), 128, 0, (cudaStream_t)stream>>>(a);
+  REHR_CHECK_LAUNCH();
+  return REHR_OK;
+}
+
+int rehr_uasr_mixture_bwd(const float* out_cl, const float* ue_cl, const float* w, const float* b, const float* d_res, const float* d_unc,
+                          float* d_out_cl, float* d_ue_cl, float* partial, long long batch, long long hw, int n_out, int experts,
+                          rehr_stream stream) {
+  if (!out_cl || !ue_cl || !w || !b || !d_out_cl || !d_ue_cl || !partial || batch <= 0 || hw <= 0 || n_out <= 0) return REHR_BAD_SHAPE;
+  if (experts != kUasrE) return REHR_UNSUPPORTED;
+  UasrArgs a{};
+  a.out = out_cl; a.ue = ue_cl; a.w = w; a.b = b; a.d_res = d_res; a.d_unc = d_unc; a.d_out = d_out_cl; a.d_ue = d_ue_cl; a.partial = partial;
+  a.pixels = batch * hw; a.HW = hw; a.n_out = n_out;
+  uasr_mixture_bwd_kernel<<<uasr_blocks(a.pixels * n_out), 128, 0, (cudaStream_t)stream>>>(a);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }

@@ -19,6 +19,8 @@ the tanh / mean restoration stay torch element-wise code.
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional
 
 import torch
@@ -244,6 +246,7 @@ def _dec_up(mod: nn.Module, x):
 
 
 _reflect_idx: dict = {}
+FUSED_UASR = os.environ.get("REHR_FUSED_UASR", "1") != "0"   # the expert mixture of the UASR head as one kernel per direction
 
 
 def _reflect_pad_hw(x: torch.Tensor, p: int) -> torch.Tensor:
@@ -257,6 +260,55 @@ def _reflect_pad_hw(x: torch.Tensor, p: int) -> torch.Tensor:
                               torch.arange(n - 2, n - 2 - p, -1, device=x.device)])
         idx = _reflect_idx[key] = (one(h), one(w))
     return x.index_select(2, idx[0]).index_select(3, idx[1])
+
+
+class _UasrMixture(torch.autograd.Function):
+    """The UASR head's expert mixture (FLAVR_arch.py:203-227,244-246) in one pass per direction: softmax over the 16 experts,
+    img = sum p (tanh(o) + 1) / 2, seg = sum p o, uncertainty = sigmoid(sum p w + b) -- straight from the two channels-last fp32
+    conv outputs (rehr_uasr_mixture_fwd / _bwd) instead of ~10 PyTorch passes over [B, 32, n_out, H, W] tensors."""
+
+    @staticmethod
+    def forward(ctx, out_cl, ue_cl, w, b, n_out):
+        from . import functional as F_
+        from ._lib import check, lib, ptr, stream_ptr
+        bsz, _, h, wd, c = out_cl.shape
+        experts = ue_cl.shape[4] // n_out
+        if c != 2 * experts * n_out:
+            raise RehrError("uasr mixture: feature_fuse1 must have twice the channels of uncertainty_early")
+        out_cl, ue_cl = out_cl.contiguous(), ue_cl.contiguous()
+        w32, b32 = w.detach().reshape(-1).float().contiguous(), b.detach().reshape(-1).float().contiguous()
+        res = torch.empty((bsz, 2, n_out, h, wd), dtype=torch.float32, device=out_cl.device)
+        unc = torch.empty((bsz, 1, n_out, h, wd), dtype=torch.float32, device=out_cl.device)
+        check(lib().rehr_uasr_mixture_fwd(ptr(out_cl), ptr(ue_cl), ptr(w32), ptr(b32), ptr(res), ptr(unc), bsz, h * wd, n_out, experts,
+                                          stream_ptr()), "uasr_mixture_fwd")
+        F_._count()
+        ctx.save_for_backward(out_cl, ue_cl, w32, b32)
+        ctx.meta = (n_out, experts, w.shape, b.shape)
+        return res, unc
+
+    @staticmethod
+    def backward(ctx, d_res, d_unc):
+        from . import functional as F_
+        from ._lib import check, lib, ptr, stream_ptr
+        out_cl, ue_cl, w32, b32 = ctx.saved_tensors
+        n_out, experts, wshape, bshape = ctx.meta
+        bsz, _, h, wd, _ = out_cl.shape
+        d_res = d_res.float().contiguous() if d_res is not None else None
+        d_unc = d_unc.float().contiguous() if d_unc is not None else None
+        d_out, d_ue = torch.empty_like(out_cl), torch.empty_like(ue_cl)
+        blocks = lib().rehr_uasr_mixture_blocks(bsz * h * wd, n_out)
+        partial = torch.empty((blocks, experts + 1), dtype=torch.float32, device=out_cl.device)
+        check(lib().rehr_uasr_mixture_bwd(ptr(out_cl), ptr(ue_cl), ptr(w32), ptr(b32), ptr(d_res), ptr(d_unc), ptr(d_out), ptr(d_ue),
+                                          ptr(partial), bsz, h * wd, n_out, experts, stream_ptr()), "uasr_mixture_bwd")
+        F_._count()
+        sums = partial.double().sum(0).float()
+        return d_out, d_ue, sums[:experts].reshape(wshape), sums[experts:].reshape(bshape), None
+
+
+def uasr_mixture(out_cl: torch.Tensor, ue_cl: torch.Tensor, uncertainty_out: nn.Module, n_outputs: int):
+    """(res [B, 2, n_out, H, W], uncertainty [B, 1, n_out, H, W]) from the channels-last fp32 outputs [B, 1, H, W, C] of
+    feature_fuse1 / uncertainty_early and the 1x1x1 `uncertainty_out` layer."""
+    return _UasrMixture.apply(out_cl, ue_cl, uncertainty_out.weight, uncertainty_out.bias, int(n_outputs))
 
 
 def flavr_forward(model: nn.Module, images: torch.Tensor, return_inetermediate_uncertainty=False,
@@ -293,6 +345,11 @@ def _flavr_forward(model: nn.Module, images: torch.Tensor, return_inetermediate_
 
     if model.use_uncertainty:
         fused = _conv(model.feature_fuse.conv[0], dx_out, act=ACT_LRELU, slope=0.2)
+        if FUSED_UASR and not return_inetermediate_uncertainty:
+            out_cl = _conv(model.feature_fuse1.conv[0], fused, out_f32=True)           # [B, 1, H, W, 32 * n_out]
+            ue_cl = _conv(model.uncertainty_early.conv[0], fused, out_f32=True)        # [B, 1, H, W, 16 * n_out]
+            if ue_cl.shape[4] == 16 * model.n_outputs and out_cl.shape[4] == 32 * model.n_outputs:
+                return uasr_mixture(out_cl, ue_cl, model.uncertainty_out, model.n_outputs)
         out = nchw(_conv(model.feature_fuse1.conv[0], fused, out_f32=True))
         out = torch.stack(torch.split(out, out.shape[1] // model.n_outputs, dim=1), dim=2)          # [B, 32, n_out, H, W]
         ue = nchw(_conv(model.uncertainty_early.conv[0], fused, out_f32=True))

@@ -176,3 +176,35 @@ def test_sr_train_step_on_the_engine_vs_oracle(unc):
         num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum())
     print("sr step", "uasr" if unc else "plain", "loss", got, want, "grads global", (num / den) ** 0.5)
     assert (num / den) ** 0.5 <= 8e-2
+
+
+def test_fused_uasr_mixture_matches_the_pytorch_formulation(monkeypatch):
+    """The UASR head's expert mixture as one kernel per direction (flavr.uasr_mixture, rehr_uasr_mixture_fwd / _bwd) against the
+    PyTorch statements of FLAVR_arch.py:203-227,244-246 on the same network: outputs, and the gradients of every parameter."""
+    from rehrseg_b200 import flavr
+    torch.manual_seed(3)
+    net = flavr.UNet_3D_3D(2, "unet_18", 4, 4, False, "concat", "transpose", use_uncertainty=True).cuda()
+    x = torch.rand((2, 2, 4, 64, 48), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(4)
+
+    def run(fused):
+        monkeypatch.setattr(flavr, "FUSED_UASR", fused)
+        for p in net.parameters():
+            p.grad = None
+        res, unc = net(x.clone())
+        cot_r = torch.randn(res.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+        cot_u = torch.randn(unc.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+        ((res * cot_r).mean() + (unc * cot_u).mean()).backward()
+        torch.cuda.synchronize()
+        return res.detach(), unc.detach(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    r1, u1, g1 = run(True)
+    r0, u0, g0 = run(False)
+    assert r1.shape == r0.shape == (2, 2, 4, 64, 48) and u1.shape == u0.shape == (2, 1, 4, 64, 48)
+    assert float((r1 - r0).abs().max()) <= 2e-6 * max(1.0, float(r0.abs().max()))
+    assert float((u1 - u0).abs().max()) <= 2e-6
+    assert set(g1) == set(g0)
+    for n in g0:
+        d = float((g1[n] - g0[n]).norm() / (g0[n].norm() + 1e-30))
+        # the head's own layers see fp32 gradients on both paths; everything upstream receives them through one bf16 rounding
+        assert d <= (1e-4 if n.startswith("uncertainty_out") else 2e-2), (n, d)
