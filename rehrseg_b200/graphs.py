@@ -11,7 +11,7 @@ import weakref
 
 import torch
 
-_graph_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # module -> (signature, GraphedForward)
+_graph_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # module -> {(shape, dtype): (signature, GraphedForward)}
 
 
 class GraphedForward:
@@ -51,12 +51,18 @@ def graphed(module, example: torch.Tensor) -> GraphedForward:
     reused only while every parameter still has the version and storage it had at capture time (an optimiser step or a
     load_state_dict invalidates it)."""
     params = list(module.parameters())
-    sig = (tuple(example.shape), example.dtype, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
-    hit = _graph_cache.get(module)
+    shape_key = (tuple(example.shape), example.dtype)
+    sig = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+    per_module = _graph_cache.get(module)
+    if per_module is None:
+        per_module = _graph_cache[module] = {}   # kept outside the module so state_dict / pickling of the model are unaffected
+    hit = per_module.get(shape_key)
     if hit is not None and hit[0] == sig:
         return hit[1]
+    for k in [k for k, v in per_module.items() if v[0] != sig]:
+        del per_module[k]                         # captures of older weights (any shape) are dead: release their memory
     g = GraphedForward(module, example)
-    _graph_cache[module] = (sig, g)   # kept outside the module so state_dict / pickling of the model are unaffected
+    per_module[shape_key] = (sig, g)              # one capture per input shape (single tiles, pairs of mirror variants, ...)
     return g
 
 
