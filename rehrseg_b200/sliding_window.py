@@ -117,7 +117,8 @@ def pad_nd_image(image, new_shape, mode="constant", kwargs=None, return_slicer=F
 # per-tile prediction with mirror test-time augmentation
 # ----------------------------------------------------------------------------------------------------------------
 MIRROR_AXES = (0, 1, 2)  # hard-coded in the reference (utils/seg_utils.py:202)
-SW_PAIR_VARIANTS = os.environ.get("REHR_SW_PAIRS", "1") != "0"   # graph-replayed tile forwards on two mirror variants at a time
+SW_PAIR_VARIANTS = os.environ.get("REHR_SW_PAIRS", "1") != "0"   # graph-replayed tile forwards on several mirror variants at a time
+SW_VARIANT_GROUP = int(os.environ.get("REHR_SW_GROUP", "8"))      # ... this many (1, 2, 4 or 8; measured on C3: 0.512 / 0.446 / 0.432 / 0.429 s per volume)
 
 
 def mirror_axes_combinations(ndim: int = 5):
@@ -132,22 +133,21 @@ def _select(out, out_idx, deep_supervision):
 
 
 def _internal_maybe_mirror_and_predict(model, x, out_idx=None, deep_supervision=True, save=False,
-                                       accum_dtype: Optional[torch.dtype] = None, pair_model=None) -> torch.Tensor:
+                                       accum_dtype: Optional[torch.dtype] = None, pair_model=None, group: int = 2) -> torch.Tensor:
     """utils/seg_utils.py:201-227: model(x) plus the 7 flipped variants, averaged.  The reference runs this under fp16
     autocast (utils/seg_utils.py:743-744), so the running sum is fp16 there; `accum_dtype` selects that (default: the
-    dtype the model returns).  `pair_model` (a callable on a batch of TWO tiles): the 8 variants run as 4 forwards of two
-    (InstanceNorm is per sample, so a variant's logits do not depend on its batch mate); they are summed in the reference's order."""
+    dtype the model returns).  `pair_model` (a callable on a batch of `group` tiles): the 8 variants run `group` per forward
+    (InstanceNorm is per sample, so a variant's logits do not depend on its batch mates); they are summed in the reference's order."""
     assert max(MIRROR_AXES) <= x.ndim - 3, 'mirror_axes does not match the dimension of the input!'
     combos = mirror_axes_combinations()
-    if pair_model is not None and x.shape[0] == 1 and len(combos) % 2 == 1:
+    if pair_model is not None and x.shape[0] == 1 and (len(combos) + 1) % group == 0:
         variants = [()] + [tuple(c) for c in combos]
         prediction = None
-        for k in range(0, len(variants), 2):
-            xa = torch.flip(x, variants[k]) if variants[k] else x
-            xb = torch.flip(x, variants[k + 1])
-            p2 = _select(pair_model(torch.cat((xa, xb), dim=0)), out_idx, deep_supervision)
-            for j, axes in ((0, variants[k]), (1, variants[k + 1])):
-                p = p2[j:j + 1]
+        for k in range(0, len(variants), group):
+            xs = [torch.flip(x, v) if v else x for v in variants[k:k + group]]
+            pg = _select(pair_model(torch.cat(xs, dim=0)), out_idx, deep_supervision)
+            for j, axes in enumerate(variants[k:k + group]):
+                p = pg[j:j + 1]
                 if prediction is None:
                     prediction = p.to(accum_dtype) if accum_dtype is not None else p.clone()
                 else:
@@ -235,21 +235,24 @@ def _internal_predict_sliding_window_return_logits(data: torch.Tensor, slicers, 
                 object.__setattr__(network, "_rehr_lr_only", wrapper)
             network = wrapper
     pair_model = None
-    if cuda_graph and len(slicers) > 0 and isinstance(network, torch.nn.Module) and not torch.is_grad_enabled():
-        from .graphs import graphed
-        module = network
-        if SW_PAIR_VARIANTS:
-            # mirror variants two per forward: the deep (<= 16^3) layers and the tails of the persistent conv kernels fill the
-            # machine better with two samples (2.15 -> 2.05 ms per variant on the C3 tile)
-            pair_model = graphed(module, data[slicers[0]][None].repeat(2, 1, 1, 1, 1))
-        else:
-            network = graphed(module, data[slicers[0]][None])
+    if len(slicers) > 0 and isinstance(network, torch.nn.Module) and not torch.is_grad_enabled():
+        # mirror variants several per forward (python-launched or graph-replayed alike, so the two give identical bits): the deep
+        # (<= 16^3) layers and the tails of the persistent conv kernels fill the machine better with more samples, and the host
+        # issues fewer launches
+        if SW_PAIR_VARIANTS and SW_VARIANT_GROUP > 1:
+            pair_model = network
+        if cuda_graph:
+            from .graphs import graphed
+            if pair_model is not None:
+                pair_model = graphed(network, data[slicers[0]][None].repeat(SW_VARIANT_GROUP, 1, 1, 1, 1))
+            else:
+                network = graphed(network, data[slicers[0]][None])
     for i, sl in enumerate(slicers):
         if tile_filter is not None and not tile_filter(i):
             continue
         workon = data[sl][None]
         prediction = _internal_maybe_mirror_and_predict(network, workon, out_idx, deep_supervision, i == len(slicers) - 1,
-                                                        accum_dtype=accum_dtype, pair_model=pair_model)
+                                                        accum_dtype=accum_dtype, pair_model=pair_model, group=SW_VARIANT_GROUP)
         prediction = prediction[0]
         origin = (sl[1].start * slice_seperation, sl[2].start, sl[3].start)
         sw_accumulate(predicted_logits, n_predictions, prediction, gaussian, origin)
