@@ -215,18 +215,22 @@ static constexpr int kFinLanes = 32;
 // norm (optional): the affine + activation of this InstanceNorm as per-(n, channel) triples for "normalise on load" consumers,
 //   norm[(n*3 + 0) * c_total + c_off + c] = gamma*rstd,  [.. + 1 ..] = beta - mean*gamma*rstd,  [.. + 2 ..] = slope;
 // channels [0, c_off) of the same rows are set to the identity (1, 0, 1): the up-sampled half of a decoder concat buffer.
+// CPB = channels per block (32, or 8 for long partial lists: four times as many blocks and tile lanes -- the stage-entry convs
+// leave 2048 partials per sample, which 4 blocks of 32 lanes took 25 us to walk)
+template <int CPB>
 __global__ void __launch_bounds__(32 * kFinLanes) in_finalize_kernel(const float* partial, int N, int tiles, int C,
                                                                       double inv_count, float eps, float* mean, float* rstd,
                                                                       const float* gamma, const float* beta, float slope,
                                                                       float* norm, int c_total, int c_off, float* norm_own) {
-  __shared__ double sh1[kFinLanes][33], sh2[kFinLanes][33];
-  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
-  const int n = blockIdx.y, c = blockIdx.x * 32 + cl;
+  constexpr int kLanes = 32 * kFinLanes / CPB;
+  __shared__ double sh1[kLanes][CPB + 1], sh2[kLanes][CPB + 1];
+  const int cl = threadIdx.x % CPB, tl = threadIdx.x / CPB;
+  const int n = blockIdx.y, c = blockIdx.x * CPB + cl;
   double s1 = 0.0, s2 = 0.0;
   if (c < C) {
     const float2* p = reinterpret_cast<const float2*>(partial) + (long long)n * tiles * C + c;
 #pragma unroll 8
-    for (int t = tl; t < tiles; t += kFinLanes) {
+    for (int t = tl; t < tiles; t += kLanes) {
       const float2 v = p[(long long)t * C];
       s1 += (double)v.x;
       s2 += (double)v.y;
@@ -237,8 +241,8 @@ __global__ void __launch_bounds__(32 * kFinLanes) in_finalize_kernel(const float
   __syncthreads();
   if (tl == 0 && c < C) {
     double a = 0.0, b = 0.0;
-#pragma unroll
-    for (int l = 0; l < kFinLanes; ++l) {
+#pragma unroll 8
+    for (int l = 0; l < kLanes; ++l) {
       a += sh1[l][cl];
       b += sh2[l][cl];
     }
@@ -552,39 +556,41 @@ __global__ void __launch_bounds__(256) pointwise_bwd_kernel(const __nv_bfloat16*
   const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(gtid % groups);
   const long long vlane = gtid / groups;
-  // two voxels per iteration: both x loads and both dy rows are issued before the arithmetic
-  for (long long vox = vlane; vlane < vlanes && vox < V; vox += 2 * vlanes) {
-    const long long v1 = vox + vlanes;
-    const bool has1 = v1 < V;
-    const uint4 r0 = __ldcs(reinterpret_cast<const uint4*>(x + vox * ldx + g * 8));
-    const uint4 r1 = has1 ? __ldcs(reinterpret_cast<const uint4*>(x + v1 * ldx + g * 8)) : make_uint4(0, 0, 0, 0);
-    float gy0[kPwMaxCout], gy1[kPwMaxCout];
+  // U voxels per iteration: all x loads and dy rows are issued before the arithmetic (the pass is bound by memory latency: 50 % of
+  // the HBM peak with two voxels in flight per thread)
+  constexpr int U = 4;
+  for (long long vox = vlane; vlane < vlanes && vox < V; vox += U * vlanes) {
+    uint4 r[U];
+    float gy[U][kPwMaxCout];
+    bool has[U];
 #pragma unroll
-    for (int o = 0; o < kPwMaxCout; ++o) {
-      gy0[o] = o < cout ? dy[(long long)o * V + vox] : 0.f;
-      gy1[o] = (o < cout && has1) ? dy[(long long)o * V + v1] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long v = vox + u * vlanes;
+      has[u] = v < V;
+      r[u] = has[u] ? __ldcs(reinterpret_cast<const uint4*>(x + v * ldx + g * 8)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int o = 0; o < kPwMaxCout; ++o) gy[u][o] = (o < cout && has[u]) ? dy[(long long)o * V + v] : 0.f;
     }
-    float f0[8], f1[8], d0[8], d1[8];
-    x16x8_to_float(r0, f0, x_f16);
-    x16x8_to_float(r1, f1, x_f16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d0[i] = d1[i] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      if (!has[u]) break;
+      const long long v = vox + u * vlanes;
+      float f[8], d[8];
+      x16x8_to_float(r[u], f, x_f16);
 #pragma unroll
-    for (int o = 0; o < kPwMaxCout; ++o)
-      if (o < cout) {
-        if (g == 0) pb[o] += gy0[o] + gy1[o];
+      for (int i = 0; i < 8; ++i) d[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float wv = sw[o * cin + g * 8 + i];
-          d0[i] = fmaf(gy0[o], wv, d0[i]);
-          d1[i] = fmaf(gy1[o], wv, d1[i]);
-          pw[o][i] = fmaf(gy0[o], f0[i], pw[o][i]);
-          pw[o][i] = fmaf(gy1[o], f1[i], pw[o][i]);
+      for (int o = 0; o < kPwMaxCout; ++o)
+        if (o < cout) {
+          if (g == 0) pb[o] += gy[u][o];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float wv = sw[o * cin + g * 8 + i];
+            d[i] = fmaf(gy[u][o], wv, d[i]);
+            pw[o][i] = fmaf(gy[u][o], f[i], pw[o][i]);
+          }
         }
-      }
-    if (dx) {
-      __stcs(reinterpret_cast<uint4*>(dx + vox * lddx + g * 8), float_to_bf16x8(d0));
-      if (has1) __stcs(reinterpret_cast<uint4*>(dx + v1 * lddx + g * 8), float_to_bf16x8(d1));
+      if (dx) __stcs(reinterpret_cast<uint4*>(dx + v * lddx + g * 8), float_to_bf16x8(d));
     }
   }
   if (vlane < vlanes)
@@ -1401,8 +1407,12 @@ int rehr_instnorm_stats(const rehr_tensor* x, float* partial, rehr_stream stream
 int rehr_instnorm_finalize(const float* partial, int n, int tiles, int c, long long count, float eps, float* mean,
                            float* rstd, rehr_stream stream) {
   if (!partial || !mean || !rstd || count <= 0) return REHR_BAD_SHAPE;
-  in_finalize_kernel<<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
-                                                                       rstd, nullptr, nullptr, 1.f, nullptr, 0, 0, nullptr);
+  if (tiles >= 256)
+    in_finalize_kernel<8><<<dim3((c + 7) / 8, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+                                                                            rstd, nullptr, nullptr, 1.f, nullptr, 0, 0, nullptr);
+  else
+    in_finalize_kernel<32><<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+                                                                              rstd, nullptr, nullptr, 1.f, nullptr, 0, 0, nullptr);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -1411,8 +1421,12 @@ int rehr_instnorm_finalize_norm(const float* partial, int n, int tiles, int c, l
                                 const float* beta, float slope, float* mean, float* rstd, float* norm, int c_total, int c_off,
                                 float* norm_own, rehr_stream stream) {
   if (!partial || !mean || !rstd || !norm || count <= 0 || c_off < 0 || c_off + c > c_total) return REHR_BAD_SHAPE;
-  in_finalize_kernel<<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
-                                                                       rstd, gamma, beta, slope, norm, c_total, c_off, norm_own);
+  if (tiles >= 256)
+    in_finalize_kernel<8><<<dim3((c + 7) / 8, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+                                                                            rstd, gamma, beta, slope, norm, c_total, c_off, norm_own);
+  else
+    in_finalize_kernel<32><<<dim3((c + 31) / 32, n), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(partial, n, tiles, c, 1.0 / (double)count, eps, mean,
+                                                                              rstd, gamma, beta, slope, norm, c_total, c_off, norm_own);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
