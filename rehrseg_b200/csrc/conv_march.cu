@@ -129,10 +129,13 @@ __device__ __forceinline__ bool elect_one_sync() {
 // the MMA issue sequence of one input plane (9 * CHUNKS * BKT/16 instructions) is fully unrolled with constant
 // descriptor increments: a single thread must issue one tcgen05.mma every ~50 clk (tools/umma_rate2.cu measures
 // 40 clk/MMA for this code shape vs 120-280 clk/MMA with run-time descriptor arithmetic).
-template <int BKT, int CHUNKS, int CT, int KS, bool XF, bool RED = false>
+// REHR_MARCH_MAXNREG (build-time, default = no cap): register cap of the 192-thread variants.  A 128-register build lets two
+// blocks of an InstanceNorm pass become resident next to a conv CTA (tools/overlap_probe.py: 55 % of a co-scheduled pass hides
+// behind a forward conv instead of 12 %) but costs the conv itself 5 % (spilled column sums); measured on the C1 step: a net loss.
 #ifndef REHR_MARCH_MAXNREG
 #define REHR_MARCH_MAXNREG 255
 #endif
+template <int BKT, int CHUNKS, int CT, int KS, bool XF, bool RED = false>
 __global__ void __launch_bounds__(XF ? kMarchThreadsXf : kMarchThreads) __maxnreg__(XF ? 224 : REHR_MARCH_MAXNREG) conv_march_kernel(const __grid_constant__ MarchParams p) {
   constexpr int R = MarchGeo<KS>::R;
   constexpr int kHaloW = MarchGeo<KS>::kHaloW;

@@ -440,20 +440,10 @@ class _fork:
             side = _side_streams[key] = torch.cuda.Stream(device=device, priority=SIDE_PRIORITY if kind == "wgrad" else 0)
         self.side = side
         self.ctx = None
-        self.ev = None
-
-    def fork_point(self):
-        """Fix the point of the main stream the side stream will wait for NOW (work issued on the main stream between this call
-        and `with self:` is not waited for)."""
-        self.ev = torch.cuda.Event()
-        self.ev.record(self.main)
 
     def __enter__(self):
-        ev = self.ev
-        if ev is None:
-            ev = torch.cuda.Event()
-            ev.record(self.main)
-        self.ev = None
+        ev = torch.cuda.Event()
+        ev.record(self.main)
         self.side.wait_event(ev)
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
@@ -475,11 +465,12 @@ class _fork:
 # gradient CTA on every SM.  The side stream is joined once, by a final callback of the autograd engine (and before any bucket
 # all-reduce, graphs.GraphedTrainStep).  Operands are kept alive until then (their memory must not be recycled by the main stream
 # while the side stream still reads it).
-# Launch order matters: two machine-filling GEMMs cannot share an SM, so the one launched first runs first.  The input gradient
-# goes first (the next layer's InstanceNorm passes depend on it), the weight gradient second, and those passes then run NEXT to
-# the weight gradient (tools/overlap_probe.py: about half of their time disappears behind it).  Measured on the C1 step
-# (tools/ab_step.py): 12.76 ms joined per layer, 12.41 ms deferred with the old weight-gradient-first order only for the small
-# layers, 12.28 ms deferred with the input gradient first everywhere.
+# Order matters: two machine-filling GEMMs cannot share an SM, so whichever starts first runs first.  The input gradient must go
+# first (the next layer's InstanceNorm passes depend on it); inside a replayed CUDA graph two independent branches start in no
+# particular order, so for layers of >= DGRAD_FIRST_MIN_VOXELS voxels the weight gradient is made to WAIT for the input gradient
+# (_dgrad_and_wgrad) -- the InstanceNorm passes of the next layer then run NEXT to it (tools/overlap_probe.py: about half of
+# their time disappears behind a weight gradient).  Measured on the C1 step (tools/ab_step.py): 12.76 ms joined per layer,
+# 12.41 ms deferred with the weight gradient launched first, 12.28-12.31 ms with the dependency.
 # The window this opens: autograd's AccumulateGrad touches the returned dW on the MAIN stream whenever it cannot simply adopt the
 # tensor (an existing .grad to add to, a hook that reads it).  So the deferral is (a) only taken for parameters whose .grad is
 # None, and (b) only ON inside `deferred_wgrad()` -- entered by graphs.GraphedTrainStep, which owns the whole step, joins before
