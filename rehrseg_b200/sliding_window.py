@@ -118,6 +118,7 @@ def pad_nd_image(image, new_shape, mode="constant", kwargs=None, return_slicer=F
 # ----------------------------------------------------------------------------------------------------------------
 MIRROR_AXES = (0, 1, 2)  # hard-coded in the reference (utils/seg_utils.py:202)
 SW_PAIR_VARIANTS = os.environ.get("REHR_SW_PAIRS", "1") != "0"   # graph-replayed tile forwards on several mirror variants at a time
+SW_SHARD_GROUP = int(os.environ.get("REHR_SW_SHARD_GROUP", "4"))   # sharded driver: this rank's (tile, variant) units per forward
 SW_VARIANT_GROUP = int(os.environ.get("REHR_SW_GROUP", "8"))      # ... this many (1, 2, 4 or 8; measured on C3: 0.512 / 0.446 / 0.432 / 0.429 s per volume)
 
 
@@ -307,6 +308,7 @@ def _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch
                         group, tiles_per_allreduce: int = 32):
     """(tile, mirror variant) units dealt round-robin; per-tile variant sums all-reduced in chunks; local blend of all tiles."""
     import torch.distributed as dist
+    group_net = None
     if not torch.is_grad_enabled() and isinstance(network, torch.nn.Module):
         if out_idx == 0 and hasattr(network, "sr_head") and hasattr(network, "upscale"):
             from .seg_model import LRHeadOnly, _EngineForward, SegModel
@@ -318,7 +320,11 @@ def _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch
                 network = wrapper
         from .graphs import graphed
         if len(slicers) > 0:
-            network = graphed(network, data[slicers[0]][None])
+            module = network
+            network = graphed(module, data[slicers[0]][None])
+            if SW_PAIR_VARIANTS and SW_SHARD_GROUP > 1:
+                # this rank's units several per forward (as in the single-GPU path); a remainder runs one by one
+                group_net = graphed(module, data[slicers[0]][None].repeat(SW_SHARD_GROUP, 1, 1, 1, 1))
     dev = data.device
     logits = torch.zeros((2, data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
     npred = torch.zeros((data.shape[1] * slice_seperation, data.shape[2], data.shape[3]), dtype=torch.half, device=dev)
@@ -328,15 +334,20 @@ def _blend_mirror_units(data, slicers, network, out_idx, slice_seperation, patch
     for c0 in range(0, len(slicers), tiles_per_allreduce):
         chunk = list(range(c0, min(len(slicers), c0 + tiles_per_allreduce)))
         sums = None
-        for k, i in enumerate(chunk):
-            sl = slicers[i]
-            workon = data[sl][None]
-            for v in range(nv):
-                if (i * nv + v) % world != rank:
-                    continue
-                axes = variants[v]
-                p = _select(network(torch.flip(workon, axes) if axes else workon), out_idx, deep_supervision)
-                p = (torch.flip(p, axes) if axes else p).float()
+        mine = [(k, i, v) for k, i in enumerate(chunk) for v in range(nv) if (i * nv + v) % world == rank]
+        pos = 0
+        while pos < len(mine):
+            take = SW_SHARD_GROUP if (group_net is not None and len(mine) - pos >= SW_SHARD_GROUP) else 1
+            units = mine[pos:pos + take]
+            pos += take
+            xs = []
+            for _k, i, v in units:
+                workon = data[slicers[i]][None]
+                xs.append(torch.flip(workon, variants[v]) if variants[v] else workon)
+            out = _select((group_net if take > 1 else network)(torch.cat(xs, dim=0) if take > 1 else xs[0]), out_idx, deep_supervision)
+            for j, (k, _i, v) in enumerate(units):          # same accumulation order as one unit per forward
+                p = out[j:j + 1]
+                p = (torch.flip(p, variants[v]) if variants[v] else p).float()
                 if sums is None:
                     sums = torch.zeros((len(chunk), *p.shape[1:]), dtype=torch.float32, device=dev)
                 sums[k] += p[0]
