@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(256) sw_accumulate_kernel(__half* logits, __ha
       // before the add; a float prediction promotes the product and the add to float, rounding once at the store.
       float prod;
       if (pred_f32)
-        prod = reinterpret_cast<const float*>(pred)[c * tv + i] * g;
+        prod = __fmul_rn(reinterpret_cast<const float*>(pred)[c * tv + i], g);  // rounded product, never contracted into an FMA
       else
         prod = __half2float(__float2half(__half2float(reinterpret_cast<const __half*>(pred)[c * tv + i]) * g));
       logits[c * vv + vi] = __float2half(__half2float(logits[c * vv + vi]) + prod);
@@ -946,6 +946,98 @@ __global__ void __launch_bounds__(256) sw_finalize_kernel(__half* logits, const 
       const __half q = __float2half(__half2float(logits[c * vv + i]) / n);
       logits[c * vv + i] = q;
       if (__hisinf(q)) bad = 1;
+    }
+  }
+  if (bad && inf_flag) atomicOr(inf_flag, 1);
+}
+
+// 16-byte variants (tile width, x offset and volume width multiples of 8, 16-byte aligned bases): eight voxels of a row per thread,
+// the per-element arithmetic (and therefore every rounding) exactly as in the scalar kernels above.
+__device__ __forceinline__ void half8_unpack(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 half8_pack(const __half (&h)[8]) {
+  uint4 u;
+  __half2* o = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = __halves2half2(h[2 * i], h[2 * i + 1]);
+  return u;
+}
+__global__ void __launch_bounds__(256) sw_accumulate_vec8_kernel(__half* logits, __half* npred, const void* pred, int pred_f32,
+                                                                 const __half* gauss, int C, int VD, int VH, int VW, int TD,
+                                                                 int TH, int TW, int od, int oh, int ow) {
+  const int TW8 = TW / 8;
+  const long long groups = (long long)TD * TH * TW8;
+  const long long tv = (long long)TD * TH * TW;
+  const long long vv = (long long)VD * VH * VW;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < groups; q += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(q % TW8) * 8;
+    const int y = (int)((q / TW8) % TH);
+    const int z = (int)(q / ((long long)TW8 * TH));
+    const long long i = ((long long)z * TH + y) * TW + x;
+    const long long vi = ((long long)(od + z) * VH + (oh + y)) * VW + (ow + x);
+    float g[8];
+    if (gauss) {
+      half8_unpack(*reinterpret_cast<const uint4*>(gauss + i), g);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = 1.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      float prod[8], acc[8];
+      if (pred_f32) {
+        const float4* pp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pred) + c * tv + i);
+        const float4 a = pp[0], b = pp[1];
+        prod[0] = __fmul_rn(a.x, g[0]); prod[1] = __fmul_rn(a.y, g[1]); prod[2] = __fmul_rn(a.z, g[2]); prod[3] = __fmul_rn(a.w, g[3]);
+        prod[4] = __fmul_rn(b.x, g[4]); prod[5] = __fmul_rn(b.y, g[5]); prod[6] = __fmul_rn(b.z, g[6]); prod[7] = __fmul_rn(b.w, g[7]);
+      } else {
+        float pv[8];
+        half8_unpack(*reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(pred) + c * tv + i), pv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) prod[e] = __half2float(__float2half(pv[e] * g[e]));
+      }
+      uint4* lp = reinterpret_cast<uint4*>(logits + c * vv + vi);
+      half8_unpack(*lp, acc);
+      __half r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = __float2half(acc[e] + prod[e]);
+      *lp = half8_pack(r);
+    }
+    if (npred) {
+      uint4* np = reinterpret_cast<uint4*>(npred + vi);
+      float a[8];
+      half8_unpack(*np, a);
+      __half r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = __float2half(a[e] + g[e]);
+      *np = half8_pack(r);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) sw_finalize_vec8_kernel(__half* logits, const __half* npred, int C, long long vv,
+                                                               int* inf_flag) {
+  int bad = 0;
+  const long long groups = vv / 8;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < groups; q += (long long)gridDim.x * blockDim.x) {
+    float n[8];
+    half8_unpack(*reinterpret_cast<const uint4*>(npred + q * 8), n);
+    for (int c = 0; c < C; ++c) {
+      uint4* lp = reinterpret_cast<uint4*>(logits + c * vv + q * 8);
+      float a[8];
+      half8_unpack(*lp, a);
+      __half r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        r[e] = __float2half(a[e] / n[e]);
+        if (__hisinf(r[e])) bad = 1;
+      }
+      *lp = half8_pack(r);
     }
   }
   if (bad && inf_flag) atomicOr(inf_flag, 1);
@@ -991,6 +1083,74 @@ __global__ void __launch_bounds__(128) blur1d_kernel(const float* x, float* y, c
         float acc = 0.f;
         for (int l = 0; l < L; ++l) acc += st[l] * tile[(r + l) * 128 + threadIdx.x];
         out[(long long)(x0 + r) * Y + yy] = acc;
+      }
+    }
+  }
+}
+
+// Same tile, 16-byte accesses (Y % 4 == 0, 16-byte aligned bases): a warp stages one 512 B row per load instruction with several rows
+// in flight, then every thread owns a 4-column strip of kBlurRows / 4 output rows and computes them four at a time -- each staged
+// float4 feeds the (up to) four outputs it belongs to, taps applied in ascending order exactly like the scalar kernel (bit-identical
+// results), one LDS.128 per staged row instead of one per tap.
+__global__ void __launch_bounds__(128) blur1d_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ taps,
+                                                          int L, long long Z, int X, int Y) {
+  extern __shared__ float tile[];  // [kBlurRows + L - 1][128]
+  __shared__ float st[kBlurMaxTaps];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) st[i] = taps[i];
+  const int left = (L - 1) / 2;
+  const int ytiles = (Y + 127) / 128, xtiles = (X + kBlurRows - 1) / kBlurRows;
+  const long long total = Z * (long long)xtiles * ytiles;
+  const int rows_in = kBlurRows + L - 1;
+  const int cq = threadIdx.x & 31, rr = threadIdx.x >> 5;  // column quad, row phase
+  constexpr int kStrip = kBlurRows / 4;                    // output rows per thread
+  float4* tile4 = reinterpret_cast<float4*>(tile);         // [rows_in][32]
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int yt = (int)(t % ytiles);
+    const int xt = (int)((t / ytiles) % xtiles);
+    const long long z = t / ((long long)ytiles * xtiles);
+    const int yy = yt * 128 + cq * 4;
+    const int x0 = xt * kBlurRows;
+    const float* base = x + z * (long long)X * Y;
+    const bool col_ok = yy < Y;  // Y % 4 == 0: the quad is inside or outside as a whole
+    __syncthreads();
+#pragma unroll 6
+    for (int r = rr; r < rows_in; r += 4) {
+      const int xs = x0 + r - left;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok && xs >= 0 && xs < X) v = *reinterpret_cast<const float4*>(base + (long long)xs * Y + yy);
+      tile4[r * 32 + cq] = v;
+    }
+    __syncthreads();
+    if (col_ok) {
+      float* out = y + z * (long long)X * Y;
+      const int nrows = min(kBlurRows, X - x0);
+      for (int r0 = rr * kStrip; r0 < min(nrows, (rr + 1) * kStrip); r0 += 4) {
+        float4 acc[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // taps j, j-1, j-2, j-3
+        for (int j = 0; j < L + 3; ++j) {
+          w3 = w2;
+          w2 = w1;
+          w1 = w0;
+          w0 = j < L ? st[j] : 0.f;
+          const float4 v = tile4[(r0 + j) * 32 + cq];  // r0 + j <= r0 + L + 2 <= kBlurRows + L - 2: inside the staged tile
+          if (j < L) {
+            acc[0].x += w0 * v.x; acc[0].y += w0 * v.y; acc[0].z += w0 * v.z; acc[0].w += w0 * v.w;
+          }
+          if (j >= 1 && j - 1 < L) {
+            acc[1].x += w1 * v.x; acc[1].y += w1 * v.y; acc[1].z += w1 * v.z; acc[1].w += w1 * v.w;
+          }
+          if (j >= 2 && j - 2 < L) {
+            acc[2].x += w2 * v.x; acc[2].y += w2 * v.y; acc[2].z += w2 * v.z; acc[2].w += w2 * v.w;
+          }
+          if (j >= 3) {
+            acc[3].x += w3 * v.x; acc[3].y += w3 * v.y; acc[3].z += w3 * v.z; acc[3].w += w3 * v.w;
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (r0 + o < nrows) *reinterpret_cast<float4*>(out + (long long)(x0 + r0 + o) * Y + yy) = acc[o];
       }
     }
   }
@@ -1319,44 +1479,106 @@ static constexpr int kMaxFuse = 16;
 struct PtrPack {
   const void* p[kMaxFuse];
 };
-__global__ void __launch_bounds__(256) fba_combine_kernel(PtrPack sp, int K, float p, float2* out, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (p < 0.f) {
-      // numpy max on complex: lexicographic (real, then imag); NaN propagates like np.maximum
-      float2 best = reinterpret_cast<const float2*>(sp.p[0])[i];
-      for (int k = 1; k < K; ++k) {
-        const float2 v = reinterpret_cast<const float2*>(sp.p[k])[i];
+// One spectral bin: the K values of that bin sit in registers (KMAX = 4 / 8 / 16, loops fully unrolled and predicated on k < K).
+template <int KMAX>
+__device__ __forceinline__ float2 fba_bin(const float2 (&v)[KMAX], int K, float p) {
+  if (p < 0.f) {
+    // numpy max on complex: lexicographic (real, then imag); NaN propagates like np.maximum
+    float2 best = v[0];
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k) {
+      if (k < K) {
         const bool best_nan = (best.x != best.x) || (best.y != best.y);
-        const bool v_nan = (v.x != v.x) || (v.y != v.y);
-        if (best_nan) continue;
-        if (v_nan || v.x > best.x || (v.x == best.x && v.y > best.y)) best = v;
+        const bool v_nan = (v[k].x != v[k].x) || (v[k].y != v[k].y);
+        if (!best_nan && (v_nan || v[k].x > best.x || (v[k].x == best.x && v[k].y > best.y))) best = v[k];
       }
-      out[i] = best;
+    }
+    return best;
+  }
+  float mag[KMAX];
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) {
+      mag[k] = powf(hypotf(v[k].x, v[k].y), p);
+      den += mag[k];
+    }
+  }
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) {
+      const float w = mag[k] / den;
+      acc.x += w * v[k].x;
+      acc.y += w * v[k].y;
+    }
+  }
+  return acc;
+}
+// V = bins per thread: 2 (one 16-byte access per spectrum; even bin count, 16-byte aligned bases) or 1.  All K loads of a thread are
+// issued before the first use.
+template <int KMAX, int V>
+__global__ void __launch_bounds__(256) fba_combine_kernel(PtrPack sp, int K, float p, float2* out, long long n) {
+  const long long items = n / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    float2 a[KMAX], b[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        if (V == 2) {
+          const float4 t = reinterpret_cast<const float4*>(sp.p[k])[i];
+          a[k] = make_float2(t.x, t.y);
+          b[k] = make_float2(t.z, t.w);
+        } else {
+          a[k] = reinterpret_cast<const float2*>(sp.p[k])[i];
+        }
+      }
+    }
+    if (V == 2) {
+      const float2 r0 = fba_bin<KMAX>(a, K, p), r1 = fba_bin<KMAX>(b, K, p);
+      reinterpret_cast<float4*>(out)[i] = make_float4(r0.x, r0.y, r1.x, r1.y);
     } else {
-      float mag[kMaxFuse];
-      float den = 0.f;
-      for (int k = 0; k < K; ++k) {
-        const float2 v = reinterpret_cast<const float2*>(sp.p[k])[i];
-        mag[k] = powf(hypotf(v.x, v.y), p);
-        den += mag[k];
-      }
-      float2 acc = make_float2(0.f, 0.f);
-      for (int k = 0; k < K; ++k) {
-        const float2 v = reinterpret_cast<const float2*>(sp.p[k])[i];
-        const float w = mag[k] / den;
-        acc.x += w * v.x;
-        acc.y += w * v.y;
-      }
-      out[i] = acc;
+      out[i] = fba_bin<KMAX>(a, K, p);
     }
   }
 }
-__global__ void __launch_bounds__(256) mean_stack_kernel(PtrPack vp, int K, float* out, long long n) {
+template <int KMAX>
+static void fba_launch(const PtrPack& pk, int K, float p, float2* out, long long n, bool vec, cudaStream_t stream) {
+  if (vec)
+    fba_combine_kernel<KMAX, 2><<<grid_for(n / 2, 256, 8), 256, 0, stream>>>(pk, K, p, out, n);
+  else
+    fba_combine_kernel<KMAX, 1><<<grid_for(n, 256, 8), 256, 0, stream>>>(pk, K, p, out, n);
+}
+// VT = float4 (element count a multiple of 4, 16-byte aligned bases) or float; same sum order and the same division as the statement.
+__device__ __forceinline__ void mean_add(float& s, const float& v) { s += v; }
+__device__ __forceinline__ void mean_add(float4& s, const float4& v) {
+  s.x += v.x;
+  s.y += v.y;
+  s.z += v.z;
+  s.w += v.w;
+}
+__device__ __forceinline__ float mean_div(const float& s, float k) { return s / k; }
+__device__ __forceinline__ float4 mean_div(const float4& s, float k) { return make_float4(s.x / k, s.y / k, s.z / k, s.w / k); }
+template <typename VT, int KMAX>
+__global__ void __launch_bounds__(256) mean_stack_kernel(PtrPack vp, int K, VT* out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float s = reinterpret_cast<const float*>(vp.p[0])[i];
-    for (int k = 1; k < K; ++k) s += reinterpret_cast<const float*>(vp.p[k])[i];
-    out[i] = s / (float)K;
+    VT v[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)  // all K loads in flight (static indices: the pointer pack stays in the parameter bank)
+      if (k < K) v[k] = reinterpret_cast<const VT*>(vp.p[k])[i];
+    VT s = v[0];
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k)
+      if (k < K) mean_add(s, v[k]);
+    out[i] = mean_div(s, (float)K);
   }
+}
+template <int KMAX>
+static void mean_launch(const PtrPack& pk, int K, float* out, long long n, bool vec, cudaStream_t stream) {
+  if (vec)
+    mean_stack_kernel<float4, KMAX><<<grid_for(n / 4, 256, 8), 256, 0, stream>>>(pk, K, reinterpret_cast<float4*>(out), n / 4);
+  else
+    mean_stack_kernel<float, KMAX><<<grid_for(n, 256, 8), 256, 0, stream>>>(pk, K, out, n);
 }
 
 // =================================================================================================
@@ -1731,6 +1953,15 @@ int rehr_sw_accumulate(void* logits_f16, void* npred_f16, const void* pred, int 
   if (!logits_f16 || !pred) return REHR_BAD_SHAPE;  // npred_f16 may be NULL: blend the logits only
   if (od < 0 || oh < 0 || ow < 0 || od + TD > VD || oh + TH > VH || ow + TW > VW) return REHR_BAD_SHAPE;
   const long long tv = (long long)TD * TH * TW;
+  const uintptr_t bases = reinterpret_cast<uintptr_t>(logits_f16) | reinterpret_cast<uintptr_t>(npred_f16) |
+                          reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(gauss_f16);  // NULL contributes nothing
+  if (TW % 8 == 0 && VW % 8 == 0 && ow % 8 == 0 && (bases & 15) == 0 && tv > 0) {
+    sw_accumulate_vec8_kernel<<<grid_for(tv / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<__half*>(logits_f16), reinterpret_cast<__half*>(npred_f16), pred, pred_is_f32,
+        reinterpret_cast<const __half*>(gauss_f16), C, VD, VH, VW, TD, TH, TW, od, oh, ow);
+    REHR_CHECK_LAUNCH();
+    return REHR_OK;
+  }
   sw_accumulate_kernel<<<grid_for(tv, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<__half*>(logits_f16), reinterpret_cast<__half*>(npred_f16), pred, pred_is_f32,
       reinterpret_cast<const __half*>(gauss_f16), C, VD, VH, VW, TD, TH, TW, od, oh, ow);
@@ -1739,6 +1970,12 @@ int rehr_sw_accumulate(void* logits_f16, void* npred_f16, const void* pred, int 
 }
 int rehr_sw_finalize(void* logits_f16, const void* npred_f16, int C, long long voxels, int* inf_flag, rehr_stream stream) {
   if (!logits_f16 || !npred_f16) return REHR_BAD_SHAPE;
+  if (voxels % 8 == 0 && voxels > 0 && ((reinterpret_cast<uintptr_t>(logits_f16) | reinterpret_cast<uintptr_t>(npred_f16)) & 15) == 0) {
+    sw_finalize_vec8_kernel<<<grid_for(voxels / 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<__half*>(logits_f16), reinterpret_cast<const __half*>(npred_f16), C, voxels, inf_flag);
+    REHR_CHECK_LAUNCH();
+    return REHR_OK;
+  }
   sw_finalize_kernel<<<grid_for(voxels, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__half*>(logits_f16),
                                                                              reinterpret_cast<const __half*>(npred_f16), C, voxels,
                                                                              inf_flag);
@@ -1753,7 +1990,13 @@ int rehr_blur1d(const float* x, const float* taps, int L, float* y, long long Z,
   if (smem > 48 * 1024) REHR_SET_MAX_SMEM_ONCE(blur1d_kernel, (kBlurRows + kBlurMaxTaps) * 128 * sizeof(float));
   const long long tiles = Z * (long long)((X + kBlurRows - 1) / kBlurRows) * ((Y + 127) / 128);
   const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 6));
-  blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  const bool vec = Y % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec) {
+    if (smem > 48 * 1024) REHR_SET_MAX_SMEM_ONCE(blur1d_vec4_kernel, (kBlurRows + kBlurMaxTaps) * 128 * sizeof(float));
+    blur1d_vec4_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  } else {
+    blur1d_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, y, taps, L, Z, X, Y);
+  }
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -1860,7 +2103,15 @@ int rehr_fba_combine(const void* const* spectra, int K, float p, void* out, long
   if (K > kMaxFuse) return REHR_UNSUPPORTED;
   PtrPack pk{};
   for (int i = 0; i < K; ++i) pk.p[i] = spectra[i];
-  fba_combine_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(pk, K, p, reinterpret_cast<float2*>(out), n);
+  uintptr_t bases = reinterpret_cast<uintptr_t>(out);
+  for (int i = 0; i < K; ++i) bases |= reinterpret_cast<uintptr_t>(spectra[i]);
+  const bool vec = n % 2 == 0 && (bases & 15) == 0;
+  if (K <= 4)
+    fba_launch<4>(pk, K, p, reinterpret_cast<float2*>(out), n, vec, (cudaStream_t)stream);
+  else if (K <= 8)
+    fba_launch<8>(pk, K, p, reinterpret_cast<float2*>(out), n, vec, (cudaStream_t)stream);
+  else
+    fba_launch<16>(pk, K, p, reinterpret_cast<float2*>(out), n, vec, (cudaStream_t)stream);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
@@ -1869,7 +2120,15 @@ int rehr_mean_stack(const float* const* vols, int K, float* out, long long n, re
   if (K > kMaxFuse) return REHR_UNSUPPORTED;
   PtrPack pk{};
   for (int i = 0; i < K; ++i) pk.p[i] = vols[i];
-  mean_stack_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(pk, K, out, n);
+  uintptr_t bases = reinterpret_cast<uintptr_t>(out);
+  for (int i = 0; i < K; ++i) bases |= reinterpret_cast<uintptr_t>(vols[i]);
+  const bool vec = n % 4 == 0 && (bases & 15) == 0;
+  if (K <= 4)
+    mean_launch<4>(pk, K, out, n, vec, (cudaStream_t)stream);
+  else if (K <= 8)
+    mean_launch<8>(pk, K, out, n, vec, (cudaStream_t)stream);
+  else
+    mean_launch<16>(pk, K, out, n, vec, (cudaStream_t)stream);
   REHR_CHECK_LAUNCH();
   return REHR_OK;
 }
