@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace rehr {
 
@@ -713,6 +714,47 @@ __global__ void __launch_bounds__(256) upsample_d_kernel(const __nv_bfloat16* x,
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = l0 * a[i] + l1 * b[i];
     *reinterpret_cast<uint4*>(y + ((n * OD + od) * HW + hw) * ldy + g * 8) = float_to_x16x8(o, y_f16);
+  }
+}
+// Source-centric variant: one thread per (n, source plane d, voxel, 8-channel group) loads planes d and d + 1 ONCE and writes every
+// output plane whose lower source index is d (OD / D of them on average).  The output-centric kernel above re-read every source plane
+// from DRAM ~3.4 times at the C4 shape (profiles/r02_ncu_families_raw.txt: 450 MB read for a 134 MB input).  Indices and weights come
+// from the same float expressions, evaluated per output plane, so the results are bit-identical.
+__global__ void __launch_bounds__(256) upsample_d_src_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* y, long long ldy,
+                                                             int N, int D, int OD, long long HW, int C, int x_f16, int y_f16) {
+  const int groups = C / 8;
+  const long long items = (long long)N * D * HW * groups;
+  const float scale = OD > 1 ? (float)(D - 1) / (float)(OD - 1) : 0.f;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    long long r = it / groups;
+    const long long hw = r % HW;
+    r /= HW;
+    const int d = (int)(r % D);
+    const long long n = r / D;
+    // first output plane with (int)(scale * od) >= d
+    int od = 0;
+    if (scale > 0.f) {
+      od = max(0, min(OD - 1, (int)((float)d / scale) - 1));
+      while (od > 0 && (int)(scale * (float)(od - 1)) >= d) --od;
+      while (od < OD && (int)(scale * (float)od) < d) ++od;
+    } else if (d > 0) {
+      od = OD;  // every output plane reads source plane 0
+    }
+    if (od >= OD || (int)(scale * (float)od) != d) continue;
+    float a[8], b[8], o[8];
+    const int d1 = d + (d < D - 1 ? 1 : 0);
+    x16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + d) * HW + hw) * ldx + g * 8), a, x_f16);
+    x16x8_to_float(*reinterpret_cast<const uint4*>(x + ((n * D + d1) * HW + hw) * ldx + g * 8), b, x_f16);
+    for (; od < OD; ++od) {
+      const float src = scale * (float)od;
+      const int i0 = (int)src;
+      if (i0 != d) break;
+      const float l1 = src - (float)i0, l0 = 1.f - l1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = l0 * a[i] + l1 * b[i];
+      *reinterpret_cast<uint4*>(y + ((n * OD + od) * HW + hw) * ldy + g * 8) = float_to_x16x8(o, y_f16);
+    }
   }
 }
 __global__ void __launch_bounds__(256) upsample_d_bwd_kernel(const __nv_bfloat16* dy, long long lddy, __nv_bfloat16* dx,
@@ -1844,6 +1886,15 @@ int rehr_channel_sum(const rehr_tensor* x, float* out, int accumulate, void* ws,
 int rehr_upsample_linear_d(const rehr_tensor* x, const rehr_tensor* y, rehr_stream stream) {
   if (!bf16_tensor_ok(x) || !bf16_tensor_ok(y) || x->c != y->c || x->n != y->n || x->h != y->h || x->w != y->w) return REHR_BAD_SHAPE;
   const long long HW = (long long)x->h * x->w;
+  static const bool legacy = getenv("REHR_UPSAMPLE_LEGACY") != nullptr;  // the output-centric kernel, for A/B runs
+  if (y->d >= x->d && !legacy) {
+    const long long items = (long long)x->n * x->d * HW * (x->c / 8);
+    upsample_d_src_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld, reinterpret_cast<__nv_bfloat16*>(y->ptr), y->ld, x->n, x->d, y->d, HW, x->c,
+        x->dtype == REHR_F16, y->dtype == REHR_F16);
+    REHR_CHECK_LAUNCH();
+    return REHR_OK;
+  }
   const long long items = (long long)y->n * y->d * HW * (y->c / 8);
   upsample_d_kernel<<<grid_for(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->ld,
                                                                            reinterpret_cast<__nv_bfloat16*>(y->ptr), y->ld, x->n, x->d,

@@ -546,3 +546,28 @@ def test_in_bwd_sums_from_dgrad_epilogue(case, monkeypatch):
         # reduce pass sees (the epilogue sums the fp32 accumulators) and by summation order
         tol = 0.0 if name in ("dw2", "dgamma2", "dbeta2") else 4e-3
         assert rel_l2(a, b) <= tol, (name, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("shape,out_d", [((2, 16, 24, 20, 32), 64), ((1, 5, 9, 7, 16), 18), ((1, 1, 8, 8, 8), 4), ((2, 7, 6, 6, 8), 7),
+                                         ((1, 6, 5, 5, 8), 1), ((1, 3, 4, 4, 8), 2)])
+def test_upsample_linear_d_matches_interpolate(shape, out_d):
+    """models/seg_model.py:197-199: F.interpolate(scale_factor=(s, 1, 1), mode='trilinear', align_corners=True) = linear along depth
+    only.  Forward against ATen on the same bf16-rounded input (one bf16 rounding of the result), backward against ATen's gradient of
+    the same map; up-sampling shapes take the source-centric kernel, the down-sampling ones the output-centric one."""
+    from rehrseg_b200 import functional as Fn
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(shape, generator=g).to(torch.bfloat16).cuda().requires_grad_(True)        # channels-last [N, D, H, W, C]
+    n, d, h, w, c = shape
+    y = Fn.upsample_linear_d(x, out_d)
+    assert tuple(y.shape) == (n, out_d, h, w, c) and y.dtype == torch.bfloat16
+    xr = x.detach().float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)           # NCDHW fp32
+    want = F.interpolate(xr, size=(out_d, h, w), mode="trilinear", align_corners=True)
+    got = y.detach().float().permute(0, 4, 1, 2, 3)
+    assert torch.all((got - want.detach()).abs() <= 1.01 * 2.0 ** -8 * want.detach().abs() + 1e-6)   # half a bf16 ulp of the fp32 result
+    if out_d < d:
+        return                                           # the reference only up-samples (upscale >= 1): no gradient contract below that
+    dy = torch.randn(y.shape, generator=g).to(torch.bfloat16).cuda()
+    y.backward(dy)
+    want.backward(dy.float().permute(0, 4, 1, 2, 3))
+    dgot = x.grad.float().permute(0, 4, 1, 2, 3)
+    assert torch.all((dgot - xr.grad).abs() <= 2.0 ** -7 * xr.grad.abs() + 1e-5)
