@@ -472,6 +472,8 @@ def get_intermediate_features(model_sr, img_lr: torch.Tensor, label_lr: torch.Te
     win = _windows(inp, 2)                                          # [D-1, B, 2, 4, H, W]
     nwin = win.shape[0]
     flat = win.reshape(nwin * b, *win.shape[2:])
+    if isinstance(model_sr, (UNet_3D_3D, _EngineForward)) and flat.is_cuda:
+        return _stitched_features_cl(model_sr, flat, nwin, b, max_batch)
     chunks: Optional[List[List[torch.Tensor]]] = None
     for s in range(0, flat.shape[0], max_batch * b):
         feats = model_sr(flat[s:s + max_batch * b].clone(), return_inetermediate_feature=True)
@@ -486,6 +488,37 @@ def get_intermediate_features(model_sr, img_lr: torch.Tensor, label_lr: torch.Te
         mid = f[:, :, :, 1]                                         # slice 1 of every window  [D-1, B, C, h, w]
         last = f[-1:, :, :, 2]                                      # slice 2 of the last window
         out[i] = torch.cat([mid, last], dim=0).permute(1, 2, 0, 3, 4).contiguous()   # [B, C, D, h, w]
+    return out
+
+
+def _stitched_features_cl(model_sr, flat: torch.Tensor, nwin: int, b: int, max_batch: int) -> dict:
+    """Engine teacher: the loop above keeps slice 1 of every window (and slice 2 of the last) of each feature map, so only those
+    depth slices of the channels-last 16-bit encoder outputs are converted to NCDHW fp32 -- a quarter of the adapter traffic of
+    converting all four slices first (2.4 GB per C4 step).  Same values: the conversion is element-wise."""
+    mids: Optional[List[List[torch.Tensor]]] = None
+    lasts: List[torch.Tensor] = []
+    total = flat.shape[0]
+    for s in range(0, total, max_batch * b):
+        images = flat[s:s + max_batch * b].clone()
+        with device_of(images):
+            # the head of UNet_3D_3D.forward (FLAVR_arch.py:171-175): mean of channel 0 removed in place, then the encoder
+            mean_ = images[:, 0:1, ...].mean(2, keepdim=True).mean(3, keepdim=True).mean(4, keepdim=True)
+            images[:, 0:1, ...] = images[:, 0:1, ...] - mean_
+            feats = encoder_forward(model_sr.encoder, images)          # channels-last [n, 4, h, w, C]
+            if mids is None:
+                mids = [[] for _ in feats]
+            def plane(f, lo, k):   # depth slice k of samples lo: as NCHW fp32 (a 16-bit payload mark does not survive slicing)
+                if F_.is_h(f):
+                    return F_.from_channels_last(f)[lo:, :, k]
+                return F_.from_channels_last(f[lo:, k:k + 1].contiguous())[:, :, 0]
+            for i, f in enumerate(feats):
+                mids[i].append(plane(f, 0, 1))                          # [n, C, h, w] fp32
+            if s + images.shape[0] == total:                            # this chunk ends with the last window's b samples
+                lasts = [plane(f, f.shape[0] - b, 2) for f in feats]
+    out = {}
+    for i, parts in enumerate(mids):
+        mid = torch.cat(parts, dim=0).reshape(nwin, b, *parts[0].shape[1:])                  # [D-1, B, C, h, w]
+        out[i] = torch.cat([mid, lasts[i][None]], dim=0).permute(1, 2, 0, 3, 4).contiguous()  # [B, C, D, h, w]
     return out
 
 

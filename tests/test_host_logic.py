@@ -146,3 +146,41 @@ def test_get_random_centers_matches_reference_fixture():
                 for ax, p in enumerate(ps):
                     if p > 1:
                         assert p // 2 + 1 <= xyz[ax] < imgs[i].shape[ax] - p // 2 - 1
+
+
+def test_stitched_teacher_features_match_the_reference_loop(monkeypatch):
+    """flavr._stitched_features_cl (engine teacher: only the kept depth slices leave the channels-last layout) against the generic loop
+    of get_intermediate_features (train_all.py:85-112) on a stand-in encoder, CPU: same windows, same slices, same order."""
+    import contextlib
+    import torch
+    from rehrseg_b200 import flavr
+
+    def fake_encoder(enc, images):                       # NCDHW fp32 -> 3 channels-last "feature maps" that depend on every input slice
+        x = images.permute(0, 2, 3, 4, 1)                # [n, 4, H, W, 2]
+        f0 = torch.cat([x, x * 2.0 + 1.0], dim=4)
+        f1 = (f0[:, :, ::2, ::2] * 3.0 - x.mean(dim=(1, 2, 3, 4), keepdim=True))
+        f2 = f1[:, :, ::2, ::2].cumsum(dim=1)
+        return f0, f1, f2
+
+    class Fake(torch.nn.Module):
+        encoder = None
+
+        def forward(self, images, return_inetermediate_feature=False):
+            mean_ = images[:, 0:1].mean(2, keepdim=True).mean(3, keepdim=True).mean(4, keepdim=True)
+            images[:, 0:1] = images[:, 0:1] - mean_
+            return tuple(f.permute(0, 4, 1, 2, 3).contiguous() for f in fake_encoder(None, images))
+
+    monkeypatch.setattr(flavr, "encoder_forward", fake_encoder)
+    monkeypatch.setattr(flavr, "device_of", lambda t: contextlib.nullcontext())
+    monkeypatch.setattr(flavr.F_, "from_channels_last", lambda t: t.permute(0, 4, 1, 2, 3).contiguous().float())
+    g = torch.Generator().manual_seed(7)
+    for b, d, max_batch in ((2, 6, 2), (1, 2, 8), (3, 5, 1), (2, 9, 3)):
+        img, lab = torch.randn((b, 1, d, 8, 12), generator=g), (torch.rand((b, 1, d, 8, 12), generator=g) > 0.8).float()
+        want = flavr.get_intermediate_features(Fake(), img.clone(), lab, max_batch=max_batch)
+        inp = torch.cat((img, lab), dim=1)
+        win = flavr._windows(inp, 2)
+        flat = win.reshape(win.shape[0] * b, *win.shape[2:])
+        got = flavr._stitched_features_cl(Fake(), flat, win.shape[0], b, max_batch)
+        assert got.keys() == want.keys()
+        for k in want:
+            assert got[k].shape == want[k].shape and got[k].shape[2] == d and torch.equal(got[k], want[k]), (b, d, max_batch, k)

@@ -80,6 +80,14 @@ for p, tag in ((-1.0, "fba_combine_inf"), (2.0, "fba_combine_p2")):
     ms = timed(lambda: check(lib().rehr_fba_combine(arr, 4, p, ptr(torch.view_as_real(outc)), n, stream_ptr()), "fba"))
     row(tag, ms, n * 8 * 5, "4 complex64 reads + 1 write")
 
+# --- depth-only linear up-sampling of the SR head at the C4 shape: [2, 16, 256, 256, 32] bf16 -> depth 64
+del vols, spec, outc, views, hr
+from rehrseg_b200 import functional as Fn
+feats = torch.randn((2, 16, 256, 256, 32), device=dev, generator=g).to(torch.bfloat16)
+with torch.no_grad():
+    ms = timed(lambda: Fn.upsample_linear_d(feats, 64))
+row("upsample_d", ms, feats.numel() * 2 * 5, "1 read + 4x write bf16 (includes the output allocation)")
+
 if len(sys.argv) > 1:
     with open(sys.argv[1], "w") as f:
         json.dump(out, f, indent=1)
