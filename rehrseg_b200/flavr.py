@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import os
 
-from typing import List, Optional
+from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -215,8 +215,9 @@ def basic_block_forward(blk: nn.Module, x):
     return _gate(blk.fg, out, pool, residual=residual, act=ACT_RELU)
 
 
-def encoder_forward(enc: nn.Module, images: torch.Tensor):
-    """VideoResNet.forward (resnet_3D.py:183-189) -> 5 channels-last bf16 feature maps."""
+def encoder_forward(enc: nn.Module, images: torch.Tensor, n_feats: int = 5):
+    """VideoResNet.forward (resnet_3D.py:183-189) -> 5 channels-last bf16 feature maps (`n_feats` < 5: only the first n_feats of
+    them; the layers behind the last requested map are not run)."""
     stem = enc.stem[0]
     if stem.in_channels <= 4:
         x0 = F_.smallcin_conv_act(images, stem.weight, stem.bias, _t3(stem.kernel_size), _t3(stem.stride), _t3(stem.padding, 0),
@@ -225,7 +226,7 @@ def encoder_forward(enc: nn.Module, images: torch.Tensor):
         x0 = _conv(stem, F_.to_channels_last(images), act=ACT_RELU)
     feats = [x0]
     x = x0
-    for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
+    for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4)[:max(0, int(n_feats) - 1)]:
         for blk in layer:
             x = basic_block_forward(blk, x)
         feats.append(x)
@@ -461,10 +462,13 @@ def zscore_normalization(image: torch.Tensor) -> torch.Tensor:
 
 
 def get_intermediate_features(model_sr, img_lr: torch.Tensor, label_lr: torch.Tensor, device=None, normalize=None,
-                              max_batch: int = 8) -> dict:
+                              max_batch: int = 8, keys: Optional[Sequence[int]] = None) -> dict:
     """train_all.py:85-112: teacher encoder features of every 4-slice window, slice 1 of each window (and slice 2 of the
     last) stitched along D.  `normalize` = the reference's `zscore_normalization` (utils/seg_utils.py:137-148), applied in
-    place to `img_lr` exactly as the reference does; the D-1 windows are batched through the encoder."""
+    place to `img_lr` exactly as the reference does; the D-1 windows are batched through the encoder.
+    `keys` (opt-in, not a reference argument): the feature maps the caller will read -- the stage-2 loop reads only `[1]`
+    (train_all.py:550).  None = all five, as the reference returns them; with keys an engine teacher stops after the last
+    requested map and converts only those (identical values for the returned entries)."""
     if normalize is not None:
         img_lr = normalize(img_lr)
     inp = torch.cat((img_lr, label_lr), dim=1)                     # [B, 2, D, H, W]
@@ -473,7 +477,7 @@ def get_intermediate_features(model_sr, img_lr: torch.Tensor, label_lr: torch.Te
     nwin = win.shape[0]
     flat = win.reshape(nwin * b, *win.shape[2:])
     if isinstance(model_sr, (UNet_3D_3D, _EngineForward)) and flat.is_cuda:
-        return _stitched_features_cl(model_sr, flat, nwin, b, max_batch)
+        return _stitched_features_cl(model_sr, flat, nwin, b, max_batch, keys)
     chunks: Optional[List[List[torch.Tensor]]] = None
     for s in range(0, flat.shape[0], max_batch * b):
         feats = model_sr(flat[s:s + max_batch * b].clone(), return_inetermediate_feature=True)
@@ -488,15 +492,20 @@ def get_intermediate_features(model_sr, img_lr: torch.Tensor, label_lr: torch.Te
         mid = f[:, :, :, 1]                                         # slice 1 of every window  [D-1, B, C, h, w]
         last = f[-1:, :, :, 2]                                      # slice 2 of the last window
         out[i] = torch.cat([mid, last], dim=0).permute(1, 2, 0, 3, 4).contiguous()   # [B, C, D, h, w]
+    if keys is not None:
+        out = {int(k): out[int(k)] for k in keys}
     return out
 
 
-def _stitched_features_cl(model_sr, flat: torch.Tensor, nwin: int, b: int, max_batch: int) -> dict:
+def _stitched_features_cl(model_sr, flat: torch.Tensor, nwin: int, b: int, max_batch: int, keys: Optional[Sequence[int]] = None) -> dict:
     """Engine teacher: the loop above keeps slice 1 of every window (and slice 2 of the last) of each feature map, so only those
     depth slices of the channels-last 16-bit encoder outputs are converted to NCDHW fp32 -- a quarter of the adapter traffic of
     converting all four slices first (2.4 GB per C4 step).  Same values: the conversion is element-wise."""
-    mids: Optional[List[List[torch.Tensor]]] = None
-    lasts: List[torch.Tensor] = []
+    want = sorted({int(k) for k in keys}) if keys is not None else list(range(5))
+    if not want or want[0] < 0 or want[-1] > 4:
+        raise RehrError("get_intermediate_features: keys must be a non-empty subset of 0..4")
+    mids: dict = {k: [] for k in want}
+    lasts: dict = {}
     total = flat.shape[0]
     for s in range(0, total, max_batch * b):
         images = flat[s:s + max_batch * b].clone()
@@ -504,19 +513,17 @@ def _stitched_features_cl(model_sr, flat: torch.Tensor, nwin: int, b: int, max_b
             # the head of UNet_3D_3D.forward (FLAVR_arch.py:171-175): mean of channel 0 removed in place, then the encoder
             mean_ = images[:, 0:1, ...].mean(2, keepdim=True).mean(3, keepdim=True).mean(4, keepdim=True)
             images[:, 0:1, ...] = images[:, 0:1, ...] - mean_
-            feats = encoder_forward(model_sr.encoder, images)          # channels-last [n, 4, h, w, C]
-            if mids is None:
-                mids = [[] for _ in feats]
+            feats = encoder_forward(model_sr.encoder, images, n_feats=want[-1] + 1)   # channels-last [n, 4, h, w, C]
             def plane(f, lo, k):   # depth slice k of samples lo: as NCHW fp32 (a 16-bit payload mark does not survive slicing)
                 if F_.is_h(f):
                     return F_.from_channels_last(f)[lo:, :, k]
                 return F_.from_channels_last(f[lo:, k:k + 1].contiguous())[:, :, 0]
-            for i, f in enumerate(feats):
-                mids[i].append(plane(f, 0, 1))                          # [n, C, h, w] fp32
+            for i in want:
+                mids[i].append(plane(feats[i], 0, 1))                   # [n, C, h, w] fp32
             if s + images.shape[0] == total:                            # this chunk ends with the last window's b samples
-                lasts = [plane(f, f.shape[0] - b, 2) for f in feats]
+                lasts = {i: plane(feats[i], feats[i].shape[0] - b, 2) for i in want}
     out = {}
-    for i, parts in enumerate(mids):
+    for i, parts in mids.items():
         mid = torch.cat(parts, dim=0).reshape(nwin, b, *parts[0].shape[1:])                  # [D-1, B, C, h, w]
         out[i] = torch.cat([mid, lasts[i][None]], dim=0).permute(1, 2, 0, 3, 4).contiguous()  # [B, C, D, h, w]
     return out

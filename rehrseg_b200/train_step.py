@@ -159,11 +159,14 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int
 # ---------------------------------------------------------------------------------------------------------------
 def joint_train_step(model_seg: nn.Module, batch: Sequence[torch.Tensor], loss_obj_lr_seg: nn.Module, loss_obj_hr_seg: nn.Module,
                      opt: Optional[torch.optim.Optimizer] = None, model_sr: Optional[nn.Module] = None,
-                     distiller: Optional[nn.Module] = None, enable_uncertainty: bool = True, group=None, device=None) -> dict:
+                     distiller: Optional[nn.Module] = None, enable_uncertainty: bool = True, group=None, device=None,
+                     teacher_keys: Optional[Sequence[int]] = None) -> dict:
     """One iteration of the stage-2 loop, train_all.py:519-558.  `batch` = (img, label_lr, label, uncertainty_lr) exactly
     as the reference DataLoader yields them; `model_sr` + `distiller` switch distillation on (train_all.py:494-495,
     530-533, 547-552).  With an initialised process group the gradients are averaged over ranks before `opt.step()`.
-    Returns the detached loss terms."""
+    `teacher_keys` (opt-in): passed to `get_intermediate_features(keys=...)`; the loop reads only `features_sr[1]` (:550), so
+    `(1,)` lets an engine teacher stop after layer1 -- same losses and gradients, none of the discarded maps computed.  Default
+    None = the reference's workload (all five maps).  Returns the detached loss terms."""
     img, label_lr, label, uncertainty_lr = batch
     device = device if device is not None else next(model_seg.parameters()).device
     model_seg.train()
@@ -176,7 +179,7 @@ def joint_train_step(model_seg: nn.Module, batch: Sequence[torch.Tensor], loss_o
             # the reference's zscore_normalization mutates `pseudo_img_lr` in place (utils/seg_utils.py:137-148), so the
             # student below sees the normalised image as well -- preserved
             features_sr = _flavr.get_intermediate_features(model_sr, pseudo_img_lr, pseudo_label_lr, device,
-                                                           normalize=_flavr.zscore_normalization)
+                                                           normalize=_flavr.zscore_normalization, keys=teacher_keys)
         pseudo_seg_lr, seg_sr, features_seg = model_seg(pseudo_img_lr, return_inetermediate_feature=True)
     else:
         pseudo_seg_lr, seg_sr = model_seg(pseudo_img_lr)
@@ -237,7 +240,7 @@ class GraphedJointStep:
 
     def __init__(self, model_seg: nn.Module, example_batch: Sequence[torch.Tensor], loss_obj_lr_seg: nn.Module,
                  loss_obj_hr_seg: nn.Module, model_sr: Optional[nn.Module] = None, distiller: Optional[nn.Module] = None,
-                 enable_uncertainty: bool = True, dp_group=None):
+                 enable_uncertainty: bool = True, dp_group=None, teacher_keys: Optional[Sequence[int]] = None):
         from .graphs import GraphedTrainStep
         device = next(model_seg.parameters()).device
         model_seg.train()
@@ -250,7 +253,7 @@ class GraphedJointStep:
             if distill:
                 with torch.no_grad():
                     features_sr = _flavr.get_intermediate_features(model_sr, pseudo_img_lr, pseudo_label_lr, device,
-                                                                   normalize=_flavr.zscore_normalization)
+                                                                   normalize=_flavr.zscore_normalization, keys=teacher_keys)
                 pseudo_seg_lr, seg_sr, features_seg = model_seg(pseudo_img_lr, return_inetermediate_feature=True)
             else:
                 pseudo_seg_lr, seg_sr = model_seg(pseudo_img_lr)

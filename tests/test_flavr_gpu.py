@@ -96,6 +96,11 @@ def test_get_intermediate_features_and_window_sweep():
     assert sorted(feats.keys()) == [0, 1, 2, 3, 4]
     for i, key in ((1, "gif_f1"), (3, "gif_f3")):
         assert feats[i].shape == z[key].shape and rel(feats[i], torch.from_numpy(z[key])) <= 1e-2, key
+    # opt-in `keys` (the stage-2 loop reads only [1]): the teacher stops after layer1, the returned map is the same tensor bit for bit
+    with torch.no_grad():
+        only1 = flavr.get_intermediate_features(teacher, torch.from_numpy(z["gif_img"]).cuda(), lab, normalize=flavr.zscore_normalization,
+                                                max_batch=3, keys=(1,))
+    assert sorted(only1.keys()) == [1] and torch.equal(only1[1], feats[1])
     # apply_to_vol_flavr: batched sweep vs the oracle's one-window-at-a-time restatement (ragged in-plane size -> pad to 16)
     ref, mine = _pair(False, seed=9)
     vol = torch.rand((6, 2, 40, 24), generator=torch.Generator().manual_seed(6))

@@ -155,12 +155,13 @@ def test_stitched_teacher_features_match_the_reference_loop(monkeypatch):
     import torch
     from rehrseg_b200 import flavr
 
-    def fake_encoder(enc, images):                       # NCDHW fp32 -> 3 channels-last "feature maps" that depend on every input slice
+    def fake_encoder(enc, images, n_feats=5):            # NCDHW fp32 -> 5 channels-last "feature maps" that depend on every input slice
         x = images.permute(0, 2, 3, 4, 1)                # [n, 4, H, W, 2]
         f0 = torch.cat([x, x * 2.0 + 1.0], dim=4)
         f1 = (f0[:, :, ::2, ::2] * 3.0 - x.mean(dim=(1, 2, 3, 4), keepdim=True))
         f2 = f1[:, :, ::2, ::2].cumsum(dim=1)
-        return f0, f1, f2
+        f3, f4 = f2 * f2, f2.flip(1) - 1.0
+        return (f0, f1, f2, f3, f4)[:n_feats]
 
     class Fake(torch.nn.Module):
         encoder = None
@@ -184,3 +185,13 @@ def test_stitched_teacher_features_match_the_reference_loop(monkeypatch):
         assert got.keys() == want.keys()
         for k in want:
             assert got[k].shape == want[k].shape and got[k].shape[2] == d and torch.equal(got[k], want[k]), (b, d, max_batch, k)
+        # opt-in `keys`: only the requested maps, the same values; the stand-in encoder is asked for no map behind the last one
+        for keys in ((1,), (0, 3), (4,)):
+            sub = flavr._stitched_features_cl(Fake(), flat, win.shape[0], b, max_batch, keys)
+            assert sorted(sub) == sorted(keys) and all(torch.equal(sub[k], want[k]) for k in keys)
+            gen = flavr.get_intermediate_features(Fake(), img.clone(), lab, max_batch=max_batch, keys=keys)   # generic (non-engine) path
+            assert sorted(gen) == sorted(keys) and all(torch.equal(gen[k], want[k]) for k in keys)
+    import pytest
+    from rehrseg_b200._lib import RehrError
+    with pytest.raises(RehrError):
+        flavr._stitched_features_cl(Fake(), flat, win.shape[0], b, max_batch, (5,))

@@ -5,4 +5,5 @@ import torch
 import bench, bench_extras
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-print(json.dumps(bench_extras.c4_joint(dev, bench.measured_peaks())))
+keys = (1,) if len(sys.argv) > 1 and sys.argv[1] == "keys" else None
+print(json.dumps(bench_extras.c4_joint(dev, bench.measured_peaks(), teacher_keys=keys)))
