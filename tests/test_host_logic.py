@@ -195,3 +195,32 @@ def test_stitched_teacher_features_match_the_reference_loop(monkeypatch):
     from rehrseg_b200._lib import RehrError
     with pytest.raises(RehrError):
         flavr._stitched_features_cl(Fake(), flat, win.shape[0], b, max_batch, (5,))
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under rehrseg_b200/ may import it, and nothing there, in bench.py / bench_extras.py
+    or in __graft_entry__.py may read /root/reference at run time (it does not exist on the GPU box).  bench.py and smoke() may use
+    the oracle, but only as the CPU baseline / the checker."""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def imported_roots(path):
+        with open(path) as f:
+            tree = ast.parse(f.read())
+        roots = set()
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import):
+                roots.update(a.name.split(".")[0] for a in node.names)
+            elif isinstance(node, ast.ImportFrom) and node.level == 0 and node.module:
+                roots.add(node.module.split(".")[0])
+        return roots
+
+    for path in glob.glob(os.path.join(root, "rehrseg_b200", "*.py")):
+        assert "oracle" not in imported_roots(path), path
+    for path in glob.glob(os.path.join(root, "rehrseg_b200", "*.py")) + [os.path.join(root, n) for n in
+                                                                          ("bench.py", "bench_extras.py", "__graft_entry__.py")]:
+        with open(path) as f:
+            for line in f:      # citations in docstrings / messages are fine; path handling is not
+                if "/root/reference" in line:
+                    assert not any(tok in line for tok in ("open(", "sys.path", "os.path", "listdir", "exists(", "insert(", "import ")), (path, line)
