@@ -286,9 +286,9 @@ def run_all(dev, peaks, rank, world, make_oracle_unet, batch, patch) -> dict:
         guarded("c2_flavr", lambda: c2_flavr(dev, peaks))
         guarded("c2_flavr_uasr", lambda: c2_flavr(dev, peaks, uasr=True))
         guarded("c4_joint", lambda: c4_joint(dev, peaks))
-        guarded("c4_joint_needed_features", lambda: c4_joint(dev, peaks, teacher_keys=(1,)))
         guarded("c5_pipeline", lambda: c5_pipeline(dev, peaks))
         guarded("loaders", lambda: loaders(dev))
         if os.environ.get("REHR_BENCH_EAGER", "1") != "0":
             guarded("eager_gpu", lambda: eager_gpu(dev, make_oracle_unet, batch, patch))
+        guarded("c4_joint_needed_features", lambda: c4_joint(dev, peaks, teacher_keys=(1,)))   # opt-in variant, last: see c4_joint
     return out if rank == 0 else {}
